@@ -1,0 +1,433 @@
+"""Seeded synthetic boxes for the constant-pH hot path.
+
+The reference ships no input decks, so every configuration that
+BASELINE.json names is generated here, identically for the CPU oracle and the
+CUDA path: SPC/E water on a jittered lattice plus 8-atom titratable solutes
+(acetic acid: carboxyl site, methylammonium: amine site) that carry a
+protonated (A) and a deprotonated (B) charge set, LAMMPS-style special-bond
+tables, and the two mask groups the reference's constructor takes
+(fix_constant_pH.cpp:39-46: hydrogen group, 3-atom water group).
+
+Pure numpy; no device code.  `units real` throughout.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+import numpy as np
+
+# ---- unit system: LAMMPS `units real` -----------------
+QQRD2E = 332.06371
+BOLTZ = 0.0019872067
+FTM2V = 1.0 / 48.88821291 / 48.88821291
+
+STYLE_COUL_CUT = 0   # pair lj/cut/coul/cut
+STYLE_COUL_DSF = 1   # pair lj/cut/coul/dsf
+
+GROUP_ALL_BIT = 1
+GROUP_H_BIT = 2      # arg[4] of the fix (fix_constant_pH.cpp:39-41)
+GROUP_W_BIT = 4      # arg[5] of the fix (fix_constant_pH.cpp:42-46), exactly 3 atoms
+
+# ---- atom types (1-based, LAMMPS convention) ----------------------------------
+#            eps [kcal/mol], sigma [A]
+_TYPES = {
+    1: ("OW", 0.1553, 3.166),
+    2: ("HW", 0.0, 0.0),
+    3: ("CT", 0.080, 3.50),
+    4: ("CC", 0.070, 3.56),
+    5: ("OC", 0.120, 3.03),
+    6: ("OH", 0.152, 3.15),
+    7: ("HO", 0.046, 0.40),
+    8: ("HC", 0.022, 2.35),
+    9: ("NH", 0.200, 3.29),
+    10: ("HN", 0.046, 0.40),
+}
+NTYPES = 10
+
+# water geometry (SPC/E)
+_R_OH = 1.0
+_THETA = np.deg2rad(109.47)
+_WATER_LOCAL = np.array([
+    [0.0, 0.0, 0.0],
+    [_R_OH * np.sin(_THETA / 2), _R_OH * np.cos(_THETA / 2), 0.0],
+    [-_R_OH * np.sin(_THETA / 2), _R_OH * np.cos(_THETA / 2), 0.0],
+])
+_WATER_Q = np.array([-0.8476, 0.4238, 0.4238])
+_WATER_TYPE = np.array([1, 2, 2], dtype=np.int32)
+_WATER_BONDS = [(0, 1), (0, 2)]
+
+# acetic acid, 8 atoms, C-C axis along x, centred near the origin
+_ACID_LOCAL = np.array([
+    [-0.76, 0.00, 0.00],    # 0 CT methyl carbon
+    [0.76, 0.00, 0.00],     # 1 CC carboxyl carbon
+    [1.38, 1.05, 0.00],     # 2 OC carbonyl oxygen
+    [1.44, -1.12, 0.00],    # 3 OH hydroxyl oxygen
+    [2.40, -1.02, 0.00],    # 4 HO titratable proton
+    [-1.14, 1.02, 0.00],    # 5 HC
+    [-1.14, -0.51, 0.88],   # 6 HC
+    [-1.14, -0.51, -0.88],  # 7 HC
+])
+_ACID_TYPE = np.array([3, 4, 5, 6, 7, 8, 8, 8], dtype=np.int32)
+_ACID_QA = np.array([-0.30, 0.75, -0.55, -0.61, 0.44, 0.09, 0.09, 0.09])   # protonated, sum 0
+_ACID_QB = np.array([-0.37, 0.62, -0.76, -0.76, 0.00, 0.09, 0.09, 0.09])   # deprotonated, sum -1
+_ACID_BONDS = [(0, 1), (1, 2), (1, 3), (3, 4), (0, 5), (0, 6), (0, 7)]
+_ACID_HGROUP = [4]
+
+# methylammonium, 8 atoms
+_AMINE_LOCAL = np.array([
+    [-0.745, 0.00, 0.00],   # 0 CT
+    [0.745, 0.00, 0.00],    # 1 NH
+    [1.105, -0.96, 0.00],   # 2 HN titratable proton
+    [1.105, 0.48, 0.83],    # 3 HN
+    [1.105, 0.48, -0.83],   # 4 HN
+    [-1.125, 1.02, 0.00],   # 5 HC
+    [-1.125, -0.51, 0.88],  # 6 HC
+    [-1.125, -0.51, -0.88], # 7 HC
+])
+_AMINE_TYPE = np.array([3, 9, 10, 10, 10, 8, 8, 8], dtype=np.int32)
+_AMINE_QA = np.array([0.13, -0.30, 0.33, 0.33, 0.33, 0.06, 0.06, 0.06])    # protonated, sum +1
+_AMINE_QB = np.array([0.10, -0.96, 0.00, 0.34, 0.34, 0.06, 0.06, 0.06])    # deprotonated, sum 0
+_AMINE_BONDS = [(0, 1), (1, 2), (1, 3), (1, 4), (0, 5), (0, 6), (0, 7)]
+_AMINE_HGROUP = [2]
+
+PK_CARBOXYL = 4.76
+PK_AMINE = 10.6
+
+
+def _special_template(natoms, bonds):
+    """1-2 / 1-3 / 1-4 partner lists of a small molecule (LAMMPS `special` layout:
+    per atom [1-2 ..., 1-3 ..., 1-4 ...] with cumulative counts in nspecial)."""
+    adj = [set() for _ in range(natoms)]
+    for a, b in bonds:
+        adj[a].add(b)
+        adj[b].add(a)
+    out = []
+    for i in range(natoms):
+        d = {i: 0}
+        frontier = [i]
+        for depth in (1, 2, 3):
+            nxt = []
+            for u in frontier:
+                for v in sorted(adj[u]):
+                    if v not in d:
+                        d[v] = depth
+                        nxt.append(v)
+            frontier = nxt
+        l12 = sorted(v for v, k in d.items() if k == 1)
+        l13 = sorted(v for v, k in d.items() if k == 2)
+        l14 = sorted(v for v, k in d.items() if k == 3)
+        out.append((l12, l13, l14))
+    return out
+
+
+@dataclass
+class Box:
+    """One synthetic system in LAMMPS per-atom layout (host arrays, caller order)."""
+    name: str
+    boxlo: np.ndarray
+    boxhi: np.ndarray
+    x: np.ndarray          # (n,3) f64
+    q: np.ndarray          # (n,) f64 -- charges at lambda0 (QL mode) / qA
+    type: np.ndarray       # (n,) i32, 1-based
+    tag: np.ndarray        # (n,) i32, 1-based global ids
+    mask: np.ndarray       # (n,) i32 group bits
+    molecule: np.ndarray   # (n,) i32
+    nspecial: np.ndarray   # (n,3) i32 cumulative 1-2,1-3,1-4 counts
+    special: np.ndarray    # (n,maxspecial) i32 partner tags
+    maxspecial: int
+    ntypes: int
+    epsilon: np.ndarray    # (ntypes+1, ntypes+1) mixed
+    sigma: np.ndarray
+    style: int
+    cut_lj: float
+    cut_coul: float
+    alpha: float
+    special_lj: np.ndarray   # (4,) [1, f12, f13, f14]
+    special_coul: np.ndarray
+    skin: float
+    # titration sites
+    nsites: int
+    pK: np.ndarray         # (S,)
+    titr_tag: np.ndarray   # (A_t,) i32 tags of atoms whose charge depends on lambda
+    titr_site: np.ndarray  # (A_t,) i32 site index
+    qA: np.ndarray         # (A_t,)
+    qB: np.ndarray         # (A_t,)
+    lambda0: np.ndarray    # (S,)
+    v0: np.ndarray         # (S,)
+    pH: float = 4.8
+    T: float = 300.0
+    dt: float = 1.0
+    meta: dict = field(default_factory=dict)
+
+    @property
+    def n(self):
+        return int(self.x.shape[0])
+
+    def charges_at(self, lam):
+        """q(lambda) = (1-lambda) qA + lambda qB for titratable atoms (north_star)."""
+        q = self.q.copy()
+        pos = self.meta["tag_to_index"][self.titr_tag]
+        q[pos] = self.qA + lam[self.titr_site] * (self.qB - self.qA)
+        return q
+
+
+def mix_geometric(eps, sig):
+    """LAMMPS default `pair_modify mix geometric`."""
+    nt = len(eps) - 1
+    e = np.zeros((nt + 1, nt + 1))
+    s = np.zeros((nt + 1, nt + 1))
+    for i in range(1, nt + 1):
+        for j in range(1, nt + 1):
+            e[i, j] = np.sqrt(eps[i] * eps[j])
+            s[i, j] = np.sqrt(sig[i] * sig[j])
+    return e, s
+
+
+def _random_rotations(rng, n):
+    """n uniformly random rotation matrices from unit quaternions."""
+    qn = rng.normal(size=(n, 4))
+    qn /= np.linalg.norm(qn, axis=1, keepdims=True)
+    w, x, y, z = qn[:, 0], qn[:, 1], qn[:, 2], qn[:, 3]
+    R = np.empty((n, 3, 3))
+    R[:, 0, 0] = 1 - 2 * (y * y + z * z)
+    R[:, 0, 1] = 2 * (x * y - z * w)
+    R[:, 0, 2] = 2 * (x * z + y * w)
+    R[:, 1, 0] = 2 * (x * y + z * w)
+    R[:, 1, 1] = 1 - 2 * (x * x + z * z)
+    R[:, 1, 2] = 2 * (y * z - x * w)
+    R[:, 2, 0] = 2 * (x * z - y * w)
+    R[:, 2, 1] = 2 * (y * z + x * w)
+    R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    return R
+
+
+def _lattice_dims(n_atoms_target):
+    """Near-cubic (nx,ny,nz) whose slot count best matches n_atoms_target/3 waters."""
+    slots = n_atoms_target / 3.0
+    c = int(round(slots ** (1.0 / 3.0)))
+    best = None
+    for nx in range(max(2, c - 2), c + 3):
+        for ny in range(nx, c + 3):
+            for nz in range(ny, c + 3):
+                err = abs(nx * ny * nz - slots)
+                if best is None or err < best[0]:
+                    best = (err, (nx, ny, nz))
+    return best[1]
+
+
+def make_box(name="custom", n_atoms=3000, n_acid=1, n_amine=0, style=STYLE_COUL_CUT,
+             seed=1, cut=10.0, skin=2.0, alpha=0.2, pH=4.8, T=300.0, dense_titr_frac=0.0,
+             jitter=0.3, shuffle=False, special_14=0.5):
+    """Build a water + solute box.
+
+    n_acid / n_amine solutes each take three lattice slots along x (the solute
+    sits in the middle one) so that no water overlaps them.  dense_titr_frac > 0
+    additionally turns that fraction of *water* atoms into single-atom sites
+    (BASELINE config 5).
+    """
+    rng = np.random.default_rng(seed)
+    spacing = (1.0 / 0.0334) ** (1.0 / 3.0)
+    nx, ny, nz = _lattice_dims(n_atoms)
+    dims = np.array([nx, ny, nz])
+    L = dims * spacing
+    nsol = n_acid + n_amine
+
+    occupied = np.zeros((nx, ny, nz), dtype=np.int8)    # 0 water, 1 solute centre, 2 emptied
+    centres = []
+    if nsol:
+        cand = [(i, j, k) for i in range(1, nx - 1, 3) for j in range(ny) for k in range(nz)]
+        if len(cand) < nsol:
+            raise ValueError("box too small for %d solutes" % nsol)
+        pick = rng.choice(len(cand), size=nsol, replace=False)
+        pick.sort()
+        for p in pick:
+            i, j, k = cand[p]
+            occupied[i, j, k] = 1
+            occupied[i - 1, j, k] = 2
+            occupied[i + 1, j, k] = 2
+            centres.append((i, j, k))
+    wi, wj, wk = np.nonzero(occupied == 0)
+    nwat = wi.size
+
+    # --- waters -------------------------------------------------------------
+    cw = (np.stack([wi, wj, wk], axis=1) + 0.5) * spacing
+    cw += rng.uniform(-jitter, jitter, size=cw.shape)
+    R = _random_rotations(rng, nwat)
+    xw = cw[:, None, :] + np.einsum("nij,aj->nai", R, _WATER_LOCAL)     # (nwat,3,3)
+    n_w_atoms = 3 * nwat
+    x = [xw.reshape(-1, 3)]
+    q = [np.tile(_WATER_Q, nwat)]
+    typ = [np.tile(_WATER_TYPE, nwat)]
+    mol = [np.repeat(np.arange(1, nwat + 1, dtype=np.int32), 3)]
+    maxspecial = 7 if nsol else 2
+    wt = _special_template(3, _WATER_BONDS)
+
+    n = n_w_atoms + 8 * nsol
+    nspecial = np.zeros((n, 3), dtype=np.int32)
+    special = np.zeros((n, maxspecial), dtype=np.int32)
+    base = np.arange(nwat, dtype=np.int32) * 3 + 1                       # tag of atom 0 of each water
+    for a in range(3):
+        l12, l13, l14 = wt[a]
+        rows = np.arange(nwat) * 3 + a
+        nspecial[rows, 0] = len(l12)
+        nspecial[rows, 1] = len(l12) + len(l13)
+        nspecial[rows, 2] = len(l12) + len(l13) + len(l14)
+        for c, b in enumerate(l12 + l13 + l14):
+            special[rows, c] = base + b
+
+    mask = np.full(n, GROUP_ALL_BIT, dtype=np.int32)
+    mask[0:3] |= GROUP_W_BIT                    # first water = the fix's 3-atom water group
+
+    # --- solutes ------------------------------------------------------------
+    titr_tag, titr_site, qA, qB, pK = [], [], [], [], []
+    at = _special_template(8, _ACID_BONDS)
+    mt = _special_template(8, _AMINE_BONDS)
+    kinds = np.array([0] * n_acid + [1] * n_amine)
+    if nsol:
+        kinds = kinds[rng.permutation(nsol)]
+    off = n_w_atoms
+    for s, (i, j, k) in enumerate(centres):
+        kind = int(kinds[s])
+        local = _ACID_LOCAL if kind == 0 else _AMINE_LOCAL
+        ang = rng.uniform(0, 2 * np.pi)
+        ca, sa = np.cos(ang), np.sin(ang)
+        Rx = np.array([[1, 0, 0], [0, ca, -sa], [0, sa, ca]])
+        c0 = (np.array([i, j, k]) + 0.5) * spacing + rng.uniform(-0.2, 0.2, size=3)
+        x.append(c0 + local @ Rx.T)
+        a_q, b_q = (_ACID_QA, _ACID_QB) if kind == 0 else (_AMINE_QA, _AMINE_QB)
+        q.append(a_q.copy())
+        typ.append(_ACID_TYPE if kind == 0 else _AMINE_TYPE)
+        mol.append(np.full(8, nwat + 1 + s, dtype=np.int32))
+        tmpl = at if kind == 0 else mt
+        for a in range(8):
+            l12, l13, l14 = tmpl[a]
+            row = off + a
+            nspecial[row] = (len(l12), len(l12) + len(l13), len(l12) + len(l13) + len(l14))
+            for c, b in enumerate(l12 + l13 + l14):
+                special[row, c] = off + b + 1
+        for a in (_ACID_HGROUP if kind == 0 else _AMINE_HGROUP):
+            mask[off + a] |= GROUP_H_BIT
+        for a in range(8):
+            if a_q[a] != b_q[a]:
+                titr_tag.append(off + a + 1)
+                titr_site.append(s)
+                qA.append(a_q[a])
+                qB.append(b_q[a])
+        pK.append(PK_CARBOXYL if kind == 0 else PK_AMINE)
+        off += 8
+
+    x = np.concatenate(x).astype(np.float64)
+    q = np.concatenate(q).astype(np.float64)
+    typ = np.concatenate(typ).astype(np.int32)
+    mol = np.concatenate(mol).astype(np.int32)
+    tag = np.arange(1, n + 1, dtype=np.int32)
+
+    nsites = nsol
+    # --- dense single-atom sites on water atoms (config 5) --------------------
+    if dense_titr_frac > 0.0:
+        nd = int(round(dense_titr_frac * n))
+        pick = rng.choice(n_w_atoms, size=nd, replace=False)
+        pick.sort()
+        dq = rng.uniform(-0.15, 0.15, size=nd)
+        for c, p in enumerate(pick):
+            titr_tag.append(int(p) + 1)
+            titr_site.append(nsites + c)
+            qA.append(q[p])
+            qB.append(q[p] + dq[c])
+            pK.append(PK_CARBOXYL if c % 2 == 0 else PK_AMINE)
+        mask[pick[typ[pick] == 2]] |= GROUP_H_BIT
+        nsites += nd
+
+    # wrap into the periodic box, atom by atom (LAMMPS remaps atoms, not molecules)
+    x -= np.floor(x / L) * L
+    x = np.minimum(x, np.nextafter(L, 0.0))
+
+    lam0 = np.zeros(nsites)
+    half = nsites // 2
+    lam0[:half] = 0.5
+    lam0[half:] = (np.arange(nsites - half) % 2).astype(np.float64)
+    if nsites == 1:
+        lam0[:] = 0.5
+
+    titr_tag = np.array(titr_tag, dtype=np.int32)
+    titr_site = np.array(titr_site, dtype=np.int32)
+    qA = np.array(qA, dtype=np.float64)
+    qB = np.array(qB, dtype=np.float64)
+    pK = np.array(pK, dtype=np.float64)
+
+    if shuffle:
+        perm = rng.permutation(n)
+        x, q, typ, tag, mask, mol = x[perm], q[perm], typ[perm], tag[perm], mask[perm], mol[perm]
+        nspecial, special = nspecial[perm], special[perm]
+    tag_to_index = np.zeros(n + 1, dtype=np.int64)
+    tag_to_index[tag] = np.arange(n)
+
+    # charges at lambda0
+    if titr_tag.size:
+        q[tag_to_index[titr_tag]] = qA + lam0[titr_site] * (qB - qA)
+
+    eps = np.zeros(NTYPES + 1)
+    sig = np.zeros(NTYPES + 1)
+    for t, (_, e, s_) in _TYPES.items():
+        eps[t], sig[t] = e, s_
+    epsilon, sigma = mix_geometric(eps, sig)
+
+    return Box(
+        name=name, boxlo=np.zeros(3), boxhi=L.astype(np.float64),
+        x=np.ascontiguousarray(x), q=np.ascontiguousarray(q), type=np.ascontiguousarray(typ),
+        tag=np.ascontiguousarray(tag), mask=np.ascontiguousarray(mask),
+        molecule=np.ascontiguousarray(mol), nspecial=np.ascontiguousarray(nspecial),
+        special=np.ascontiguousarray(special), maxspecial=maxspecial, ntypes=NTYPES,
+        epsilon=epsilon, sigma=sigma, style=style, cut_lj=cut, cut_coul=cut, alpha=alpha,
+        special_lj=np.array([1.0, 0.0, 0.0, special_14]),
+        special_coul=np.array([1.0, 0.0, 0.0, special_14]),
+        skin=skin, nsites=nsites, pK=pK, titr_tag=titr_tag, titr_site=titr_site, qA=qA, qB=qB,
+        lambda0=lam0, v0=np.zeros(nsites), pH=pH, T=T, dt=1.0,
+        meta={"seed": seed, "lattice": (nx, ny, nz), "n_water": int(nwat), "n_acid": n_acid,
+              "n_amine": n_amine, "tag_to_index": tag_to_index},
+    )
+
+
+# ---- the configurations BASELINE.json names ---------------------
+def config(k, scale=1.0, **kw):
+    """BASELINE.json configs[k-1].  `scale` < 1 shrinks atom and site counts
+    proportionally (parity tests run the large configs at reduced size)."""
+    if k == 1:
+        return make_box("cfg1", n_atoms=3000, n_acid=1, style=STYLE_COUL_CUT, seed=1, pH=4.8, **kw)
+    if k == 2:
+        return make_box("cfg2", n_atoms=int(32000 * scale), n_acid=max(1, int(10 * scale)),
+                        n_amine=max(1, int(10 * scale)), style=STYLE_COUL_DSF, seed=2,
+                        pH=kw.pop("pH", 7.0), **kw)
+    if k == 3:
+        ns = max(2, int(2000 * scale))
+        return make_box("cfg3", n_atoms=int(1_000_000 * scale), n_acid=ns // 2, n_amine=ns - ns // 2,
+                        style=STYLE_COUL_DSF, seed=3, pH=kw.pop("pH", 7.0), **kw)
+    if k == 4:
+        # stand-in for the 4M-atom PAA melt: same atom / site counts, solutes as monomers
+        ns = max(2, int(50_000 * scale))
+        return make_box("cfg4", n_atoms=int(4_000_000 * scale), n_acid=ns, n_amine=0,
+                        style=STYLE_COUL_DSF, seed=4, pH=kw.pop("pH", 4.8), **kw)
+    if k == 5:
+        return make_box("cfg5", n_atoms=int(512_000 * scale), n_acid=0, n_amine=0,
+                        style=STYLE_COUL_DSF, seed=5, dense_titr_frac=0.10,
+                        pH=kw.pop("pH", 7.0), **kw)
+    raise ValueError("unknown config %r" % (k,))
+
+
+def jiggle_params(box, amp=0.45, period_lo=60.0, period_hi=140.0, seed=12345):
+    """Prescribed rigid-molecule motion x_i(t) = x_i(0) + A_m sin(w_m t + p_m) used by the
+    tests and the bench as the stand-in for the host MD integrator (which is LAMMPS's
+    job, not the fix's).  Keyed on molecule id so every rank derives the same motion."""
+    nm = int(box.molecule.max()) + 1
+    rng = np.random.default_rng(seed)
+    A = rng.uniform(-amp, amp, size=(nm, 3))
+    w = 2 * np.pi / rng.uniform(period_lo, period_hi, size=(nm, 3))
+    p = rng.uniform(0, 2 * np.pi, size=(nm, 3))
+    return A, w, p
+
+
+def jiggle_positions(box, params, t, x0=None):
+    """Positions at time t (fs) under `jiggle_params`; not wrapped (drift is < 1 A)."""
+    A, w, p = params
+    x0 = box.x if x0 is None else x0
+    m = box.molecule
+    return x0 + A[m] * (np.sin(w[m] * t + p[m]) - np.sin(p[m]))

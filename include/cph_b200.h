@@ -1,0 +1,197 @@
+/* cph_b200.h -- C ABI of libcph_b200.so: the sm_100a CUDA implementation of the
+ * per-timestep hot path of LAMMPS `fix constant_pH`.
+ *
+ * Reference being replaced: MahdiTavakol/Constant_pH, fix_constant_pH.{h,cpp}
+ * (cited below as h:N / cpp:N).  Each entry point names the reference interface
+ * it stands in for.  Where the reference has nothing (pair
+ * re-evaluation, q(lambda), per-site dU/dlambda, neighbour list, restart) the
+ * comment says "north_star" and the CPU oracle under oracle/ is the spec.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative CPH_ERR_* otherwise; it never
+ *     throws and never aborts.  cph_last_error() gives the message.
+ *   - plain pointers and sizes only.  `where` selects the address space of the
+ *     caller's per-atom buffers: CPH_HOST (pageable or pinned host memory; the
+ *     library copies) or CPH_DEVICE (device memory on the handle's GPU; the library
+ *     reads/writes it in place on its own stream).
+ *   - per-atom arrays are in the CALLER's order (LAMMPS local index 0..nlocal-1);
+ *     the library keeps its own cell-sorted order internally.
+ *   - one handle per rank/GPU; a handle is not thread-safe, distinct handles are
+ *     independent.  All device work is issued on one library-owned stream;
+ *     functions that return data to the host synchronise that stream themselves.
+ *   - types follow the default LAMMPS build (-DLAMMPS_SMALLBIG): tagint = int32,
+ *     bigint = int64.
+ *
+ * The CPU oracle exports the same functions with the prefix orc_ (oracle/), so the
+ * parity tests drive both through one table (constant_ph_b200/capi.py).
+ */
+#ifndef CPH_B200_H
+#define CPH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cph_handle cph_handle;
+
+/* ---- error codes ------------------------------------------------------------ */
+#define CPH_OK            0
+#define CPH_ERR_ARG      -1   /* bad argument (the reference's error->all on bad input, cpp:36-45) */
+#define CPH_ERR_STATE    -2   /* call out of order (e.g. pair pass before atoms were set) */
+#define CPH_ERR_CUDA     -3   /* CUDA runtime failure, or no CUDA device: there is no CPU fallback */
+#define CPH_ERR_COMM     -4   /* NCCL / rank-group failure */
+#define CPH_ERR_OVERFLOW -5   /* capacity exceeded after automatic regrow failed */
+#define CPH_ERR_DOMAIN   -6   /* box / sub-box smaller than the ghost cutoff allows */
+
+#define CPH_HOST   0
+#define CPH_DEVICE 1
+
+/* pair styles named by BASELINE.json */
+#define CPH_PAIR_LJ_CUT_COUL_CUT 0
+#define CPH_PAIR_LJ_CUT_COUL_DSF 1
+
+/* what drives the lambda force (cph_set_mode) */
+#define CPH_DUDL_REFERENCE 0  /* HB-HA from the per-atom energy partition, cpp:264-267 + cpp:111 */
+#define CPH_DUDL_CHARGE    1  /* north_star: dU/dlambda_s = sum_i dq_i (phi_i + 2 q_i C_self) with q(lambda) */
+
+/* how lambda is advanced */
+#define CPH_INTEGRATE_REFERENCE 0  /* one kinematic step inside post_force, cpp:109-117 */
+#define CPH_INTEGRATE_VV        1  /* velocity-Verlet halves in initial/final_integrate (north_star) */
+
+/* bias derivative flavour */
+#define CPH_BIAS_EXACT      0  /* exact d/dlambda of cpp:132-136, erf in fp64 */
+#define CPH_BIAS_AS_WRITTEN 1  /* cpp:123, cpp:137-141 verbatim, erff in fp32 */
+
+/* force scale of cpp:162-170 */
+#define CPH_FSCALE_LAMBDA     0  /* f *= lambda, as written (cpp:166-168) */
+#define CPH_FSCALE_ONE_MINUS  1  /* f *= (1-lambda), consistent with cpp:114 */
+
+/* ---- lifecycle -------------------------------------------------------------- */
+int cph_version(void);
+/* FixConstantPH::FixConstantPH (cpp:33) owns one of these per MPI rank. */
+int cph_create(int device, cph_handle **out);
+/* FixConstantPH::~FixConstantPH (cpp:60-63; leaks H_atom there). */
+int cph_destroy(cph_handle *h);
+/* error->all message text (cpp:38-45, 183).  h may be NULL (last error of cph_create). */
+const char *cph_last_error(cph_handle *h);
+
+/* ---- configuration (any time before cph_set_atoms) ---------------------------- */
+/* force->qqrd2e, force->boltz (the undeclared `R` of cpp:111), force->ftm2v (D9). */
+int cph_set_units(cph_handle *h, double qqrd2e, double boltz, double ftm2v);
+/* The pair style whose eatom the reference reads at cpp:216-219, restated inside the path.
+ * epsilon/sigma: (ntypes+1)^2 row-major mixed coefficients (index 0 unused);
+ * cut_lj: (ntypes+1)^2 per-pair LJ cutoffs or NULL for cut_lj_global everywhere;
+ * special_lj/special_coul: force->special_lj / special_coul [0..3]. */
+int cph_set_pair(cph_handle *h, int style, int ntypes, const double *epsilon, const double *sigma,
+                 const double *cut_lj, double cut_lj_global, double cut_coul, double alpha,
+                 const double *special_lj, const double *special_coul);
+/* domain->boxlo/boxhi/periodicity, domain->sublo/subhi, comm->procgrid/myloc, neighbor->skin. */
+int cph_set_domain(cph_handle *h, const double *boxlo, const double *boxhi, const int *periodic,
+                   const double *sublo, const double *subhi, const int *procgrid, const int *myloc,
+                   double skin);
+/* Constructor arguments arg[3..8] (cpp:37-49): nevery, hydrogen-group bit, water-group bit, pK, pH, T. */
+int cph_set_fix(cph_handle *h, int nevery, int groupHbit, int groupWbit, double pK, double pH, double T);
+/* init() constants (cpp:86-96): w s h k a b r m d, m_lambda; plus the derivative flavour. */
+int cph_set_bias(cph_handle *h, double w, double s, double hbar, double k, double a, double b,
+                 double r, double m, double d, double m_lambda, int bias_mode);
+int cph_set_mode(cph_handle *h, int dudl_mode, int integrator_mode, int fscale_mode);
+/* north_star multi-site tables.  Site s has pK[s]; titratable atom t (global tag titr_tag[t])
+ * belongs to site titr_site[t] and has end-state charges qA[t], qB[t].  With nsites == 0 the
+ * reference's single global lambda (one site = the whole hydrogen group, pK from cph_set_fix) is used. */
+int cph_set_sites(cph_handle *h, int nsites, const double *pK, int ntitr, const int *titr_tag,
+                  const int *titr_site, const double *qA, const double *qB);
+/* lambda / v_lambda initial values (never initialised in the reference). */
+int cph_set_lambda(cph_handle *h, const double *lambda, const double *v_lambda);
+
+/* ---- rank group: replaces MPI_Allreduce (cpp:274) and comm->reverse_comm (cpp:253) --- */
+int cph_comm_unique_id(char *id128);                                   /* ncclGetUniqueId */
+int cph_comm_init_nccl(cph_handle *h, int nranks, int rank, const char *id128);
+/* in-process group of `nranks` handles driven by one host thread each (tests; 1 GPU) */
+int cph_comm_init_local(cph_handle *h, int nranks, int rank, int group_key);
+
+/* ---- atoms: called on every re-neighbouring step (LAMMPS post_neighbor) ------- */
+/* atom->x q type tag mask molecule nspecial special of the nlocal OWNED atoms (inside
+ * [sublo,subhi)).  The library sorts them into cells, builds its own ghost atoms
+ * (periodic images and neighbour-rank copies), maps tags to titration sites and builds
+ * the Verlet list (init_list, h:40, never defined in the reference). */
+int cph_set_atoms(cph_handle *h, int where, int nlocal, const double *x, const double *q,
+                  const int *type, const int *tag, const int *mask, const int *molecule,
+                  const int *nspecial, const int *special, int maxspecial);
+
+/* ---- per step ------------------------------------------------------------------ */
+/* atom->x of the owned atoms after the host integrator moved them. */
+int cph_set_x(cph_handle *h, int where, const double *x);
+/* neighbor->decide(): has any owned atom (on any rank) moved more than skin/2 since the list was built? */
+int cph_check_rebuild(cph_handle *h, int *flag);
+/* comm->forward_comm(): refresh ghost x and q. */
+int cph_forward(cph_handle *h);
+/* pair->compute(eflag): forces, and with eflag per-atom energy (the eatom of cpp:217) and the
+ * electrostatic potential phi_i. */
+int cph_pair_pass(cph_handle *h, int eflag);
+/* compute_Hs() (cpp:177-280): HA, HB, per-site HB_s-HA_s and dU/dlambda_s, summed over ranks. */
+int cph_site_reduce(cph_handle *h);
+/* calculate_df + calculate_dU + integrate_lambda (cpp:109-145), dt = nevery*update->dt. */
+int cph_integrate_lambda(cph_handle *h, double dt);
+/* north_star hooks absent from the reference. */
+int cph_initial_integrate(cph_handle *h, double dt);
+int cph_final_integrate(cph_handle *h, double dt);
+/* q_i = (1-lambda_s) qA_i + lambda_s qB_i on the titratable atoms (north_star). */
+int cph_apply_charges(cph_handle *h);
+/* set_force() (cpp:149-171): scale the forces of hydrogen-group atoms. */
+int cph_set_force(cph_handle *h);
+/* post_force() (cpp:67-79) in one call: [set_x] forward, pair pass, and on nevery steps
+ * site reduce + lambda update; then set_force / charge update as the modes require.
+ * x may be NULL (positions already set); f may be NULL (forces stay on the device),
+ * otherwise the owned atoms' forces are written to it (caller order). */
+int cph_post_force(cph_handle *h, int64_t ntimestep, double dt, int where, const double *x, double *f);
+
+/* ---- results ---------------------------------------------------------------------- */
+int cph_get_forces(cph_handle *h, int where, double *f);     /* nlocal*3 */
+int cph_get_eatom(cph_handle *h, int where, double *eatom);  /* nlocal; pair eatom of cpp:217 */
+int cph_get_phi(cph_handle *h, int where, double *phi);      /* nlocal; d E_coul / d q_i */
+int cph_get_q(cph_handle *h, int where, double *q);          /* nlocal; current charges */
+/* out[0]=HA out[1]=HB (cpp:276-277) out[2]=E_vdwl out[3]=E_coul out[4]=H_lambda (cpp:114)
+ * out[5]=sum of site kinetic energies out[6]=max displacement^2 at the last check out[7]=reserved */
+int cph_get_scalars(cph_handle *h, double *out8);
+/* per-site arrays, each nsites long or NULL: lambda, v_lambda, dU/dlambda (charge), HB_s-HA_s,
+ * F_lambda (cpp:111), f, df (cpp:122-123), U, dU (cpp:143-144). */
+int cph_get_sites(cph_handle *h, double *lambda, double *v_lambda, double *dudl, double *hdiff,
+                  double *f_lambda, double *f, double *df, double *U, double *dU);
+/* compute_scalar() (h:37) = H_lambda; compute_vector(i) (h:38) = [lambda_s, v_s, dudl_s, F_s] * S */
+int cph_compute_scalar(cph_handle *h, double *out);
+int cph_compute_vector(cph_handle *h, int i, double *out);
+/* memory_usage() (cpp:314-318): bytes held on the device. */
+int cph_memory_usage(cph_handle *h, double *bytes);
+/* out[0]=nlocal out[1]=nghost out[2]=stored neighbours (sum) out[3]=max per atom out[4]=special pairs
+ * out[5]=list builds so far out[6]=titratable atoms owned out[7]=nsites */
+int cph_get_counts(cph_handle *h, int64_t *out8);
+/* bookkeeping checks (bit-exact parity): site index of every owned atom (-1 = none), caller order */
+int cph_get_site_map(cph_handle *h, int *site_of_atom);
+/* neighbour list as sets: numneigh[i] per owned atom (caller order), then keys
+ * ((int64)tag_j << 8 | special_class << 5 | image_code), image_code = (ix+1)+3(iy+1)+9(iz+1)
+ * of the periodic shift of j.  Pass keys == NULL to get the counts only. */
+int cph_get_neighbors(cph_handle *h, int *numneigh, int64_t *keys, int64_t keys_capacity);
+
+/* ---- restart (absent from the reference; LAMMPS write_restart/restart layout) ---------- */
+int cph_restart_size(cph_handle *h, int *ndoubles);
+int cph_pack_restart(cph_handle *h, double *buf);
+int cph_unpack_restart(cph_handle *h, const double *buf, int ndoubles);
+
+/* ---- timing -------------------------------------------------------------------------- */
+int cph_sync(cph_handle *h);
+/* Library stream (cudaStream_t as void*), so callers can order their own device work on it. */
+int cph_stream(cph_handle *h, void **stream);
+/* CUDA-event stopwatch on the library stream: whole region ... */
+int cph_timer_start(cph_handle *h);
+int cph_timer_stop(cph_handle *h, double *ms);
+/* ... and per kernel class while enabled.  which: 0 pair, 1 special pairs, 2 site reduce,
+ * 3 lambda integrator, 4 charge update, 5 halo, 6 list build (all stages), 7 displacement check. */
+int cph_profile(cph_handle *h, int enable);
+int cph_profile_get(cph_handle *h, int which, double *ms_total, int64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPH_B200_H */
