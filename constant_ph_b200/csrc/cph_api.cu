@@ -1,0 +1,658 @@
+// cph_api.cu -- the C ABI of include/cph_b200.h: argument checking, host orchestration,
+// host<->device staging.  Every entry point cites the reference interface it replaces in
+// the header.  No CPU fallback exists: without a CUDA device cph_create fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+#include "cph_internal.h"
+
+static thread_local std::string g_create_error;
+
+int cph_fail(cph_handle *h, int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+
+namespace {
+
+int need(cph_handle *h, bool cond, const char *what) {
+  if (!cond) return cph_fail(h, CPH_ERR_STATE, "%s", what);
+  return 0;
+}
+
+int ensure_pinned(cph_handle *h, size_t bytes) {
+  if (bytes <= h->h_pin_bytes) return 0;
+  if (h->h_pin) cudaFreeHost(h->h_pin);
+  h->h_pin = nullptr;
+  h->h_pin_bytes = 0;
+  CPH_CUDA(h, cudaMallocHost((void **)&h->h_pin, bytes + bytes / 8));
+  h->h_pin_bytes = bytes + bytes / 8;
+  return 0;
+}
+
+template <typename T>
+int upload(cph_handle *h, DevBuf<T> &buf, const T *src, size_t n, int where = CPH_HOST) {
+  CPH_CUDA(h, buf.reserve(n + 1));
+  if (n)
+    CPH_CUDA(h, cudaMemcpyAsync(buf.p, src, n * sizeof(T),
+                                where == CPH_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
+  return 0;
+}
+
+int size_sites(cph_handle *h) {
+  size_t S = (size_t)h->S;
+  DevBuf<double> *bufs[] = {&h->d_lam, &h->d_vlam, &h->d_alam, &h->d_flam, &h->d_fs, &h->d_dfs, &h->d_Us, &h->d_dUs};
+  for (auto *b : bufs) {
+    CPH_CUDA(h, b->reserve(S + 1));
+    CPH_CUDA(h, cudaMemsetAsync(b->p, 0, (S + 1) * sizeof(double), h->stream));
+  }
+  CPH_CUDA(h, h->d_red.reserve(4 + 2 * S + 4));
+  CPH_CUDA(h, cudaMemsetAsync(h->d_red.p, 0, (4 + 2 * S + 4) * sizeof(double), h->stream));
+  CPH_CUDA(h, h->d_scal.reserve(16));
+  CPH_CUDA(h, cudaMemsetAsync(h->d_scal.p, 0, 16 * sizeof(double), h->stream));
+  std::vector<double> half(S, 0.5);
+  CPH_CUDA(h, cudaMemcpyAsync(h->d_lam.p, half.data(), S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// caller-order per-atom result to the caller's buffer (host or device)
+int fetch_atoms(cph_handle *h, int what, int width, int where, double *out) {
+  const size_t n = (size_t)h->nlocal * width;
+  if (n == 0) return 0;
+  if (where == CPH_DEVICE) return cph_launch_gather_out(h, what, out);
+  CPH_CUDA(h, h->d_stage.reserve(n));
+  CPH_TRY(cph_launch_gather_out(h, what, h->d_stage.p));
+  CPH_CUDA(h, cudaMemcpyAsync(out, h->d_stage.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int read_flags(cph_handle *h, unsigned int *flags_h) {
+  CPH_CUDA(h, cudaMemcpyAsync(flags_h, h->d_flags.p, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+  CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cph_version(void) { return 100; }
+
+int cph_create(int device, cph_handle **out) {
+  if (!out) return cph_fail(nullptr, CPH_ERR_ARG, "cph_create: out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return cph_fail(nullptr, CPH_ERR_CUDA, "no CUDA device (%s); libcph_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (device < 0 || device >= ndev) return cph_fail(nullptr, CPH_ERR_ARG, "device %d out of range [0,%d)", device, ndev);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major < 10)
+    return cph_fail(nullptr, CPH_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+  cph_handle *h = new cph_handle();
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return cph_fail(nullptr, CPH_ERR_CUDA, "cannot create a stream on device %d", device);
+  }
+  cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->pev0); cudaEventCreate(&h->pev1);
+  h->d_flags.reserve(16);
+  cudaMemsetAsync(h->d_flags.p, 0, 8 * sizeof(unsigned int), h->stream);
+  int rc = size_sites(h);
+  if (rc) { g_create_error = h->err; delete h; return rc; }
+  *out = h;
+  return CPH_OK;
+}
+
+int cph_destroy(cph_handle *h) {
+  if (!h) return CPH_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  cph_comm_destroy(h);
+  DevBuf<double> *db[] = {&h->d_pK, &h->d_lam, &h->d_vlam, &h->d_alam, &h->d_flam, &h->d_fs, &h->d_dfs, &h->d_Us,
+                          &h->d_dUs, &h->d_red, &h->d_titr_qA, &h->d_titr_dq, &h->d_scal, &h->d_part, &h->d_xbuild,
+                          &h->d_f, &h->d_evdwl, &h->d_phi, &h->d_eatom, &h->d_stage};
+  for (auto *b : db) b->release();
+  DevBuf<int> *ib[] = {&h->d_titr_tag_sorted, &h->d_titr_entry_of_sorted, &h->d_titr_site, &h->d_titr_local, &h->d_type,
+                       &h->d_tag, &h->d_mask, &h->d_perm, &h->d_inv, &h->d_site_of, &h->d_titr_of, &h->d_nspecial,
+                       &h->d_special, &h->d_ghost_src, &h->d_ghost_code, &h->d_hlist, &h->d_istage, &h->d_vals,
+                       &h->d_vals2, &h->d_tmpi, &h->d_cell_start_o, &h->d_cell_start_g, &h->d_neigh, &h->d_numneigh};
+  for (auto *b : ib) b->release();
+  h->d_coef.release(); h->d_xq.release(); h->d_xq2.release(); h->d_keys.release(); h->d_keys2.release();
+  h->d_cubtmp.release(); h->d_flags.release();
+  if (h->h_pin) cudaFreeHost(h->h_pin);
+  cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->pev0); cudaEventDestroy(h->pev1);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return CPH_OK;
+}
+
+const char *cph_last_error(cph_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+// ---- configuration ---------------------------------------------------------------------------
+int cph_set_units(cph_handle *h, double qqrd2e, double boltz, double ftm2v) {
+  if (!(ftm2v > 0)) return cph_fail(h, CPH_ERR_ARG, "ftm2v must be positive");
+  h->qqrd2e = qqrd2e;
+  h->pp.qqrd2e = qqrd2e;
+  h->fix.boltz = boltz;
+  h->fix.ftm2v = ftm2v;
+  return CPH_OK;
+}
+
+int cph_set_pair(cph_handle *h, int style, int ntypes, const double *epsilon, const double *sigma,
+                 const double *cut_lj, double cut_lj_global, double cut_coul, double alpha,
+                 const double *special_lj, const double *special_coul) {
+  if (style != CPH_PAIR_LJ_CUT_COUL_CUT && style != CPH_PAIR_LJ_CUT_COUL_DSF)
+    return cph_fail(h, CPH_ERR_ARG, "unknown pair style %d", style);
+  if (ntypes < 1 || ntypes + 1 > CPH_MAXNT1) return cph_fail(h, CPH_ERR_ARG, "ntypes %d outside [1,%d]", ntypes, CPH_MAXNT1 - 1);
+  if (!epsilon || !sigma || !special_lj || !special_coul) return cph_fail(h, CPH_ERR_ARG, "NULL coefficient table");
+  if (!(cut_coul > 0)) return cph_fail(h, CPH_ERR_ARG, "cut_coul must be positive");
+  cudaSetDevice(h->device);
+  const int nt1 = ntypes + 1;
+  h->coef_h.assign((size_t)nt1 * nt1, PairCoef{0, 0, 0, 0});
+  h->cut_lj_max = 0;
+  const double cut_coulsq = cut_coul * cut_coul;
+  for (int t = 0; t < nt1 * nt1; t++) {
+    double e = epsilon[t], s = sigma[t];
+    double c = cut_lj ? cut_lj[t] : cut_lj_global;
+    h->coef_h[t].lj3 = 4.0 * e * std::pow(s, 12.0);
+    h->coef_h[t].lj4 = 4.0 * e * std::pow(s, 6.0);
+    h->coef_h[t].cut_ljsq = c * c;
+    h->coef_h[t].cutsq = std::max(c * c, cut_coulsq);
+    h->cut_lj_max = std::max(h->cut_lj_max, c);
+  }
+  PairParams &pp = h->pp;
+  pp.style = style;
+  pp.ntypes = ntypes;
+  pp.qqrd2e = h->qqrd2e;
+  pp.alpha = alpha;
+  pp.cut_coulsq = cut_coulsq;
+  double cm = std::max(h->cut_lj_max, cut_coul);
+  pp.cutsq_max = cm * cm;
+  pp.e_shift = pp.f_shift = pp.c_self = 0.0;
+  if (style == CPH_PAIR_LJ_CUT_COUL_DSF) {   // init_style of coul/dsf
+    const double MY_PIS = 1.77245385090551602729;
+    double erfcc = std::erfc(alpha * cut_coul);
+    double erfcd = std::exp(-alpha * alpha * cut_coul * cut_coul);
+    pp.f_shift = -(erfcc / cut_coulsq + 2.0 / MY_PIS * alpha * erfcd / cut_coul);
+    pp.e_shift = erfcc / cut_coul - pp.f_shift * cut_coul;
+    pp.c_self = -(pp.e_shift / 2.0 + alpha / MY_PIS) * h->qqrd2e;
+  }
+  for (int k = 0; k < 4; k++) { pp.special_lj[k] = special_lj[k]; pp.special_coul[k] = special_coul[k]; }
+  h->cut_coul = cut_coul;
+  CPH_TRY(upload(h, h->d_coef, h->coef_h.data(), h->coef_h.size()));
+  CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->have_pair = true;
+  h->rowcap = 0;
+  return CPH_OK;
+}
+
+int cph_set_domain(cph_handle *h, const double *boxlo, const double *boxhi, const int *periodic,
+                   const double *sublo, const double *subhi, const int *procgrid, const int *myloc, double skin) {
+  if (!boxlo || !boxhi || !periodic) return cph_fail(h, CPH_ERR_ARG, "NULL box");
+  if (!(skin >= 0)) return cph_fail(h, CPH_ERR_ARG, "skin must be >= 0");
+  for (int k = 0; k < 3; k++) {
+    if (!(boxhi[k] > boxlo[k])) return cph_fail(h, CPH_ERR_ARG, "box dimension %d is empty", k);
+    h->boxlo[k] = boxlo[k]; h->boxhi[k] = boxhi[k]; h->periodic[k] = periodic[k];
+    h->sublo[k] = sublo ? sublo[k] : boxlo[k];
+    h->subhi[k] = subhi ? subhi[k] : boxhi[k];
+    h->procgrid[k] = procgrid ? procgrid[k] : 1;
+    h->myloc[k] = myloc ? myloc[k] : 0;
+    if (h->procgrid[k] < 1 || h->myloc[k] < 0 || h->myloc[k] >= h->procgrid[k])
+      return cph_fail(h, CPH_ERR_ARG, "bad processor grid in dim %d", k);
+  }
+  int np = h->procgrid[0] * h->procgrid[1] * h->procgrid[2];
+  if (np != h->nranks && !(np > 1 && h->nranks == 1 && false))
+    if (np != h->nranks) return cph_fail(h, CPH_ERR_ARG, "procgrid has %d ranks but the rank group has %d", np, h->nranks);
+  h->skin = skin;
+  h->have_domain = true;
+  h->rowcap = 0;
+  return CPH_OK;
+}
+
+int cph_set_fix(cph_handle *h, int nevery, int groupHbit, int groupWbit, double pK, double pH, double T) {
+  if (nevery <= 0) return cph_fail(h, CPH_ERR_ARG, "Illegal fix constant_pH every value %d", nevery);  // cpp:38 (+D4)
+  h->fix.nevery = nevery; h->fix.Hbit = groupHbit; h->fix.Wbit = groupWbit;
+  h->fix.pK = pK; h->fix.pH = pH; h->fix.T = T;
+  return CPH_OK;
+}
+
+int cph_set_bias(cph_handle *h, double w, double s, double hbar, double k, double a, double b, double r, double m,
+                 double d, double m_lambda, int bias_mode) {
+  if (bias_mode != CPH_BIAS_EXACT && bias_mode != CPH_BIAS_AS_WRITTEN) return cph_fail(h, CPH_ERR_ARG, "bad bias mode");
+  if (!(m_lambda > 0) || a == 0 || s == 0) return cph_fail(h, CPH_ERR_ARG, "bad bias constants");
+  h->bias = BiasParams{w, s, hbar, k, a, b, r, m, d, m_lambda, bias_mode};
+  return CPH_OK;
+}
+
+int cph_set_mode(cph_handle *h, int dudl_mode, int integrator_mode, int fscale_mode) {
+  if ((dudl_mode | 1) != 1 || (integrator_mode | 1) != 1 || (fscale_mode | 1) != 1) return cph_fail(h, CPH_ERR_ARG, "bad mode");
+  h->fix.dudl_mode = dudl_mode; h->fix.integ_mode = integrator_mode; h->fix.fscale_mode = fscale_mode;
+  return CPH_OK;
+}
+
+int cph_set_sites(cph_handle *h, int nsites, const double *pK, int ntitr, const int *titr_tag, const int *titr_site,
+                  const double *qA, const double *qB) {
+  if (nsites < 0 || ntitr < 0) return cph_fail(h, CPH_ERR_ARG, "negative site/atom count");
+  if (nsites > 0 && !pK) return cph_fail(h, CPH_ERR_ARG, "pK is NULL");
+  if (ntitr > 0 && (!titr_tag || !titr_site || !qA || !qB)) return cph_fail(h, CPH_ERR_ARG, "NULL titratable-atom table");
+  cudaSetDevice(h->device);
+  h->fix.implicit_site = (nsites == 0);
+  h->S = nsites == 0 ? 1 : nsites;
+  h->ntitr = ntitr;
+  for (int t = 0; t < ntitr; t++)
+    if (titr_site[t] < 0 || titr_site[t] >= h->S) return cph_fail(h, CPH_ERR_ARG, "site index %d out of range", titr_site[t]);
+  // site-major order (stable in tag) so the per-site reduction is a segmented scan
+  std::vector<int> order(ntitr);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    return titr_site[a] != titr_site[b] ? titr_site[a] < titr_site[b] : titr_tag[a] < titr_tag[b];
+  });
+  std::vector<int> site(ntitr), tag(ntitr);
+  std::vector<double> a(ntitr), dq(ntitr);
+  for (int k = 0; k < ntitr; k++) {
+    int t = order[k];
+    site[k] = titr_site[t]; tag[k] = titr_tag[t]; a[k] = qA[t]; dq[k] = qB[t] - qA[t];
+  }
+  // tag-sorted view for the device binary search
+  std::vector<int> byt(ntitr);
+  std::iota(byt.begin(), byt.end(), 0);
+  std::sort(byt.begin(), byt.end(), [&](int x, int y) { return tag[x] < tag[y]; });
+  h->titr_tag_sorted_h.resize(ntitr);
+  h->titr_entry_of_sorted_h.resize(ntitr);
+  for (int k = 0; k < ntitr; k++) {
+    h->titr_tag_sorted_h[k] = tag[byt[k]];
+    h->titr_entry_of_sorted_h[k] = byt[k];
+    if (k && h->titr_tag_sorted_h[k] == h->titr_tag_sorted_h[k - 1])
+      return cph_fail(h, CPH_ERR_ARG, "atom tag %d appears twice in the titratable-atom table", tag[byt[k]]);
+  }
+  CPH_TRY(upload(h, h->d_titr_site, site.data(), ntitr));
+  CPH_TRY(upload(h, h->d_titr_qA, a.data(), ntitr));
+  CPH_TRY(upload(h, h->d_titr_dq, dq.data(), ntitr));
+  CPH_TRY(upload(h, h->d_titr_tag_sorted, h->titr_tag_sorted_h.data(), ntitr));
+  CPH_TRY(upload(h, h->d_titr_entry_of_sorted, h->titr_entry_of_sorted_h.data(), ntitr));
+  CPH_TRY(upload(h, h->d_pK, pK, nsites));
+  CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  CPH_TRY(size_sites(h));
+  h->have_sites = true;
+  return CPH_OK;
+}
+
+int cph_set_lambda(cph_handle *h, const double *lambda, const double *v_lambda) {
+  cudaSetDevice(h->device);
+  size_t b = (size_t)h->S * sizeof(double);
+  if (lambda) CPH_CUDA(h, cudaMemcpyAsync(h->d_lam.p, lambda, b, cudaMemcpyHostToDevice, h->stream));
+  if (v_lambda) CPH_CUDA(h, cudaMemcpyAsync(h->d_vlam.p, v_lambda, b, cudaMemcpyHostToDevice, h->stream));
+  CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->have_atoms && h->fix.dudl_mode == CPH_DUDL_CHARGE) {
+    CPH_TRY(cph_launch_apply_charges(h));
+    CPH_TRY(cph_forward_ghosts(h));
+  }
+  return CPH_OK;
+}
+
+// ---- atoms -------------------------------------------------------------------------------------
+int cph_set_atoms(cph_handle *h, int where, int nlocal, const double *x, const double *q, const int *type,
+                  const int *tag, const int *mask, const int *molecule, const int *nspecial, const int *special,
+                  int maxspecial) {
+  (void)molecule;
+  CPH_TRY(need(h, h->have_pair && h->have_domain, "cph_set_pair and cph_set_domain must precede cph_set_atoms"));
+  if (nlocal < 0) return cph_fail(h, CPH_ERR_ARG, "nlocal < 0");
+  if (nlocal > 0 && (!x || !q || !type || !tag || !mask)) return cph_fail(h, CPH_ERR_ARG, "NULL per-atom array");
+  if (nlocal > CPH_NEIGHMASK / 2) return cph_fail(h, CPH_ERR_OVERFLOW, "too many atoms for 29-bit neighbour indices");
+  if (maxspecial < 0 || (maxspecial > 0 && (!nspecial || !special))) return cph_fail(h, CPH_ERR_ARG, "bad special tables");
+  cudaSetDevice(h->device);
+  cudaStream_t st = h->stream;
+  const size_t n = (size_t)nlocal;
+  h->nlocal = nlocal;
+  h->maxspecial = maxspecial;
+  // pack {x,y,z,q} on the host side of the copy: one pinned staging buffer, one H2D
+  CPH_CUDA(h, h->d_xq.reserve(n + 1));
+  if (where == CPH_HOST) {
+    CPH_TRY(ensure_pinned(h, n * sizeof(double4) + 64));
+    double4 *p = (double4 *)h->h_pin;
+    for (size_t i = 0; i < n; i++) p[i] = make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], q[i]);
+    CPH_CUDA(h, cudaMemcpyAsync(h->d_xq.p, p, n * sizeof(double4), cudaMemcpyHostToDevice, st));
+  } else {
+    CPH_TRY(cph_launch_pack_xq(h, nlocal, x, q));
+  }
+  CPH_TRY(upload(h, h->d_type, type, n, where));
+  CPH_TRY(upload(h, h->d_tag, tag, n, where));
+  CPH_TRY(upload(h, h->d_mask, mask, n, where));
+  if (maxspecial) {
+    CPH_TRY(upload(h, h->d_nspecial, nspecial, 3 * n, where));
+    CPH_TRY(upload(h, h->d_special, special, n * maxspecial, where));
+  }
+  std::vector<int> ident(n);
+  std::iota(ident.begin(), ident.end(), 0);
+  CPH_TRY(upload(h, h->d_perm, ident.data(), n));
+  CPH_CUDA(h, cudaStreamSynchronize(st));
+  for (size_t i = 0; i < n; i++)
+    if (type[i] < 1 || type[i] > h->pp.ntypes) {
+      if (where == CPH_HOST) return cph_fail(h, CPH_ERR_ARG, "atom %zu has type %d outside [1,%d]", i, type[i], h->pp.ntypes);
+      break;
+    }
+  h->have_atoms = false;
+  CPH_TRY(cph_rebuild(h));
+  h->have_atoms = true;
+  h->have_pass = false;
+  if (h->fix.dudl_mode == CPH_DUDL_CHARGE && h->ntitr) {
+    // charges follow lambda from the first pass on (q(lambda), north_star)
+    CPH_TRY(cph_launch_apply_charges(h));
+    CPH_TRY(cph_forward_ghosts(h));
+  }
+  return CPH_OK;
+}
+
+// ---- per step -------------------------------------------------------------------------------------
+int cph_set_x(cph_handle *h, int where, const double *x) {
+  CPH_TRY(need(h, h->have_atoms, "cph_set_atoms first"));
+  if (!x) return cph_fail(h, CPH_ERR_ARG, "x is NULL");
+  cudaSetDevice(h->device);
+  const size_t n3 = 3 * (size_t)h->nlocal;
+  const double *xd = x;
+  if (where == CPH_HOST) {
+    CPH_CUDA(h, h->d_stage.reserve(n3 + 1));
+    CPH_CUDA(h, cudaMemcpyAsync(h->d_stage.p, x, n3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    xd = h->d_stage.p;
+  }
+  return cph_launch_set_x(h, xd);
+}
+
+int cph_check_rebuild(cph_handle *h, int *flag) {
+  CPH_TRY(need(h, h->have_atoms, "cph_set_atoms first"));
+  cudaSetDevice(h->device);
+  CPH_TRY(cph_launch_set_x(h, nullptr));
+  unsigned int fl[8];
+  CPH_TRY(read_flags(h, fl));
+  unsigned int any = fl[4];
+  CPH_TRY(cph_comm_allreduce_max_u32(h, &any, 1));
+  float md;
+  memcpy(&md, &fl[0], 4);
+  h->scal_h[6] = md;
+  if (flag) *flag = any ? 1 : 0;
+  return CPH_OK;
+}
+
+int cph_forward(cph_handle *h) {
+  CPH_TRY(need(h, h->have_atoms, "cph_set_atoms first"));
+  cudaSetDevice(h->device);
+  return cph_forward_ghosts(h);
+}
+
+int cph_pair_pass(cph_handle *h, int eflag) {
+  CPH_TRY(need(h, h->have_atoms, "cph_set_atoms first"));
+  cudaSetDevice(h->device);
+  CPH_TRY(cph_launch_pair(h, eflag ? 1 : 0));
+  h->have_pass = true;
+  return CPH_OK;
+}
+
+int cph_site_reduce(cph_handle *h) {
+  CPH_TRY(need(h, h->have_pass, "cph_pair_pass (with eflag) first"));
+  cudaSetDevice(h->device);
+  CPH_TRY(cph_launch_partition(h));
+  CPH_TRY(cph_comm_allreduce(h, h->d_red.p, 4 + 2 * h->S));   // cpp:274
+  return CPH_OK;
+}
+
+int cph_integrate_lambda(cph_handle *h, double dt) {
+  cudaSetDevice(h->device);
+  return cph_launch_integrate(h, dt, h->fix.integ_mode == CPH_INTEGRATE_REFERENCE ? 0 : 2);
+}
+
+int cph_initial_integrate(cph_handle *h, double dt) {
+  if (h->fix.integ_mode != CPH_INTEGRATE_VV) return CPH_OK;
+  cudaSetDevice(h->device);
+  CPH_TRY(cph_launch_integrate(h, dt, 1));
+  if (h->fix.dudl_mode == CPH_DUDL_CHARGE && h->have_atoms) {
+    CPH_TRY(cph_launch_apply_charges(h));
+    CPH_TRY(cph_forward_ghosts(h));
+  }
+  return CPH_OK;
+}
+
+int cph_final_integrate(cph_handle *h, double dt) {
+  if (h->fix.integ_mode != CPH_INTEGRATE_VV) return CPH_OK;
+  cudaSetDevice(h->device);
+  return cph_launch_integrate(h, dt, 3);
+}
+
+int cph_apply_charges(cph_handle *h) {
+  CPH_TRY(need(h, h->have_atoms, "cph_set_atoms first"));
+  cudaSetDevice(h->device);
+  CPH_TRY(cph_launch_apply_charges(h));
+  return cph_forward_ghosts(h);
+}
+
+int cph_set_force(cph_handle *h) {
+  CPH_TRY(need(h, h->have_pass, "cph_pair_pass first"));
+  cudaSetDevice(h->device);
+  return cph_launch_set_force(h);
+}
+
+int cph_post_force(cph_handle *h, int64_t ntimestep, double dt, int where, const double *x, double *f) {
+  CPH_TRY(need(h, h->have_atoms, "cph_set_atoms first"));
+  cudaSetDevice(h->device);
+  // new positions + neighbor->decide()
+  if (x) CPH_TRY(cph_set_x(h, where, x));
+  else CPH_TRY(cph_launch_set_x(h, nullptr));
+  unsigned int fl[8];
+  CPH_TRY(read_flags(h, fl));
+  unsigned int any = fl[4];
+  CPH_TRY(cph_comm_allreduce_max_u32(h, &any, 1));
+  float md;
+  memcpy(&md, &fl[0], 4);
+  h->scal_h[6] = md;
+  if (any) CPH_TRY(cph_rebuild(h));
+  else CPH_TRY(cph_forward_ghosts(h));
+  const bool active = (ntimestep % h->fix.nevery) == 0;                 // cpp:69
+  CPH_TRY(cph_launch_pair(h, active ? 1 : 0));
+  h->have_pass = true;
+  if (active) {
+    CPH_TRY(cph_site_reduce(h));                                        // cpp:70
+    const int phase = h->fix.integ_mode == CPH_INTEGRATE_REFERENCE ? 0 : 2;
+    CPH_TRY(cph_launch_integrate(h, dt * h->fix.nevery, phase));        // cpp:71-73; t_lambda = nevery*dt (cpp:113)
+    if (h->fix.dudl_mode == CPH_DUDL_CHARGE && phase == 0) CPH_TRY(cph_launch_apply_charges(h));
+  }
+  if (h->fix.dudl_mode == CPH_DUDL_REFERENCE) CPH_TRY(cph_launch_set_force(h));   // cpp:78, every step
+  if (f) CPH_TRY(fetch_atoms(h, 0, 3, where, f));
+  return CPH_OK;
+}
+
+// ---- results -----------------------------------------------------------------------------------------
+int cph_get_forces(cph_handle *h, int where, double *f) {
+  CPH_TRY(need(h, h->have_pass, "no pair pass yet"));
+  cudaSetDevice(h->device);
+  return fetch_atoms(h, 0, 3, where, f);
+}
+int cph_get_eatom(cph_handle *h, int where, double *e) {
+  CPH_TRY(need(h, h->have_pass, "no pair pass yet"));
+  cudaSetDevice(h->device);
+  return fetch_atoms(h, 1, 1, where, e);
+}
+int cph_get_phi(cph_handle *h, int where, double *p) {
+  CPH_TRY(need(h, h->have_pass, "no pair pass yet"));
+  cudaSetDevice(h->device);
+  return fetch_atoms(h, 2, 1, where, p);
+}
+int cph_get_q(cph_handle *h, int where, double *q) {
+  CPH_TRY(need(h, h->have_atoms, "cph_set_atoms first"));
+  cudaSetDevice(h->device);
+  return fetch_atoms(h, 3, 1, where, q);
+}
+
+int cph_get_scalars(cph_handle *h, double *out8) {
+  cudaSetDevice(h->device);
+  double red[4], sc[8];
+  CPH_CUDA(h, cudaMemcpyAsync(red, h->d_red.p, sizeof(red), cudaMemcpyDeviceToHost, h->stream));
+  CPH_CUDA(h, cudaMemcpyAsync(sc, h->d_scal.p, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
+  CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  out8[0] = red[0]; out8[1] = red[1]; out8[2] = red[2]; out8[3] = red[3];
+  out8[4] = sc[4]; out8[5] = sc[5]; out8[6] = h->scal_h[6]; out8[7] = 0;
+  return CPH_OK;
+}
+
+int cph_get_sites(cph_handle *h, double *lambda, double *v_lambda, double *dudl, double *hdiff, double *f_lambda,
+                  double *f, double *df, double *U, double *dU) {
+  cudaSetDevice(h->device);
+  const size_t S = (size_t)h->S, b = S * sizeof(double);
+  struct { double *dst; const double *src; } m[] = {
+      {lambda, h->d_lam.p}, {v_lambda, h->d_vlam.p}, {dudl, h->d_red.p + 4}, {hdiff, h->d_red.p + 4 + S},
+      {f_lambda, h->d_flam.p}, {f, h->d_fs.p}, {df, h->d_dfs.p}, {U, h->d_Us.p}, {dU, h->d_dUs.p}};
+  for (auto &e : m)
+    if (e.dst) CPH_CUDA(h, cudaMemcpyAsync(e.dst, e.src, b, cudaMemcpyDeviceToHost, h->stream));
+  CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CPH_OK;
+}
+
+int cph_compute_scalar(cph_handle *h, double *out) {
+  double s[8];
+  CPH_TRY(cph_get_scalars(h, s));
+  *out = s[4];
+  return CPH_OK;
+}
+
+int cph_compute_vector(cph_handle *h, int i, double *out) {
+  if (i < 0 || i >= 4 * h->S) return cph_fail(h, CPH_ERR_ARG, "compute_vector index %d out of range [0,%d)", i, 4 * h->S);
+  cudaSetDevice(h->device);
+  const int s = i / 4;
+  const size_t S = (size_t)h->S;
+  const double *src;
+  switch (i % 4) {
+    case 0: src = h->d_lam.p + s; break;
+    case 1: src = h->d_vlam.p + s; break;
+    case 2: src = h->d_red.p + 4 + (h->fix.dudl_mode == CPH_DUDL_REFERENCE ? S : 0) + s; break;
+    default: src = h->d_flam.p + s;
+  }
+  CPH_CUDA(h, cudaMemcpyAsync(out, src, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CPH_OK;
+}
+
+int cph_memory_usage(cph_handle *h, double *bytes) {
+  double b = 0;
+  b += h->d_xq.bytes() + h->d_xq2.bytes() + h->d_neigh.bytes() + h->d_numneigh.bytes();
+  b += h->d_type.bytes() + h->d_tag.bytes() + h->d_mask.bytes() + h->d_perm.bytes() + h->d_inv.bytes();
+  b += h->d_f.bytes() + h->d_evdwl.bytes() + h->d_phi.bytes() + h->d_eatom.bytes() + h->d_xbuild.bytes();
+  b += h->d_keys.bytes() + h->d_keys2.bytes() + h->d_vals.bytes() + h->d_vals2.bytes() + h->d_tmpi.bytes();
+  b += h->d_stage.bytes() + h->d_cubtmp.bytes() + h->d_cell_start_o.bytes() + h->d_cell_start_g.bytes();
+  b += h->d_nspecial.bytes() + h->d_special.bytes() + h->d_ghost_src.bytes() + h->d_ghost_code.bytes();
+  *bytes = b;
+  return CPH_OK;
+}
+
+int cph_get_counts(cph_handle *h, int64_t *out8) {
+  cudaSetDevice(h->device);
+  int64_t nt = 0;
+  if (h->ntitr && h->have_atoms) {
+    std::vector<int> loc(h->ntitr);
+    CPH_CUDA(h, cudaMemcpyAsync(loc.data(), h->d_titr_local.p, h->ntitr * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int v : loc) nt += v >= 0;
+  }
+  out8[0] = h->nlocal; out8[1] = h->nghost; out8[2] = h->stored_neigh; out8[3] = h->maxneigh;
+  out8[4] = h->special_pairs; out8[5] = h->nbuilds; out8[6] = nt; out8[7] = h->fix.implicit_site ? 0 : h->S;
+  return CPH_OK;
+}
+
+int cph_get_site_map(cph_handle *h, int *site_of_atom) {
+  CPH_TRY(need(h, h->have_atoms, "cph_set_atoms first"));
+  cudaSetDevice(h->device);
+  const int n = h->nlocal;
+  std::vector<int> s(n), perm(n);
+  CPH_CUDA(h, cudaMemcpyAsync(s.data(), h->d_site_of.p, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CPH_CUDA(h, cudaMemcpyAsync(perm.data(), h->d_perm.p, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int k = 0; k < n; k++) site_of_atom[perm[k]] = s[k];
+  return CPH_OK;
+}
+
+int cph_get_neighbors(cph_handle *h, int *numneigh, int64_t *keys, int64_t keys_capacity) {
+  CPH_TRY(need(h, h->have_atoms, "cph_set_atoms first"));
+  cudaSetDevice(h->device);
+  return cph_neighbors_to_host(h, numneigh, keys, keys_capacity);
+}
+
+// ---- restart: [version, S, (lambda, v, a) * S] as doubles (LAMMPS write_restart layout) ----------------------
+int cph_restart_size(cph_handle *h, int *ndoubles) { *ndoubles = 2 + 3 * h->S; return CPH_OK; }
+
+int cph_pack_restart(cph_handle *h, double *buf) {
+  cudaSetDevice(h->device);
+  const int S = h->S;
+  std::vector<double> l(S), v(S), a(S);
+  CPH_CUDA(h, cudaMemcpyAsync(l.data(), h->d_lam.p, S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CPH_CUDA(h, cudaMemcpyAsync(v.data(), h->d_vlam.p, S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CPH_CUDA(h, cudaMemcpyAsync(a.data(), h->d_alam.p, S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  buf[0] = 1.0; buf[1] = S;
+  for (int s = 0; s < S; s++) { buf[2 + 3 * s] = l[s]; buf[3 + 3 * s] = v[s]; buf[4 + 3 * s] = a[s]; }
+  return CPH_OK;
+}
+
+int cph_unpack_restart(cph_handle *h, const double *buf, int nd) {
+  cudaSetDevice(h->device);
+  const int S = h->S;
+  if (!buf || nd < 2 || (int)buf[1] != S || nd != 2 + 3 * S)
+    return cph_fail(h, CPH_ERR_ARG, "restart record does not match the site table (%d sites)", S);
+  std::vector<double> l(S), v(S), a(S);
+  for (int s = 0; s < S; s++) { l[s] = buf[2 + 3 * s]; v[s] = buf[3 + 3 * s]; a[s] = buf[4 + 3 * s]; }
+  CPH_CUDA(h, cudaMemcpyAsync(h->d_lam.p, l.data(), S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CPH_CUDA(h, cudaMemcpyAsync(h->d_vlam.p, v.data(), S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CPH_CUDA(h, cudaMemcpyAsync(h->d_alam.p, a.data(), S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->have_atoms && h->fix.dudl_mode == CPH_DUDL_CHARGE) {
+    CPH_TRY(cph_launch_apply_charges(h));
+    CPH_TRY(cph_forward_ghosts(h));
+  }
+  return CPH_OK;
+}
+
+// ---- timing ----------------------------------------------------------------------------------------------------
+int cph_sync(cph_handle *h) {
+  cudaSetDevice(h->device);
+  CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CPH_OK;
+}
+int cph_stream(cph_handle *h, void **stream) { *stream = (void *)h->stream; return CPH_OK; }
+int cph_timer_start(cph_handle *h) {
+  cudaSetDevice(h->device);
+  CPH_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  return CPH_OK;
+}
+int cph_timer_stop(cph_handle *h, double *ms) {
+  cudaSetDevice(h->device);
+  CPH_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  CPH_CUDA(h, cudaEventSynchronize(h->ev1));
+  float t = 0;
+  CPH_CUDA(h, cudaEventElapsedTime(&t, h->ev0, h->ev1));
+  *ms = t;
+  return CPH_OK;
+}
+int cph_profile(cph_handle *h, int enable) {
+  h->profiling = enable != 0;
+  if (enable) for (auto &p : h->prof) p = ProfSlot{};
+  return CPH_OK;
+}
+int cph_profile_get(cph_handle *h, int which, double *ms_total, int64_t *launches) {
+  if (which < 0 || which >= 8) return cph_fail(h, CPH_ERR_ARG, "profile slot %d out of range", which);
+  *ms_total = h->prof[which].ms;
+  *launches = h->prof[which].launches;
+  return CPH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,207 @@
+// cph_internal.h -- handle layout and kernel entry points of libcph_b200.so (sm_100a only).
+// Not part of the ABI; the ABI is include/cph_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/cph_b200.h"
+
+#define CPH_NEIGHMASK 0x1FFFFFFF   // LAMMPS NEIGHMASK: low 29 bits = atom index
+#define CPH_SBSHIFT 30             // LAMMPS SBBITS: top 2 bits = special-bond class
+#define CPH_MAXNT1 16              // ntypes+1 <= 16: the (ntypes+1)^2 * 32 B coefficient table lives in shared memory
+
+// device buffer that only ever grows
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;  // elements
+  cudaError_t reserve(size_t n, bool keep = false, cudaStream_t s = 0) {
+    if (n <= cap) return cudaSuccess;
+    size_t ncap = n + n / 8 + 64;
+    T *np_ = nullptr;
+    cudaError_t e = cudaMalloc((void **)&np_, ncap * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (keep && p && cap) {
+      e = cudaMemcpyAsync(np_, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s);
+      if (e != cudaSuccess) return e;
+      cudaStreamSynchronize(s);
+    }
+    if (p) cudaFree(p);
+    p = np_;
+    cap = ncap;
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  size_t bytes() const { return cap * sizeof(T); }
+};
+
+// per type pair: lj3, lj4, cut_ljsq, cutsq (max of lj and coul cutoffs) -- 32 B, one LDS.128 x2
+struct PairCoef {
+  double lj3, lj4, cut_ljsq, cutsq;
+};
+
+struct PairParams {
+  int style, ntypes;
+  double qqrd2e, alpha, cut_coulsq, cutsq_max, e_shift, f_shift, c_self;
+  double special_lj[4], special_coul[4];
+};
+
+struct BiasParams {
+  double w, s, h, k, a, b, r, m, d, m_lambda;
+  int mode;
+};
+
+struct FixParams {
+  int nevery, Hbit, Wbit;
+  double pK, pH, T, boltz, ftm2v;
+  int dudl_mode, integ_mode, fscale_mode, implicit_site;
+};
+
+struct Grid {         // cell grid over the extended sub-box
+  double lo[3];       // origin (sublo - ghost cutoff)
+  double inv[3];      // 1 / cell width
+  int n[3];           // cells per dim
+  int ncell;
+};
+
+struct ProfSlot {
+  double ms = 0;
+  int64_t launches = 0;
+};
+
+struct NcclApi;  // comm.cu
+
+struct cph_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  // configuration
+  PairParams pp{};
+  std::vector<PairCoef> coef_h;
+  double cut_lj_max = 0, cut_coul = 0, skin = 2.0;
+  bool have_pair = false, have_domain = false, have_atoms = false, have_pass = false, have_sites = false;
+  double boxlo[3]{}, boxhi[3]{}, sublo[3]{}, subhi[3]{};
+  int periodic[3]{1, 1, 1}, procgrid[3]{1, 1, 1}, myloc[3]{0, 0, 0};
+  BiasParams bias{200.0, 0.3, 4.0, 2.533, 0.034041, 0.005238, 16.458, 0.1507, 2.0, 20.0, 0};
+  FixParams fix{1, 0, 0, 0.0, 7.0, 300.0, 0.0019872067, 1.0, 1, 0, 0, 1};
+  double qqrd2e = 332.06371;
+  // sites (host copies, site-major order)
+  int S = 1, ntitr = 0;
+  std::vector<int> titr_tag_sorted_h;  // titr tags sorted ascending (for the device binary search)
+  std::vector<int> titr_entry_of_sorted_h;
+  // device: sites
+  DevBuf<double> d_pK, d_lam, d_vlam, d_alam, d_flam, d_fs, d_dfs, d_Us, d_dUs;
+  // one contiguous reduction buffer so a single allreduce covers everything (cpp:274):
+  // [0]=HA [1]=HB [2]=E_vdwl [3]=E_coul [4..4+S)=dU/dlambda_s [4+S..4+2S)=HB_s-HA_s
+  DevBuf<double> d_red;
+  DevBuf<PairCoef> d_coef;
+  DevBuf<int> d_titr_tag_sorted, d_titr_entry_of_sorted;  // [ntitr]
+  DevBuf<int> d_titr_site, d_titr_local;                   // [ntitr] site-major; local = owned index or -1
+  DevBuf<double> d_titr_qA, d_titr_dq;                     // [ntitr]
+  DevBuf<double> d_scal;                                   // 16 doubles of scalar results
+  DevBuf<double> d_part;                                   // block partials for deterministic sums
+  // device: atoms in internal (cell-sorted) order; owned [0,nlocal), ghosts [nlocal,nall)
+  int nlocal = 0, nghost = 0, nall = 0, maxspecial = 0;
+  DevBuf<double4> d_xq;
+  DevBuf<int> d_type, d_tag, d_mask;
+  DevBuf<int> d_perm;       // internal -> caller index   [nlocal]
+  DevBuf<int> d_inv;        // caller -> internal index   [nlocal]
+  DevBuf<int> d_site_of;    // [nlocal] internal order
+  DevBuf<int> d_titr_of;    // [nlocal] internal order, entry in site-major titr arrays
+  DevBuf<int> d_nspecial, d_special;  // caller order, as uploaded
+  DevBuf<double> d_xbuild;  // [3*nlocal] positions at list build
+  DevBuf<int> d_ghost_src;  // [nghost] owned internal index (local images) or slot in recv buffer
+  DevBuf<int> d_ghost_code; // [nghost] periodic image code
+  DevBuf<double> d_f, d_evdwl, d_phi, d_eatom;  // [3*nlocal], [nlocal]...
+  DevBuf<int> d_hlist;      // owned atoms in the hydrogen group
+  int nh = 0;
+  // staging
+  DevBuf<double> d_stage;   // H2D / D2H staging for caller-order arrays
+  DevBuf<int> d_istage;
+  DevBuf<unsigned long long> d_keys, d_keys2;
+  DevBuf<int> d_vals, d_vals2, d_tmpi;
+  DevBuf<double4> d_xq2;
+  DevBuf<unsigned char> d_cubtmp;
+  double *h_pin = nullptr;  // pinned host scratch
+  size_t h_pin_bytes = 0;
+  // cells + list
+  Grid grid{};
+  double ghost_cut = 0;
+  DevBuf<int> d_cell_start_o, d_cell_start_g;
+  DevBuf<int> d_neigh, d_numneigh;
+  int rowcap = 0;
+  int64_t nbuilds = 0, stored_neigh = 0, special_pairs = 0;
+  int maxneigh = 0;
+  DevBuf<unsigned int> d_flags;  // [0] max displacement^2 as float bits, [1] overflow, [2] drift...
+  // scalars mirrored on host after site_reduce / integrate
+  double scal_h[16]{};
+  // comm
+  int nranks = 1, rank = 0;
+  void *nccl_comm = nullptr;
+  // timing
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool profiling = false;
+  ProfSlot prof[8];
+  cudaEvent_t pev0 = nullptr, pev1 = nullptr;
+};
+
+// ---- kernels (launchers) ----------------------------------------------------------------
+// neigh.cu
+int cph_rebuild(cph_handle *h);                 // sort, ghosts, cells, list, site map
+int cph_forward_ghosts(cph_handle *h);          // refresh ghost x and q
+int cph_neighbors_to_host(cph_handle *h, int *numneigh, int64_t *keys, int64_t cap);
+// pair.cu
+int cph_launch_pair(cph_handle *h, int eflag);
+// sites.cu
+int cph_launch_partition(cph_handle *h);        // HA, HB, E_vdwl, E_coul + per-site sums
+int cph_launch_integrate(cph_handle *h, double dt, int phase);
+int cph_launch_apply_charges(cph_handle *h);
+int cph_launch_set_force(cph_handle *h);
+int cph_launch_set_x(cph_handle *h, const double *x_dev_caller_order);
+int cph_launch_gather_out(cph_handle *h, int what, double *out_dev);  // 0 f, 1 eatom, 2 phi, 3 q
+int cph_launch_pack_xq(cph_handle *h, int n, const double *x, const double *q);
+// comm.cu
+int cph_comm_allreduce(cph_handle *h, double *buf, int n);            // sum
+int cph_comm_allreduce_max_u32(cph_handle *h, unsigned int *buf, int n);
+void cph_comm_destroy(cph_handle *h);
+
+int cph_fail(cph_handle *h, int code, const char *fmt, ...);
+
+#define CPH_CUDA(h, call)                                                                   \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return cph_fail(h, CPH_ERR_CUDA, "%s at %s:%d: %s", #call, __FILE__, __LINE__,        \
+                      cudaGetErrorString(e__));                                             \
+  } while (0)
+
+#define CPH_TRY(call)          \
+  do {                         \
+    int rc__ = (call);         \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+struct ProfScope {
+  cph_handle *h;
+  int which;
+  ProfScope(cph_handle *h_, int w) : h(h_), which(w) {
+    if (h->profiling) cudaEventRecord(h->pev0, h->stream);
+  }
+  ~ProfScope() {
+    if (h->profiling) {
+      cudaEventRecord(h->pev1, h->stream);
+      cudaEventSynchronize(h->pev1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, h->pev0, h->pev1);
+      h->prof[which].ms += ms;
+      h->prof[which].launches += 1;
+    }
+  }
+};

@@ -1,0 +1,372 @@
+// sites.cu -- K3 (energy partition + per-site reduction), K4 (lambda integrator),
+// K5 (charge / force update) and the caller-order <-> internal-order movers.
+//
+// Reference lines restated here (cpp:N = fix_constant_pH.cpp):
+//   partition_kernel    cpp:259-267  HA = sum eatom, HB = sum eatom over atoms NOT in the hydrogen group
+//   site_sum_kernel     cpp:264-267 per site, plus north_star's dU/dlambda_s = sum dq_i * dE/dq_i
+//   integrate_kernel    cpp:109-117 (integrator), cpp:120-124 (f, df), cpp:128-145 (U, dU)
+//   set_force_kernel    cpp:149-171
+// All sums are two-stage with a fixed block count so results are bit-reproducible run to run.
+#include <cmath>
+
+#include "cph_internal.h"
+
+namespace {
+
+constexpr int TPB = 256;
+constexpr int MAXPART = 1024;   // stage-1 blocks
+
+inline int nblk(int n) { return (n + TPB - 1) / TPB; }
+
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double (&v)[NV], double *partials) {
+  __shared__ double sm[NV][TPB / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < NV; c++) {
+    double x = v[c];
+    for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) sm[c][w] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0;
+    for (int k = 0; k < TPB / 32; k++) s += sm[threadIdx.x][k];
+    partials[(size_t)blockIdx.x * NV + threadIdx.x] = s;
+  }
+}
+
+// stage 2: out[c] = sum_b partials[b][c], one warp per value, fixed order
+template <int NV>
+__global__ void final_sum_kernel(int nb, const double *__restrict__ partials, double *out) {
+  const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
+  if (c >= NV) return;
+  double s = 0;
+  for (int b = lane; b < nb; b += 32) s += partials[(size_t)b * NV + c];
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[c] = s;
+}
+
+// compute_Hs tail (cpp:259-267) over the owned atoms + energy totals
+__global__ void __launch_bounds__(TPB)
+partition_kernel(int n, const double *__restrict__ eatom, const double *__restrict__ evdwl,
+                 const int *__restrict__ mask, int Hbit, double *partials) {
+  double v[4] = {0, 0, 0, 0};   // HA, HB, E_vdwl, E_coul
+  for (int k = blockIdx.x * TPB + threadIdx.x; k < n; k += gridDim.x * TPB) {
+    double e = eatom[k], ev = evdwl[k];
+    v[0] += e;                                  // cpp:265
+    if (!(mask[k] & Hbit)) v[1] += e;           // cpp:266
+    v[2] += ev;
+    v[3] += e - ev;
+  }
+  block_reduce_store<4>(v, partials);
+}
+
+__global__ void partition_final_kernel(int nb, const double *__restrict__ partials, double *red, int implicit_site,
+                                       int S) {
+  const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
+  __shared__ double out[4];
+  if (c < 4) {
+    double s = 0;
+    for (int b = lane; b < nb; b += 32) s += partials[(size_t)b * 4 + c];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) { out[c] = s; red[c] = s; }
+  }
+  __syncthreads();
+  // reference single site: HB - HA of the whole hydrogen group (cpp:111)
+  if (implicit_site && threadIdx.x == 0) red[4 + S] = out[1] - out[0];
+}
+
+// warp-shuffle segmented reduction over the site-major titratable-atom table
+__global__ void __launch_bounds__(TPB)
+site_sum_kernel(int ntitr, const int *__restrict__ titr_site, const int *__restrict__ titr_local,
+                const double *__restrict__ titr_dq, const double *__restrict__ phi, const double *__restrict__ eatom,
+                const int *__restrict__ mask, int Hbit, int S, int implicit_site, double *red) {
+  const int t = blockIdx.x * TPB + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int site = -1;
+  double d = 0, hd = 0;
+  if (t < ntitr) {
+    site = titr_site[t];
+    int k = titr_local[t];
+    if (k >= 0) {                                         // owned by this rank (cpp:264: i < nlocal)
+      d = titr_dq[t] * phi[k];                            // Appendix B
+      if (mask[k] & Hbit) hd = -eatom[k];                 // HB_s - HA_s
+    }
+  }
+  for (int o = 1; o < 32; o <<= 1) {
+    double ud = __shfl_up_sync(0xffffffffu, d, o), uh = __shfl_up_sync(0xffffffffu, hd, o);
+    int us = __shfl_up_sync(0xffffffffu, site, o);
+    if (lane >= o && us == site) { d += ud; hd += uh; }
+  }
+  int next = __shfl_down_sync(0xffffffffu, site, 1);
+  bool tail = (lane == 31) || (next != site);
+  if (site >= 0 && tail) {
+    atomicAdd(red + 4 + site, d);
+    if (!implicit_site) atomicAdd(red + 4 + S + site, hd);
+  }
+}
+
+struct BiasOut { double f, df, U, dU; };
+
+__device__ __forceinline__ BiasOut bias_terms(const BiasParams &bp, double lambda) {
+  const double a = bp.a, b = bp.b, s = bp.s, k = bp.k, d = bp.d, w = bp.w, r = bp.r, m = bp.m;
+  const double SQRT_PI = 1.77245385090551602729;
+  BiasOut o;
+  double ex = exp(-50.0 * (lambda - 0.5));
+  o.f = 1.0 / (1.0 + ex);                                                        // cpp:122
+  double U1 = -k * exp(-(lambda - 1 - b) * (lambda - 1 - b) / (2 * a * a));      // cpp:132
+  double U2 = -k * exp(-(lambda + b) * (lambda + b) / (2 * a * a));              // cpp:133
+  double U3 = d * exp(-(lambda - 0.5) * (lambda - 0.5) / (2 * s * s));           // cpp:134
+  double U4, U5, dU1, dU2, dU3, dU4, dU5;
+  if (bp.mode == CPH_BIAS_EXACT) {
+    o.df = 50.0 * ex * o.f * o.f;
+    U4 = 0.5 * w * (1 - erf(r * (lambda + m)));                                  // cpp:135, erf (D16)
+    U5 = 0.5 * w * (1 + erf(r * (lambda - 1 - m)));                              // cpp:136
+    dU1 = -((lambda - 1 - b) / (a * a)) * U1;                                    // D14
+    dU2 = -((lambda + b) / (a * a)) * U2;
+    dU3 = -((lambda - 0.5) / (s * s)) * U3;                                      // cpp:139
+    dU4 = -0.5 * w * r * 2 * exp(-r * r * (lambda + m) * (lambda + m)) / SQRT_PI;          // D15
+    dU5 = 0.5 * w * r * 2 * exp(-r * r * (lambda - 1 - m) * (lambda - 1 - m)) / SQRT_PI;   // cpp:141
+  } else {
+    o.df = 50.0 * ex / (o.f * o.f);                                              // cpp:123 verbatim
+    U4 = 0.5 * w * (1 - (double)erff((float)(r * (lambda + m))));                // cpp:135 verbatim
+    U5 = 0.5 * w * (1 + (double)erff((float)(r * (lambda - 1 - m))));            // cpp:136
+    dU1 = -((lambda - 1 - b) / (2 * a * a)) * U1;                                // cpp:137
+    dU2 = -((lambda + b) / (2 * a * a)) * U2;                                    // cpp:138
+    dU3 = -((lambda - 0.5) / (s * s)) * U3;                                      // cpp:139
+    dU4 = -0.5 * w * r * 2 * exp(-r * r * (lambda + 0.5) * (lambda + 0.5)) / SQRT_PI;      // cpp:140
+    dU5 = 0.5 * w * r * 2 * exp(-r * r * (lambda - 1 - m) * (lambda - 1 - m)) / SQRT_PI;   // cpp:141
+  }
+  o.U = U1 + U2 + U3 + U4 + U5;             // cpp:143
+  o.dU = dU1 + dU2 + dU3 + dU4 + dU5;       // cpp:144
+  return o;
+}
+
+// phase 0: reference kinematic step (cpp:109-117)   phase 1: VV kick+drift
+// phase 2: VV force evaluation (a <- F/m)           phase 3: VV second kick + H_lambda
+__global__ void __launch_bounds__(TPB)
+integrate_kernel(int S, double dt, int phase, BiasParams bp, FixParams fx, const double *__restrict__ pK,
+                 const double *__restrict__ red, double *lam, double *vlam, double *alam, double *flam, double *fs,
+                 double *dfs, double *Us, double *dUs, double *partials) {
+  double v[3] = {0, 0, 0};   // sum of site terms of H_lambda, sum lambda*(HB_s-HA_s), kinetic
+  for (int s = blockIdx.x * TPB + threadIdx.x; s < S; s += gridDim.x * TPB) {
+    double lambda = lam[s], vel = vlam[s], acc = alam[s];
+    if (phase == 1) {
+      vel += 0.5 * acc * dt;
+      lambda += vel * dt;
+      lam[s] = lambda;
+      vlam[s] = vel;
+      continue;
+    }
+    if (phase == 3) vel += 0.5 * acc * dt;
+    BiasOut b = bias_terms(bp, lambda);
+    const double pk = fx.implicit_site ? fx.pK : pK[s];
+    const double hd = red[4 + S + s];
+    const double dE = (fx.dudl_mode == CPH_DUDL_REFERENCE) ? hd : red[4 + s];
+    const double ph = fx.boltz * fx.T * log(10.0) * (pk - fx.pH);
+    const double f_lambda = -(dE + b.df * ph + b.dU);                 // cpp:111
+    const double a_lambda = f_lambda / bp.m_lambda * fx.ftm2v;        // cpp:112 (+ SURVEY D9)
+    const double kin = 0.5 * bp.m_lambda * vel * vel / fx.ftm2v;
+    v[0] += b.f * ph + b.U + kin;                                     // cpp:114 site terms
+    v[1] += lambda * hd;                                              // cpp:114 lambda*(HB-HA)
+    v[2] += kin;
+    fs[s] = b.f; dfs[s] = b.df; Us[s] = b.U; dUs[s] = b.dU; flam[s] = f_lambda;
+    if (phase == 0) {
+      lambda = 0.5 * a_lambda * dt * dt + vel * dt + lambda;          // cpp:115
+      vel = a_lambda * dt + vel;                                      // cpp:116
+    }
+    lam[s] = lambda;
+    vlam[s] = vel;
+    alam[s] = a_lambda;
+  }
+  if (phase != 1) block_reduce_store<3>(v, partials);
+}
+
+__global__ void integrate_final_kernel(int nb, const double *__restrict__ partials, const double *__restrict__ red,
+                                       int dudl_mode, double *scal) {
+  const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
+  __shared__ double out[3];
+  if (c < 3) {
+    double s = 0;
+    for (int b = lane; b < nb; b += 32) s += partials[(size_t)b * 3 + c];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[c] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // cpp:114: (1-lambda)HA + lambda HB = HA + lambda (HB-HA); charge mode: E_ff at the current charges
+    double eff = (dudl_mode == CPH_DUDL_REFERENCE) ? red[0] + out[1] : red[2] + red[3];
+    scal[4] = eff + out[0];
+    scal[5] = out[2];
+  }
+}
+
+// q_i = (1-lambda_s) qA_i + lambda_s qB_i  (north_star; the reference never touches atom->q)
+__global__ void apply_charges_kernel(int ntitr, const int *__restrict__ titr_site, const int *__restrict__ titr_local,
+                                     const double *__restrict__ qA, const double *__restrict__ dq,
+                                     const double *__restrict__ lam, double4 *xq) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntitr) return;
+  int k = titr_local[t];
+  if (k < 0) return;
+  xq[k].w = qA[t] + lam[titr_site[t]] * dq[t];
+}
+
+// set_force (cpp:149-171) over the compact hydrogen-group list instead of a scan of mask[]
+__global__ void set_force_kernel(int nh, const int *__restrict__ hlist, const int *__restrict__ site_of,
+                                 const double *__restrict__ lam, int fscale_mode, double *f) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= nh) return;
+  int k = hlist[m];
+  double l = lam[site_of[k]];
+  double sc = fscale_mode == CPH_FSCALE_LAMBDA ? l : 1.0 - l;   // cpp:166-168 / SURVEY D17
+  f[3 * (size_t)k] *= sc;
+  f[3 * (size_t)k + 1] *= sc;
+  f[3 * (size_t)k + 2] *= sc;
+}
+
+// new positions from the caller (caller order) + the neighbor->decide() displacement test
+__global__ void set_x_kernel(int n, const double *__restrict__ xc, const int *__restrict__ perm,
+                             const double *__restrict__ xbuild, double thresh2, double4 *xq, unsigned int *flags) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  float d2f = 0.f;
+  bool over = false;
+  if (k < n) {
+    size_t c = (size_t)perm[k] * 3;
+    double x = xc[c], y = xc[c + 1], z = xc[c + 2];
+    xq[k].x = x; xq[k].y = y; xq[k].z = z;
+    double dx = x - xbuild[3 * (size_t)k], dy = y - xbuild[3 * (size_t)k + 1], dz = z - xbuild[3 * (size_t)k + 2];
+    double d2 = dx * dx + dy * dy + dz * dz;
+    over = d2 > thresh2;
+    d2f = __double2float_ru(d2);
+  }
+  for (int o = 16; o; o >>= 1) d2f = fmaxf(d2f, __shfl_xor_sync(0xffffffffu, d2f, o));
+  unsigned int any = __ballot_sync(0xffffffffu, over);
+  if ((threadIdx.x & 31) == 0) {
+    if (d2f > 0.f) atomicMax(flags + 0, __float_as_uint(d2f));
+    if (any) atomicOr(flags + 4, 1u);
+  }
+}
+
+__global__ void check_kernel(int n, const double *__restrict__ xbuild, double thresh2, const double4 *__restrict__ xq,
+                             unsigned int *flags) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  float d2f = 0.f;
+  bool over = false;
+  if (k < n) {
+    double4 p = xq[k];
+    double dx = p.x - xbuild[3 * (size_t)k], dy = p.y - xbuild[3 * (size_t)k + 1], dz = p.z - xbuild[3 * (size_t)k + 2];
+    double d2 = dx * dx + dy * dy + dz * dz;
+    over = d2 > thresh2;
+    d2f = __double2float_ru(d2);
+  }
+  for (int o = 16; o; o >>= 1) d2f = fmaxf(d2f, __shfl_xor_sync(0xffffffffu, d2f, o));
+  unsigned int any = __ballot_sync(0xffffffffu, over);
+  if ((threadIdx.x & 31) == 0) {
+    if (d2f > 0.f) atomicMax(flags + 0, __float_as_uint(d2f));
+    if (any) atomicOr(flags + 4, 1u);
+  }
+}
+
+// internal order -> caller order
+__global__ void gather_out_kernel(int n, int width, const int *__restrict__ inv, const double *__restrict__ src,
+                                  const double4 *__restrict__ xq, double *out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  int k = inv[c];
+  if (xq) { out[c] = xq[k].w; return; }
+  for (int d = 0; d < width; d++) out[(size_t)c * width + d] = src[(size_t)k * width + d];
+}
+
+}  // namespace
+
+int cph_launch_partition(cph_handle *h) {
+  ProfScope ps(h, 2);
+  const int n = h->nlocal, S = h->S;
+  cudaStream_t st = h->stream;
+  CPH_CUDA(h, h->d_part.reserve((size_t)MAXPART * 4));
+  CPH_CUDA(h, cudaMemsetAsync(h->d_red.p, 0, (4 + 2 * (size_t)S) * sizeof(double), st));
+  int nb = std::max(1, std::min(MAXPART, nblk(n)));
+  partition_kernel<<<nb, TPB, 0, st>>>(n, h->d_eatom.p, h->d_evdwl.p, h->d_mask.p, h->fix.Hbit, h->d_part.p);
+  partition_final_kernel<<<1, 128, 0, st>>>(nb, h->d_part.p, h->d_red.p, h->fix.implicit_site, S);
+  if (h->ntitr)
+    site_sum_kernel<<<nblk(h->ntitr), TPB, 0, st>>>(h->ntitr, h->d_titr_site.p, h->d_titr_local.p, h->d_titr_dq.p,
+                                                    h->d_phi.p, h->d_eatom.p, h->d_mask.p, h->fix.Hbit, S,
+                                                    h->fix.implicit_site, h->d_red.p);
+  CPH_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+int cph_launch_integrate(cph_handle *h, double dt, int phase) {
+  ProfScope ps(h, 3);
+  const int S = h->S;
+  cudaStream_t st = h->stream;
+  CPH_CUDA(h, h->d_part.reserve((size_t)MAXPART * 4));
+  int nb = std::max(1, std::min(MAXPART, nblk(S)));
+  integrate_kernel<<<nb, TPB, 0, st>>>(S, dt, phase, h->bias, h->fix, h->d_pK.p, h->d_red.p, h->d_lam.p, h->d_vlam.p,
+                                       h->d_alam.p, h->d_flam.p, h->d_fs.p, h->d_dfs.p, h->d_Us.p, h->d_dUs.p,
+                                       h->d_part.p);
+  if (phase != 1)
+    integrate_final_kernel<<<1, 96, 0, st>>>(nb, h->d_part.p, h->d_red.p, h->fix.dudl_mode, h->d_scal.p);
+  CPH_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+int cph_launch_apply_charges(cph_handle *h) {
+  if (h->ntitr == 0) return 0;
+  ProfScope ps(h, 4);
+  apply_charges_kernel<<<nblk(h->ntitr), TPB, 0, h->stream>>>(h->ntitr, h->d_titr_site.p, h->d_titr_local.p,
+                                                             h->d_titr_qA.p, h->d_titr_dq.p, h->d_lam.p, h->d_xq.p);
+  CPH_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+int cph_launch_set_force(cph_handle *h) {
+  if (h->nh == 0) return 0;
+  ProfScope ps(h, 4);
+  set_force_kernel<<<nblk(h->nh), TPB, 0, h->stream>>>(h->nh, h->d_hlist.p, h->d_site_of.p, h->d_lam.p,
+                                                      h->fix.fscale_mode, h->d_f.p);
+  CPH_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+int cph_launch_set_x(cph_handle *h, const double *xc) {
+  ProfScope ps(h, 7);
+  const int n = h->nlocal;
+  cudaStream_t st = h->stream;
+  CPH_CUDA(h, cudaMemsetAsync(h->d_flags.p, 0, sizeof(unsigned int), st));
+  CPH_CUDA(h, cudaMemsetAsync(h->d_flags.p + 4, 0, sizeof(unsigned int), st));
+  const double thresh2 = 0.25 * h->skin * h->skin;
+  if (n) {
+    if (xc) set_x_kernel<<<nblk(n), TPB, 0, st>>>(n, xc, h->d_perm.p, h->d_xbuild.p, thresh2, h->d_xq.p, h->d_flags.p);
+    else check_kernel<<<nblk(n), TPB, 0, st>>>(n, h->d_xbuild.p, thresh2, h->d_xq.p, h->d_flags.p);
+  }
+  CPH_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+int cph_launch_gather_out(cph_handle *h, int what, double *out) {
+  const int n = h->nlocal;
+  if (n == 0) return 0;
+  const double *src = what == 0 ? h->d_f.p : what == 1 ? h->d_eatom.p : h->d_phi.p;
+  gather_out_kernel<<<nblk(n), TPB, 0, h->stream>>>(n, what == 0 ? 3 : 1, h->d_inv.p, src,
+                                                   what == 3 ? h->d_xq.p : nullptr, out);
+  CPH_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+namespace {
+__global__ void pack_xq_kernel(int n, const double *__restrict__ x, const double *__restrict__ q, double4 *xq) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) xq[k] = make_double4(x[3 * (size_t)k], x[3 * (size_t)k + 1], x[3 * (size_t)k + 2], q[k]);
+}
+}  // namespace
+
+// device-resident caller arrays -> packed {x,y,z,q} (cph_set_atoms with CPH_DEVICE)
+int cph_launch_pack_xq(cph_handle *h, int n, const double *x, const double *q) {
+  if (n == 0) return 0;
+  pack_xq_kernel<<<nblk(n), TPB, 0, h->stream>>>(n, x, q, h->d_xq.p);
+  CPH_CUDA(h, cudaGetLastError());
+  return 0;
+}

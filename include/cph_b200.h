@@ -22,8 +22,9 @@
  *   - types follow the default LAMMPS build (-DLAMMPS_SMALLBIG): tagint = int32,
  *     bigint = int64.
  *
- * The CPU oracle exports the same functions with the prefix orc_ (oracle/), so the
- * parity tests drive both through one table (constant_ph_b200/capi.py).
+ * The CPU oracle (oracle/cph_oracle.cpp, test infrastructure only) exports the
+ * single-rank subset of these functions with the prefix orc_, so the parity tests
+ * drive both through one table (constant_ph_b200/capi.py).
  */
 #ifndef CPH_B200_H
 #define CPH_B200_H
@@ -108,8 +109,6 @@ int cph_set_lambda(cph_handle *h, const double *lambda, const double *v_lambda);
 /* ---- rank group: replaces MPI_Allreduce (cpp:274) and comm->reverse_comm (cpp:253) --- */
 int cph_comm_unique_id(char *id128);                                   /* ncclGetUniqueId */
 int cph_comm_init_nccl(cph_handle *h, int nranks, int rank, const char *id128);
-/* in-process group of `nranks` handles driven by one host thread each (tests; 1 GPU) */
-int cph_comm_init_local(cph_handle *h, int nranks, int rank, int group_key);
 
 /* ---- atoms: called on every re-neighbouring step (LAMMPS post_neighbor) ------- */
 /* atom->x q type tag mask molecule nspecial special of the nlocal OWNED atoms (inside

@@ -1,0 +1,181 @@
+"""CPU tests of the oracle: closed-form known answers (the only values the reference pins,
+SURVEY.md §4), internal consistency of the restated pair arithmetic, and the committed
+golden fixtures.  No GPU."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from constant_ph_b200 import capi, synth
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def orc(built):
+    return capi.Engine("orc")
+
+
+# ---- known answers from the reference's formulae (fix_constant_pH.cpp:86-94, 122, 132-136, 143) -----
+def test_bias_potential_known_answers(orc):
+    orc.set_bias(capi.BIAS_EXACT)
+    for lam, want in [(0.0, -1.95926), (1.0, -1.95926), (0.5, 2.00000), (-0.12, 47.71667), (1.12, 47.71667)]:
+        assert abs(orc.bias_terms(lam)["U"] - want) < 6e-6
+    for lam, want in [(0.0, 10.12944), (0.02, 44.18287), (0.97, -47.87055), (1.05, 158.05091), (-0.05, -158.05091)]:
+        assert abs(orc.bias_terms(lam)["dU"] - want) < 6e-6
+    b = orc.bias_terms(0.5)
+    assert b["f"] == 0.5 and abs(b["df"] - 12.5) < 1e-12
+    assert abs(orc.bias_terms(0.3)["df"] - 2.27e-3) < 1e-5
+
+
+def test_exact_derivatives_match_finite_differences(orc):
+    orc.set_bias(capi.BIAS_EXACT)
+    for lam in np.linspace(-0.1, 1.1, 25):
+        h = 1e-6
+        up, dn, mid = orc.bias_terms(lam + h), orc.bias_terms(lam - h), orc.bias_terms(lam)
+        assert abs((up["U"] - dn["U"]) / (2 * h) - mid["dU"]) < 2e-5 * max(1.0, abs(mid["dU"]))
+        assert abs((up["f"] - dn["f"]) / (2 * h) - mid["df"]) < 1e-6 * max(1.0, abs(mid["df"]))
+
+
+def test_as_written_mode_reproduces_the_reference_lines(orc):
+    """cpp:123 and cpp:137-141 verbatim, including their arithmetic slips."""
+    orc.set_bias(capi.BIAS_AS_WRITTEN)
+    b = orc.bias_terms(0.5)
+    assert abs(b["df"] - 200.0) < 1e-9                       # 50*exp(0)/(0.5^2)
+    lam = -0.05
+    p = capi.BIAS_DEFAULT
+    U1 = -p["k"] * np.exp(-(lam - 1 - p["b"]) ** 2 / (2 * p["a"] ** 2))
+    U2 = -p["k"] * np.exp(-(lam + p["b"]) ** 2 / (2 * p["a"] ** 2))
+    U3 = p["d"] * np.exp(-(lam - 0.5) ** 2 / (2 * p["s"] ** 2))
+    dU = (-((lam - 1 - p["b"]) / (2 * p["a"] ** 2)) * U1 - ((lam + p["b"]) / (2 * p["a"] ** 2)) * U2
+          - ((lam - 0.5) / p["s"] ** 2) * U3
+          - 0.5 * p["w"] * p["r"] * 2 * np.exp(-p["r"] ** 2 * (lam + 0.5) ** 2) / np.sqrt(np.pi)
+          + 0.5 * p["w"] * p["r"] * 2 * np.exp(-p["r"] ** 2 * (lam - 1 - p["m"]) ** 2) / np.sqrt(np.pi))
+    assert abs(orc.bias_terms(lam)["dU"] - dU) < 1e-10
+    assert abs(dU - (-18.33)) < 0.01                         # the value SURVEY.md D15 measured
+    orc.set_bias(capi.BIAS_EXACT)
+
+
+def test_integrator_step_is_cpp_111_116():
+    """One reference step with a hand-computed force: lambda += v t + a t^2/2, v += a t."""
+    box = synth.config(1)
+    o = capi.configure(capi.Engine("orc"), box, nevery=3, ftm2v=1.0)
+    o.set_lambda(np.array([0.4]), np.array([0.01]))
+    o.apply_charges()
+    o.pair_pass(1); o.site_reduce()
+    dudl = o.get_sites()["dudl"][0]
+    b = o.bias_terms(0.4)
+    ph = synth.BOLTZ * box.T * np.log(10.0) * (box.pK[0] - box.pH)
+    F = -(dudl + b["df"] * ph + b["dU"])
+    a = F / 20.0
+    t = 3 * box.dt
+    o.integrate_lambda(t)
+    s = o.get_sites()
+    assert abs(s["f_lambda"][0] - F) < 1e-12 * abs(F)
+    assert abs(s["lambda"][0] - (0.4 + 0.01 * t + 0.5 * a * t * t)) < 1e-12
+    assert abs(s["v_lambda"][0] - (0.01 + a * t)) < 1e-12
+
+
+def test_nevery_gate_and_argument_errors():
+    o = capi.Engine("orc")
+    with pytest.raises(capi.CphError):
+        o.set_fix(0, 2, 4, 4.76, 4.8, 300.0)
+    box = synth.config(1)
+    o = capi.configure(capi.Engine("orc"), box, nevery=4)
+    lam = []
+    for step in range(9):
+        o.post_force(step, box.dt, box.x, None)
+        lam.append(o.get_sites()["lambda"][0])
+    lam = np.array(lam)
+    changed = np.nonzero(np.diff(np.concatenate([[box.lambda0[0]], lam])) != 0)[0]
+    assert set(changed.tolist()) <= {0, 4, 8} and 4 in changed      # cpp:69
+
+
+# ---- internal consistency of the restated pair arithmetic ----------------------------------------------
+@pytest.mark.parametrize("cfg,scale", [(1, 1.0), (2, 0.2)])
+def test_energy_partition_and_newton(cfg, scale):
+    box = synth.config(cfg, scale=scale)
+    o = capi.configure(capi.Engine("orc"), box)
+    o.pair_pass(1); o.site_reduce()
+    s = o.get_scalars()
+    e = o.get_eatom()
+    f = o.get_forces()
+    assert abs(e.sum() - (s["evdwl"] + s["ecoul"])) < 1e-10 * abs(s["evdwl"] + s["ecoul"])
+    assert abs(s["HA"] - e.sum()) < 1e-11 * abs(s["HA"])
+    H = (box.mask & synth.GROUP_H_BIT) != 0
+    assert abs((s["HA"] - s["HB"]) - e[H].sum()) < 1e-9 * max(1.0, abs(e[H].sum()))      # cpp:264-267
+    assert np.abs(f.sum(axis=0)).max() < 1e-9 * np.abs(f).max()
+    # E_coul = 1/2 sum q_i phi_i  (phi = dE/dq including the dsf self term)
+    q, phi = o.get_q(), o.get_phi()
+    assert abs(0.5 * (q * phi).sum() - s["ecoul"]) < 1e-10 * abs(s["ecoul"])
+
+
+@pytest.mark.parametrize("cfg,scale", [(1, 1.0), (2, 0.2)])
+def test_analytic_dudl_equals_perturbed_charge_reevaluation(cfg, scale):
+    """north_star: dU/dlambda from re-evaluating the pair energy at lambda +- dlambda.  E is
+    quadratic in each lambda_s, so the central difference equals the analytic value."""
+    box = synth.config(cfg, scale=scale)
+    o = capi.configure(capi.Engine("orc"), box)
+    o.pair_pass(1); o.site_reduce()
+    dudl = o.get_sites()["dudl"].copy()
+    for site in range(min(box.nsites, 3)):
+        es = []
+        for sign in (+1, -1):
+            lam = box.lambda0.copy(); lam[site] += sign * 0.05
+            o.set_lambda(lam); o.apply_charges(); o.pair_pass(1); o.site_reduce()
+            sc = o.get_scalars(); es.append(sc["evdwl"] + sc["ecoul"])
+        fd = (es[0] - es[1]) / 0.1
+        assert abs(fd - dudl[site]) < 1e-8 * max(1.0, abs(dudl[site]))
+
+
+def test_neighbor_list_is_symmetric_and_complete():
+    box = synth.config(1)
+    o = capi.configure(capi.Engine("orc"), box)
+    num, keys = o.get_neighbors()
+    assert num.sum() == keys.size == o.get_counts()["neighbors"]
+    # brute force count of pairs within cutoff+skin under minimum image (special pairs with zero weights dropped)
+    L = box.boxhi - box.boxlo
+    sub = np.arange(0, box.n, 37)
+    d = box.x[sub][:, None, :] - box.x[None, :, :]
+    d -= L * np.round(d / L)
+    within = (d ** 2).sum(-1) < (box.cut_coul + box.skin) ** 2
+    brute = within.sum(1) - 1
+    nsp = np.array([box.nspecial[i, 1] for i in sub])      # 1-2 and 1-3 partners have weight 0 -> dropped
+    assert np.array_equal(num[sub], brute - nsp)
+
+
+def test_restart_roundtrip_and_site_map():
+    box = synth.config(2, scale=0.2)
+    a = capi.configure(capi.Engine("orc"), box)
+    sm = a.get_site_map()
+    want = np.full(box.n, -1, dtype=np.int32)
+    want[box.meta["tag_to_index"][box.titr_tag]] = box.titr_site
+    assert np.array_equal(sm, want)
+    for step in range(5):
+        a.post_force(step, box.dt, box.x, None)
+    buf = a.pack_restart()
+    assert buf.size == 2 + 3 * box.nsites
+    b = capi.configure(capi.Engine("orc"), box)
+    b.unpack_restart(buf)
+    assert np.array_equal(a.get_sites()["lambda"], b.get_sites()["lambda"])
+    assert np.array_equal(a.get_q(), b.get_q())
+
+
+# ---- committed golden fixtures (tests/golden/make_golden.py) -----------------------------------------------
+def test_oracle_matches_golden_fixtures():
+    g = json.load(open(os.path.join(GOLDEN, "oracle_golden.json")))
+    for case in g["cases"]:
+        box = synth.config(case["config"], scale=case["scale"])
+        o = capi.configure(capi.Engine("orc"), box, **{k: v for k, v in case["kw"].items()})
+        for step in range(case["steps"]):
+            o.post_force(step, box.dt, box.x, None)
+        s, t = o.get_scalars(), o.get_sites()
+        for k, v in case["scalars"].items():
+            assert abs(s[k] - v) <= 1e-11 * max(1.0, abs(v)), (case["name"], k, s[k], v)
+        assert np.allclose(t["lambda"], case["lambda"], rtol=0, atol=1e-12)
+        assert np.allclose(t["dudl"], case["dudl"], rtol=1e-11, atol=1e-11)
+        f = o.get_forces()
+        assert abs(np.abs(f).sum() - case["f_abs_sum"]) <= 1e-11 * case["f_abs_sum"]
+        c = o.get_counts()
+        assert c["neighbors"] == case["neighbors"] and c["special_pairs"] == case["special_pairs"]
