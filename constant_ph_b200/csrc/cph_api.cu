@@ -123,6 +123,7 @@ int cph_destroy(cph_handle *h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   cph_comm_destroy(h);
+  cph_pair_forget(h);
   DevBuf<double> *db[] = {&h->d_pK, &h->d_lam, &h->d_vlam, &h->d_alam, &h->d_flam, &h->d_fs, &h->d_dfs, &h->d_Us,
                           &h->d_dUs, &h->d_red, &h->d_titr_qA, &h->d_titr_dq, &h->d_scal, &h->d_part, &h->d_xbuild,
                           &h->d_f, &h->d_evdwl, &h->d_phi, &h->d_eatom, &h->d_stage};
@@ -132,7 +133,7 @@ int cph_destroy(cph_handle *h) {
                        &h->d_special, &h->d_ghost_src, &h->d_ghost_code, &h->d_hlist, &h->d_istage, &h->d_vals,
                        &h->d_vals2, &h->d_tmpi, &h->d_cell_start_o, &h->d_cell_start_g, &h->d_neigh, &h->d_numneigh};
   for (auto *b : ib) b->release();
-  h->d_coef.release(); h->d_xq.release(); h->d_xq2.release(); h->d_keys.release(); h->d_keys2.release();
+  h->d_coef.release(); h->d_coef4.release(); h->d_cut2.release(); h->d_type_has_lj.release(); h->d_xt.release(); h->d_xq.release(); h->d_xq2.release(); h->d_keys.release(); h->d_keys2.release();
   h->d_cubtmp.release(); h->d_flags.release();
   if (h->h_pin) cudaFreeHost(h->h_pin);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->pev0); cudaEventDestroy(h->pev1);
@@ -148,6 +149,7 @@ int cph_set_units(cph_handle *h, double qqrd2e, double boltz, double ftm2v) {
   if (!(ftm2v > 0)) return cph_fail(h, CPH_ERR_ARG, "ftm2v must be positive");
   h->qqrd2e = qqrd2e;
   h->pp.qqrd2e = qqrd2e;
+  h->kc_dirty = true;
   h->fix.boltz = boltz;
   h->fix.ftm2v = ftm2v;
   return CPH_OK;
@@ -194,8 +196,27 @@ int cph_set_pair(cph_handle *h, int style, int ntypes, const double *epsilon, co
   }
   for (int k = 0; k < 4; k++) { pp.special_lj[k] = special_lj[k]; pp.special_coul[k] = special_coul[k]; }
   h->cut_coul = cut_coul;
+  if (style == CPH_PAIR_LJ_CUT_COUL_DSF && alpha * alpha * cut_coulsq > 700.0)
+    return cph_fail(h, CPH_ERR_ARG, "alpha*cut_coul = %g is outside the range of the damped kernel", alpha * cut_coul);
   CPH_TRY(upload(h, h->d_coef, h->coef_h.data(), h->coef_h.size()));
+  {
+    std::vector<double4> c4((size_t)nt1 * nt1);
+    std::vector<double2> c2((size_t)nt1 * nt1);
+    std::vector<int> has(nt1, 0);
+    h->uniform_cut = true;
+    for (int t = 0; t < nt1 * nt1; t++) {
+      const PairCoef &c = h->coef_h[t];
+      c4[t] = make_double4(12.0 * c.lj3, 6.0 * c.lj4, c.lj3, c.lj4);
+      c2[t] = make_double2(c.cut_ljsq, c.cutsq);
+      if ((c.lj3 != 0.0 || c.lj4 != 0.0) && t / nt1 >= 1 && t % nt1 >= 1) has[t / nt1] = 1;
+      if (t / nt1 >= 1 && t % nt1 >= 1 && (c.cut_ljsq != pp.cutsq_max || cut_coulsq != pp.cutsq_max)) h->uniform_cut = false;
+    }
+    CPH_TRY(upload(h, h->d_coef4, c4.data(), c4.size()));
+    CPH_TRY(upload(h, h->d_cut2, c2.data(), c2.size()));
+    CPH_TRY(upload(h, h->d_type_has_lj, has.data(), has.size()));
+  }
   CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->kc_dirty = true;
   h->have_pair = true;
   h->rowcap = 0;
   return CPH_OK;

@@ -11,7 +11,7 @@
 
 #define CPH_NEIGHMASK 0x1FFFFFFF   // LAMMPS NEIGHMASK: low 29 bits = atom index
 #define CPH_SBSHIFT 30             // LAMMPS SBBITS: top 2 bits = special-bond class
-#define CPH_MAXNT1 16              // ntypes+1 <= 16: the (ntypes+1)^2 * 32 B coefficient table lives in shared memory
+#define CPH_MAXNT1 12              // ntypes+1 <= 12: the (ntypes+1)^2 * 32 B coefficient table lives in shared memory
 
 // device buffer that only ever grows
 template <typename T>
@@ -102,6 +102,10 @@ struct cph_handle {
   // [0]=HA [1]=HB [2]=E_vdwl [3]=E_coul [4..4+S)=dU/dlambda_s [4+S..4+2S)=HB_s-HA_s
   DevBuf<double> d_red;
   DevBuf<PairCoef> d_coef;
+  DevBuf<double4> d_coef4;      // {12 lj3, 6 lj4, lj3, lj4} per type pair
+  DevBuf<double2> d_cut2;       // {cut_ljsq, cutsq} per type pair
+  DevBuf<int> d_type_has_lj;    // type i has a non-zero LJ partner
+  bool uniform_cut = true, kc_dirty = true;
   DevBuf<int> d_titr_tag_sorted, d_titr_entry_of_sorted;  // [ntitr]
   DevBuf<int> d_titr_site, d_titr_local;                   // [ntitr] site-major; local = owned index or -1
   DevBuf<double> d_titr_qA, d_titr_dq;                     // [ntitr]
@@ -110,6 +114,7 @@ struct cph_handle {
   // device: atoms in internal (cell-sorted) order; owned [0,nlocal), ghosts [nlocal,nall)
   int nlocal = 0, nghost = 0, nall = 0, maxspecial = 0;
   DevBuf<double4> d_xq;
+  DevBuf<float4> d_xt;      // fp32 {x-origin, y-origin, z-origin, type}: prefilter record
   DevBuf<int> d_type, d_tag, d_mask;
   DevBuf<int> d_perm;       // internal -> caller index   [nlocal]
   DevBuf<int> d_inv;        // caller -> internal index   [nlocal]
@@ -159,6 +164,8 @@ int cph_forward_ghosts(cph_handle *h);          // refresh ghost x and q
 int cph_neighbors_to_host(cph_handle *h, int *numneigh, int64_t *keys, int64_t cap);
 // pair.cu
 int cph_launch_pair(cph_handle *h, int eflag);
+int cph_pair_upload_constants(cph_handle *h);
+void cph_pair_forget(cph_handle *h);
 // sites.cu
 int cph_launch_partition(cph_handle *h);        // HA, HB, E_vdwl, E_coul + per-site sums
 int cph_launch_integrate(cph_handle *h, double dt, int phase);

@@ -162,7 +162,8 @@ list_build_kernel(int nlocal, const double4 *__restrict__ xq, const int *__restr
                   const int *__restrict__ perm, const int *__restrict__ nspecial, const int *__restrict__ special,
                   int maxspecial, Grid g, const int *__restrict__ start_o, const int *__restrict__ start_g,
                   double rlist2, int keep_all_special, double4 slj_scoul_lo, double4 slj_scoul_hi,
-                  int rowcap, int *neigh, int *numneigh, unsigned int *flags, unsigned long long *stats) {
+                  int rowcap, int dummy, int *neigh, int *numneigh, unsigned int *flags,
+                  unsigned long long *stats) {
   const int lane = threadIdx.x & 31;
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= nlocal) return;
@@ -221,6 +222,9 @@ list_build_kernel(int nlocal, const double4 *__restrict__ xq, const int *__restr
       }
     }
   }
+  // pad the row to a whole 128-entry tile with the far-away dummy atom, so the pair kernel
+  // streams full tiles and needs no tail logic
+  for (int k = cnt + lane; k < min((cnt + 127) & ~127, rowcap); k += 32) row[k] = dummy;
   if (lane == 0) {
     numneigh[i] = min(cnt, rowcap);
     if (cnt > rowcap) atomicMax(flags + 1, (unsigned int)cnt);
@@ -423,7 +427,7 @@ int cph_rebuild(cph_handle *h) {
   h->nghost = nghost;
   h->nall = n + nghost;
   {
-    size_t nall = (size_t)h->nall;
+    size_t nall = (size_t)h->nall + 1;   // + the far-away dummy atom that pads neighbour rows
     CPH_CUDA(h, h->d_xq.reserve(nall, true, st));
     CPH_CUDA(h, h->d_type.reserve(nall, true, st));
     CPH_CUDA(h, h->d_tag.reserve(nall, true, st));
@@ -460,6 +464,18 @@ int cph_rebuild(cph_handle *h) {
     fill_int_kernel<<<nblk(g.ncell + 1), TPB, 0, st>>>(g.ncell + 1, h->d_cell_start_g.p, 0);
   }
 
+  {
+    // dummy atom at index nall: far outside any cutoff, zero charge, a valid type
+    const double far = 1.0e15;
+    double4 dq = make_double4(far, far, far, 0.0);
+    int one = 1, zero = 0;
+    CPH_CUDA(h, cudaMemcpyAsync(h->d_xq.p + h->nall, &dq, sizeof(dq), cudaMemcpyHostToDevice, st));
+    CPH_CUDA(h, cudaMemcpyAsync(h->d_type.p + h->nall, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+    CPH_CUDA(h, cudaMemcpyAsync(h->d_tag.p + h->nall, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+    CPH_CUDA(h, cudaMemcpyAsync(h->d_mask.p + h->nall, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+    CPH_CUDA(h, cudaStreamSynchronize(st));
+  }
+
   // ---- Verlet list ----------------------------------------------------------------------------------
   if (h->rowcap == 0) {
     // expected row length from the mean density, with head room; regrown on overflow
@@ -467,7 +483,7 @@ int cph_rebuild(cph_handle *h) {
     for (int k = 0; k < 3; k++) vol *= (h->subhi[k] - h->sublo[k]);
     double rho = n / std::max(vol, 1e-30);
     double expect = 4.0 / 3.0 * M_PI * rlist * rlist * rlist * rho;
-    h->rowcap = ((int)(expect * 1.25) + 96 + 31) / 32 * 32;
+    h->rowcap = ((int)(expect * 1.25) + 96 + 127) / 128 * 128;
   }
   CPH_CUDA(h, h->d_numneigh.reserve(n + 1));
   DevBuf<unsigned long long> stats;
@@ -485,7 +501,7 @@ int cph_rebuild(cph_handle *h) {
     list_build_kernel<<<blocks, TPB, 0, st>>>(
         n, h->d_xq.p, h->d_tag.p, h->d_perm.p, h->maxspecial ? h->d_nspecial.p : nullptr,
         h->maxspecial ? h->d_special.p : nullptr, h->maxspecial, g, h->d_cell_start_o.p, h->d_cell_start_g.p,
-        rlist * rlist, pp.style == CPH_PAIR_LJ_CUT_COUL_DSF ? 1 : 0, slj, sco, h->rowcap, h->d_neigh.p,
+        rlist * rlist, pp.style == CPH_PAIR_LJ_CUT_COUL_DSF ? 1 : 0, slj, sco, h->rowcap, h->nall, h->d_neigh.p,
         h->d_numneigh.p, h->d_flags.p, stats.p);
     CPH_CUDA(h, cudaGetLastError());
     unsigned long long stats_h[2];
@@ -493,7 +509,7 @@ int cph_rebuild(cph_handle *h) {
     CPH_CUDA(h, cudaMemcpyAsync(stats_h, stats.p, sizeof(stats_h), cudaMemcpyDeviceToHost, st));
     CPH_CUDA(h, cudaStreamSynchronize(st));
     if (flags_h[1] > (unsigned int)h->rowcap) {
-      h->rowcap = ((int)flags_h[1] + 64 + 31) / 32 * 32;  // regrow and redo
+      h->rowcap = ((int)flags_h[1] + 64 + 127) / 128 * 128;  // regrow and redo
       if (attempt == 3) return cph_fail(h, CPH_ERR_OVERFLOW, "neighbour rows overflowed after regrow");
       continue;
     }

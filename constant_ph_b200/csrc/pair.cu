@@ -6,13 +6,28 @@
 // potential phi_i = dE_coul/dq_i that gives every site's dU/dlambda analytically
 // (Appendix B), and the van-der-Waals share of the per-atom energy.
 //
-// Mapping: one warp per owned atom.  The warp streams the atom's neighbour row with
-// 128-byte coalesced loads, gathers {x,y,z,q} of each candidate (one 32-byte sector),
-// and tests the cutoff.  Because the Verlet skin makes ~40 % of the candidates fail the
-// test, accepted candidates are ballot-compacted into a per-warp shared-memory tile; the
-// expensive fp64 evaluation (rsqrt, exp, polynomial erfc) then runs on full tiles of 32
-// with every lane active.  Accumulators are reduced across the warp with shuffles; a full
-// list means no atomics and a fixed summation order (run-to-run bit reproducible).
+// Mapping: one warp per owned atom, APW atoms per warp in sequence.
+//   1. The atom's neighbour row streams HBM -> shared memory through a per-warp ring of
+//      512-byte tiles filled by TMA bulk copies (cp.async.bulk + mbarrier), issued several
+//      tiles ahead so the index stream's DRAM latency is never on the critical path.  Rows
+//      are padded to whole tiles with a far-away dummy atom, so there is no tail logic.
+//   2. Filter: each lane takes 4 candidates of a tile, gathers their packed fp32
+//      {x,y,z,type} (16 B; half the traffic of the fp64 record) and applies a CONSERVATIVE
+//      fp32 cutoff test (cutoff^2 + margin).  The Verlet skin makes ~40 % of candidates fail.
+//   3. Survivors are ballot-compacted into a per-warp shared-memory queue; whenever 32 are
+//      queued the warp evaluates them with every lane active: one 256-bit load of the fp64
+//      {x,y,z,q}, the exact fp64 cutoff test, rsqrt / exp / polynomial erfc in fp64.
+//      Special-bond pairs (2 of ~420 per water atom) take a separate slow path so the hot
+//      evaluation carries no exclusion arithmetic.
+//   4. Accumulators are reduced across the warp with shuffles; a full list means no
+//      atomics and a fixed summation order (bit reproducible run to run).
+// The fp32 test only prunes; every pair inside the cutoff is decided and evaluated in fp64,
+// so results are identical to an all-fp64 filter.
+//
+// The kernel is issue-bound, not HBM-bound: all polynomial constants live in
+// __constant__ memory so DFMA takes them as c[bank][offset] operands instead of two UMOVs
+// each, exp() is a 32-entry-table + degree-6 polynomial without special cases (its argument
+// is in [-alpha^2 rc^2, 0]), 1/sqrt and 1/x are the hardware seed plus one third-order step.
 //
 // Per-atom outputs: f (3), evdwl_i = 1/2 sum_j evdwl_ij, phi_i, eatom_i = evdwl_i +
 // 1/2 q_i phi_i  (== ev_tally's half-half split plus the dsf self term).
@@ -22,14 +37,29 @@ namespace {
 
 constexpr int WARPS = 8;
 constexpr int TPB = WARPS * 32;
-constexpr int QCAP = 64;  // per-warp compaction tile (ring)
+constexpr int APW = 4;            // atoms per warp (sequential)
+constexpr int APB = WARPS * APW;  // atoms per block
+constexpr int CH = 128;           // candidates per tile (4 per lane)
+constexpr int NBUF = 4;           // tiles in flight per warp
+constexpr int QCAP = 64;          // per-warp compaction queue (ring)
+constexpr int MAXTILES = 64;      // per-warp tile schedule entries (rows of up to 2048 neighbours)
 
-constexpr double EWALD_P = 0.3275911;
-constexpr double A1 = 0.254829592, A2 = -0.284496736, A3 = 1.421413741, A4 = -1.453152027, A5 = 1.061405429;
-constexpr double MY_PIS = 1.77245385090551602729;
+// constants of the hot evaluation, addressed as c[3][..] operands
+struct EvalConst {
+  double ewp_alpha;        // EWALD_P * alpha
+  double a1, a2, a3, a4, a5;
+  double neg_alpha2;       // -alpha^2
+  double two_alpha_pis;    // 2 alpha / sqrt(pi)
+  double qqrd2e, e_shift, f_shift, cut_coulsq, cutsq_max;
+  double exp_scale;        // 32 / ln 2
+  double exp_magic;        // 2^52 + 2^51
+  double exp_c1;           // ln2/32
+  double p2, p3, p4, p5, p6;
+  double one_m_fc[4], flj[4], fcoul[4];   // special-bond factors (slow path only)
+};
+__constant__ EvalConst kc;
+__constant__ double kexp2[32];   // 2^(j/32)
 
-// 1/sqrt(x): hardware seed (2^-23) + one third-order step -> ~2^-66, i.e. correctly rounded
-// to within 1 ulp; far inside the 1e-10 parity budget and ~4x cheaper than the IEEE path.
 __device__ __forceinline__ double fast_rsqrt(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
@@ -46,53 +76,104 @@ __device__ __forceinline__ double fast_rcp(double x) {
   double p = fma(e, e, e);
   return fma(y, p, y);
 }
+// exp(x) for x in [-700, 0]: x = (32k + j) ln2/32 + r, |r| <= ln2/64; exp = 2^k * 2^(j/32) * P6(r).
+// Relative error < 2e-16 (P6 truncation 4e-18, table correctly rounded).
+__device__ __forceinline__ double fast_exp_neg(double x, const double *s_exp2) {
+  const double tm = fma(x, kc.exp_scale, kc.exp_magic);
+  const int ni = __double2loint(tm);
+  const double nd = tm - kc.exp_magic;
+  const double r = fma(nd, -kc.exp_c1, x);   // |nd| < 2^15: representation error of c1 adds < 1e-13 relative
+  double p = fma(r, kc.p6, kc.p5);
+  p = fma(r, p, kc.p4);
+  p = fma(r, p, kc.p3);
+  p = fma(r, p, kc.p2);
+  p = fma(r, p, 1.0);
+  p = fma(r, p, 1.0);
+  const double v = s_exp2[ni & 31] * p;
+  return __hiloint2double(__double2hiint(v) + ((ni >> 5) << 20), __double2loint(v));
+}
 
-template <int STYLE, int EFLAG>
+// one 32-byte request per lane (LDG.E.256 on sm_100a)
+__device__ __forceinline__ double4 ld256(const double4 *p) {
+  double4 v;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+
+// ---- TMA bulk copy + mbarrier (per-warp ring) -------------------------------------------------
+__device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned int bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned int bar, unsigned int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned int dst, const void *src, unsigned int bytes, unsigned int bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned int bar, unsigned int parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
 struct Acc {
   double fx = 0, fy = 0, fz = 0, ev = 0, phi = 0;
 };
 
-// evaluate one in-range pair; del = xi - xj
-template <int STYLE, int EFLAG>
-__device__ __forceinline__ void eval_pair(const PairParams &pp, const PairCoef &c, double delx, double dely,
-                                          double delz, double rsq, double qi, double qj, int sb,
-                                          Acc<STYLE, EFLAG> &a) {
-  if (rsq >= c.cutsq) return;
-  double factor_lj = 1.0, factor_coul = 1.0;
-  if (sb) {   // rare (2 of ~420 pairs in water); selects instead of indexing keep pp out of local memory
-    factor_lj = sb == 1 ? pp.special_lj[1] : (sb == 2 ? pp.special_lj[2] : pp.special_lj[3]);
-    factor_coul = sb == 1 ? pp.special_coul[1] : (sb == 2 ? pp.special_coul[2] : pp.special_coul[3]);
+// Hot evaluation of one pair without special-bond factors.  del = xi - xj.
+// UNI: every type pair has cut_lj == cut_coul == the global cutoff (one exact test).
+template <int STYLE, int EFLAG, int UNI, int LJ>
+__device__ __forceinline__ void eval_pair(const double4 *s_coef, const double2 *s_cut, int tt, double delx,
+                                          double dely, double delz, double rsq, double qi, double qj,
+                                          const double *s_exp2, Acc &a) {
+  bool lj_on = true, coul_on = true;
+  if (UNI) {
+    if (rsq >= kc.cutsq_max) return;   // the exact (fp64) cutoff decision
+  } else {
+    const double2 cc = s_cut[tt];      // {cut_ljsq, cutsq}
+    if (rsq >= cc.y) return;
+    lj_on = rsq < cc.x;
+    coul_on = rsq < kc.cut_coulsq;
   }
   const double rinv = fast_rsqrt(rsq);
   const double r2inv = rinv * rinv;
   double fpair = 0.0;
-  if (rsq < c.cut_ljsq) {
+  if (LJ && lj_on) {
+    const double4 c = s_coef[tt];      // {12*lj3, 6*lj4, lj3, lj4}
     const double r6inv = r2inv * r2inv * r2inv;
-    // lj1 = 12*lj3, lj2 = 6*lj4 (Appendix A coefficients)
-    double forcelj = r6inv * (12.0 * c.lj3 * r6inv - 6.0 * c.lj4);
-    fpair = factor_lj * forcelj * r2inv;
-    if (EFLAG) a.ev += factor_lj * (r6inv * (c.lj3 * r6inv - c.lj4));
+    fpair = r6inv * fma(c.x, r6inv, -c.y) * r2inv;
+    if (EFLAG) a.ev = fma(r6inv, fma(c.z, r6inv, -c.w), a.ev);
   }
-  if (rsq < pp.cut_coulsq) {
+  if (coul_on) {
     if (STYLE == CPH_PAIR_LJ_CUT_COUL_CUT) {
-      const double k = pp.qqrd2e * factor_coul * rinv;   // E_ij = qi qj k
-      fpair += qi * qj * k * r2inv;
-      if (EFLAG) a.phi += qj * k;
+      const double k = kc.qqrd2e * rinv;   // E_ij = qi qj k
+      fpair = fma(qi * qj * k, r2inv, fpair);
+      if (EFLAG) a.phi = fma(qj, k, a.phi);
     } else {
       const double r = rsq * rinv;
-      const double erfcd = exp(-pp.alpha * pp.alpha * rsq);
-      const double t = fast_rcp(fma(EWALD_P * pp.alpha, r, 1.0));
-      const double erfcc = t * (A1 + t * (A2 + t * (A3 + t * (A4 + t * A5)))) * erfcd;
-      const double pre = pp.qqrd2e * rinv;               // prefactor / (qi qj)
+      const double erfcd = fast_exp_neg(kc.neg_alpha2 * rsq, s_exp2);
+      const double t = fast_rcp(fma(kc.ewp_alpha, r, 1.0));
+      double poly = fma(t, kc.a5, kc.a4);
+      poly = fma(t, poly, kc.a3);
+      poly = fma(t, poly, kc.a2);
+      poly = fma(t, poly, kc.a1);
+      const double erfcc = t * poly * erfcd;
+      const double pre = kc.qqrd2e * rinv;               // prefactor / (qi qj)
       // forcecoul*r2inv = prefactor*(erfcc/r + 2a/sqrt(pi)*erfcd + r*f_shift)*r * r2inv
-      double fc = fma(erfcc, rinv, fma(2.0 * pp.alpha / MY_PIS, erfcd, r * pp.f_shift));
-      double kk = erfcc - r * pp.e_shift - rsq * pp.f_shift;
-      if (sb) {
-        fc -= (1.0 - factor_coul) * rinv;
-        kk -= (1.0 - factor_coul);
+      const double fc = fma(erfcc, rinv, fma(kc.two_alpha_pis, erfcd, r * kc.f_shift));
+      fpair = fma(qi * qj * pre, fc * rinv, fpair);
+      if (EFLAG) {
+        const double kk = fma(-rsq, kc.f_shift, fma(-r, kc.e_shift, erfcc));
+        a.phi = fma(qj * pre, kk, a.phi);
       }
-      fpair += qi * qj * pre * fc * rinv;
-      if (EFLAG) a.phi += qj * pre * kk;
     }
   }
   a.fx = fma(delx, fpair, a.fx);
@@ -100,107 +181,297 @@ __device__ __forceinline__ void eval_pair(const PairParams &pp, const PairCoef &
   a.fz = fma(delz, fpair, a.fz);
 }
 
+// Slow path for special-bond pairs (factor_lj / factor_coul and, under
+// dsf, the -(1-factor_coul)*prefactor correction).  A handful of lanes per atom.
 template <int STYLE, int EFLAG>
-__global__ void __launch_bounds__(TPB)
-pair_kernel(int nlocal, const double4 *__restrict__ xq, const int *__restrict__ type,
-            const int *__restrict__ neigh, const int *__restrict__ numneigh, int rowcap, PairParams pp,
-            const PairCoef *__restrict__ coef, double *__restrict__ f, double *__restrict__ evdwl,
-            double *__restrict__ phi, double *__restrict__ eatom) {
-  __shared__ PairCoef s_coef[CPH_MAXNT1 * CPH_MAXNT1];
-  __shared__ int s_q[WARPS][QCAP];
-  const int nt1 = pp.ntypes + 1;
-  for (int k = threadIdx.x; k < nt1 * nt1; k += TPB) s_coef[k] = coef[k];
+__device__ __noinline__ void eval_special(const double4 *s_coef, const double2 *s_cut, int tt, double delx,
+                                          double dely, double delz, double rsq, double qi, double qj, int sb,
+                                          double *out5) {
+  const double2 cc = s_cut[tt];
+  out5[0] = out5[1] = out5[2] = out5[3] = out5[4] = 0.0;
+  if (rsq >= cc.y) return;
+  const double factor_lj = kc.flj[sb], factor_coul = kc.fcoul[sb];
+  const double rinv = 1.0 / sqrt(rsq);
+  const double r2inv = rinv * rinv;
+  double fpair = 0.0, ev = 0.0, ph = 0.0;
+  if (rsq < cc.x) {
+    const double4 c = s_coef[tt];
+    const double r6inv = r2inv * r2inv * r2inv;
+    fpair = factor_lj * r6inv * (c.x * r6inv - c.y) * r2inv;
+    ev = factor_lj * (r6inv * (c.z * r6inv - c.w));
+  }
+  if (rsq < kc.cut_coulsq) {
+    if (STYLE == CPH_PAIR_LJ_CUT_COUL_CUT) {
+      const double k = kc.qqrd2e * factor_coul * rinv;
+      fpair += qi * qj * k * r2inv;
+      ph = qj * k;
+    } else {
+      const double r = rsq * rinv;
+      const double erfcd = exp(kc.neg_alpha2 * rsq);
+      const double t = 1.0 / (1.0 + kc.ewp_alpha * r);
+      const double erfcc = t * (kc.a1 + t * (kc.a2 + t * (kc.a3 + t * (kc.a4 + t * kc.a5)))) * erfcd;
+      const double pre = kc.qqrd2e * rinv;
+      double fc = erfcc * rinv + kc.two_alpha_pis * erfcd + r * kc.f_shift;
+      double kk = erfcc - r * kc.e_shift - rsq * kc.f_shift;
+      fc -= kc.one_m_fc[sb] * rinv;
+      kk -= kc.one_m_fc[sb];
+      fpair += qi * qj * pre * fc * rinv;
+      ph = qj * pre * kk;
+    }
+  }
+  out5[0] = delx * fpair; out5[1] = dely * fpair; out5[2] = delz * fpair; out5[3] = ev; out5[4] = ph;
+}
+
+struct WarpSmem {
+  int tile[NBUF][CH];                 // neighbour tiles (TMA destination), 16-byte aligned
+  int2 queue[QCAP];                   // {neighbour index, type pair index}
+  unsigned long long bar[NBUF];
+  int sched[MAXTILES];                // tile schedule: row offset (in ints / CH) of each tile of this warp
+};
+
+#ifndef CPH_PAIR_MINBLOCKS
+#define CPH_PAIR_MINBLOCKS 3
+#endif
+
+template <int STYLE, int EFLAG, int UNI>
+__global__ void __launch_bounds__(TPB, CPH_PAIR_MINBLOCKS)
+pair_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__restrict__ xt,
+            const int *__restrict__ neigh, const int *__restrict__ numneigh, int rowcap, int nt1, float cutf,
+            const double4 *__restrict__ coef, const double2 *__restrict__ cuts, const int *__restrict__ type_has_lj,
+            double *__restrict__ f, double *__restrict__ evdwl, double *__restrict__ phi,
+            double *__restrict__ eatom, double c_self) {
+  __shared__ double4 s_coef[CPH_MAXNT1 * CPH_MAXNT1];
+  __shared__ double2 s_cut[CPH_MAXNT1 * CPH_MAXNT1];
+  __shared__ double s_exp2[32];
+  __shared__ __align__(128) WarpSmem s_w[WARPS];
+  for (int k = threadIdx.x; k < nt1 * nt1; k += TPB) {
+    s_coef[k] = coef[k];
+    s_cut[k] = cuts[k];
+  }
+  if (threadIdx.x < 32) s_exp2[threadIdx.x] = kexp2[threadIdx.x];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  WarpSmem &sm = s_w[w];
+  const unsigned int bar0 = smem_u32(&sm.bar[0]);
+  const unsigned int tile0 = smem_u32(&sm.tile[0][0]);
+  if (lane == 0)
+    for (int b = 0; b < NBUF; b++) mbar_init(bar0 + 8 * b, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+
+  // this warp's atoms: base + n*WARPS, n = 0..APW-1 (the block's warps walk adjacent atoms together)
+  const int base = blockIdx.x * APB + w;
+  const int my_atom = base + lane * WARPS;
+  const int nn_mine = (lane < APW && my_atom < nlocal) ? numneigh[my_atom] : 0;
+  const int nt_mine = (nn_mine + CH - 1) / CH;            // tiles of "my" atom
+  // exclusive scan over the APW atoms -> tile schedule in shared memory
+  int pre = nt_mine;
+  for (int o = 1; o < APW; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, pre, o);
+    if (lane >= o) pre += v;
+  }
+  const int total_tiles = min(__shfl_sync(0xffffffffu, pre, APW - 1), MAXTILES);
+  if (lane < APW) {
+    int t0 = pre - nt_mine;
+    for (int c = 0; c < nt_mine && t0 + c < MAXTILES; c++)
+      sm.sched[t0 + c] = (base + lane * WARPS) * (rowcap / CH) + c;   // tile index in the list
+  }
   __syncthreads();
 
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int i = blockIdx.x * WARPS + w;
-  if (i >= nlocal) return;
-  int *q = s_q[w];
-  const double4 pi = xq[i];
-  const int ti = type[i];
-  const PairCoef *ci = s_coef + ti * nt1;
-  const int nn = numneigh[i];
-  const int *row = neigh + (size_t)i * rowcap;
-  Acc<STYLE, EFLAG> a;
-  int head = 0, tail = 0;   // ring indices (warp-uniform)
-
-  auto drain = [&](int count) {
-    // lanes [0,count) each evaluate one queued pair
-    if (lane < count) {
-      int raw = q[(head + lane) & (QCAP - 1)];
-      int j = raw & CPH_NEIGHMASK, sb = (raw >> CPH_SBSHIFT) & 3;
-      double4 pj = xq[j];
-      int tj = type[j];
-      double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
-      double rsq = delx * delx + dely * dely + delz * delz;
-      eval_pair<STYLE, EFLAG>(pp, ci[tj], delx, dely, delz, rsq, pi.w, pj.w, sb, a);
+  int issued = 0;
+  auto issue = [&]() {
+    if (issued < total_tiles && lane == 0) {
+      const unsigned int slot = issued & (NBUF - 1);
+      mbar_expect_tx(bar0 + 8 * slot, CH * 4);
+      bulk_g2s(tile0 + slot * (CH * 4), neigh + (size_t)sm.sched[issued] * CH, CH * 4, bar0 + 8 * slot);
     }
-    head += count;
+    issued++;
   };
+#pragma unroll
+  for (int b = 0; b < NBUF; b++) issue();
 
-  for (int k0 = 0; k0 < nn; k0 += 32) {
-    int k = k0 + lane;
-    bool in = false;
-    int raw = 0;
-    if (k < nn) {
-      raw = row[k];
-      double4 pj = xq[raw & CPH_NEIGHMASK];
-      double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
-      double rsq = delx * delx + dely * dely + delz * delz;
-      in = rsq < pp.cutsq_max;
-    }
-    unsigned int m = __ballot_sync(0xffffffffu, in);
-    if (in) q[(tail + __popc(m & ((1u << lane) - 1))) & (QCAP - 1)] = raw;
-    tail += __popc(m);
-    __syncwarp();
-    if (tail - head >= 32) {
-      drain(32);
+  int cslot = 0;
+  for (int n = 0; n < APW; n++) {
+    const int i = base + n * WARPS;
+    if (i >= nlocal) break;
+    const int ntile = __shfl_sync(0xffffffffu, nt_mine, n);
+    const double4 pi = xq[i];
+    const float4 pti = xt[i];
+    const int ti = __float_as_int(pti.w);
+    const int tbase = ti * nt1;
+    const bool has_lj = type_has_lj[ti] != 0;       // warp-uniform: water H (2/3 of atoms) skips all LJ work
+    Acc a;
+    int head = 0, tail = 0;   // queue ring indices (warp-uniform)
+
+    auto drain = [&](int count) {
+      if (lane < count) {
+        const int2 e = sm.queue[(head + lane) & (QCAP - 1)];
+        const double4 pj = ld256(xq + e.x);
+        const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
+        const double rsq = fma(delz, delz, fma(dely, dely, delx * delx));
+        if (has_lj) eval_pair<STYLE, EFLAG, UNI, 1>(s_coef, s_cut, e.y, delx, dely, delz, rsq, pi.w, pj.w, s_exp2, a);
+        else eval_pair<STYLE, EFLAG, UNI, 0>(s_coef, s_cut, e.y, delx, dely, delz, rsq, pi.w, pj.w, s_exp2, a);
+      }
+      head += count;
+    };
+
+    for (int t = 0; t < ntile; t++) {
+      const unsigned int slot = cslot & (NBUF - 1);
+      mbar_wait(bar0 + 8 * slot, (cslot / NBUF) & 1);
+      const int *tp = &sm.tile[slot][lane];
+      const int r0 = tp[0], r1 = tp[32], r2 = tp[64], r3 = tp[96];
       __syncwarp();
+      cslot++;
+      issue();                      // refill the slot just consumed
+      const float4 p0 = xt[r0 & CPH_NEIGHMASK], p1 = xt[r1 & CPH_NEIGHMASK];
+      const float4 p2 = xt[r2 & CPH_NEIGHMASK], p3 = xt[r3 & CPH_NEIGHMASK];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int raw = u == 0 ? r0 : u == 1 ? r1 : u == 2 ? r2 : r3;
+        const float4 pj = u == 0 ? p0 : u == 1 ? p1 : u == 2 ? p2 : p3;
+        const float dx = pti.x - pj.x, dy = pti.y - pj.y, dz = pti.z - pj.z;
+        const float rr = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+        bool in = rr < cutf;
+        const int tt = tbase + __float_as_int(pj.w);
+        if (__any_sync(0xffffffffu, in && (raw & (3 << CPH_SBSHIFT)))) {
+          // special-bond pairs: evaluated right here by the few lanes that hold one
+          if (in && (raw & (3 << CPH_SBSHIFT))) {
+            const int j = raw & CPH_NEIGHMASK, sb = (raw >> CPH_SBSHIFT) & 3;
+            const double4 pq = ld256(xq + j);
+            const double delx = pi.x - pq.x, dely = pi.y - pq.y, delz = pi.z - pq.z;
+            const double rsq = fma(delz, delz, fma(dely, dely, delx * delx));
+            double o5[5];
+            eval_special<STYLE, EFLAG>(s_coef, s_cut, tt, delx, dely, delz, rsq, pi.w, pq.w, sb, o5);
+            a.fx += o5[0]; a.fy += o5[1]; a.fz += o5[2];
+            if (EFLAG) { a.ev += o5[3]; a.phi += o5[4]; }
+            in = false;
+          }
+        }
+        const unsigned int m = __ballot_sync(0xffffffffu, in);
+        if (in) sm.queue[(tail + __popc(m & ((1u << lane) - 1))) & (QCAP - 1)] = make_int2(raw, tt);
+        tail += __popc(m);
+        __syncwarp();
+        if (tail - head >= 32) {
+          drain(32);
+          __syncwarp();
+        }
+      }
     }
-  }
-  if (tail - head > 0) drain(tail - head);
+    if (tail - head > 0) drain(tail - head);
+    __syncwarp();
 
-  // warp reduction in a fixed order
-  for (int o = 16; o; o >>= 1) {
-    a.fx += __shfl_xor_sync(0xffffffffu, a.fx, o);
-    a.fy += __shfl_xor_sync(0xffffffffu, a.fy, o);
-    a.fz += __shfl_xor_sync(0xffffffffu, a.fz, o);
-    if (EFLAG) {
-      a.ev += __shfl_xor_sync(0xffffffffu, a.ev, o);
-      a.phi += __shfl_xor_sync(0xffffffffu, a.phi, o);
+    // warp reduction in a fixed order
+    for (int o = 16; o; o >>= 1) {
+      a.fx += __shfl_xor_sync(0xffffffffu, a.fx, o);
+      a.fy += __shfl_xor_sync(0xffffffffu, a.fy, o);
+      a.fz += __shfl_xor_sync(0xffffffffu, a.fz, o);
+      if (EFLAG) {
+        a.ev += __shfl_xor_sync(0xffffffffu, a.ev, o);
+        a.phi += __shfl_xor_sync(0xffffffffu, a.phi, o);
+      }
     }
-  }
-  if (lane == 0) {
-    f[3 * (size_t)i] = a.fx;
-    f[3 * (size_t)i + 1] = a.fy;
-    f[3 * (size_t)i + 2] = a.fz;
-    if (EFLAG) {
-      double ev = 0.5 * a.ev;
-      double ph = a.phi + 2.0 * pi.w * pp.c_self;   // dE_coul/dq_i including the dsf self term
-      evdwl[i] = ev;
-      phi[i] = ph;
-      eatom[i] = ev + 0.5 * pi.w * ph;
+    if (lane == 0) {
+      f[3 * (size_t)i] = a.fx;
+      f[3 * (size_t)i + 1] = a.fy;
+      f[3 * (size_t)i + 2] = a.fz;
+      if (EFLAG) {
+        const double ev = 0.5 * a.ev;
+        const double ph = a.phi + 2.0 * pi.w * c_self;   // dE_coul/dq_i including the dsf self term
+        evdwl[i] = ev;
+        phi[i] = ph;
+        eatom[i] = ev + 0.5 * pi.w * ph;
+      }
     }
   }
 }
 
+// packed fp32 {x - origin, y - origin, z - origin, type} for the prefilter
+__global__ void xt_kernel(int nall, const double4 *__restrict__ xq, const int *__restrict__ type, double3 origin,
+                          float4 *xt) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > nall) return;   // index nall is the far-away dummy atom
+  double4 p = xq[k];
+  xt[k] = make_float4((float)(p.x - origin.x), (float)(p.y - origin.y), (float)(p.z - origin.z),
+                      __int_as_float(type[k]));
+}
+
 }  // namespace
 
+// Constants of the hot loop live in __constant__ memory, which is per device, not per handle:
+// the handle that launches re-uploads them when another handle (other pair parameters) was the
+// last user of the device.  Handles with DIFFERENT pair parameters must not run concurrently.
+static const cph_handle *g_kc_owner[64] = {nullptr};
+
+int cph_pair_upload_constants(cph_handle *h) {
+  if (h->device >= 0 && h->device < 64) {
+    if (g_kc_owner[h->device] && g_kc_owner[h->device] != h) cudaDeviceSynchronize();
+    g_kc_owner[h->device] = h;
+  }
+  const PairParams &pp = h->pp;
+  EvalConst c{};
+  c.ewp_alpha = 0.3275911 * pp.alpha;
+  c.a1 = 0.254829592; c.a2 = -0.284496736; c.a3 = 1.421413741; c.a4 = -1.453152027; c.a5 = 1.061405429;
+  c.neg_alpha2 = -pp.alpha * pp.alpha;
+  c.two_alpha_pis = 2.0 * pp.alpha / 1.77245385090551602729;
+  c.qqrd2e = pp.qqrd2e; c.e_shift = pp.e_shift; c.f_shift = pp.f_shift;
+  c.cut_coulsq = pp.cut_coulsq; c.cutsq_max = pp.cutsq_max;
+  const double ln2 = 0.693147180559945309417232121458;
+  c.exp_scale = 32.0 / ln2;
+  c.exp_magic = 6755399441055744.0;
+  c.exp_c1 = ln2 / 32.0;
+  c.p2 = 1.0 / 2; c.p3 = 1.0 / 6; c.p4 = 1.0 / 24; c.p5 = 1.0 / 120; c.p6 = 1.0 / 720;
+  for (int k = 0; k < 4; k++) {
+    c.flj[k] = pp.special_lj[k];
+    c.fcoul[k] = pp.special_coul[k];
+    c.one_m_fc[k] = 1.0 - pp.special_coul[k];
+  }
+  double e2[32];
+  for (int j = 0; j < 32; j++) e2[j] = (double)exp2l((long double)j / 32.0L);
+  CPH_CUDA(h, cudaMemcpyToSymbolAsync(kc, &c, sizeof(c), 0, cudaMemcpyHostToDevice, h->stream));
+  CPH_CUDA(h, cudaMemcpyToSymbolAsync(kexp2, e2, sizeof(e2), 0, cudaMemcpyHostToDevice, h->stream));
+  CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+void cph_pair_forget(cph_handle *h) {
+  for (auto &o : g_kc_owner)
+    if (o == h) o = nullptr;
+}
+
 int cph_launch_pair(cph_handle *h, int eflag) {
-  ProfScope ps(h, 0);
   const int n = h->nlocal;
   if (n == 0) return 0;
-  const int blocks = (n + WARPS - 1) / WARPS;
-  const PairCoef *dc = h->d_coef.p;
-#define LAUNCH(S, E)                                                                                             \
-  pair_kernel<S, E><<<blocks, TPB, 0, h->stream>>>(n, h->d_xq.p, h->d_type.p, h->d_neigh.p, h->d_numneigh.p,    \
-                                                   h->rowcap, h->pp, dc, h->d_f.p, h->d_evdwl.p, h->d_phi.p,   \
-                                                   h->d_eatom.p)
-  if (h->pp.style == CPH_PAIR_LJ_CUT_COUL_CUT) {
-    if (eflag) LAUNCH(CPH_PAIR_LJ_CUT_COUL_CUT, 1); else LAUNCH(CPH_PAIR_LJ_CUT_COUL_CUT, 0);
-  } else {
-    if (eflag) LAUNCH(CPH_PAIR_LJ_CUT_COUL_DSF, 1); else LAUNCH(CPH_PAIR_LJ_CUT_COUL_DSF, 0);
+  const double3 origin = make_double3(h->grid.lo[0], h->grid.lo[1], h->grid.lo[2]);
+  {
+    ProfScope ps(h, 1);
+    CPH_CUDA(h, h->d_xt.reserve((size_t)h->nall + 2));
+    xt_kernel<<<(h->nall + 256) / 256, 256, 0, h->stream>>>(h->nall, h->d_xq.p, h->d_type.p, origin, h->d_xt.p);
   }
+  if (h->device < 0 || h->device >= 64 || g_kc_owner[h->device] != h || h->kc_dirty) {
+    CPH_TRY(cph_pair_upload_constants(h));
+    h->kc_dirty = false;
+  }
+  ProfScope ps(h, 0);
+  // conservative fp32 cutoff: coordinates relative to the grid origin are below `extent`, so
+  // |r2_fp32 - r2_fp64| <= ~8 * cut * extent * 2^-24; the margin is 4x that plus a relative term
+  double extent = 0;
+  for (int k = 0; k < 3; k++) extent = std::max(extent, h->grid.n[k] / h->grid.inv[k]);
+  const double cut = std::sqrt(h->pp.cutsq_max);
+  const float cutf = (float)(h->pp.cutsq_max + 32.0 * cut * extent * 5.97e-8 + 1e-5 * h->pp.cutsq_max);
+  const int blocks = (n + APB - 1) / APB;
+  if (h->rowcap / CH * APW > MAXTILES)
+    return cph_fail(h, CPH_ERR_OVERFLOW, "neighbour rows of %d entries exceed the pair kernel's tile schedule", h->rowcap);
+  const int nt1 = h->pp.ntypes + 1;
+#define LAUNCH(S, E, U)                                                                                           \
+  pair_kernel<S, E, U><<<blocks, TPB, 0, h->stream>>>(n, h->d_xq.p, h->d_xt.p, h->d_neigh.p, h->d_numneigh.p,    \
+                                                      h->rowcap, nt1, cutf, h->d_coef4.p, h->d_cut2.p,           \
+                                                      h->d_type_has_lj.p, h->d_f.p, h->d_evdwl.p, h->d_phi.p,    \
+                                                      h->d_eatom.p, h->pp.c_self)
+#define LAUNCH_E(S, U) do { if (eflag) LAUNCH(S, 1, U); else LAUNCH(S, 0, U); } while (0)
+  if (h->pp.style == CPH_PAIR_LJ_CUT_COUL_CUT) {
+    if (h->uniform_cut) LAUNCH_E(CPH_PAIR_LJ_CUT_COUL_CUT, 1); else LAUNCH_E(CPH_PAIR_LJ_CUT_COUL_CUT, 0);
+  } else {
+    if (h->uniform_cut) LAUNCH_E(CPH_PAIR_LJ_CUT_COUL_DSF, 1); else LAUNCH_E(CPH_PAIR_LJ_CUT_COUL_DSF, 0);
+  }
+#undef LAUNCH_E
 #undef LAUNCH
   CPH_CUDA(h, cudaGetLastError());
   return 0;
