@@ -132,6 +132,8 @@ struct cph_handle {
   DevBuf<int> d_istage;
   DevBuf<unsigned long long> d_keys, d_keys2;
   DevBuf<int> d_vals, d_vals2, d_tmpi;
+  DevBuf<int> d_scr_i, d_scr_src, d_scr_code, d_scr_off;   // persistent rebuild scratch (no malloc/free per rebuild)
+  DevBuf<unsigned long long> d_scr_stats;
   DevBuf<double4> d_xq2;
   DevBuf<unsigned char> d_cubtmp;
   double *h_pin = nullptr;  // pinned host scratch
@@ -140,7 +142,9 @@ struct cph_handle {
   Grid grid{};
   double ghost_cut = 0;
   DevBuf<int> d_cell_start_o, d_cell_start_g;
-  DevBuf<int> d_neigh, d_numneigh;
+  // row i: [0,numneigh) ordinary neighbours, padded to a 128 multiple with the dummy atom;
+  // special-bond partners (entry = j | class<<30) at the END of the row, numspec of them
+  DevBuf<int> d_neigh, d_numneigh, d_numspec;
   int rowcap = 0;
   int64_t nbuilds = 0, stored_neigh = 0, special_pairs = 0;
   int maxneigh = 0;

@@ -15,7 +15,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 
 #include "cph_internal.h"
 
@@ -162,7 +164,7 @@ list_build_kernel(int nlocal, const double4 *__restrict__ xq, const int *__restr
                   const int *__restrict__ perm, const int *__restrict__ nspecial, const int *__restrict__ special,
                   int maxspecial, Grid g, const int *__restrict__ start_o, const int *__restrict__ start_g,
                   double rlist2, int keep_all_special, double4 slj_scoul_lo, double4 slj_scoul_hi,
-                  int rowcap, int dummy, int *neigh, int *numneigh, unsigned int *flags,
+                  int rowcap, int dummy, int *neigh, int *numneigh, int *numspec, unsigned int *flags,
                   unsigned long long *stats) {
   const int lane = threadIdx.x & 31;
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -213,24 +215,32 @@ list_build_kernel(int nlocal, const double4 *__restrict__ xq, const int *__restr
               if ((sb == 1 && drop1) || (sb == 2 && drop2) || (sb == 3 && drop3)) ok = false;
             }
           }
-          unsigned int m = __ballot_sync(0xffffffffu, ok);
+          // ordinary neighbours fill the row from the front, special-bond partners from the back
+          unsigned int m = __ballot_sync(0xffffffffu, ok && !sb);
+          unsigned int ms = __ballot_sync(0xffffffffu, ok && sb);
           int pos = cnt + __popc(m & ((1u << lane) - 1));
-          if (ok && pos < rowcap) row[pos] = j | (sb << CPH_SBSHIFT);
+          int poss = nsp + __popc(ms & ((1u << lane) - 1));
+          if (ok && !sb && pos < rowcap) row[pos] = j;
+          if (ok && sb && poss < rowcap) row[rowcap - 1 - poss] = j | (sb << CPH_SBSHIFT);
           cnt += __popc(m);
-          nsp += __popc(__ballot_sync(0xffffffffu, ok && sb));
+          nsp += __popc(ms);
         }
       }
     }
   }
   // pad the row to a whole 128-entry tile with the far-away dummy atom, so the pair kernel
   // streams full tiles and needs no tail logic
-  for (int k = cnt + lane; k < min((cnt + 127) & ~127, rowcap); k += 32) row[k] = dummy;
+  const int padded = (cnt + 127) & ~127;
+  const bool fits = padded + nsp <= rowcap;
+  if (fits)
+    for (int k = cnt + lane; k < padded; k += 32) row[k] = dummy;
   if (lane == 0) {
-    numneigh[i] = min(cnt, rowcap);
-    if (cnt > rowcap) atomicMax(flags + 1, (unsigned int)cnt);
-    atomicAdd(stats, (unsigned long long)cnt);
+    numneigh[i] = fits ? cnt : 0;
+    numspec[i] = fits ? nsp : 0;
+    if (!fits) atomicMax(flags + 1, (unsigned int)(padded + nsp));
+    atomicAdd(stats, (unsigned long long)(cnt + nsp));
     if (nsp) atomicAdd(stats + 1, (unsigned long long)nsp);
-    atomicMax(flags + 3, (unsigned int)cnt);
+    atomicMax(flags + 3, (unsigned int)(cnt + nsp));
   }
 }
 
@@ -339,8 +349,25 @@ int cph_forward_ghosts(cph_handle *h) {
   return 0;
 }
 
+// CPH_TRACE=1 prints host wall-clock per rebuild phase (debug aid; adds stream syncs)
+struct PhaseTrace {
+  cph_handle *h;
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  explicit PhaseTrace(cph_handle *h_) : h(h_), on(getenv("CPH_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char *what) {
+    if (!on) return;
+    cudaStreamSynchronize(h->stream);
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[cph rebuild %lld] %-12s %8.3f ms\n", (long long)h->nbuilds, what,
+            std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 int cph_rebuild(cph_handle *h) {
   ProfScope ps(h, 6);
+  PhaseTrace tr(h);
   const int n = h->nlocal;
   cudaStream_t st = h->stream;
   const double cutmax = std::max(h->cut_lj_max, h->cut_coul);
@@ -382,6 +409,7 @@ int cph_rebuild(cph_handle *h) {
                       h->subhi[k] - h->sublo[k], k, h->ghost_cut);
   }
 
+  tr.mark("drift");
   // ---- sort owned atoms by (cell, tag) -------------------------------------------------------
   CPH_CUDA(h, h->d_keys.reserve(n + 1));
   CPH_CUDA(h, h->d_keys2.reserve(n + 1));
@@ -394,17 +422,18 @@ int cph_rebuild(cph_handle *h) {
     // d_vals2 = old index of the atom now at position k
     size_t tot = h->d_xq.cap;
     CPH_TRY(permute_buf(h, n, h->d_vals2.p, h->d_xq, h->d_xq2, tot));
-    DevBuf<int> tmp;  // one scratch int buffer reused for the four int arrays
-    CPH_CUDA(h, tmp.reserve(h->d_type.cap));
-    CPH_TRY(permute_buf(h, n, h->d_vals2.p, h->d_type, tmp, h->d_type.cap));
-    CPH_CUDA(h, tmp.reserve(h->d_tag.cap));
-    CPH_TRY(permute_buf(h, n, h->d_vals2.p, h->d_tag, tmp, h->d_tag.cap));
-    CPH_CUDA(h, tmp.reserve(h->d_mask.cap));
-    CPH_TRY(permute_buf(h, n, h->d_vals2.p, h->d_mask, tmp, h->d_mask.cap));
-    CPH_CUDA(h, tmp.reserve(h->d_perm.cap));
-    CPH_TRY(permute_buf(h, n, h->d_vals2.p, h->d_perm, tmp, h->d_perm.cap));
-    CPH_CUDA(h, cudaStreamSynchronize(st));
-    tmp.release();
+    // d_scr_i is a persistent scratch buffer; after each swap it holds the previous array
+    DevBuf<int> &tmp = h->d_scr_i;
+    size_t icap = std::max(std::max(h->d_type.cap, h->d_tag.cap), std::max(h->d_mask.cap, h->d_perm.cap));
+    CPH_CUDA(h, tmp.reserve(icap));
+    CPH_CUDA(h, h->d_type.reserve(icap, true, st));
+    CPH_CUDA(h, h->d_tag.reserve(icap, true, st));
+    CPH_CUDA(h, h->d_mask.reserve(icap, true, st));
+    CPH_CUDA(h, h->d_perm.reserve(icap, true, st));
+    CPH_TRY(permute_buf(h, n, h->d_vals2.p, h->d_type, tmp, icap));
+    CPH_TRY(permute_buf(h, n, h->d_vals2.p, h->d_tag, tmp, icap));
+    CPH_TRY(permute_buf(h, n, h->d_vals2.p, h->d_mask, tmp, icap));
+    CPH_TRY(permute_buf(h, n, h->d_vals2.p, h->d_perm, tmp, icap));
     CPH_CUDA(h, h->d_inv.reserve(n));
     CPH_CUDA(h, h->d_xbuild.reserve(3 * (size_t)n));
     after_sort_kernel<<<nblk(n), TPB, 0, st>>>(n, h->d_keys2.p, h->d_perm.p, h->d_xq.p, h->d_inv.p, h->d_xbuild.p,
@@ -414,6 +443,7 @@ int cph_rebuild(cph_handle *h) {
   CPH_CUDA(h, h->d_cell_start_g.reserve(g.ncell + 1));
   cell_start_kernel<<<nblk(n + 1), TPB, 0, st>>>(n, g.ncell, h->d_tmpi.p, h->d_cell_start_o.p);
 
+  tr.mark("sort");
   // ---- ghosts: periodic self images (neighbour-rank copies arrive through comm.cu) --------------
   GhostDirs gd;
   make_ghost_dirs(h, gd);
@@ -434,7 +464,7 @@ int cph_rebuild(cph_handle *h) {
     CPH_CUDA(h, h->d_mask.reserve(nall, true, st));
   }
   if (nghost) {
-    DevBuf<int> src_u, code_u, offs;
+    DevBuf<int> &src_u = h->d_scr_src, &code_u = h->d_scr_code, &offs = h->d_scr_off;
     CPH_CUDA(h, src_u.reserve(nghost));
     CPH_CUDA(h, code_u.reserve(nghost));
     CPH_CUDA(h, offs.reserve(n + 1));
@@ -456,10 +486,6 @@ int cph_rebuild(cph_handle *h) {
     after_sort_kernel<<<nblk(nghost), TPB, 0, st>>>(nghost, h->d_keys2.p, nullptr, nullptr, nullptr, nullptr,
                                                     h->d_tmpi.p);
     cell_start_kernel<<<nblk(nghost + 1), TPB, 0, st>>>(nghost, g.ncell, h->d_tmpi.p, h->d_cell_start_g.p);
-    CPH_CUDA(h, cudaStreamSynchronize(st));
-    src_u.release();
-    code_u.release();
-    offs.release();
   } else {
     fill_int_kernel<<<nblk(g.ncell + 1), TPB, 0, st>>>(g.ncell + 1, h->d_cell_start_g.p, 0);
   }
@@ -476,6 +502,7 @@ int cph_rebuild(cph_handle *h) {
     CPH_CUDA(h, cudaStreamSynchronize(st));
   }
 
+  tr.mark("ghosts");
   // ---- Verlet list ----------------------------------------------------------------------------------
   if (h->rowcap == 0) {
     // expected row length from the mean density, with head room; regrown on overflow
@@ -486,7 +513,8 @@ int cph_rebuild(cph_handle *h) {
     h->rowcap = ((int)(expect * 1.25) + 96 + 127) / 128 * 128;
   }
   CPH_CUDA(h, h->d_numneigh.reserve(n + 1));
-  DevBuf<unsigned long long> stats;
+  CPH_CUDA(h, h->d_numspec.reserve(n + 1));
+  DevBuf<unsigned long long> &stats = h->d_scr_stats;
   CPH_CUDA(h, stats.reserve(2));
   const PairParams &pp = h->pp;
   double4 slj = make_double4(pp.special_lj[0], pp.special_lj[1], pp.special_lj[2], pp.special_lj[3]);
@@ -502,7 +530,7 @@ int cph_rebuild(cph_handle *h) {
         n, h->d_xq.p, h->d_tag.p, h->d_perm.p, h->maxspecial ? h->d_nspecial.p : nullptr,
         h->maxspecial ? h->d_special.p : nullptr, h->maxspecial, g, h->d_cell_start_o.p, h->d_cell_start_g.p,
         rlist * rlist, pp.style == CPH_PAIR_LJ_CUT_COUL_DSF ? 1 : 0, slj, sco, h->rowcap, h->nall, h->d_neigh.p,
-        h->d_numneigh.p, h->d_flags.p, stats.p);
+        h->d_numneigh.p, h->d_numspec.p, h->d_flags.p, stats.p);
     CPH_CUDA(h, cudaGetLastError());
     unsigned long long stats_h[2];
     CPH_CUDA(h, cudaMemcpyAsync(flags_h, h->d_flags.p, sizeof(flags_h), cudaMemcpyDeviceToHost, st));
@@ -518,8 +546,8 @@ int cph_rebuild(cph_handle *h) {
     h->maxneigh = (int)flags_h[3];
     break;
   }
-  stats.release();
 
+  tr.mark("list");
   // ---- site bookkeeping -----------------------------------------------------------------------------
   CPH_CUDA(h, h->d_site_of.reserve(n + 1));
   CPH_CUDA(h, h->d_titr_of.reserve(n + 1));
@@ -547,6 +575,7 @@ int cph_rebuild(cph_handle *h) {
   CPH_CUDA(h, h->d_phi.reserve(n + 1));
   CPH_CUDA(h, h->d_eatom.reserve(n + 1));
   CPH_CUDA(h, cudaGetLastError());
+  tr.mark("sites");
   h->nbuilds++;
   return 0;
 }
@@ -554,15 +583,15 @@ int cph_rebuild(cph_handle *h) {
 // ---- bookkeeping getters (bit-exact parity checks) -------------------------------------------------------
 namespace {
 __global__ void neighbor_keys_kernel(int nlocal, const int *__restrict__ neigh, const int *__restrict__ numneigh,
-                                     int rowcap, const int *__restrict__ tag, const int *__restrict__ ghost_code,
+                                     const int *__restrict__ numspec, int rowcap, const int *__restrict__ tag, const int *__restrict__ ghost_code,
                                      GhostDirs gd, const int *__restrict__ perm, const long long *__restrict__ off,
                                      long long *keys) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nlocal) return;
   long long o = off[perm[i]];
-  int nn = numneigh[i];
-  for (int k = 0; k < nn; k++) {
-    int raw = neigh[(size_t)i * rowcap + k];
+  int nn = numneigh[i], ns = numspec[i];
+  for (int k = 0; k < nn + ns; k++) {
+    int raw = neigh[(size_t)i * rowcap + (k < nn ? k : rowcap - 1 - (k - nn))];
     int j = raw & CPH_NEIGHMASK, sb = (raw >> CPH_SBSHIFT) & 3;
     int code = 13;
     if (j >= nlocal) code = gd.imgcode[ghost_code[j - nlocal]];
@@ -575,11 +604,12 @@ __global__ void neighbor_keys_kernel(int nlocal, const int *__restrict__ neigh, 
 int cph_neighbors_to_host(cph_handle *h, int *numneigh, int64_t *keys, int64_t cap) {
   const int n = h->nlocal;
   cudaStream_t st = h->stream;
-  std::vector<int> nn_int(n), perm(n);
+  std::vector<int> nn_int(n), ns_int(n), perm(n);
   CPH_CUDA(h, cudaMemcpyAsync(nn_int.data(), h->d_numneigh.p, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CPH_CUDA(h, cudaMemcpyAsync(ns_int.data(), h->d_numspec.p, n * sizeof(int), cudaMemcpyDeviceToHost, st));
   CPH_CUDA(h, cudaMemcpyAsync(perm.data(), h->d_perm.p, n * sizeof(int), cudaMemcpyDeviceToHost, st));
   CPH_CUDA(h, cudaStreamSynchronize(st));
-  for (int k = 0; k < n; k++) numneigh[perm[k]] = nn_int[k];
+  for (int k = 0; k < n; k++) numneigh[perm[k]] = nn_int[k] + ns_int[k];
   if (!keys) return 0;
   std::vector<long long> off(n + 1, 0);
   for (int c = 0; c < n; c++) off[c + 1] = off[c] + numneigh[c];
@@ -590,7 +620,7 @@ int cph_neighbors_to_host(cph_handle *h, int *numneigh, int64_t *keys, int64_t c
   CPH_CUDA(h, cudaMemcpyAsync(d_off.p, off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
   GhostDirs gd;
   make_ghost_dirs(h, gd);
-  neighbor_keys_kernel<<<nblk(n), TPB, 0, st>>>(n, h->d_neigh.p, h->d_numneigh.p, h->rowcap, h->d_tag.p,
+  neighbor_keys_kernel<<<nblk(n), TPB, 0, st>>>(n, h->d_neigh.p, h->d_numneigh.p, h->d_numspec.p, h->rowcap, h->d_tag.p,
                                                 h->d_ghost_code.p, gd, h->d_perm.p, d_off.p, d_keys.p);
   CPH_CUDA(h, cudaMemcpyAsync(keys, d_keys.p, off[n] * sizeof(long long), cudaMemcpyDeviceToHost, st));
   CPH_CUDA(h, cudaStreamSynchronize(st));

@@ -41,7 +41,7 @@ constexpr int APW = 4;            // atoms per warp (sequential)
 constexpr int APB = WARPS * APW;  // atoms per block
 constexpr int CH = 128;           // candidates per tile (4 per lane)
 constexpr int NBUF = 4;           // tiles in flight per warp
-constexpr int QCAP = 64;          // per-warp compaction queue (ring)
+constexpr int QCAP = 128;         // per-warp compaction queue (ring): <= 31 left over + 64 pushed
 constexpr int MAXTILES = 64;      // per-warp tile schedule entries (rows of up to 2048 neighbours)
 
 // constants of the hot evaluation, addressed as c[3][..] operands
@@ -226,7 +226,7 @@ struct WarpSmem {
   int tile[NBUF][CH];                 // neighbour tiles (TMA destination), 16-byte aligned
   int2 queue[QCAP];                   // {neighbour index, type pair index}
   unsigned long long bar[NBUF];
-  int sched[MAXTILES];                // tile schedule: row offset (in ints / CH) of each tile of this warp
+  int sched[MAXTILES];                // tile schedule: tile index (row offset / CH) of each tile of this warp
 };
 
 #ifndef CPH_PAIR_MINBLOCKS
@@ -236,10 +236,10 @@ struct WarpSmem {
 template <int STYLE, int EFLAG, int UNI>
 __global__ void __launch_bounds__(TPB, CPH_PAIR_MINBLOCKS)
 pair_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__restrict__ xt,
-            const int *__restrict__ neigh, const int *__restrict__ numneigh, int rowcap, int nt1, float cutf,
-            const double4 *__restrict__ coef, const double2 *__restrict__ cuts, const int *__restrict__ type_has_lj,
-            double *__restrict__ f, double *__restrict__ evdwl, double *__restrict__ phi,
-            double *__restrict__ eatom, double c_self) {
+            const int *__restrict__ neigh, const int *__restrict__ numneigh, const int *__restrict__ numspec,
+            int rowcap, int nt1, float cutf, const double4 *__restrict__ coef, const double2 *__restrict__ cuts,
+            const int *__restrict__ type_has_lj, double *__restrict__ f, double *__restrict__ evdwl,
+            double *__restrict__ phi, double *__restrict__ eatom, double c_self) {
   __shared__ double4 s_coef[CPH_MAXNT1 * CPH_MAXNT1];
   __shared__ double2 s_cut[CPH_MAXNT1 * CPH_MAXNT1];
   __shared__ double s_exp2[32];
@@ -250,6 +250,7 @@ pair_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__restrict
   }
   if (threadIdx.x < 32) s_exp2[threadIdx.x] = kexp2[threadIdx.x];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned int ltmask = (1u << lane) - 1;
   WarpSmem &sm = s_w[w];
   const unsigned int bar0 = smem_u32(&sm.bar[0]);
   const unsigned int tile0 = smem_u32(&sm.tile[0][0]);
@@ -260,7 +261,9 @@ pair_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__restrict
   // this warp's atoms: base + n*WARPS, n = 0..APW-1 (the block's warps walk adjacent atoms together)
   const int base = blockIdx.x * APB + w;
   const int my_atom = base + lane * WARPS;
-  const int nn_mine = (lane < APW && my_atom < nlocal) ? numneigh[my_atom] : 0;
+  const bool mine = lane < APW && my_atom < nlocal;
+  const int nn_mine = mine ? numneigh[my_atom] : 0;
+  const int nsp_mine = mine ? numspec[my_atom] : 0;
   const int nt_mine = (nn_mine + CH - 1) / CH;            // tiles of "my" atom
   // exclusive scan over the APW atoms -> tile schedule in shared memory
   int pre = nt_mine;
@@ -272,7 +275,7 @@ pair_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__restrict
   if (lane < APW) {
     int t0 = pre - nt_mine;
     for (int c = 0; c < nt_mine && t0 + c < MAXTILES; c++)
-      sm.sched[t0 + c] = (base + lane * WARPS) * (rowcap / CH) + c;   // tile index in the list
+      sm.sched[t0 + c] = (base + lane * WARPS) * (rowcap / CH) + c;
   }
   __syncthreads();
 
@@ -293,6 +296,7 @@ pair_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__restrict
     const int i = base + n * WARPS;
     if (i >= nlocal) break;
     const int ntile = __shfl_sync(0xffffffffu, nt_mine, n);
+    const int nsp = __shfl_sync(0xffffffffu, nsp_mine, n);
     const double4 pi = xq[i];
     const float4 pti = xt[i];
     const int ti = __float_as_int(pti.w);
@@ -300,6 +304,23 @@ pair_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__restrict
     const bool has_lj = type_has_lj[ti] != 0;       // warp-uniform: water H (2/3 of atoms) skips all LJ work
     Acc a;
     int head = 0, tail = 0;   // queue ring indices (warp-uniform)
+
+    // special-bond partners sit at the end of the row; a handful of lanes take the slow path
+    if (nsp > 0) {
+      if (lane < nsp) {
+        const int raw = neigh[(size_t)i * rowcap + (rowcap - 1 - lane)];
+        const int j = raw & CPH_NEIGHMASK, sb = (raw >> CPH_SBSHIFT) & 3;
+        const double4 pq = ld256(xq + j);
+        const int tt = tbase + __float_as_int(xt[j].w);
+        const double delx = pi.x - pq.x, dely = pi.y - pq.y, delz = pi.z - pq.z;
+        const double rsq = fma(delz, delz, fma(dely, dely, delx * delx));
+        double o5[5];
+        eval_special<STYLE, EFLAG>(s_coef, s_cut, tt, delx, dely, delz, rsq, pi.w, pq.w, sb, o5);
+        a.fx = o5[0]; a.fy = o5[1]; a.fz = o5[2];
+        if (EFLAG) { a.ev = o5[3]; a.phi = o5[4]; }
+      }
+      __syncwarp();
+    }
 
     auto drain = [&](int count) {
       if (lane < count) {
@@ -312,6 +333,21 @@ pair_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__restrict
       }
       head += count;
     };
+    // two candidates per lane: fp32 test, ballot-compact into the queue
+    auto push2 = [&](int ra, const float4 &pa, int rb, const float4 &pb) {
+      const float dxa = pti.x - pa.x, dya = pti.y - pa.y, dza = pti.z - pa.z;
+      const float dxb = pti.x - pb.x, dyb = pti.y - pb.y, dzb = pti.z - pb.z;
+      const bool ina = fmaf(dxa, dxa, fmaf(dya, dya, dza * dza)) < cutf;
+      const bool inb = fmaf(dxb, dxb, fmaf(dyb, dyb, dzb * dzb)) < cutf;
+      const unsigned int ma = __ballot_sync(0xffffffffu, ina);
+      const unsigned int mb = __ballot_sync(0xffffffffu, inb);
+      const int ca = __popc(ma);
+      if (ina) sm.queue[(tail + __popc(ma & ltmask)) & (QCAP - 1)] = make_int2(ra, tbase + __float_as_int(pa.w));
+      if (inb) sm.queue[(tail + ca + __popc(mb & ltmask)) & (QCAP - 1)] = make_int2(rb, tbase + __float_as_int(pb.w));
+      tail += ca + __popc(mb);
+      __syncwarp();
+      while (tail - head >= 32) drain(32);
+    };
 
     for (int t = 0; t < ntile; t++) {
       const unsigned int slot = cslot & (NBUF - 1);
@@ -321,39 +357,9 @@ pair_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__restrict
       __syncwarp();
       cslot++;
       issue();                      // refill the slot just consumed
-      const float4 p0 = xt[r0 & CPH_NEIGHMASK], p1 = xt[r1 & CPH_NEIGHMASK];
-      const float4 p2 = xt[r2 & CPH_NEIGHMASK], p3 = xt[r3 & CPH_NEIGHMASK];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int raw = u == 0 ? r0 : u == 1 ? r1 : u == 2 ? r2 : r3;
-        const float4 pj = u == 0 ? p0 : u == 1 ? p1 : u == 2 ? p2 : p3;
-        const float dx = pti.x - pj.x, dy = pti.y - pj.y, dz = pti.z - pj.z;
-        const float rr = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-        bool in = rr < cutf;
-        const int tt = tbase + __float_as_int(pj.w);
-        if (__any_sync(0xffffffffu, in && (raw & (3 << CPH_SBSHIFT)))) {
-          // special-bond pairs: evaluated right here by the few lanes that hold one
-          if (in && (raw & (3 << CPH_SBSHIFT))) {
-            const int j = raw & CPH_NEIGHMASK, sb = (raw >> CPH_SBSHIFT) & 3;
-            const double4 pq = ld256(xq + j);
-            const double delx = pi.x - pq.x, dely = pi.y - pq.y, delz = pi.z - pq.z;
-            const double rsq = fma(delz, delz, fma(dely, dely, delx * delx));
-            double o5[5];
-            eval_special<STYLE, EFLAG>(s_coef, s_cut, tt, delx, dely, delz, rsq, pi.w, pq.w, sb, o5);
-            a.fx += o5[0]; a.fy += o5[1]; a.fz += o5[2];
-            if (EFLAG) { a.ev += o5[3]; a.phi += o5[4]; }
-            in = false;
-          }
-        }
-        const unsigned int m = __ballot_sync(0xffffffffu, in);
-        if (in) sm.queue[(tail + __popc(m & ((1u << lane) - 1))) & (QCAP - 1)] = make_int2(raw, tt);
-        tail += __popc(m);
-        __syncwarp();
-        if (tail - head >= 32) {
-          drain(32);
-          __syncwarp();
-        }
-      }
+      const float4 p0 = xt[r0], p1 = xt[r1], p2 = xt[r2], p3 = xt[r3];
+      push2(r0, p0, r1, p1);
+      push2(r2, p2, r3, p3);
     }
     if (tail - head > 0) drain(tail - head);
     __syncwarp();
@@ -462,7 +468,7 @@ int cph_launch_pair(cph_handle *h, int eflag) {
   const int nt1 = h->pp.ntypes + 1;
 #define LAUNCH(S, E, U)                                                                                           \
   pair_kernel<S, E, U><<<blocks, TPB, 0, h->stream>>>(n, h->d_xq.p, h->d_xt.p, h->d_neigh.p, h->d_numneigh.p,    \
-                                                      h->rowcap, nt1, cutf, h->d_coef4.p, h->d_cut2.p,           \
+                                                      h->d_numspec.p, h->rowcap, nt1, cutf, h->d_coef4.p, h->d_cut2.p,           \
                                                       h->d_type_has_lj.p, h->d_f.p, h->d_evdwl.p, h->d_phi.p,    \
                                                       h->d_eatom.p, h->pp.c_self)
 #define LAUNCH_E(S, U) do { if (eflag) LAUNCH(S, 1, U); else LAUNCH(S, 0, U); } while (0)
