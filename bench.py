@@ -53,13 +53,18 @@ class ClockSampler:
         self.lines = []
         self.gpu = gpu_index
 
+    def wait_first(self, timeout=5.0):
+        t0 = time.perf_counter()
+        while self.proc and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.05)
+
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -155,7 +160,7 @@ def run_cpu(args, box, params, nthreads=None, steps=None, warmup=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--atoms", type=int, default=1_000_000, help="atoms in the box (config 3 = 1M)")
@@ -270,6 +275,7 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_first()
     ms_dev, wall_dev = timed(step_dev, W, K)
     clocks = sampler.stop() if rank == 0 else None
     builds1 = eng.get_counts()["builds"]

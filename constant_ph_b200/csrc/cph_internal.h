@@ -34,6 +34,22 @@ struct DevBuf {
     cap = ncap;
     return cudaSuccess;
   }
+  // exactly n elements (no head room): used where several buffers must share one capacity
+  cudaError_t reserve_exact(size_t n, bool keep = false, cudaStream_t s = 0) {
+    if (n <= cap) return cudaSuccess;
+    T *np_ = nullptr;
+    cudaError_t e = cudaMalloc((void **)&np_, n * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (keep && p && cap) {
+      e = cudaMemcpyAsync(np_, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s);
+      if (e != cudaSuccess) return e;
+      cudaStreamSynchronize(s);
+    }
+    if (p) cudaFree(p);
+    p = np_;
+    cap = n;
+    return cudaSuccess;
+  }
   void release() {
     if (p) cudaFree(p);
     p = nullptr;
@@ -113,6 +129,7 @@ struct cph_handle {
   DevBuf<double> d_part;                                   // block partials for deterministic sums
   // device: atoms in internal (cell-sorted) order; owned [0,nlocal), ghosts [nlocal,nall)
   int nlocal = 0, nghost = 0, nall = 0, maxspecial = 0;
+  size_t atom_cap = 0;      // common capacity of every per-atom buffer (owned + ghost + dummy)
   DevBuf<double4> d_xq;
   DevBuf<float4> d_xt;      // fp32 {x-origin, y-origin, z-origin, type}: prefilter record
   DevBuf<int> d_type, d_tag, d_mask;
@@ -169,6 +186,7 @@ int cph_neighbors_to_host(cph_handle *h, int *numneigh, int64_t *keys, int64_t c
 // pair.cu
 int cph_launch_pair(cph_handle *h, int eflag);
 int cph_pair_upload_constants(cph_handle *h);
+int cph_launch_xt(cph_handle *h);
 void cph_pair_forget(cph_handle *h);
 // sites.cu
 int cph_launch_partition(cph_handle *h);        // HA, HB, E_vdwl, E_coul + per-site sums

@@ -157,19 +157,24 @@ __global__ void ghost_copy_kernel(int nghost, int nlocal, const int *__restrict_
   }
 }
 
-// One warp per owned atom; lanes sweep the 5x5 columns of 5 x-adjacent cells (contiguous in
-// the sorted order), ballot-compact accepted candidates into the atom's row.
+// One warp per owned atom.  Lanes sweep, for each of the 5x5 (y,z) cell rows around the atom,
+// the x-run of cells that can hold a neighbour (contiguous in the sorted order; the run is
+// trimmed to the chord of the cutoff sphere at that row), test candidates on the packed fp32
+// record with a +-margin band, re-test the few borderline ones in fp64 (so membership is
+// exactly the fp64 rule), and ballot-compact accepted candidates into the atom's row:
+// ordinary neighbours from the front, special-bond partners from the back.
 __global__ void __launch_bounds__(TPB)
-list_build_kernel(int nlocal, const double4 *__restrict__ xq, const int *__restrict__ tag,
-                  const int *__restrict__ perm, const int *__restrict__ nspecial, const int *__restrict__ special,
-                  int maxspecial, Grid g, const int *__restrict__ start_o, const int *__restrict__ start_g,
-                  double rlist2, int keep_all_special, double4 slj_scoul_lo, double4 slj_scoul_hi,
-                  int rowcap, int dummy, int *neigh, int *numneigh, int *numspec, unsigned int *flags,
-                  unsigned long long *stats) {
+list_build_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__restrict__ xt,
+                  const int *__restrict__ tag, const int *__restrict__ perm, const int *__restrict__ nspecial,
+                  const int *__restrict__ special, int maxspecial, Grid g, const int *__restrict__ start_o,
+                  const int *__restrict__ start_g, double rlist2, float margin, int keep_all_special,
+                  double4 slj_scoul_lo, double4 slj_scoul_hi, int rowcap, int dummy, int *neigh, int *numneigh,
+                  int *numspec, unsigned int *flags, unsigned long long *stats) {
   const int lane = threadIdx.x & 31;
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= nlocal) return;
   const double4 pi = xq[i];
+  const float4 pti = xt[i];
   const int ci = cell_of(g, pi.x, pi.y, pi.z);
   const int cx = ci % g.n[0], cy = (ci / g.n[0]) % g.n[1], cz = ci / (g.n[0] * g.n[1]);
   // special partners of i (tags), by class
@@ -187,39 +192,55 @@ list_build_kernel(int nlocal, const double4 *__restrict__ xq, const int *__restr
   const bool drop3 = !keep_all_special && slj_scoul_lo.w == 0.0 && slj_scoul_hi.w == 0.0;
   int *row = neigh + (size_t)i * rowcap;
   int cnt = 0, nsp = 0;
-  const int x0 = max(cx - 2, 0), x1 = min(cx + 2, g.n[0] - 1);
+  const float rl2 = (float)rlist2;
+  const float lo2 = rl2 - margin, hi2 = rl2 + margin;
+  const float wx = (float)(1.0 / g.inv[0]), wy = (float)(1.0 / g.inv[1]), wz = (float)(1.0 / g.inv[2]);
   for (int dz = -2; dz <= 2; dz++) {
-    int z = cz + dz;
+    const int z = cz + dz;
     if (z < 0 || z >= g.n[2]) continue;
+    // distance from the atom to the z-slab of that cell row (xt is relative to the grid origin)
+    const float gz = dz == 0 ? 0.f : (dz > 0 ? z * wz - pti.z : pti.z - (z + 1) * wz);
     for (int dy = -2; dy <= 2; dy++) {
-      int y = cy + dy;
+      const int y = cy + dy;
       if (y < 0 || y >= g.n[1]) continue;
-      int c0 = (z * g.n[1] + y) * g.n[0];
+      const float gy = dy == 0 ? 0.f : (dy > 0 ? y * wy - pti.y : pti.y - (y + 1) * wy);
+      const float rem = hi2 - fmaxf(gz, 0.f) * fmaxf(gz, 0.f) - fmaxf(gy, 0.f) * fmaxf(gy, 0.f);
+      if (rem < 0.f) continue;
+      const float xr = sqrtf(rem) * 1.0001f + 1e-3f;
+      const int x0 = max((int)floorf((pti.x - xr) / wx), 0), x1 = min((int)floorf((pti.x + xr) / wx), g.n[0] - 1);
+      if (x1 < x0) continue;
+      const int c0 = (z * g.n[1] + y) * g.n[0];
       for (int set = 0; set < 2; set++) {
         const int *st = set ? start_g : start_o;
         const int base = set ? nlocal : 0;
         const int s = st[c0 + x0], e = st[c0 + x1 + 1];
         for (int p0 = s; p0 < e; p0 += 32) {
-          int p = p0 + lane;
+          const int p = p0 + lane;
           bool ok = p < e;
-          int j = base + p, sb = 0;
+          const int j = base + p;
+          int sb = 0;
           if (ok) {
-            double4 pj = xq[j];
-            double dx = pi.x - pj.x, dy_ = pi.y - pj.y, dz_ = pi.z - pj.z;
-            double rsq = dx * dx + dy_ * dy_ + dz_ * dz_;
-            ok = rsq < rlist2 && j != i;
+            const float4 pj = xt[j];
+            const float fx = pti.x - pj.x, fy = pti.y - pj.y, fz = pti.z - pj.z;
+            const float r2 = fmaf(fx, fx, fmaf(fy, fy, fz * fz));
+            ok = r2 < hi2 && j != i;
+            if (ok && r2 > lo2) {   // borderline: decide in fp64, exactly as the reference rule
+              const double4 qj = xq[j];
+              const double dx = pi.x - qj.x, dy_ = pi.y - qj.y, dz_ = pi.z - qj.z;
+              ok = dx * dx + dy_ * dy_ + dz_ * dz_ < rlist2;
+            }
             if (ok && ns3) {
-              int tj = tag[j];
+              const int tj = tag[j];
               for (int k = 0; k < ns3; k++)
                 if (sp[k] == tj) { sb = k < ns1 ? 1 : (k < ns2 ? 2 : 3); break; }
               if ((sb == 1 && drop1) || (sb == 2 && drop2) || (sb == 3 && drop3)) ok = false;
             }
           }
           // ordinary neighbours fill the row from the front, special-bond partners from the back
-          unsigned int m = __ballot_sync(0xffffffffu, ok && !sb);
-          unsigned int ms = __ballot_sync(0xffffffffu, ok && sb);
-          int pos = cnt + __popc(m & ((1u << lane) - 1));
-          int poss = nsp + __popc(ms & ((1u << lane) - 1));
+          const unsigned int m = __ballot_sync(0xffffffffu, ok && !sb);
+          const unsigned int ms = __ballot_sync(0xffffffffu, ok && sb);
+          const int pos = cnt + __popc(m & ((1u << lane) - 1));
+          const int poss = nsp + __popc(ms & ((1u << lane) - 1));
           if (ok && !sb && pos < rowcap) row[pos] = j;
           if (ok && sb && poss < rowcap) row[rowcap - 1 - poss] = j | (sb << CPH_SBSHIFT);
           cnt += __popc(m);
@@ -349,6 +370,33 @@ int cph_forward_ghosts(cph_handle *h) {
   return 0;
 }
 
+// cudaMalloc/cudaFree cost hundreds of milliseconds on this platform, so every per-atom buffer
+// is sized once, to one common capacity with head room, and a steady-state rebuild allocates
+// nothing.  `need` counts owned + ghost atoms + the dummy.
+static int ensure_atom_capacity(cph_handle *h, size_t need) {
+  cudaStream_t st = h->stream;
+  if (need <= h->atom_cap) return 0;
+  const size_t cap = need + need / 8 + 1024;   // head room once; all buffers get exactly this
+  CPH_CUDA(h, h->d_xq.reserve_exact(cap, true, st));
+  CPH_CUDA(h, h->d_type.reserve_exact(cap, true, st));
+  CPH_CUDA(h, h->d_tag.reserve_exact(cap, true, st));
+  CPH_CUDA(h, h->d_mask.reserve_exact(cap, true, st));
+  CPH_CUDA(h, h->d_perm.reserve_exact(cap, true, st));
+  CPH_CUDA(h, h->d_scr_off.reserve_exact(cap, true, st));   // holds the ghost offsets across the regrow
+  CPH_CUDA(h, h->d_xq2.reserve_exact(cap));
+  CPH_CUDA(h, h->d_xt.reserve_exact(cap));
+  DevBuf<int> *ib[] = {&h->d_scr_i, &h->d_vals, &h->d_vals2, &h->d_tmpi, &h->d_scr_src, &h->d_scr_code,
+                       &h->d_ghost_src, &h->d_ghost_code};
+  for (auto *b : ib) CPH_CUDA(h, b->reserve_exact(cap));
+  CPH_CUDA(h, h->d_keys.reserve_exact(cap));
+  CPH_CUDA(h, h->d_keys2.reserve_exact(cap));
+  // the swap-based permutation needs identical capacities
+  h->d_xq.cap = h->d_xq2.cap = cap;
+  h->d_type.cap = h->d_tag.cap = h->d_mask.cap = h->d_perm.cap = h->d_scr_i.cap = cap;
+  h->atom_cap = cap;
+  return 0;
+}
+
 // CPH_TRACE=1 prints host wall-clock per rebuild phase (debug aid; adds stream syncs)
 struct PhaseTrace {
   cph_handle *h;
@@ -410,6 +458,13 @@ int cph_rebuild(cph_handle *h) {
   }
 
   tr.mark("drift");
+  {
+    // expected owned + ghost count from the shell volume, with head room
+    double fac = 1.0;
+    for (int k = 0; k < 3; k++)
+      if (h->periodic[k] || h->procgrid[k] > 1) fac *= 1.0 + 2.0 * (rlist + h->skin) / (h->subhi[k] - h->sublo[k]);
+    CPH_TRY(ensure_atom_capacity(h, (size_t)(n * fac * 1.05) + 4096));
+  }
   // ---- sort owned atoms by (cell, tag) -------------------------------------------------------
   CPH_CUDA(h, h->d_keys.reserve(n + 1));
   CPH_CUDA(h, h->d_keys2.reserve(n + 1));
@@ -420,16 +475,10 @@ int cph_rebuild(cph_handle *h) {
     key_kernel<<<nblk(n), TPB, 0, st>>>(n, h->d_xq.p, h->d_tag.p, g, h->d_keys.p, h->d_vals.p);
     CPH_TRY(sort_pairs(h, n, h->d_keys, h->d_keys2, h->d_vals, h->d_vals2, 64));
     // d_vals2 = old index of the atom now at position k
-    size_t tot = h->d_xq.cap;
-    CPH_TRY(permute_buf(h, n, h->d_vals2.p, h->d_xq, h->d_xq2, tot));
+    CPH_TRY(permute_buf(h, n, h->d_vals2.p, h->d_xq, h->d_xq2, h->atom_cap));
     // d_scr_i is a persistent scratch buffer; after each swap it holds the previous array
     DevBuf<int> &tmp = h->d_scr_i;
-    size_t icap = std::max(std::max(h->d_type.cap, h->d_tag.cap), std::max(h->d_mask.cap, h->d_perm.cap));
-    CPH_CUDA(h, tmp.reserve(icap));
-    CPH_CUDA(h, h->d_type.reserve(icap, true, st));
-    CPH_CUDA(h, h->d_tag.reserve(icap, true, st));
-    CPH_CUDA(h, h->d_mask.reserve(icap, true, st));
-    CPH_CUDA(h, h->d_perm.reserve(icap, true, st));
+    const size_t icap = h->d_type.cap;   // == tag/mask/perm/scr_i capacity (ensure_atom_capacity)
     CPH_TRY(permute_buf(h, n, h->d_vals2.p, h->d_type, tmp, icap));
     CPH_TRY(permute_buf(h, n, h->d_vals2.p, h->d_tag, tmp, icap));
     CPH_TRY(permute_buf(h, n, h->d_vals2.p, h->d_mask, tmp, icap));
@@ -456,19 +505,12 @@ int cph_rebuild(cph_handle *h) {
   }
   h->nghost = nghost;
   h->nall = n + nghost;
-  {
-    size_t nall = (size_t)h->nall + 1;   // + the far-away dummy atom that pads neighbour rows
-    CPH_CUDA(h, h->d_xq.reserve(nall, true, st));
-    CPH_CUDA(h, h->d_type.reserve(nall, true, st));
-    CPH_CUDA(h, h->d_tag.reserve(nall, true, st));
-    CPH_CUDA(h, h->d_mask.reserve(nall, true, st));
-  }
+  if (n) CPH_CUDA(h, cudaMemcpyAsync(h->d_scr_off.p, h->d_vals2.p, (n + 1) * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  CPH_TRY(ensure_atom_capacity(h, (size_t)h->nall + 2));   // + the far-away dummy atom that pads neighbour rows
   if (nghost) {
     DevBuf<int> &src_u = h->d_scr_src, &code_u = h->d_scr_code, &offs = h->d_scr_off;
     CPH_CUDA(h, src_u.reserve(nghost));
     CPH_CUDA(h, code_u.reserve(nghost));
-    CPH_CUDA(h, offs.reserve(n + 1));
-    CPH_CUDA(h, cudaMemcpyAsync(offs.p, h->d_vals2.p, (n + 1) * sizeof(int), cudaMemcpyDeviceToDevice, st));
     CPH_CUDA(h, h->d_keys.reserve(nghost));
     CPH_CUDA(h, h->d_keys2.reserve(nghost));
     CPH_CUDA(h, h->d_vals.reserve(nghost));
@@ -519,6 +561,10 @@ int cph_rebuild(cph_handle *h) {
   const PairParams &pp = h->pp;
   double4 slj = make_double4(pp.special_lj[0], pp.special_lj[1], pp.special_lj[2], pp.special_lj[3]);
   double4 sco = make_double4(pp.special_coul[0], pp.special_coul[1], pp.special_coul[2], pp.special_coul[3]);
+  CPH_TRY(cph_launch_xt(h));   // fp32 records of all atoms (owned + ghost + dummy) for the prefilter
+  double extent = 0;
+  for (int k = 0; k < 3; k++) extent = std::max(extent, g.n[k] / g.inv[k]);
+  const float fmargin = (float)(32.0 * rlist * extent * 5.97e-8 + 1e-5 * rlist * rlist);
   for (int attempt = 0; attempt < 4 && n; attempt++) {
     CPH_CUDA(h, h->d_neigh.reserve((size_t)n * h->rowcap));
     CPH_CUDA(h, cudaMemsetAsync(stats.p, 0, 2 * sizeof(unsigned long long), st));
@@ -527,9 +573,9 @@ int cph_rebuild(cph_handle *h) {
     int warps_per_block = TPB / 32;
     int blocks = (n + warps_per_block - 1) / warps_per_block;
     list_build_kernel<<<blocks, TPB, 0, st>>>(
-        n, h->d_xq.p, h->d_tag.p, h->d_perm.p, h->maxspecial ? h->d_nspecial.p : nullptr,
+        n, h->d_xq.p, h->d_xt.p, h->d_tag.p, h->d_perm.p, h->maxspecial ? h->d_nspecial.p : nullptr,
         h->maxspecial ? h->d_special.p : nullptr, h->maxspecial, g, h->d_cell_start_o.p, h->d_cell_start_g.p,
-        rlist * rlist, pp.style == CPH_PAIR_LJ_CUT_COUL_DSF ? 1 : 0, slj, sco, h->rowcap, h->nall, h->d_neigh.p,
+        rlist * rlist, fmargin, pp.style == CPH_PAIR_LJ_CUT_COUL_DSF ? 1 : 0, slj, sco, h->rowcap, h->nall, h->d_neigh.p,
         h->d_numneigh.p, h->d_numspec.p, h->d_flags.p, stats.p);
     CPH_CUDA(h, cudaGetLastError());
     unsigned long long stats_h[2];

@@ -437,6 +437,16 @@ int cph_pair_upload_constants(cph_handle *h) {
   return 0;
 }
 
+// fp32 prefilter records of every atom (owned, ghost, dummy); positions relative to the grid origin
+int cph_launch_xt(cph_handle *h) {
+  ProfScope ps(h, 1);
+  const double3 origin = make_double3(h->grid.lo[0], h->grid.lo[1], h->grid.lo[2]);
+  CPH_CUDA(h, h->d_xt.reserve((size_t)h->nall + 2));
+  xt_kernel<<<(h->nall + 256) / 256, 256, 0, h->stream>>>(h->nall, h->d_xq.p, h->d_type.p, origin, h->d_xt.p);
+  CPH_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
 void cph_pair_forget(cph_handle *h) {
   for (auto &o : g_kc_owner)
     if (o == h) o = nullptr;
@@ -445,12 +455,7 @@ void cph_pair_forget(cph_handle *h) {
 int cph_launch_pair(cph_handle *h, int eflag) {
   const int n = h->nlocal;
   if (n == 0) return 0;
-  const double3 origin = make_double3(h->grid.lo[0], h->grid.lo[1], h->grid.lo[2]);
-  {
-    ProfScope ps(h, 1);
-    CPH_CUDA(h, h->d_xt.reserve((size_t)h->nall + 2));
-    xt_kernel<<<(h->nall + 256) / 256, 256, 0, h->stream>>>(h->nall, h->d_xq.p, h->d_type.p, origin, h->d_xt.p);
-  }
+  CPH_TRY(cph_launch_xt(h));
   if (h->device < 0 || h->device >= 64 || g_kc_owner[h->device] != h || h->kc_dirty) {
     CPH_TRY(cph_pair_upload_constants(h));
     h->kc_dirty = false;
