@@ -133,7 +133,7 @@ int cph_destroy(cph_handle *h) {
                        &h->d_special, &h->d_ghost_src, &h->d_ghost_code, &h->d_hlist, &h->d_istage, &h->d_vals,
                        &h->d_vals2, &h->d_tmpi, &h->d_cell_start_o, &h->d_cell_start_g, &h->d_neigh, &h->d_numneigh, &h->d_numspec, &h->d_scr_i, &h->d_scr_src, &h->d_scr_code, &h->d_scr_off};
   for (auto *b : ib) b->release();
-  h->d_coef.release(); h->d_coef4.release(); h->d_cut2.release(); h->d_type_has_lj.release(); h->d_xt.release(); h->d_xq.release(); h->d_xq2.release(); h->d_keys.release(); h->d_keys2.release();
+  h->d_xb.release(); h->d_molecule.release(); h->d_coef.release(); h->d_coef4.release(); h->d_cut2.release(); h->d_type_has_lj.release(); h->d_xt.release(); h->d_xq.release(); h->d_xq2.release(); h->d_keys.release(); h->d_keys2.release();
   h->d_cubtmp.release(); h->d_flags.release(); h->d_scr_stats.release();
   if (h->h_pin) cudaFreeHost(h->h_pin);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->pev0); cudaEventDestroy(h->pev1);
@@ -330,7 +330,6 @@ int cph_set_lambda(cph_handle *h, const double *lambda, const double *v_lambda) 
 int cph_set_atoms(cph_handle *h, int where, int nlocal, const double *x, const double *q, const int *type,
                   const int *tag, const int *mask, const int *molecule, const int *nspecial, const int *special,
                   int maxspecial) {
-  (void)molecule;
   CPH_TRY(need(h, h->have_pair && h->have_domain, "cph_set_pair and cph_set_domain must precede cph_set_atoms"));
   if (nlocal < 0) return cph_fail(h, CPH_ERR_ARG, "nlocal < 0");
   if (nlocal > 0 && (!x || !q || !type || !tag || !mask)) return cph_fail(h, CPH_ERR_ARG, "NULL per-atom array");
@@ -354,6 +353,8 @@ int cph_set_atoms(cph_handle *h, int where, int nlocal, const double *x, const d
   CPH_TRY(upload(h, h->d_type, type, n, where));
   CPH_TRY(upload(h, h->d_tag, tag, n, where));
   CPH_TRY(upload(h, h->d_mask, mask, n, where));
+  h->have_mol = molecule != nullptr && maxspecial > 0;
+  if (h->have_mol) CPH_TRY(upload(h, h->d_molecule, molecule, n, where));
   if (maxspecial) {
     CPH_TRY(upload(h, h->d_nspecial, nspecial, 3 * n, where));
     CPH_TRY(upload(h, h->d_special, special, n * maxspecial, where));

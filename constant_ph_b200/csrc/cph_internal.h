@@ -132,6 +132,9 @@ struct cph_handle {
   size_t atom_cap = 0;      // common capacity of every per-atom buffer (owned + ghost + dummy)
   DevBuf<double4> d_xq;
   DevBuf<float4> d_xt;      // fp32 {x-origin, y-origin, z-origin, type}: prefilter record
+  DevBuf<float4> d_xb;      // fp32 {x-origin, y-origin, z-origin, molecule id}: list-build record
+  DevBuf<int> d_molecule;   // caller order, optional
+  bool have_mol = false;
   DevBuf<int> d_type, d_tag, d_mask;
   DevBuf<int> d_perm;       // internal -> caller index   [nlocal]
   DevBuf<int> d_inv;        // caller -> internal index   [nlocal]

@@ -167,8 +167,8 @@ __global__ void __launch_bounds__(TPB)
 list_build_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__restrict__ xt,
                   const int *__restrict__ tag, const int *__restrict__ perm, const int *__restrict__ nspecial,
                   const int *__restrict__ special, int maxspecial, Grid g, const int *__restrict__ start_o,
-                  const int *__restrict__ start_g, double rlist2, float margin, int keep_all_special,
-                  double4 slj_scoul_lo, double4 slj_scoul_hi, int rowcap, int dummy, int *neigh, int *numneigh,
+                  const int *__restrict__ start_g, double rlist2, float margin, int dropmask,
+                  int rowcap, int dummy, int *neigh, int *numneigh,
                   int *numspec, unsigned int *flags, unsigned long long *stats) {
   const int lane = threadIdx.x & 31;
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -186,10 +186,8 @@ list_build_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__re
     ns3 = min(nspecial[3 * ic + 2], maxspecial);
   }
   const int *sp = special ? special + (size_t)ic * maxspecial : nullptr;
-  // weights zero => dropped (unless dsf): class 1..3
-  const bool drop1 = !keep_all_special && slj_scoul_lo.y == 0.0 && slj_scoul_hi.y == 0.0;
-  const bool drop2 = !keep_all_special && slj_scoul_lo.z == 0.0 && slj_scoul_hi.z == 0.0;
-  const bool drop3 = !keep_all_special && slj_scoul_lo.w == 0.0 && slj_scoul_hi.w == 0.0;
+  // xt.w here is the molecule id (0 = unknown): only same-molecule candidates can be special partners
+  const int moli = __float_as_int(pti.w);
   int *row = neigh + (size_t)i * rowcap;
   int cnt = 0, nsp = 0;
   const float rl2 = (float)rlist2;
@@ -229,11 +227,11 @@ list_build_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__re
               const double dx = pi.x - qj.x, dy_ = pi.y - qj.y, dz_ = pi.z - qj.z;
               ok = dx * dx + dy_ * dy_ + dz_ * dz_ < rlist2;
             }
-            if (ok && ns3) {
+            if (ok && ns3 && __float_as_int(pj.w) == moli) {
               const int tj = tag[j];
               for (int k = 0; k < ns3; k++)
                 if (sp[k] == tj) { sb = k < ns1 ? 1 : (k < ns2 ? 2 : 3); break; }
-              if ((sb == 1 && drop1) || (sb == 2 && drop2) || (sb == 3 && drop3)) ok = false;
+              if ((dropmask >> sb) & 1) ok = false;   // both weights zero (and not dsf): not stored
             }
           }
           // ordinary neighbours fill the row from the front, special-bond partners from the back
@@ -263,6 +261,18 @@ list_build_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__re
     if (nsp) atomicAdd(stats + 1, (unsigned long long)nsp);
     atomicMax(flags + 3, (unsigned int)(cnt + nsp));
   }
+}
+
+// fp32 build records: position relative to the grid origin + molecule id (0 when the caller gave none)
+__global__ void xb_kernel(int nall, int nlocal, const double4 *__restrict__ xq, const int *__restrict__ perm,
+                          const int *__restrict__ ghost_src, const int *__restrict__ molecule, double3 origin,
+                          float4 *xb) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > nall) return;
+  double4 p = xq[k];
+  int m = 0;
+  if (molecule && k < nall) m = molecule[perm[k < nlocal ? k : ghost_src[k - nlocal]]];
+  xb[k] = make_float4((float)(p.x - origin.x), (float)(p.y - origin.y), (float)(p.z - origin.z), __int_as_float(m));
 }
 
 // site bookkeeping: owned atom -> titration entry by binary search of its tag
@@ -385,6 +395,7 @@ static int ensure_atom_capacity(cph_handle *h, size_t need) {
   CPH_CUDA(h, h->d_scr_off.reserve_exact(cap, true, st));   // holds the ghost offsets across the regrow
   CPH_CUDA(h, h->d_xq2.reserve_exact(cap));
   CPH_CUDA(h, h->d_xt.reserve_exact(cap));
+  CPH_CUDA(h, h->d_xb.reserve_exact(cap));
   DevBuf<int> *ib[] = {&h->d_scr_i, &h->d_vals, &h->d_vals2, &h->d_tmpi, &h->d_scr_src, &h->d_scr_code,
                        &h->d_ghost_src, &h->d_ghost_code};
   for (auto *b : ib) CPH_CUDA(h, b->reserve_exact(cap));
@@ -559,9 +570,14 @@ int cph_rebuild(cph_handle *h) {
   DevBuf<unsigned long long> &stats = h->d_scr_stats;
   CPH_CUDA(h, stats.reserve(2));
   const PairParams &pp = h->pp;
-  double4 slj = make_double4(pp.special_lj[0], pp.special_lj[1], pp.special_lj[2], pp.special_lj[3]);
-  double4 sco = make_double4(pp.special_coul[0], pp.special_coul[1], pp.special_coul[2], pp.special_coul[3]);
-  CPH_TRY(cph_launch_xt(h));   // fp32 records of all atoms (owned + ghost + dummy) for the prefilter
+  // build-time fp32 records {x, y, z, molecule id} of all atoms (owned + ghost + dummy)
+  xb_kernel<<<nblk(h->nall + 1), TPB, 0, st>>>(h->nall, n, h->d_xq.p, h->d_perm.p, h->d_ghost_src.p,
+                                              h->have_mol ? h->d_molecule.p : nullptr,
+                                              make_double3(g.lo[0], g.lo[1], g.lo[2]), h->d_xb.p);
+  int dropmask = 0;   // special class c is not stored when both weights are zero, except under coul/dsf
+  if (h->pp.style != CPH_PAIR_LJ_CUT_COUL_DSF)
+    for (int c = 1; c <= 3; c++)
+      if (h->pp.special_lj[c] == 0.0 && h->pp.special_coul[c] == 0.0) dropmask |= 1 << c;
   double extent = 0;
   for (int k = 0; k < 3; k++) extent = std::max(extent, g.n[k] / g.inv[k]);
   const float fmargin = (float)(32.0 * rlist * extent * 5.97e-8 + 1e-5 * rlist * rlist);
@@ -573,9 +589,9 @@ int cph_rebuild(cph_handle *h) {
     int warps_per_block = TPB / 32;
     int blocks = (n + warps_per_block - 1) / warps_per_block;
     list_build_kernel<<<blocks, TPB, 0, st>>>(
-        n, h->d_xq.p, h->d_xt.p, h->d_tag.p, h->d_perm.p, h->maxspecial ? h->d_nspecial.p : nullptr,
+        n, h->d_xq.p, h->d_xb.p, h->d_tag.p, h->d_perm.p, h->maxspecial ? h->d_nspecial.p : nullptr,
         h->maxspecial ? h->d_special.p : nullptr, h->maxspecial, g, h->d_cell_start_o.p, h->d_cell_start_g.p,
-        rlist * rlist, fmargin, pp.style == CPH_PAIR_LJ_CUT_COUL_DSF ? 1 : 0, slj, sco, h->rowcap, h->nall, h->d_neigh.p,
+        rlist * rlist, fmargin, dropmask, h->rowcap, h->nall, h->d_neigh.p,
         h->d_numneigh.p, h->d_numspec.p, h->d_flags.p, stats.p);
     CPH_CUDA(h, cudaGetLastError());
     unsigned long long stats_h[2];

@@ -114,7 +114,10 @@ int cph_comm_init_nccl(cph_handle *h, int nranks, int rank, const char *id128);
 /* atom->x q type tag mask molecule nspecial special of the nlocal OWNED atoms (inside
  * [sublo,subhi)).  The library sorts them into cells, builds its own ghost atoms
  * (periodic images and neighbour-rank copies), maps tags to titration sites and builds
- * the Verlet list (init_list, h:40, never defined in the reference). */
+ * the Verlet list (init_list, h:40, never defined in the reference).
+ * molecule may be NULL.  When given it is used only to prune the special-bond lookup during
+ * the list build (a candidate is compared with special[i] only if molecule[j] == molecule[i]),
+ * so it must be LAMMPS-consistent: bonded atoms share a molecule id.  Pass NULL otherwise. */
 int cph_set_atoms(cph_handle *h, int where, int nlocal, const double *x, const double *q,
                   const int *type, const int *tag, const int *mask, const int *molecule,
                   const int *nspecial, const int *special, int maxspecial);
