@@ -41,7 +41,7 @@ constexpr int APW = 4;            // atoms per warp (sequential)
 constexpr int APB = WARPS * APW;  // atoms per block
 constexpr int CH = 128;           // candidates per tile (4 per lane)
 constexpr int NBUF = 4;           // tiles in flight per warp
-constexpr int QCAP = 128;         // per-warp compaction queue (ring): <= 31 left over + 64 pushed
+constexpr int QCAP = 128;         // per-warp compaction queue (ring): <= 63 left over + 64 pushed
 constexpr int MAXTILES = 64;      // per-warp tile schedule entries (rows of up to 2048 neighbours)
 
 // constants of the hot evaluation, addressed as c[3][..] operands
@@ -128,57 +128,64 @@ struct Acc {
   double fx = 0, fy = 0, fz = 0, ev = 0, phi = 0;
 };
 
-// Hot evaluation of one pair without special-bond factors.  del = xi - xj.
+// Hot evaluation of one pair without special-bond factors, as STRAIGHT-LINE code (selects, no
+// branches) so that two independent pairs per lane interleave in the fp64 pipe.  Returns
+// fpair (force / r), the vdW energy and qj*K (the pair's contribution to phi_i).
 // UNI: every type pair has cut_lj == cut_coul == the global cutoff (one exact test).
 template <int STYLE, int EFLAG, int UNI, int LJ>
-__device__ __forceinline__ void eval_pair(const double4 *s_coef, const double2 *s_cut, int tt, double delx,
-                                          double dely, double delz, double rsq, double qi, double qj,
-                                          const double *s_exp2, Acc &a) {
-  bool lj_on = true, coul_on = true;
+__device__ __forceinline__ void eval_pair(const double4 *s_coef, const double2 *s_cut, int tt, double rsq,
+                                          double qi, double qj, const double *s_exp2, double &fpair_out,
+                                          double &ev_out, double &phi_out) {
+  bool in, lj_on = true, coul_on = true;
   if (UNI) {
-    if (rsq >= kc.cutsq_max) return;   // the exact (fp64) cutoff decision
+    in = rsq < kc.cutsq_max;           // the exact (fp64) cutoff decision
   } else {
     const double2 cc = s_cut[tt];      // {cut_ljsq, cutsq}
-    if (rsq >= cc.y) return;
+    in = rsq < cc.y;
     lj_on = rsq < cc.x;
     coul_on = rsq < kc.cut_coulsq;
   }
   const double rinv = fast_rsqrt(rsq);
   const double r2inv = rinv * rinv;
-  double fpair = 0.0;
-  if (LJ && lj_on) {
+  double fpair = 0.0, ev = 0.0, ph = 0.0;
+  if (LJ) {
     const double4 c = s_coef[tt];      // {12*lj3, 6*lj4, lj3, lj4}
     const double r6inv = r2inv * r2inv * r2inv;
     fpair = r6inv * fma(c.x, r6inv, -c.y) * r2inv;
-    if (EFLAG) a.ev = fma(r6inv, fma(c.z, r6inv, -c.w), a.ev);
-  }
-  if (coul_on) {
-    if (STYLE == CPH_PAIR_LJ_CUT_COUL_CUT) {
-      const double k = kc.qqrd2e * rinv;   // E_ij = qi qj k
-      fpair = fma(qi * qj * k, r2inv, fpair);
-      if (EFLAG) a.phi = fma(qj, k, a.phi);
-    } else {
-      const double r = rsq * rinv;
-      const double erfcd = fast_exp_neg(kc.neg_alpha2 * rsq, s_exp2);
-      const double t = fast_rcp(fma(kc.ewp_alpha, r, 1.0));
-      double poly = fma(t, kc.a5, kc.a4);
-      poly = fma(t, poly, kc.a3);
-      poly = fma(t, poly, kc.a2);
-      poly = fma(t, poly, kc.a1);
-      const double erfcc = t * poly * erfcd;
-      const double pre = kc.qqrd2e * rinv;               // prefactor / (qi qj)
-      // forcecoul*r2inv = prefactor*(erfcc/r + 2a/sqrt(pi)*erfcd + r*f_shift)*r * r2inv
-      const double fc = fma(erfcc, rinv, fma(kc.two_alpha_pis, erfcd, r * kc.f_shift));
-      fpair = fma(qi * qj * pre, fc * rinv, fpair);
-      if (EFLAG) {
-        const double kk = fma(-rsq, kc.f_shift, fma(-r, kc.e_shift, erfcc));
-        a.phi = fma(qj * pre, kk, a.phi);
-      }
+    if (EFLAG) ev = r6inv * fma(c.z, r6inv, -c.w);
+    if (!UNI) {
+      fpair = lj_on ? fpair : 0.0;
+      ev = lj_on ? ev : 0.0;
     }
   }
-  a.fx = fma(delx, fpair, a.fx);
-  a.fy = fma(dely, fpair, a.fy);
-  a.fz = fma(delz, fpair, a.fz);
+  double fcoul;
+  if (STYLE == CPH_PAIR_LJ_CUT_COUL_CUT) {
+    const double k = kc.qqrd2e * rinv;   // E_ij = qi qj k
+    fcoul = qi * qj * k * r2inv;
+    if (EFLAG) ph = qj * k;
+  } else {
+    const double r = rsq * rinv;
+    const double erfcd = fast_exp_neg(kc.neg_alpha2 * rsq, s_exp2);
+    const double t = fast_rcp(fma(kc.ewp_alpha, r, 1.0));
+    double poly = fma(t, kc.a5, kc.a4);
+    poly = fma(t, poly, kc.a3);
+    poly = fma(t, poly, kc.a2);
+    poly = fma(t, poly, kc.a1);
+    const double erfcc = t * poly * erfcd;
+    const double pre = kc.qqrd2e * rinv;               // prefactor / (qi qj)
+    // forcecoul*r2inv = prefactor*(erfcc/r + 2a/sqrt(pi)*erfcd + r*f_shift)*r * r2inv
+    const double fc = fma(erfcc, rinv, fma(kc.two_alpha_pis, erfcd, r * kc.f_shift));
+    fcoul = qi * qj * pre * (fc * rinv);
+    if (EFLAG) ph = qj * pre * fma(-rsq, kc.f_shift, fma(-r, kc.e_shift, erfcc));
+  }
+  if (!UNI) {
+    fcoul = coul_on ? fcoul : 0.0;
+    ph = coul_on ? ph : 0.0;
+  }
+  fpair += fcoul;
+  fpair_out = in ? fpair : 0.0;
+  ev_out = in ? ev : 0.0;
+  phi_out = in ? ph : 0.0;
 }
 
 // Slow path for special-bond pairs (factor_lj / factor_coul and, under
@@ -229,6 +236,12 @@ struct WarpSmem {
   int sched[MAXTILES];                // tile schedule: tile index (row offset / CH) of each tile of this warp
 };
 
+#ifndef CPH_DRAIN64
+#define CPH_DRAIN64 0
+#endif
+#ifndef CPH_PREFETCH
+#define CPH_PREFETCH 0
+#endif
 #ifndef CPH_PAIR_MINBLOCKS
 #define CPH_PAIR_MINBLOCKS 3
 #endif
@@ -322,16 +335,42 @@ pair_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__restrict
       __syncwarp();
     }
 
+    // evaluate `count` (<= 32) queued pairs, one per lane
     auto drain = [&](int count) {
       if (lane < count) {
         const int2 e = sm.queue[(head + lane) & (QCAP - 1)];
         const double4 pj = ld256(xq + e.x);
         const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
         const double rsq = fma(delz, delz, fma(dely, dely, delx * delx));
-        if (has_lj) eval_pair<STYLE, EFLAG, UNI, 1>(s_coef, s_cut, e.y, delx, dely, delz, rsq, pi.w, pj.w, s_exp2, a);
-        else eval_pair<STYLE, EFLAG, UNI, 0>(s_coef, s_cut, e.y, delx, dely, delz, rsq, pi.w, pj.w, s_exp2, a);
+        double fp, ev, ph;
+        if (has_lj) eval_pair<STYLE, EFLAG, UNI, 1>(s_coef, s_cut, e.y, rsq, pi.w, pj.w, s_exp2, fp, ev, ph);
+        else eval_pair<STYLE, EFLAG, UNI, 0>(s_coef, s_cut, e.y, rsq, pi.w, pj.w, s_exp2, fp, ev, ph);
+        a.fx = fma(delx, fp, a.fx); a.fy = fma(dely, fp, a.fy); a.fz = fma(delz, fp, a.fz);
+        if (EFLAG) { a.ev += ev; a.phi += ph; }
       }
       head += count;
+    };
+    // evaluate 64 queued pairs, two independent ones per lane (ILP 2 on the dependent fp64 chains)
+    auto drain64 = [&]() {
+      const int2 e0 = sm.queue[(head + lane) & (QCAP - 1)];
+      const int2 e1 = sm.queue[(head + 32 + lane) & (QCAP - 1)];
+      const double4 p0 = ld256(xq + e0.x), p1 = ld256(xq + e1.x);
+      const double dx0 = pi.x - p0.x, dy0 = pi.y - p0.y, dz0 = pi.z - p0.z;
+      const double dx1 = pi.x - p1.x, dy1 = pi.y - p1.y, dz1 = pi.z - p1.z;
+      const double rs0 = fma(dz0, dz0, fma(dy0, dy0, dx0 * dx0));
+      const double rs1 = fma(dz1, dz1, fma(dy1, dy1, dx1 * dx1));
+      double f0, f1, v0, v1, h0, h1;
+      if (has_lj) {
+        eval_pair<STYLE, EFLAG, UNI, 1>(s_coef, s_cut, e0.y, rs0, pi.w, p0.w, s_exp2, f0, v0, h0);
+        eval_pair<STYLE, EFLAG, UNI, 1>(s_coef, s_cut, e1.y, rs1, pi.w, p1.w, s_exp2, f1, v1, h1);
+      } else {
+        eval_pair<STYLE, EFLAG, UNI, 0>(s_coef, s_cut, e0.y, rs0, pi.w, p0.w, s_exp2, f0, v0, h0);
+        eval_pair<STYLE, EFLAG, UNI, 0>(s_coef, s_cut, e1.y, rs1, pi.w, p1.w, s_exp2, f1, v1, h1);
+      }
+      a.fx = fma(dx0, f0, a.fx); a.fy = fma(dy0, f0, a.fy); a.fz = fma(dz0, f0, a.fz);
+      a.fx = fma(dx1, f1, a.fx); a.fy = fma(dy1, f1, a.fy); a.fz = fma(dz1, f1, a.fz);
+      if (EFLAG) { a.ev += v0 + v1; a.phi += h0 + h1; }
+      head += 64;
     };
     // two candidates per lane: fp32 test, ballot-compact into the queue
     auto push2 = [&](int ra, const float4 &pa, int rb, const float4 &pb) {
@@ -344,9 +383,18 @@ pair_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__restrict
       const int ca = __popc(ma);
       if (ina) sm.queue[(tail + __popc(ma & ltmask)) & (QCAP - 1)] = make_int2(ra, tbase + __float_as_int(pa.w));
       if (inb) sm.queue[(tail + ca + __popc(mb & ltmask)) & (QCAP - 1)] = make_int2(rb, tbase + __float_as_int(pb.w));
+#if CPH_PREFETCH
+      // pull the fp64 records of the survivors towards L1 while the filter keeps going
+      if (ina) asm volatile("prefetch.global.L1 [%0];" ::"l"(xq + ra));
+      if (inb) asm volatile("prefetch.global.L1 [%0];" ::"l"(xq + rb));
+#endif
       tail += ca + __popc(mb);
       __syncwarp();
+#if CPH_DRAIN64
+      if (tail - head >= 64) drain64();
+#else
       while (tail - head >= 32) drain(32);
+#endif
     };
 
     for (int t = 0; t < ntile; t++) {
@@ -361,6 +409,7 @@ pair_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__restrict
       push2(r0, p0, r1, p1);
       push2(r2, p2, r3, p3);
     }
+    if (tail - head >= 32) drain(32);
     if (tail - head > 0) drain(tail - head);
     __syncwarp();
 
