@@ -431,3 +431,27 @@ def jiggle_positions(box, params, t, x0=None):
     x0 = box.x if x0 is None else x0
     m = box.molecule
     return x0 + A[m] * (np.sin(w[m] * t + p[m]) - np.sin(p[m]))
+
+
+def write_harness_input(box, path_bin, path_sites=None):
+    """Binary box + text site table for src/cph_harness (the drop-in fix driven through the
+    LAMMPS shim).  Layout documented in src/harness.cpp."""
+    pK0 = float(box.pK[0]) if box.nsites else 0.0
+    with open(path_bin, "wb") as fh:
+        np.array([box.n, box.ntypes, box.maxspecial, box.style, box.nsites, box.titr_tag.size,
+                  GROUP_H_BIT, GROUP_W_BIT], dtype=np.int32).tofile(fh)
+        hd = np.concatenate([box.boxlo, box.boxhi, [box.cut_lj, box.cut_coul, box.alpha, box.skin],
+                             box.special_lj, box.special_coul, [box.pH, box.T, box.dt, pK0]]).astype(np.float64)
+        assert hd.size == 22
+        hd.tofile(fh)
+        for arr, dt in ((box.x, np.float64), (box.q, np.float64), (box.type, np.int32), (box.tag, np.int32),
+                        (box.mask, np.int32), (box.molecule, np.int32), (box.nspecial, np.int32),
+                        (box.special, np.int32), (box.epsilon, np.float64), (box.sigma, np.float64)):
+            np.ascontiguousarray(arr, dtype=dt).tofile(fh)
+    if path_sites is not None:
+        with open(path_sites, "w") as fh:
+            fh.write("%d %d\n" % (box.nsites, box.titr_tag.size))
+            for s in range(box.nsites):
+                fh.write("%.17g %.17g\n" % (box.pK[s], box.lambda0[s]))
+            for t in range(box.titr_tag.size):
+                fh.write("%d %d %.17g %.17g\n" % (box.titr_tag[t], box.titr_site[t], box.qA[t], box.qB[t]))
