@@ -119,3 +119,21 @@ int cph_comm_exchange(cph_handle *h, int npeers, const int *peers, const void *c
   CPH_NCCL(h, n.GroupEnd());
   return CPH_OK;
 }
+
+// one int per direction: how many copies each neighbour is about to send (host values in and out)
+int cph_comm_exchange_counts(cph_handle *h, const int *active, const int *peer, const int *from, const int *send_count,
+                             int *recv_count) {
+  Nccl &n = nccl();
+  int *d = (int *)(h->d_flags.p + 16);      // 27 ints out, 27 ints in (d_flags holds >= 80 words)
+  CPH_CUDA(h, cudaMemcpyAsync(d, send_count, 27 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CPH_CUDA(h, cudaMemsetAsync(d + 27, 0, 27 * sizeof(int), h->stream));
+  CPH_NCCL(h, n.GroupStart());
+  for (int k = 0; k < 27; k++) {
+    if (active[k] == 2) CPH_NCCL(h, n.Send(d + k, 1, ncclInt32, peer[k], (ncclComm_t)h->nccl_comm, h->stream));
+    if (from[k] >= 0) CPH_NCCL(h, n.Recv(d + 27 + k, 1, ncclInt32, from[k], (ncclComm_t)h->nccl_comm, h->stream));
+  }
+  CPH_NCCL(h, n.GroupEnd());
+  CPH_CUDA(h, cudaMemcpyAsync(recv_count, d + 27, 27 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CPH_OK;
+}

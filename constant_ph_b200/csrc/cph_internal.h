@@ -142,8 +142,15 @@ struct cph_handle {
   DevBuf<int> d_titr_of;    // [nlocal] internal order, entry in site-major titr arrays
   DevBuf<int> d_nspecial, d_special;  // caller order, as uploaded
   DevBuf<double> d_xbuild;  // [3*nlocal] positions at list build
-  DevBuf<int> d_ghost_src;  // [nghost] owned internal index (local images) or slot in recv buffer
-  DevBuf<int> d_ghost_code; // [nghost] periodic image code
+  DevBuf<int> d_ghost_src;  // [nghost] owned internal index (self image) or -1-slot in the receive buffer
+  DevBuf<int> d_ghost_code; // [nghost] direction 0..26 (self image) or 32+image code (received copy)
+  DevBuf<int> d_mol;        // molecule id, internal order, owned + ghost (optional)
+  // halo (K6): records (owner, direction) sorted by direction; send/receive staging
+  int nrec = 0, nsend = 0, nrecv = 0;
+  int rec_start[28]{}, send_count[27]{}, send_off[27]{}, recv_count[27]{}, recv_off[27]{};
+  DevBuf<int> d_rec_src, d_rec_dir;
+  DevBuf<double4> d_sendx, d_recvx;
+  DevBuf<int4> d_sendmeta, d_recvmeta;
   DevBuf<double> d_f, d_evdwl, d_phi, d_eatom;  // [3*nlocal], [nlocal]...
   DevBuf<int> d_hlist;      // owned atoms in the hydrogen group
   int nh = 0;
@@ -202,6 +209,10 @@ int cph_launch_pack_xq(cph_handle *h, int n, const double *x, const double *q);
 // comm.cu
 int cph_comm_allreduce(cph_handle *h, double *buf, int n);            // sum
 int cph_comm_allreduce_max_u32(cph_handle *h, unsigned int *buf, int n);
+int cph_comm_exchange(cph_handle *h, int npeers, const int *peers, const void *const *sendbuf, const size_t *sendbytes,
+                      void *const *recvbuf, const size_t *recvbytes);
+int cph_comm_exchange_counts(cph_handle *h, const int *active, const int *peer, const int *from, const int *send_count,
+                             int *recv_count);
 void cph_comm_destroy(cph_handle *h);
 
 int cph_fail(cph_handle *h, int code, const char *fmt, ...);

@@ -90,8 +90,15 @@ __global__ void cell_start_kernel(int n, int ncell, const int *__restrict__ cell
 
 struct GhostDirs {
   double shift[27][3];   // translation applied to the copy
-  int active[27];        // this direction produces a ghost on THIS rank (periodic self image)
+  int active[27];        // 0: no copy in this direction, 1: periodic self image, 2: copy goes to another rank
   int imgcode[27];       // (ix+1)+3(iy+1)+9(iz+1) of the periodic shift
+  int peer[27];          // rank the copy goes to (active == 2)
+  int from[27];          // rank whose direction-d copies arrive here
+};
+
+struct DirTable {        // record layout of the direction-sorted ghost records
+  int start[28];         // first record of direction d
+  int out[27];           // output offset of direction d (send buffer for remote, ghost slot for local), -1 = unused
 };
 
 // bit d of the result is set when the atom must be copied in direction d
@@ -117,44 +124,119 @@ __global__ void ghost_count_kernel(int n, const double4 *__restrict__ xq, double
   count[k] = __popc(ghost_mask(xq[k], lo, hi, gc, gd));
 }
 
-__global__ void ghost_fill_kernel(int n, int nlocal, const double4 *__restrict__ xq, const int *__restrict__ tag,
-                                  double3 lo, double3 hi, double gc, GhostDirs gd, Grid g,
-                                  const int *__restrict__ offset, int *src, int *code,
-                                  unsigned long long *keys, int *vals) {
+__global__ void ghost_fill_kernel(int n, const double4 *__restrict__ xq, double3 lo, double3 hi, double gc,
+                                  GhostDirs gd, const int *__restrict__ offset, int *src, unsigned long long *dirkey,
+                                  int *vals) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  double4 p = xq[k];
-  unsigned int m = ghost_mask(p, lo, hi, gc, gd);
+  unsigned int m = ghost_mask(xq[k], lo, hi, gc, gd);
   int o = offset[k];
   while (m) {
     int d = __ffs(m) - 1;
     m &= m - 1;
     src[o] = k;
-    code[o] = d;
-    double x = p.x + gd.shift[d][0], y = p.y + gd.shift[d][1], z = p.z + gd.shift[d][2];
-    unsigned long long c = (unsigned long long)cell_of(g, x, y, z);
-    keys[o] = (c << 32) | (unsigned int)tag[k];
+    dirkey[o] = (unsigned long long)d;
     vals[o] = o;
     o++;
   }
 }
 
-// xq/type/tag/mask of ghost g from its owner; used at build (all fields) and every step (xq only)
-__global__ void ghost_copy_kernel(int nghost, int nlocal, const int *__restrict__ src, const int *__restrict__ code,
-                                  GhostDirs gd, double4 *xq, int *type, int *tag, int *mask, int all) {
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= nghost) return;
-  int s = src[g], d = code[g];
+__global__ void dir_of_key_kernel(int n, const unsigned long long *__restrict__ keys, int *dir) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) dir[k] = (int)keys[k];
+}
+
+// K6 pack: copies that go to other ranks.  Records are sorted by direction; tab.out[d] is the
+// offset of direction d in the send buffer.  meta (build only): {type | imgcode<<8, tag, mask, molecule}
+__global__ void halo_pack_kernel(int nrec, const int *__restrict__ rsrc, const int *__restrict__ rdir, DirTable tab,
+                                 GhostDirs gd, const double4 *__restrict__ xq, const int *__restrict__ type,
+                                 const int *__restrict__ tag, const int *__restrict__ mask,
+                                 const int *__restrict__ mol, double4 *sendx, int4 *sendmeta) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrec) return;
+  const int d = rdir[r];
+  if (gd.active[d] != 2) return;
+  const int o = tab.out[d] + (r - tab.start[d]);
+  const int s = rsrc[r];
   double4 p = xq[s];
   p.x += gd.shift[d][0];
   p.y += gd.shift[d][1];
   p.z += gd.shift[d][2];
-  xq[nlocal + g] = p;
-  if (all) {
-    type[nlocal + g] = type[s];
-    tag[nlocal + g] = tag[s];
-    mask[nlocal + g] = mask[s];
+  sendx[o] = p;
+  if (sendmeta) sendmeta[o] = make_int4(type[s] | (gd.imgcode[d] << 8), tag[s], mask[s], mol ? mol[s] : 0);
+}
+
+// unsorted ghost candidates: local self images first (direction order), then received copies
+__global__ void ghost_candidates_kernel(int nrec, const int *__restrict__ rsrc, const int *__restrict__ rdir,
+                                        DirTable tab, GhostDirs gd, int nloc, int nrecv,
+                                        const double4 *__restrict__ xq, const int *__restrict__ tag,
+                                        const double4 *__restrict__ recvx, const int4 *__restrict__ recvmeta, Grid g,
+                                        int *gsrc, int *gcode, unsigned long long *keys, int *vals) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < nrec) {
+    const int d = rdir[r];
+    if (gd.active[d] == 1) {
+      const int o = tab.out[d] + (r - tab.start[d]);
+      const int s = rsrc[r];
+      const double4 p = xq[s];
+      const unsigned long long c = (unsigned long long)cell_of(g, p.x + gd.shift[d][0], p.y + gd.shift[d][1],
+                                                               p.z + gd.shift[d][2]);
+      gsrc[o] = s;
+      gcode[o] = d;
+      keys[o] = (c << 32) | (unsigned int)tag[s];
+      vals[o] = o;
+    }
   }
+  if (r < nrecv) {
+    const int o = nloc + r;
+    const double4 p = recvx[r];
+    const int4 m = recvmeta[r];
+    const unsigned long long c = (unsigned long long)cell_of(g, p.x, p.y, p.z);
+    gsrc[o] = -1 - r;
+    gcode[o] = 32 + (m.x >> 8);
+    keys[o] = (c << 32) | (unsigned int)m.y;
+    vals[o] = o;
+  }
+}
+
+// xq/type/tag/mask/molecule of ghost g from its owner (a local self image: owned atom + shift) or
+// from the receive buffer (a copy another rank sent, already shifted); used at build (all fields)
+// and every step (xq only)
+__global__ void ghost_copy_kernel(int nghost, int nlocal, const int *__restrict__ src, const int *__restrict__ code,
+                                  GhostDirs gd, const double4 *__restrict__ recvx, const int4 *__restrict__ recvmeta,
+                                  double4 *xq, int *type, int *tag, int *mask, int *mol, int all) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nghost) return;
+  const int s = src[g];
+  double4 p;
+  if (s >= 0) {
+    const int d = code[g];
+    p = xq[s];
+    p.x += gd.shift[d][0];
+    p.y += gd.shift[d][1];
+    p.z += gd.shift[d][2];
+    if (all) {
+      type[nlocal + g] = type[s];
+      tag[nlocal + g] = tag[s];
+      mask[nlocal + g] = mask[s];
+      if (mol) mol[nlocal + g] = mol[s];
+    }
+  } else {
+    p = recvx[-1 - s];
+    if (all) {
+      const int4 m = recvmeta[-1 - s];
+      type[nlocal + g] = m.x & 255;
+      tag[nlocal + g] = m.y;
+      mask[nlocal + g] = m.z;
+      if (mol) mol[nlocal + g] = m.w;
+    }
+  }
+  xq[nlocal + g] = p;
+}
+
+__global__ void mol_owned_kernel(int n, const int *__restrict__ perm, const int *__restrict__ molecule, int *mol) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) mol[k] = molecule[perm[k]];
 }
 
 // One warp per owned atom.  Lanes sweep, for each of the 5x5 (y,z) cell rows around the atom,
@@ -264,14 +346,12 @@ list_build_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__re
 }
 
 // fp32 build records: position relative to the grid origin + molecule id (0 when the caller gave none)
-__global__ void xb_kernel(int nall, int nlocal, const double4 *__restrict__ xq, const int *__restrict__ perm,
-                          const int *__restrict__ ghost_src, const int *__restrict__ molecule, double3 origin,
+__global__ void xb_kernel(int nall, const double4 *__restrict__ xq, const int *__restrict__ mol, double3 origin,
                           float4 *xb) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k > nall) return;
   double4 p = xq[k];
-  int m = 0;
-  if (molecule && k < nall) m = molecule[perm[k < nlocal ? k : ghost_src[k - nlocal]]];
+  int m = (mol && k < nall) ? mol[k] : 0;
   xb[k] = make_float4((float)(p.x - origin.x), (float)(p.y - origin.y), (float)(p.z - origin.z), __int_as_float(m));
 }
 
@@ -331,30 +411,42 @@ int exclusive_scan(cph_handle *h, int n, int *in, int *out) {
 }
 
 void make_ghost_dirs(const cph_handle *h, GhostDirs &gd) {
+  auto rank_of = [&](const int *loc) { return (loc[2] * h->procgrid[1] + loc[1]) * h->procgrid[0] + loc[0]; };
   for (int d = 0; d < 27; d++) {
     int dv[3] = {d % 3 - 1, (d / 3) % 3 - 1, d / 9 - 1};
-    int active = (d != 13), img[3] = {0, 0, 0};
+    int active = (d != 13), img[3] = {0, 0, 0}, to[3], fr[3];
+    bool remote = false;
     for (int k = 0; k < 3; k++) {
       gd.shift[d][k] = 0.0;
+      to[k] = fr[k] = h->myloc[k];
       if (dv[k] == 0) continue;
+      const int pg = h->procgrid[k];
+      int nb = h->myloc[k] + dv[k], nf = h->myloc[k] - dv[k];
       if (!h->periodic[k]) {
         // non-periodic: a copy only exists if there is a neighbour rank in that direction
-        int nb = h->myloc[k] + dv[k];
-        if (nb < 0 || nb >= h->procgrid[k]) active = 0;
-        continue;
+        if (nb < 0 || nb >= pg) active = 0;
+        // (the mirror test for `from` is done by the sender; counts of absent senders are zero)
+      } else {
+        // periodic wrap: the copy lands across the box
+        if (dv[k] > 0 && h->myloc[k] == pg - 1) { gd.shift[d][k] = -(h->boxhi[k] - h->boxlo[k]); img[k] = -1; }
+        if (dv[k] < 0 && h->myloc[k] == 0) { gd.shift[d][k] = (h->boxhi[k] - h->boxlo[k]); img[k] = 1; }
       }
-      // periodic wrap: the copy lands across the box
-      if (dv[k] > 0 && h->myloc[k] == h->procgrid[k] - 1) { gd.shift[d][k] = -(h->boxhi[k] - h->boxlo[k]); img[k] = -1; }
-      if (dv[k] < 0 && h->myloc[k] == 0) { gd.shift[d][k] = (h->boxhi[k] - h->boxlo[k]); img[k] = 1; }
+      to[k] = ((nb % pg) + pg) % pg;
+      fr[k] = ((nf % pg) + pg) % pg;
+      if (pg > 1) remote = true;
     }
-    // single rank: every active direction is a self image.  (multi-rank directions whose
-    // destination is another rank are handled by comm.cu and marked inactive here.)
-    if (active) {
-      for (int k = 0; k < 3; k++)
-        if (dv[k] != 0 && h->procgrid[k] > 1) active = 0;
-    }
-    gd.active[d] = active;
+    gd.active[d] = active ? (remote ? 2 : 1) : 0;
     gd.imgcode[d] = (img[0] + 1) + 3 * (img[1] + 1) + 9 * (img[2] + 1);
+    gd.peer[d] = rank_of(to);
+    gd.from[d] = rank_of(fr);
+    // does the rank at `fr` really send in direction d?  (non-periodic edges)
+    bool from_ok = (d != 13);
+    for (int k = 0; k < 3; k++)
+      if (dv[k] != 0 && !h->periodic[k]) {
+        int nf = h->myloc[k] - dv[k];
+        if (nf < 0 || nf >= h->procgrid[k]) from_ok = false;
+      }
+    if (!from_ok || !remote) gd.from[d] = -1;
   }
 }
 
@@ -369,13 +461,63 @@ int permute_buf(cph_handle *h, int n, const int *idx, DevBuf<T> &buf, DevBuf<T> 
 
 }  // namespace
 
+// exchange the packed copies with the spatial neighbours (grouped ncclSend/ncclRecv, one message
+// per direction and array); with_meta: also the build-time records
+static int halo_exchange(cph_handle *h, const GhostDirs &gd, bool with_meta) {
+  const void *sb[54]; void *rb[54]; size_t sn[54], rn[54]; int peers[54];
+  int np = 0;
+  for (int d = 0; d < 27; d++) {
+    const bool snd = gd.active[d] == 2 && h->send_count[d] > 0;
+    const bool rcv = gd.from[d] >= 0 && h->recv_count[d] > 0;
+    if (!snd && !rcv) continue;
+    // a direction's send peer and receive peer differ in general: two entries
+    if (snd) {
+      peers[np] = gd.peer[d]; sb[np] = h->d_sendx.p + h->send_off[d]; sn[np] = (size_t)h->send_count[d] * sizeof(double4);
+      rb[np] = nullptr; rn[np] = 0; np++;
+      if (with_meta) {
+        peers[np] = gd.peer[d]; sb[np] = h->d_sendmeta.p + h->send_off[d]; sn[np] = (size_t)h->send_count[d] * sizeof(int4);
+        rb[np] = nullptr; rn[np] = 0; np++;
+      }
+    }
+    if (rcv) {
+      peers[np] = gd.from[d]; rb[np] = h->d_recvx.p + h->recv_off[d]; rn[np] = (size_t)h->recv_count[d] * sizeof(double4);
+      sb[np] = nullptr; sn[np] = 0; np++;
+      if (with_meta) {
+        peers[np] = gd.from[d]; rb[np] = h->d_recvmeta.p + h->recv_off[d]; rn[np] = (size_t)h->recv_count[d] * sizeof(int4);
+        sb[np] = nullptr; sn[np] = 0; np++;
+      }
+    }
+    if (np > 50) { CPH_TRY(cph_comm_exchange(h, np, peers, sb, sn, rb, rn)); np = 0; }
+  }
+  if (np) CPH_TRY(cph_comm_exchange(h, np, peers, sb, sn, rb, rn));
+  return 0;
+}
+
+static DirTable send_table(const cph_handle *h) {
+  DirTable t;
+  for (int d = 0; d < 27; d++) { t.start[d] = h->rec_start[d]; t.out[d] = h->send_off[d]; }
+  t.start[27] = h->rec_start[27];
+  return t;
+}
+
+// comm->forward_comm(): refresh ghost x and q (every step)
 int cph_forward_ghosts(cph_handle *h) {
-  if (h->nghost == 0) return 0;
+  if (h->nghost == 0 && h->nsend == 0) return 0;
   ProfScope ps(h, 5);
   GhostDirs gd;
   make_ghost_dirs(h, gd);
-  ghost_copy_kernel<<<nblk(h->nghost), TPB, 0, h->stream>>>(h->nghost, h->nlocal, h->d_ghost_src.p, h->d_ghost_code.p,
-                                                           gd, h->d_xq.p, nullptr, nullptr, nullptr, 0);
+  cudaStream_t st = h->stream;
+  if (h->nranks > 1) {
+    if (h->nsend)
+      halo_pack_kernel<<<nblk(h->nrec), TPB, 0, st>>>(h->nrec, h->d_rec_src.p, h->d_rec_dir.p, send_table(h), gd,
+                                                     h->d_xq.p, nullptr, nullptr, nullptr, nullptr, h->d_sendx.p,
+                                                     nullptr);
+    CPH_TRY(halo_exchange(h, gd, false));
+  }
+  if (h->nghost)
+    ghost_copy_kernel<<<nblk(h->nghost), TPB, 0, st>>>(h->nghost, h->nlocal, h->d_ghost_src.p, h->d_ghost_code.p, gd,
+                                                      h->d_recvx.p, nullptr, h->d_xq.p, nullptr, nullptr, nullptr,
+                                                      nullptr, 0);
   CPH_CUDA(h, cudaGetLastError());
   return 0;
 }
@@ -393,6 +535,9 @@ static int ensure_atom_capacity(cph_handle *h, size_t need) {
   CPH_CUDA(h, h->d_mask.reserve_exact(cap, true, st));
   CPH_CUDA(h, h->d_perm.reserve_exact(cap, true, st));
   CPH_CUDA(h, h->d_scr_off.reserve_exact(cap, true, st));   // holds the ghost offsets across the regrow
+  CPH_CUDA(h, h->d_rec_src.reserve_exact(cap, true, st));   // halo records live from build to build
+  CPH_CUDA(h, h->d_rec_dir.reserve_exact(cap, true, st));
+  CPH_CUDA(h, h->d_mol.reserve_exact(cap, true, st));
   CPH_CUDA(h, h->d_xq2.reserve_exact(cap));
   CPH_CUDA(h, h->d_xt.reserve_exact(cap));
   CPH_CUDA(h, h->d_xb.reserve_exact(cap));
@@ -504,38 +649,78 @@ int cph_rebuild(cph_handle *h) {
   cell_start_kernel<<<nblk(n + 1), TPB, 0, st>>>(n, g.ncell, h->d_tmpi.p, h->d_cell_start_o.p);
 
   tr.mark("sort");
-  // ---- ghosts: periodic self images (neighbour-rank copies arrive through comm.cu) --------------
+  // ---- ghosts: periodic self images + copies from the spatial neighbours (K6) ---------------------
   GhostDirs gd;
   make_ghost_dirs(h, gd);
-  int nghost = 0;
+  int nrec = 0;
+  if (h->have_mol && n) mol_owned_kernel<<<nblk(n), TPB, 0, st>>>(n, h->d_perm.p, h->d_molecule.p, h->d_mol.p);
   if (n) {
     ghost_count_kernel<<<nblk(n), TPB, 0, st>>>(n, h->d_xq.p, slo, shi, h->ghost_cut, gd, h->d_vals.p);
     CPH_TRY(exclusive_scan(h, n + 1, h->d_vals.p, h->d_vals2.p));
-    CPH_CUDA(h, cudaMemcpyAsync(&nghost, h->d_vals2.p + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CPH_CUDA(h, cudaMemcpyAsync(&nrec, h->d_vals2.p + n, sizeof(int), cudaMemcpyDeviceToHost, st));
     CPH_CUDA(h, cudaStreamSynchronize(st));
   }
+  if (n) CPH_CUDA(h, cudaMemcpyAsync(h->d_scr_off.p, h->d_vals2.p, (n + 1) * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  CPH_TRY(ensure_atom_capacity(h, (size_t)n + nrec + 2));
+  h->nrec = nrec;
+  for (int d = 0; d < 28; d++) h->rec_start[d] = 0;
+  if (nrec) {
+    // records (owner, direction), sorted by direction (stable: owner order kept)
+    ghost_fill_kernel<<<nblk(n), TPB, 0, st>>>(n, h->d_xq.p, slo, shi, h->ghost_cut, gd, h->d_scr_off.p,
+                                               h->d_scr_src.p, h->d_keys.p, h->d_vals.p);
+    CPH_TRY(sort_pairs(h, nrec, h->d_keys, h->d_keys2, h->d_vals, h->d_vals2, 5));
+    gather_kernel<int><<<nblk(nrec), TPB, 0, st>>>(nrec, h->d_vals2.p, h->d_scr_src.p, h->d_rec_src.p);
+    dir_of_key_kernel<<<nblk(nrec), TPB, 0, st>>>(nrec, h->d_keys2.p, h->d_rec_dir.p);
+    cell_start_kernel<<<nblk(nrec + 1), TPB, 0, st>>>(nrec, 27, h->d_rec_dir.p, h->d_scr_code.p);
+    CPH_CUDA(h, cudaMemcpyAsync(h->rec_start, h->d_scr_code.p, 28 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CPH_CUDA(h, cudaStreamSynchronize(st));
+  }
+  // offsets: self images -> ghost slots [0,nloc); remote copies -> send buffer [0,nsend)
+  int nloc = 0, nsend = 0;
+  DirTable ltab;
+  for (int d = 0; d < 27; d++) {
+    const int c = h->rec_start[d + 1] - h->rec_start[d];
+    ltab.start[d] = h->rec_start[d];
+    ltab.out[d] = -1;
+    h->send_count[d] = 0;
+    h->send_off[d] = 0;
+    if (gd.active[d] == 1) { ltab.out[d] = nloc; nloc += c; }
+    if (gd.active[d] == 2) { h->send_off[d] = nsend; h->send_count[d] = c; nsend += c; }
+  }
+  ltab.start[27] = h->rec_start[27];
+  h->nsend = nsend;
+  int nrecv = 0;
+  for (int d = 0; d < 27; d++) { h->recv_count[d] = 0; h->recv_off[d] = 0; }
+  if (h->nranks > 1) {
+    // counts first (one int per direction), then the records
+    CPH_TRY(cph_comm_exchange_counts(h, gd.active, gd.peer, gd.from, h->send_count, h->recv_count));
+    for (int d = 0; d < 27; d++) { h->recv_off[d] = nrecv; nrecv += h->recv_count[d]; }
+    CPH_CUDA(h, h->d_sendx.reserve(nsend + 1));
+    CPH_CUDA(h, h->d_sendmeta.reserve(nsend + 1));
+    CPH_CUDA(h, h->d_recvx.reserve(nrecv + 1));
+    CPH_CUDA(h, h->d_recvmeta.reserve(nrecv + 1));
+    if (nsend)
+      halo_pack_kernel<<<nblk(nrec), TPB, 0, st>>>(nrec, h->d_rec_src.p, h->d_rec_dir.p, send_table(h), gd, h->d_xq.p,
+                                                  h->d_type.p, h->d_tag.p, h->d_mask.p,
+                                                  h->have_mol ? h->d_mol.p : nullptr, h->d_sendx.p, h->d_sendmeta.p);
+    CPH_TRY(halo_exchange(h, gd, true));
+  }
+  h->nrecv = nrecv;
+  const int nghost = nloc + nrecv;
   h->nghost = nghost;
   h->nall = n + nghost;
-  if (n) CPH_CUDA(h, cudaMemcpyAsync(h->d_scr_off.p, h->d_vals2.p, (n + 1) * sizeof(int), cudaMemcpyDeviceToDevice, st));
   CPH_TRY(ensure_atom_capacity(h, (size_t)h->nall + 2));   // + the far-away dummy atom that pads neighbour rows
   if (nghost) {
-    DevBuf<int> &src_u = h->d_scr_src, &code_u = h->d_scr_code, &offs = h->d_scr_off;
-    CPH_CUDA(h, src_u.reserve(nghost));
-    CPH_CUDA(h, code_u.reserve(nghost));
-    CPH_CUDA(h, h->d_keys.reserve(nghost));
-    CPH_CUDA(h, h->d_keys2.reserve(nghost));
-    CPH_CUDA(h, h->d_vals.reserve(nghost));
-    CPH_CUDA(h, h->d_vals2.reserve(nghost));
-    CPH_CUDA(h, h->d_tmpi.reserve(std::max(nghost, n) + 1));
-    ghost_fill_kernel<<<nblk(n), TPB, 0, st>>>(n, n, h->d_xq.p, h->d_tag.p, slo, shi, h->ghost_cut, gd, g, offs.p,
-                                               src_u.p, code_u.p, h->d_keys.p, h->d_vals.p);
+    const int nthreads = std::max(nrec, nrecv);
+    ghost_candidates_kernel<<<nblk(nthreads), TPB, 0, st>>>(nrec, h->d_rec_src.p, h->d_rec_dir.p, ltab, gd, nloc, nrecv,
+                                                           h->d_xq.p, h->d_tag.p, h->d_recvx.p, h->d_recvmeta.p, g,
+                                                           h->d_scr_src.p, h->d_scr_code.p, h->d_keys.p, h->d_vals.p);
     CPH_TRY(sort_pairs(h, nghost, h->d_keys, h->d_keys2, h->d_vals, h->d_vals2, 64));
-    CPH_CUDA(h, h->d_ghost_src.reserve(nghost));
-    CPH_CUDA(h, h->d_ghost_code.reserve(nghost));
-    gather_kernel<int><<<nblk(nghost), TPB, 0, st>>>(nghost, h->d_vals2.p, src_u.p, h->d_ghost_src.p);
-    gather_kernel<int><<<nblk(nghost), TPB, 0, st>>>(nghost, h->d_vals2.p, code_u.p, h->d_ghost_code.p);
-    ghost_copy_kernel<<<nblk(nghost), TPB, 0, st>>>(nghost, n, h->d_ghost_src.p, h->d_ghost_code.p, gd, h->d_xq.p,
-                                                    h->d_type.p, h->d_tag.p, h->d_mask.p, 1);
+    gather_kernel<int><<<nblk(nghost), TPB, 0, st>>>(nghost, h->d_vals2.p, h->d_scr_src.p, h->d_ghost_src.p);
+    gather_kernel<int><<<nblk(nghost), TPB, 0, st>>>(nghost, h->d_vals2.p, h->d_scr_code.p, h->d_ghost_code.p);
+    ghost_copy_kernel<<<nblk(nghost), TPB, 0, st>>>(nghost, n, h->d_ghost_src.p, h->d_ghost_code.p, gd, h->d_recvx.p,
+                                                    h->d_recvmeta.p, h->d_xq.p, h->d_type.p, h->d_tag.p, h->d_mask.p,
+                                                    h->have_mol ? h->d_mol.p : nullptr, 1);
     after_sort_kernel<<<nblk(nghost), TPB, 0, st>>>(nghost, h->d_keys2.p, nullptr, nullptr, nullptr, nullptr,
                                                     h->d_tmpi.p);
     cell_start_kernel<<<nblk(nghost + 1), TPB, 0, st>>>(nghost, g.ncell, h->d_tmpi.p, h->d_cell_start_g.p);
@@ -571,8 +756,7 @@ int cph_rebuild(cph_handle *h) {
   CPH_CUDA(h, stats.reserve(2));
   const PairParams &pp = h->pp;
   // build-time fp32 records {x, y, z, molecule id} of all atoms (owned + ghost + dummy)
-  xb_kernel<<<nblk(h->nall + 1), TPB, 0, st>>>(h->nall, n, h->d_xq.p, h->d_perm.p, h->d_ghost_src.p,
-                                              h->have_mol ? h->d_molecule.p : nullptr,
+  xb_kernel<<<nblk(h->nall + 1), TPB, 0, st>>>(h->nall, h->d_xq.p, h->have_mol ? h->d_mol.p : nullptr,
                                               make_double3(g.lo[0], g.lo[1], g.lo[2]), h->d_xb.p);
   int dropmask = 0;   // special class c is not stored when both weights are zero, except under coul/dsf
   if (h->pp.style != CPH_PAIR_LJ_CUT_COUL_DSF)
@@ -656,7 +840,10 @@ __global__ void neighbor_keys_kernel(int nlocal, const int *__restrict__ neigh, 
     int raw = neigh[(size_t)i * rowcap + (k < nn ? k : rowcap - 1 - (k - nn))];
     int j = raw & CPH_NEIGHMASK, sb = (raw >> CPH_SBSHIFT) & 3;
     int code = 13;
-    if (j >= nlocal) code = gd.imgcode[ghost_code[j - nlocal]];
+    if (j >= nlocal) {
+      int c = ghost_code[j - nlocal];
+      code = c >= 32 ? c - 32 : gd.imgcode[c];
+    }
     keys[o + k] = ((long long)tag[j] << 8) | (sb << 5) | code;
   }
 }
