@@ -107,6 +107,12 @@ int cph_comm_allreduce_max_u32(cph_handle *h, unsigned int *buf, int n) {
   return CPH_OK;
 }
 
+int cph_comm_allreduce_max_u32_dev(cph_handle *h, unsigned int *dbuf, int n) {
+  if (h->nranks == 1) return CPH_OK;
+  CPH_NCCL(h, nccl().AllReduce(dbuf, dbuf, (size_t)n, ncclUint32, ncclMax, (ncclComm_t)h->nccl_comm, h->stream));
+  return CPH_OK;
+}
+
 // grouped point-to-point exchange used by the halo (halo.cu)
 int cph_comm_exchange(cph_handle *h, int npeers, const int *peers, const void *const *sendbuf, const size_t *sendbytes,
                       void *const *recvbuf, const size_t *recvbytes) {

@@ -401,9 +401,9 @@ int cph_check_rebuild(cph_handle *h, int *flag) {
   cudaSetDevice(h->device);
   CPH_TRY(cph_launch_set_x(h, nullptr));
   unsigned int fl[8];
+  CPH_TRY(cph_comm_allreduce_max_u32_dev(h, h->d_flags.p, 5));   // global neighbor->decide()
   CPH_TRY(read_flags(h, fl));
   unsigned int any = fl[4];
-  CPH_TRY(cph_comm_allreduce_max_u32(h, &any, 1));
   float md;
   memcpy(&md, &fl[0], 4);
   h->scal_h[6] = md;
@@ -475,9 +475,9 @@ int cph_post_force(cph_handle *h, int64_t ntimestep, double dt, int where, const
   if (x) CPH_TRY(cph_set_x(h, where, x));
   else CPH_TRY(cph_launch_set_x(h, nullptr));
   unsigned int fl[8];
+  CPH_TRY(cph_comm_allreduce_max_u32_dev(h, h->d_flags.p, 5));   // global decision, one host sync
   CPH_TRY(read_flags(h, fl));
   unsigned int any = fl[4];
-  CPH_TRY(cph_comm_allreduce_max_u32(h, &any, 1));
   float md;
   memcpy(&md, &fl[0], 4);
   h->scal_h[6] = md;

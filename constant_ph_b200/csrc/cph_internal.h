@@ -149,6 +149,7 @@ struct cph_handle {
   int nrec = 0, nsend = 0, nrecv = 0;
   int rec_start[28]{}, send_count[27]{}, send_off[27]{}, recv_count[27]{}, recv_off[27]{};
   DevBuf<int> d_rec_src, d_rec_dir;
+  std::vector<int> peer_rank, peer_soff, peer_scnt, peer_roff, peer_rcnt;   // one message per neighbour rank
   DevBuf<double4> d_sendx, d_recvx;
   DevBuf<int4> d_sendmeta, d_recvmeta;
   DevBuf<double> d_f, d_evdwl, d_phi, d_eatom;  // [3*nlocal], [nlocal]...
@@ -209,6 +210,7 @@ int cph_launch_pack_xq(cph_handle *h, int n, const double *x, const double *q);
 // comm.cu
 int cph_comm_allreduce(cph_handle *h, double *buf, int n);            // sum
 int cph_comm_allreduce_max_u32(cph_handle *h, unsigned int *buf, int n);
+int cph_comm_allreduce_max_u32_dev(cph_handle *h, unsigned int *dbuf, int n);   // in place, on the stream
 int cph_comm_exchange(cph_handle *h, int npeers, const int *peers, const void *const *sendbuf, const size_t *sendbytes,
                       void *const *recvbuf, const size_t *recvbytes);
 int cph_comm_exchange_counts(cph_handle *h, const int *active, const int *peer, const int *from, const int *send_count,

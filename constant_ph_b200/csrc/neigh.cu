@@ -463,31 +463,28 @@ int permute_buf(cph_handle *h, int n, const int *idx, DevBuf<T> &buf, DevBuf<T> 
 
 // exchange the packed copies with the spatial neighbours (grouped ncclSend/ncclRecv, one message
 // per direction and array); with_meta: also the build-time records
-static int halo_exchange(cph_handle *h, const GhostDirs &gd, bool with_meta) {
-  const void *sb[54]; void *rb[54]; size_t sn[54], rn[54]; int peers[54];
+static int halo_exchange(cph_handle *h, const GhostDirs &, bool with_meta) {
+  // one message per neighbour RANK (all directions that point at it are contiguous in the
+  // staging buffers): on a 2x2x2 grid 7 sends + 7 receives instead of 26 + 26
+  const void *sb[64]; void *rb[64]; size_t sn[64], rn[64]; int peers[64];
   int np = 0;
-  for (int d = 0; d < 27; d++) {
-    const bool snd = gd.active[d] == 2 && h->send_count[d] > 0;
-    const bool rcv = gd.from[d] >= 0 && h->recv_count[d] > 0;
-    if (!snd && !rcv) continue;
-    // a direction's send peer and receive peer differ in general: two entries
-    if (snd) {
-      peers[np] = gd.peer[d]; sb[np] = h->d_sendx.p + h->send_off[d]; sn[np] = (size_t)h->send_count[d] * sizeof(double4);
+  for (size_t k = 0; k < h->peer_rank.size() && np < 60; k++) {
+    if (h->peer_scnt[k]) {
+      peers[np] = h->peer_rank[k]; sb[np] = h->d_sendx.p + h->peer_soff[k]; sn[np] = (size_t)h->peer_scnt[k] * sizeof(double4);
       rb[np] = nullptr; rn[np] = 0; np++;
       if (with_meta) {
-        peers[np] = gd.peer[d]; sb[np] = h->d_sendmeta.p + h->send_off[d]; sn[np] = (size_t)h->send_count[d] * sizeof(int4);
+        peers[np] = h->peer_rank[k]; sb[np] = h->d_sendmeta.p + h->peer_soff[k]; sn[np] = (size_t)h->peer_scnt[k] * sizeof(int4);
         rb[np] = nullptr; rn[np] = 0; np++;
       }
     }
-    if (rcv) {
-      peers[np] = gd.from[d]; rb[np] = h->d_recvx.p + h->recv_off[d]; rn[np] = (size_t)h->recv_count[d] * sizeof(double4);
+    if (h->peer_rcnt[k]) {
+      peers[np] = h->peer_rank[k]; rb[np] = h->d_recvx.p + h->peer_roff[k]; rn[np] = (size_t)h->peer_rcnt[k] * sizeof(double4);
       sb[np] = nullptr; sn[np] = 0; np++;
       if (with_meta) {
-        peers[np] = gd.from[d]; rb[np] = h->d_recvmeta.p + h->recv_off[d]; rn[np] = (size_t)h->recv_count[d] * sizeof(int4);
+        peers[np] = h->peer_rank[k]; rb[np] = h->d_recvmeta.p + h->peer_roff[k]; rn[np] = (size_t)h->peer_rcnt[k] * sizeof(int4);
         sb[np] = nullptr; sn[np] = 0; np++;
       }
     }
-    if (np > 50) { CPH_TRY(cph_comm_exchange(h, np, peers, sb, sn, rb, rn)); np = 0; }
   }
   if (np) CPH_TRY(cph_comm_exchange(h, np, peers, sb, sn, rb, rn));
   return 0;
@@ -675,26 +672,37 @@ int cph_rebuild(cph_handle *h) {
     CPH_CUDA(h, cudaMemcpyAsync(h->rec_start, h->d_scr_code.p, 28 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CPH_CUDA(h, cudaStreamSynchronize(st));
   }
-  // offsets: self images -> ghost slots [0,nloc); remote copies -> send buffer [0,nsend)
+  // offsets: self images -> ghost slots [0,nloc); remote copies -> send buffer [0,nsend), grouped
+  // by destination rank so that each neighbour rank gets ONE contiguous message
   int nloc = 0, nsend = 0;
   DirTable ltab;
   for (int d = 0; d < 27; d++) {
     const int c = h->rec_start[d + 1] - h->rec_start[d];
     ltab.start[d] = h->rec_start[d];
     ltab.out[d] = -1;
-    h->send_count[d] = 0;
+    h->send_count[d] = gd.active[d] == 2 ? c : 0;
     h->send_off[d] = 0;
     if (gd.active[d] == 1) { ltab.out[d] = nloc; nloc += c; }
-    if (gd.active[d] == 2) { h->send_off[d] = nsend; h->send_count[d] = c; nsend += c; }
   }
   ltab.start[27] = h->rec_start[27];
-  h->nsend = nsend;
   int nrecv = 0;
   for (int d = 0; d < 27; d++) { h->recv_count[d] = 0; h->recv_off[d] = 0; }
+  h->peer_rank.clear(); h->peer_soff.clear(); h->peer_scnt.clear(); h->peer_roff.clear(); h->peer_rcnt.clear();
   if (h->nranks > 1) {
     // counts first (one int per direction), then the records
     CPH_TRY(cph_comm_exchange_counts(h, gd.active, gd.peer, gd.from, h->send_count, h->recv_count));
-    for (int d = 0; d < 27; d++) { h->recv_off[d] = nrecv; nrecv += h->recv_count[d]; }
+    for (int p = 0; p < h->nranks; p++) {
+      int so = nsend, sc = 0, ro = nrecv, rc = 0;
+      for (int d = 0; d < 27; d++) {
+        if (gd.active[d] == 2 && gd.peer[d] == p) { h->send_off[d] = nsend; nsend += h->send_count[d]; sc += h->send_count[d]; }
+        if (gd.from[d] == p) { h->recv_off[d] = nrecv; nrecv += h->recv_count[d]; rc += h->recv_count[d]; }
+      }
+      if (sc || rc) {
+        h->peer_rank.push_back(p); h->peer_soff.push_back(so); h->peer_scnt.push_back(sc);
+        h->peer_roff.push_back(ro); h->peer_rcnt.push_back(rc);
+      }
+    }
+    h->nsend = nsend;
     CPH_CUDA(h, h->d_sendx.reserve(nsend + 1));
     CPH_CUDA(h, h->d_sendmeta.reserve(nsend + 1));
     CPH_CUDA(h, h->d_recvx.reserve(nrecv + 1));
