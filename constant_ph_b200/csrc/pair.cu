@@ -132,9 +132,9 @@ struct Acc {
 // branches) so that two independent pairs per lane interleave in the fp64 pipe.  Returns
 // fpair (force / r), the vdW energy and qj*K (the pair's contribution to phi_i).
 // UNI: every type pair has cut_lj == cut_coul == the global cutoff (one exact test).
-template <int STYLE, int EFLAG, int UNI, int LJ>
+template <int STYLE, int EFLAG, int UNI>
 __device__ __forceinline__ void eval_pair(const double4 *s_coef, const double2 *s_cut, int tt, double rsq,
-                                          double qi, double qj, const double *s_exp2, double &fpair_out,
+                                          double qi, double qj, const double *s_exp2, bool LJ, double &fpair_out,
                                           double &ev_out, double &phi_out) {
   bool in, lj_on = true, coul_on = true;
   if (UNI) {
@@ -343,8 +343,9 @@ pair_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__restrict
         const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
         const double rsq = fma(delz, delz, fma(dely, dely, delx * delx));
         double fp, ev, ph;
-        if (has_lj) eval_pair<STYLE, EFLAG, UNI, 1>(s_coef, s_cut, e.y, rsq, pi.w, pj.w, s_exp2, fp, ev, ph);
-        else eval_pair<STYLE, EFLAG, UNI, 0>(s_coef, s_cut, e.y, rsq, pi.w, pj.w, s_exp2, fp, ev, ph);
+        // has_lj is warp-uniform: one copy of the evaluation, the LJ block behind a uniform branch
+        // (two template copies per call site pushed the kernel body past the 32 KB L1.5 I-cache)
+        eval_pair<STYLE, EFLAG, UNI>(s_coef, s_cut, e.y, rsq, pi.w, pj.w, s_exp2, has_lj, fp, ev, ph);
         a.fx = fma(delx, fp, a.fx); a.fy = fma(dely, fp, a.fy); a.fz = fma(delz, fp, a.fz);
         if (EFLAG) { a.ev += ev; a.phi += ph; }
       }
@@ -360,13 +361,8 @@ pair_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__restrict
       const double rs0 = fma(dz0, dz0, fma(dy0, dy0, dx0 * dx0));
       const double rs1 = fma(dz1, dz1, fma(dy1, dy1, dx1 * dx1));
       double f0, f1, v0, v1, h0, h1;
-      if (has_lj) {
-        eval_pair<STYLE, EFLAG, UNI, 1>(s_coef, s_cut, e0.y, rs0, pi.w, p0.w, s_exp2, f0, v0, h0);
-        eval_pair<STYLE, EFLAG, UNI, 1>(s_coef, s_cut, e1.y, rs1, pi.w, p1.w, s_exp2, f1, v1, h1);
-      } else {
-        eval_pair<STYLE, EFLAG, UNI, 0>(s_coef, s_cut, e0.y, rs0, pi.w, p0.w, s_exp2, f0, v0, h0);
-        eval_pair<STYLE, EFLAG, UNI, 0>(s_coef, s_cut, e1.y, rs1, pi.w, p1.w, s_exp2, f1, v1, h1);
-      }
+      eval_pair<STYLE, EFLAG, UNI>(s_coef, s_cut, e0.y, rs0, pi.w, p0.w, s_exp2, has_lj, f0, v0, h0);
+      eval_pair<STYLE, EFLAG, UNI>(s_coef, s_cut, e1.y, rs1, pi.w, p1.w, s_exp2, has_lj, f1, v1, h1);
       a.fx = fma(dx0, f0, a.fx); a.fy = fma(dy0, f0, a.fy); a.fz = fma(dz0, f0, a.fz);
       a.fx = fma(dx1, f1, a.fx); a.fy = fma(dy1, f1, a.fy); a.fz = fma(dz1, f1, a.fz);
       if (EFLAG) { a.ev += v0 + v1; a.phi += h0 + h1; }

@@ -313,3 +313,35 @@ def test_full_size_properties_config3_1M_atoms(built):
     f2 = gpu.get_forces()
     assert np.array_equal(f, f2)
     assert np.array_equal(dudl, gpu.get_sites()["dudl"])
+
+
+def test_full_size_config5_dense_sites_against_oracle(built):
+    """BASELINE config 5 at full size: 512k atoms, 10 % of them titratable, one site each
+    (51 200 sites): the per-site reduction and the lambda integrator at scale, against the oracle."""
+    box = synth.config(5)
+    assert box.n > 500_000 and box.nsites > 50_000
+    gpu, orc = engines(box, bias=HEAVY)
+    for step in range(3):
+        gpu.post_force(step, box.dt, box.x, None)
+        orc.post_force(step, box.dt, box.x, None)
+    tg, to = gpu.get_sites(), orc.get_sites()
+    close(tg["dudl"], to["dudl"])
+    assert np.abs(tg["lambda"] - to["lambda"]).max() <= 1e-10
+    close(tg["f_lambda"], to["f_lambda"], rtol=1e-9)
+    sg, so = gpu.get_scalars(), orc.get_scalars()
+    for k in ("HA", "HB", "evdwl", "ecoul", "H_lambda"):
+        assert abs(sg[k] - so[k]) <= RTOL * abs(so[k]), (k, sg[k], so[k])
+    assert np.array_equal(gpu.get_site_map(), orc.get_site_map())
+    assert gpu.get_counts()["titr_owned"] == orc.get_counts()["titr_owned"] == box.titr_tag.size
+
+
+def test_config4_scaled_many_solutes(built):
+    """BASELINE config 4 (polyelectrolyte stand-in: many titratable solutes) at 1/40 size:
+    100k atoms, 1250 eight-atom sites, against the oracle."""
+    box = synth.config(4, scale=0.025)
+    assert box.nsites == 1250
+    gpu, orc = engines(box, bias=HEAVY)
+    check_pass(gpu, orc)
+    ng, kg = gpu.get_neighbors()
+    no, ko = orc.get_neighbors()
+    assert np.array_equal(ng, no) and np.array_equal(kg, ko)
