@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -112,6 +113,8 @@ int cph_create(int device, cph_handle **out) {
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->pev0); cudaEventCreate(&h->pev1);
   h->d_flags.reserve(96);
   cudaMemsetAsync(h->d_flags.p, 0, 8 * sizeof(unsigned int), h->stream);
+  if (const char *e = getenv("CPH_INNER_SKIN")) h->inner_skin = std::max(0.0, atof(e));   // tuning knobs
+  if (const char *e = getenv("CPH_PAIR_FUSED")) h->fused_pair = atoi(e) != 0;
   int rc = size_sites(h);
   if (rc) { g_create_error = h->err; delete h; return rc; }
   *out = h;
@@ -131,10 +134,10 @@ int cph_destroy(cph_handle *h) {
   DevBuf<int> *ib[] = {&h->d_titr_tag_sorted, &h->d_titr_entry_of_sorted, &h->d_titr_site, &h->d_titr_local, &h->d_type,
                        &h->d_tag, &h->d_mask, &h->d_perm, &h->d_inv, &h->d_site_of, &h->d_titr_of, &h->d_nspecial,
                        &h->d_special, &h->d_ghost_src, &h->d_ghost_code, &h->d_hlist, &h->d_istage, &h->d_vals,
-                       &h->d_vals2, &h->d_tmpi, &h->d_cell_start_o, &h->d_cell_start_g, &h->d_neigh, &h->d_numneigh, &h->d_numspec, &h->d_scr_i, &h->d_scr_src, &h->d_scr_code, &h->d_scr_off, &h->d_mol, &h->d_rec_src, &h->d_rec_dir};
+                       &h->d_vals2, &h->d_tmpi, &h->d_cell_start_o, &h->d_cell_start_g, &h->d_neigh, &h->d_numneigh, &h->d_numspec, &h->d_neigh2, &h->d_numneigh2, &h->d_scr_i, &h->d_scr_src, &h->d_scr_code, &h->d_scr_off, &h->d_mol, &h->d_rec_src, &h->d_rec_dir};
   for (auto *b : ib) b->release();
   h->d_xb.release(); h->d_molecule.release(); h->d_coef.release(); h->d_coef4.release(); h->d_cut2.release(); h->d_type_has_lj.release(); h->d_xt.release(); h->d_xq.release(); h->d_xq2.release(); h->d_keys.release(); h->d_keys2.release();
-  h->d_cubtmp.release(); h->d_flags.release(); h->d_scr_stats.release();
+  h->d_xinner.release(); h->d_cubtmp.release(); h->d_flags.release(); h->d_scr_stats.release();
   h->d_sendx.release(); h->d_recvx.release(); h->d_sendmeta.release(); h->d_recvmeta.release();
   if (h->h_pin) cudaFreeHost(h->h_pin);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->pev0); cudaEventDestroy(h->pev1);
@@ -401,9 +404,10 @@ int cph_check_rebuild(cph_handle *h, int *flag) {
   cudaSetDevice(h->device);
   CPH_TRY(cph_launch_set_x(h, nullptr));
   unsigned int fl[8];
-  CPH_TRY(cph_comm_allreduce_max_u32_dev(h, h->d_flags.p, 5));   // global neighbor->decide()
+  CPH_TRY(cph_comm_allreduce_max_u32_dev(h, h->d_flags.p, 6));   // global neighbor->decide()
   CPH_TRY(read_flags(h, fl));
   unsigned int any = fl[4];
+  if (fl[5]) h->inner_valid = false;      // someone moved more than inner_skin/2 since the last prune
   float md;
   memcpy(&md, &fl[0], 4);
   h->scal_h[6] = md;
@@ -475,9 +479,10 @@ int cph_post_force(cph_handle *h, int64_t ntimestep, double dt, int where, const
   if (x) CPH_TRY(cph_set_x(h, where, x));
   else CPH_TRY(cph_launch_set_x(h, nullptr));
   unsigned int fl[8];
-  CPH_TRY(cph_comm_allreduce_max_u32_dev(h, h->d_flags.p, 5));   // global decision, one host sync
+  CPH_TRY(cph_comm_allreduce_max_u32_dev(h, h->d_flags.p, 6));   // global decision, one host sync
   CPH_TRY(read_flags(h, fl));
   unsigned int any = fl[4];
+  if (fl[5]) h->inner_valid = false;      // someone moved more than inner_skin/2 since the last prune
   float md;
   memcpy(&md, &fl[0], 4);
   h->scal_h[6] = md;

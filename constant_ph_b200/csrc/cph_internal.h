@@ -10,7 +10,9 @@
 #include "../../include/cph_b200.h"
 
 #define CPH_NEIGHMASK 0x1FFFFFFF   // LAMMPS NEIGHMASK: low 29 bits = atom index
-#define CPH_SBSHIFT 30             // LAMMPS SBBITS: top 2 bits = special-bond class
+#define CPH_SBSHIFT 30             // LAMMPS SBBITS: top 2 bits = special-bond class (outer rows)
+#define CPH_TYPESHIFT 28           // inner rows: type of j in the top 4 bits, index in the low 28
+#define CPH_JMASK 0x0FFFFFFF
 #define CPH_MAXNT1 12              // ntypes+1 <= 12: the (ntypes+1)^2 * 32 B coefficient table lives in shared memory
 
 // device buffer that only ever grows
@@ -173,6 +175,12 @@ struct cph_handle {
   // row i: [0,numneigh) ordinary neighbours, padded to a 128 multiple with the dummy atom;
   // special-bond partners (entry = j | class<<30) at the END of the row, numspec of them
   DevBuf<int> d_neigh, d_numneigh, d_numspec;
+  // inner rows (rolling prune): pairs within rc + inner_skin, entry = j | type_j<<28
+  DevBuf<int> d_neigh2, d_numneigh2;
+  DevBuf<double> d_xinner;           // positions at the last prune
+  double inner_skin = 0.5;
+  bool inner_valid = false, fused_pair = false;
+  int64_t nprunes = 0;
   int rowcap = 0;
   int64_t nbuilds = 0, stored_neigh = 0, special_pairs = 0;
   int maxneigh = 0;
@@ -196,6 +204,8 @@ int cph_forward_ghosts(cph_handle *h);          // refresh ghost x and q
 int cph_neighbors_to_host(cph_handle *h, int *numneigh, int64_t *keys, int64_t cap);
 // pair.cu
 int cph_launch_pair(cph_handle *h, int eflag);
+int cph_launch_pair_fused(cph_handle *h, int eflag);
+int cph_launch_prune(cph_handle *h);
 int cph_pair_upload_constants(cph_handle *h);
 int cph_launch_xt(cph_handle *h);
 void cph_pair_forget(cph_handle *h);

@@ -830,6 +830,7 @@ int cph_rebuild(cph_handle *h) {
   CPH_CUDA(h, h->d_eatom.reserve(n + 1));
   CPH_CUDA(h, cudaGetLastError());
   tr.mark("sites");
+  h->inner_valid = false;    // the inner (pruned) rows are rebuilt from the new Verlet rows
   h->nbuilds++;
   return 0;
 }

@@ -248,7 +248,7 @@ struct WarpSmem {
 
 template <int STYLE, int EFLAG, int UNI>
 __global__ void __launch_bounds__(TPB, CPH_PAIR_MINBLOCKS)
-pair_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__restrict__ xt,
+pair_fused_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__restrict__ xt,
             const int *__restrict__ neigh, const int *__restrict__ numneigh, const int *__restrict__ numspec,
             int rowcap, int nt1, float cutf, const double4 *__restrict__ coef, const double2 *__restrict__ cuts,
             const int *__restrict__ type_has_lj, double *__restrict__ f, double *__restrict__ evdwl,
@@ -434,6 +434,192 @@ pair_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__restrict
   }
 }
 
+
+// ============================================================================================
+// Two-level list ("rolling prune"): K2a prunes each Verlet row (rc + skin, rebuilt from cells
+// every ~20 steps) down to an inner row (rc + inner skin) every few steps, in fp32, without any
+// fp64 math; K2b evaluates the inner rows every step with all lanes busy.  The inner row is a
+// conservative superset of the pairs in range while no atom has moved more than inner_skin/2
+// since the prune (tracked next to neighbor->decide()); K2b still decides every pair in fp64.
+// ============================================================================================
+
+// K2a: one warp per atom; TMA tile ring over the outer row; survivors written to the inner row
+// as (j | type_j << 28), padded to a multiple of 32 with the dummy atom.
+__global__ void __launch_bounds__(TPB, 4)
+prune_kernel(int nlocal, const float4 *__restrict__ xt, const int *__restrict__ neigh,
+             const int *__restrict__ numneigh, int rowcap, float cutf_inner, int dummy, int *__restrict__ neigh2,
+             int *__restrict__ numneigh2) {
+  __shared__ __align__(128) WarpSmem s_w[WARPS];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned int ltmask = (1u << lane) - 1;
+  WarpSmem &sm = s_w[w];
+  const unsigned int bar0 = smem_u32(&sm.bar[0]);
+  const unsigned int tile0 = smem_u32(&sm.tile[0][0]);
+  if (lane == 0)
+    for (int b = 0; b < NBUF; b++) mbar_init(bar0 + 8 * b, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  const int base = blockIdx.x * APB + w;
+  const int my_atom = base + lane * WARPS;
+  const bool mine = lane < APW && my_atom < nlocal;
+  const int nn_mine = mine ? numneigh[my_atom] : 0;
+  const int nt_mine = (nn_mine + CH - 1) / CH;
+  int pre = nt_mine;
+  for (int o = 1; o < APW; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, pre, o);
+    if (lane >= o) pre += v;
+  }
+  const int total_tiles = min(__shfl_sync(0xffffffffu, pre, APW - 1), MAXTILES);
+  if (lane < APW) {
+    int t0 = pre - nt_mine;
+    for (int c = 0; c < nt_mine && t0 + c < MAXTILES; c++) sm.sched[t0 + c] = (base + lane * WARPS) * (rowcap / CH) + c;
+  }
+  __syncthreads();
+  int issued = 0;
+  auto issue = [&]() {
+    if (issued < total_tiles && lane == 0) {
+      const unsigned int slot = issued & (NBUF - 1);
+      mbar_expect_tx(bar0 + 8 * slot, CH * 4);
+      bulk_g2s(tile0 + slot * (CH * 4), neigh + (size_t)sm.sched[issued] * CH, CH * 4, bar0 + 8 * slot);
+    }
+    issued++;
+  };
+#pragma unroll
+  for (int b = 0; b < NBUF; b++) issue();
+
+  int cslot = 0;
+  for (int n = 0; n < APW; n++) {
+    const int i = base + n * WARPS;
+    if (i >= nlocal) break;
+    const int ntile = __shfl_sync(0xffffffffu, nt_mine, n);
+    const float4 pti = xt[i];
+    int *row2 = neigh2 + (size_t)i * rowcap;
+    int cnt = 0;
+    for (int t = 0; t < ntile; t++) {
+      const unsigned int slot = cslot & (NBUF - 1);
+      mbar_wait(bar0 + 8 * slot, (cslot / NBUF) & 1);
+      const int *tp = &sm.tile[slot][lane];
+      const int r0 = tp[0], r1 = tp[32], r2 = tp[64], r3 = tp[96];
+      __syncwarp();
+      cslot++;
+      issue();
+      const float4 p0 = xt[r0], p1 = xt[r1], p2 = xt[r2], p3 = xt[r3];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int raw = u == 0 ? r0 : u == 1 ? r1 : u == 2 ? r2 : r3;
+        const float4 pj = u == 0 ? p0 : u == 1 ? p1 : u == 2 ? p2 : p3;
+        const float dx = pti.x - pj.x, dy = pti.y - pj.y, dz = pti.z - pj.z;
+        const bool in = fmaf(dx, dx, fmaf(dy, dy, dz * dz)) < cutf_inner;
+        const unsigned int m = __ballot_sync(0xffffffffu, in);
+        if (in) row2[cnt + __popc(m & ltmask)] = raw | (__float_as_int(pj.w) << CPH_TYPESHIFT);
+        cnt += __popc(m);
+      }
+    }
+    const int padded = (cnt + 31) & ~31;
+    if (cnt + lane < padded) row2[cnt + lane] = dummy | (1 << CPH_TYPESHIFT);
+    if (lane == 0) numneigh2[i] = cnt;
+  }
+}
+
+#ifndef CPH_EVAL_MINBLOCKS
+#define CPH_EVAL_MINBLOCKS 3
+#endif
+constexpr int EAPW = 8;   // atoms per warp in the evaluation kernel
+
+// K2b: one warp per atom over the pruned inner row.  Every lane evaluates one pair per
+// iteration with the next entry already loaded; no queue, no ballots: all issue slots go to the
+// fp64 evaluation.
+template <int STYLE, int EFLAG, int UNI>
+__global__ void __launch_bounds__(TPB, CPH_EVAL_MINBLOCKS)
+pair_eval_kernel(int nlocal, const double4 *__restrict__ xq, const int *__restrict__ type,
+                 const int *__restrict__ neigh, const int *__restrict__ numspec, const int *__restrict__ neigh2,
+                 const int *__restrict__ numneigh2, int rowcap, int nt1, const double4 *__restrict__ coef,
+                 const double2 *__restrict__ cuts, const int *__restrict__ type_has_lj, double *__restrict__ f,
+                 double *__restrict__ evdwl, double *__restrict__ phi, double *__restrict__ eatom, double c_self) {
+  __shared__ double4 s_coef[CPH_MAXNT1 * CPH_MAXNT1];
+  __shared__ double2 s_cut[CPH_MAXNT1 * CPH_MAXNT1];
+  __shared__ double s_exp2[32];
+  for (int k = threadIdx.x; k < nt1 * nt1; k += TPB) {
+    s_coef[k] = coef[k];
+    s_cut[k] = cuts[k];
+  }
+  if (threadIdx.x < 32) s_exp2[threadIdx.x] = kexp2[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int base = blockIdx.x * (WARPS * EAPW) + w;
+  for (int n = 0; n < EAPW; n++) {
+    const int i = base + n * WARPS;
+    if (i >= nlocal) break;
+    const double4 pi = xq[i];
+    const int ti = type[i];
+    const int tbase = ti * nt1;
+    const bool has_lj = type_has_lj[ti] != 0;
+    const int n2 = numneigh2[i];
+    const int *row2 = neigh2 + (size_t)i * rowcap;
+    int e_nxt = lane < n2 ? row2[lane] : 0;
+    Acc a;
+    const int nsp = numspec[i];
+    if (nsp > 0) {   // special-bond partners sit at the end of the OUTER row
+      if (lane < nsp) {
+        const int raw = neigh[(size_t)i * rowcap + (rowcap - 1 - lane)];
+        const int j = raw & CPH_NEIGHMASK, sb = (raw >> CPH_SBSHIFT) & 3;
+        const double4 pq = ld256(xq + j);
+        const int tt = tbase + type[j];
+        const double delx = pi.x - pq.x, dely = pi.y - pq.y, delz = pi.z - pq.z;
+        const double rsq = fma(delz, delz, fma(dely, dely, delx * delx));
+        double o5[5];
+        eval_special<STYLE, EFLAG>(s_coef, s_cut, tt, delx, dely, delz, rsq, pi.w, pq.w, sb, o5);
+        a.fx = o5[0]; a.fy = o5[1]; a.fz = o5[2];
+        if (EFLAG) { a.ev = o5[3]; a.phi = o5[4]; }
+      }
+      __syncwarp();
+    }
+    for (int k0 = 0; k0 < n2; k0 += 32) {
+      const int e = e_nxt;
+      const int kn = k0 + 32 + lane;
+      e_nxt = kn < n2 ? row2[kn] : 0;                  // next entry in flight during the evaluation
+      if (k0 + lane < n2) {
+        const int j = e & CPH_JMASK;
+        const double4 pj = ld256(xq + j);
+        const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
+        const double rsq = fma(delz, delz, fma(dely, dely, delx * delx));
+        double fp, ev, ph;
+        eval_pair<STYLE, EFLAG, UNI>(s_coef, s_cut, tbase + ((e >> CPH_TYPESHIFT) & 15), rsq, pi.w, pj.w, s_exp2,
+                                     has_lj, fp, ev, ph);
+        a.fx = fma(delx, fp, a.fx); a.fy = fma(dely, fp, a.fy); a.fz = fma(delz, fp, a.fz);
+        if (EFLAG) { a.ev += ev; a.phi += ph; }
+      }
+    }
+    for (int o = 16; o; o >>= 1) {
+      a.fx += __shfl_xor_sync(0xffffffffu, a.fx, o);
+      a.fy += __shfl_xor_sync(0xffffffffu, a.fy, o);
+      a.fz += __shfl_xor_sync(0xffffffffu, a.fz, o);
+      if (EFLAG) {
+        a.ev += __shfl_xor_sync(0xffffffffu, a.ev, o);
+        a.phi += __shfl_xor_sync(0xffffffffu, a.phi, o);
+      }
+    }
+    if (lane == 0) {
+      f[3 * (size_t)i] = a.fx;
+      f[3 * (size_t)i + 1] = a.fy;
+      f[3 * (size_t)i + 2] = a.fz;
+      if (EFLAG) {
+        const double ev = 0.5 * a.ev;
+        const double ph = a.phi + 2.0 * pi.w * c_self;
+        evdwl[i] = ev;
+        phi[i] = ph;
+        eatom[i] = ev + 0.5 * pi.w * ph;
+      }
+    }
+  }
+}
+
+__global__ void snapshot_kernel(int n, const double4 *__restrict__ xq, double *xs) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  double4 p = xq[k];
+  xs[3 * (size_t)k] = p.x; xs[3 * (size_t)k + 1] = p.y; xs[3 * (size_t)k + 2] = p.z;
+}
+
 // packed fp32 {x - origin, y - origin, z - origin, type} for the prefilter
 __global__ void xt_kernel(int nall, const double4 *__restrict__ xq, const int *__restrict__ type, double3 origin,
                           float4 *xt) {
@@ -497,7 +683,62 @@ void cph_pair_forget(cph_handle *h) {
     if (o == h) o = nullptr;
 }
 
+// K2a launcher: prune the Verlet rows to rc + inner skin and remember where the atoms were
+int cph_launch_prune(cph_handle *h) {
+  const int n = h->nlocal;
+  if (n == 0) { h->inner_valid = true; return 0; }
+  CPH_TRY(cph_launch_xt(h));
+  ProfScope ps(h, 1);
+  double extent = 0;
+  for (int k = 0; k < 3; k++) extent = std::max(extent, h->grid.n[k] / h->grid.inv[k]);
+  const double cut = std::sqrt(h->pp.cutsq_max) + h->inner_skin;
+  const float cutf = (float)(cut * cut + 32.0 * cut * extent * 5.97e-8 + 1e-5 * cut * cut);
+  CPH_CUDA(h, h->d_neigh2.reserve((size_t)n * h->rowcap));
+  CPH_CUDA(h, h->d_numneigh2.reserve(n + 1));
+  CPH_CUDA(h, h->d_xinner.reserve(3 * (size_t)n + 3));
+  if (h->rowcap / CH * APW > MAXTILES)
+    return cph_fail(h, CPH_ERR_OVERFLOW, "neighbour rows of %d entries exceed the prune kernel's tile schedule", h->rowcap);
+  prune_kernel<<<(n + APB - 1) / APB, TPB, 0, h->stream>>>(n, h->d_xt.p, h->d_neigh.p, h->d_numneigh.p, h->rowcap, cutf,
+                                                          h->nall, h->d_neigh2.p, h->d_numneigh2.p);
+  snapshot_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(n, h->d_xq.p, h->d_xinner.p);
+  CPH_CUDA(h, cudaGetLastError());
+  h->inner_valid = true;
+  h->nprunes++;
+  return 0;
+}
+
 int cph_launch_pair(cph_handle *h, int eflag) {
+  const int n = h->nlocal;
+  if (n == 0) return 0;
+  if (h->device < 0 || h->device >= 64 || g_kc_owner[h->device] != h || h->kc_dirty) {
+    CPH_TRY(cph_pair_upload_constants(h));
+    h->kc_dirty = false;
+  }
+  if (h->fused_pair) return cph_launch_pair_fused(h, eflag);
+  if (!h->inner_valid) CPH_TRY(cph_launch_prune(h));
+  ProfScope ps(h, 0);
+  const int nt1 = h->pp.ntypes + 1;
+  const int blocks = (n + WARPS * EAPW - 1) / (WARPS * EAPW);
+#define LAUNCH(S, E, U)                                                                                             \
+  pair_eval_kernel<S, E, U><<<blocks, TPB, 0, h->stream>>>(n, h->d_xq.p, h->d_type.p, h->d_neigh.p, h->d_numspec.p, \
+                                                           h->d_neigh2.p, h->d_numneigh2.p, h->rowcap, nt1,        \
+                                                           h->d_coef4.p, h->d_cut2.p, h->d_type_has_lj.p,          \
+                                                           h->d_f.p, h->d_evdwl.p, h->d_phi.p, h->d_eatom.p,       \
+                                                           h->pp.c_self)
+#define LAUNCH_E(S, U) do { if (eflag) LAUNCH(S, 1, U); else LAUNCH(S, 0, U); } while (0)
+  if (h->pp.style == CPH_PAIR_LJ_CUT_COUL_CUT) {
+    if (h->uniform_cut) LAUNCH_E(CPH_PAIR_LJ_CUT_COUL_CUT, 1); else LAUNCH_E(CPH_PAIR_LJ_CUT_COUL_CUT, 0);
+  } else {
+    if (h->uniform_cut) LAUNCH_E(CPH_PAIR_LJ_CUT_COUL_DSF, 1); else LAUNCH_E(CPH_PAIR_LJ_CUT_COUL_DSF, 0);
+  }
+#undef LAUNCH_E
+#undef LAUNCH
+  CPH_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+// single-kernel variant (filter + evaluation fused), kept for A/B runs: CPH_PAIR_FUSED=1
+int cph_launch_pair_fused(cph_handle *h, int eflag) {
   const int n = h->nlocal;
   if (n == 0) return 0;
   CPH_TRY(cph_launch_xt(h));
@@ -517,7 +758,7 @@ int cph_launch_pair(cph_handle *h, int eflag) {
     return cph_fail(h, CPH_ERR_OVERFLOW, "neighbour rows of %d entries exceed the pair kernel's tile schedule", h->rowcap);
   const int nt1 = h->pp.ntypes + 1;
 #define LAUNCH(S, E, U)                                                                                           \
-  pair_kernel<S, E, U><<<blocks, TPB, 0, h->stream>>>(n, h->d_xq.p, h->d_xt.p, h->d_neigh.p, h->d_numneigh.p,    \
+  pair_fused_kernel<S, E, U><<<blocks, TPB, 0, h->stream>>>(n, h->d_xq.p, h->d_xt.p, h->d_neigh.p, h->d_numneigh.p,    \
                                                       h->d_numspec.p, h->rowcap, nt1, cutf, h->d_coef4.p, h->d_cut2.p,           \
                                                       h->d_type_has_lj.p, h->d_f.p, h->d_evdwl.p, h->d_phi.p,    \
                                                       h->d_eatom.p, h->pp.c_self)

@@ -228,10 +228,11 @@ __global__ void set_force_kernel(int nh, const int *__restrict__ hlist, const in
 
 // new positions from the caller (caller order) + the neighbor->decide() displacement test
 __global__ void set_x_kernel(int n, const double *__restrict__ xc, const int *__restrict__ perm,
-                             const double *__restrict__ xbuild, double thresh2, double4 *xq, unsigned int *flags) {
+                             const double *__restrict__ xbuild, double thresh2, const double *__restrict__ xinner,
+                             double thresh2_inner, double4 *xq, unsigned int *flags) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   float d2f = 0.f;
-  bool over = false;
+  bool over = false, over_in = false;
   if (k < n) {
     size_t c = (size_t)perm[k] * 3;
     double x = xc[c], y = xc[c + 1], z = xc[c + 2];
@@ -240,32 +241,44 @@ __global__ void set_x_kernel(int n, const double *__restrict__ xc, const int *__
     double d2 = dx * dx + dy * dy + dz * dz;
     over = d2 > thresh2;
     d2f = __double2float_ru(d2);
+    if (xinner) {   // the pruned inner rows stay valid while nobody moved more than inner_skin/2
+      dx = x - xinner[3 * (size_t)k]; dy = y - xinner[3 * (size_t)k + 1]; dz = z - xinner[3 * (size_t)k + 2];
+      over_in = dx * dx + dy * dy + dz * dz > thresh2_inner;
+    }
   }
   for (int o = 16; o; o >>= 1) d2f = fmaxf(d2f, __shfl_xor_sync(0xffffffffu, d2f, o));
   unsigned int any = __ballot_sync(0xffffffffu, over);
+  unsigned int any_in = __ballot_sync(0xffffffffu, over_in);
   if ((threadIdx.x & 31) == 0) {
     if (d2f > 0.f) atomicMax(flags + 0, __float_as_uint(d2f));
     if (any) atomicOr(flags + 4, 1u);
+    if (any_in) atomicOr(flags + 5, 1u);
   }
 }
 
-__global__ void check_kernel(int n, const double *__restrict__ xbuild, double thresh2, const double4 *__restrict__ xq,
-                             unsigned int *flags) {
+__global__ void check_kernel(int n, const double *__restrict__ xbuild, double thresh2, const double *__restrict__ xinner,
+                             double thresh2_inner, const double4 *__restrict__ xq, unsigned int *flags) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   float d2f = 0.f;
-  bool over = false;
+  bool over = false, over_in = false;
   if (k < n) {
     double4 p = xq[k];
     double dx = p.x - xbuild[3 * (size_t)k], dy = p.y - xbuild[3 * (size_t)k + 1], dz = p.z - xbuild[3 * (size_t)k + 2];
     double d2 = dx * dx + dy * dy + dz * dz;
     over = d2 > thresh2;
     d2f = __double2float_ru(d2);
+    if (xinner) {
+      dx = p.x - xinner[3 * (size_t)k]; dy = p.y - xinner[3 * (size_t)k + 1]; dz = p.z - xinner[3 * (size_t)k + 2];
+      over_in = dx * dx + dy * dy + dz * dz > thresh2_inner;
+    }
   }
   for (int o = 16; o; o >>= 1) d2f = fmaxf(d2f, __shfl_xor_sync(0xffffffffu, d2f, o));
   unsigned int any = __ballot_sync(0xffffffffu, over);
+  unsigned int any_in = __ballot_sync(0xffffffffu, over_in);
   if ((threadIdx.x & 31) == 0) {
     if (d2f > 0.f) atomicMax(flags + 0, __float_as_uint(d2f));
     if (any) atomicOr(flags + 4, 1u);
+    if (any_in) atomicOr(flags + 5, 1u);
   }
 }
 
@@ -336,11 +349,14 @@ int cph_launch_set_x(cph_handle *h, const double *xc) {
   const int n = h->nlocal;
   cudaStream_t st = h->stream;
   CPH_CUDA(h, cudaMemsetAsync(h->d_flags.p, 0, sizeof(unsigned int), st));
-  CPH_CUDA(h, cudaMemsetAsync(h->d_flags.p + 4, 0, sizeof(unsigned int), st));
+  CPH_CUDA(h, cudaMemsetAsync(h->d_flags.p + 4, 0, 2 * sizeof(unsigned int), st));
   const double thresh2 = 0.25 * h->skin * h->skin;
+  const double thresh2_in = 0.25 * h->inner_skin * h->inner_skin;
+  const double *xin = h->inner_valid ? h->d_xinner.p : nullptr;
   if (n) {
-    if (xc) set_x_kernel<<<nblk(n), TPB, 0, st>>>(n, xc, h->d_perm.p, h->d_xbuild.p, thresh2, h->d_xq.p, h->d_flags.p);
-    else check_kernel<<<nblk(n), TPB, 0, st>>>(n, h->d_xbuild.p, thresh2, h->d_xq.p, h->d_flags.p);
+    if (xc) set_x_kernel<<<nblk(n), TPB, 0, st>>>(n, xc, h->d_perm.p, h->d_xbuild.p, thresh2, xin, thresh2_in, h->d_xq.p,
+                                                 h->d_flags.p);
+    else check_kernel<<<nblk(n), TPB, 0, st>>>(n, h->d_xbuild.p, thresh2, xin, thresh2_in, h->d_xq.p, h->d_flags.p);
   }
   CPH_CUDA(h, cudaGetLastError());
   return 0;
