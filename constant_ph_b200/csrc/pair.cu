@@ -532,7 +532,7 @@ template <int STYLE, int EFLAG, int UNI>
 __global__ void __launch_bounds__(TPB, CPH_EVAL_MINBLOCKS)
 pair_eval_kernel(int nlocal, const double4 *__restrict__ xq, const int *__restrict__ type,
                  const int *__restrict__ neigh, const int *__restrict__ numspec, const int *__restrict__ neigh2,
-                 const int *__restrict__ numneigh2, int rowcap, int nt1, const double4 *__restrict__ coef,
+                 const int *__restrict__ numneigh2, int rowcap, int dummy, int nt1, const double4 *__restrict__ coef,
                  const double2 *__restrict__ cuts, const int *__restrict__ type_has_lj, double *__restrict__ f,
                  double *__restrict__ evdwl, double *__restrict__ phi, double *__restrict__ eatom, double c_self) {
   __shared__ double4 s_coef[CPH_MAXNT1 * CPH_MAXNT1];
@@ -555,7 +555,11 @@ pair_eval_kernel(int nlocal, const double4 *__restrict__ xq, const int *__restri
     const bool has_lj = type_has_lj[ti] != 0;
     const int n2 = numneigh2[i];
     const int *row2 = neigh2 + (size_t)i * rowcap;
-    int e_nxt = lane < n2 ? row2[lane] : 0;
+    // software pipeline: entry k+64 and the fp64 record of entry k+32 are in flight while
+    // entry k is evaluated (the gather latency was the top stall of the unpipelined loop)
+    int e0 = lane < n2 ? row2[lane] : dummy;
+    int e1 = lane + 32 < n2 ? row2[lane + 32] : dummy;
+    double4 p0 = ld256(xq + (e0 & CPH_JMASK));
     Acc a;
     const int nsp = numspec[i];
     if (nsp > 0) {   // special-bond partners sit at the end of the OUTER row
@@ -574,20 +578,19 @@ pair_eval_kernel(int nlocal, const double4 *__restrict__ xq, const int *__restri
       __syncwarp();
     }
     for (int k0 = 0; k0 < n2; k0 += 32) {
-      const int e = e_nxt;
-      const int kn = k0 + 32 + lane;
-      e_nxt = kn < n2 ? row2[kn] : 0;                  // next entry in flight during the evaluation
+      const double4 p1 = ld256(xq + (e1 & CPH_JMASK));
+      const int kn = k0 + 64 + lane;
+      const int e2 = kn < n2 ? row2[kn] : dummy;
       if (k0 + lane < n2) {
-        const int j = e & CPH_JMASK;
-        const double4 pj = ld256(xq + j);
-        const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
+        const double delx = pi.x - p0.x, dely = pi.y - p0.y, delz = pi.z - p0.z;
         const double rsq = fma(delz, delz, fma(dely, dely, delx * delx));
         double fp, ev, ph;
-        eval_pair<STYLE, EFLAG, UNI>(s_coef, s_cut, tbase + ((e >> CPH_TYPESHIFT) & 15), rsq, pi.w, pj.w, s_exp2,
+        eval_pair<STYLE, EFLAG, UNI>(s_coef, s_cut, tbase + ((e0 >> CPH_TYPESHIFT) & 15), rsq, pi.w, p0.w, s_exp2,
                                      has_lj, fp, ev, ph);
         a.fx = fma(delx, fp, a.fx); a.fy = fma(dely, fp, a.fy); a.fz = fma(delz, fp, a.fz);
         if (EFLAG) { a.ev += ev; a.phi += ph; }
       }
+      e0 = e1; p0 = p1; e1 = e2;
     }
     for (int o = 16; o; o >>= 1) {
       a.fx += __shfl_xor_sync(0xffffffffu, a.fx, o);
@@ -721,7 +724,7 @@ int cph_launch_pair(cph_handle *h, int eflag) {
   const int blocks = (n + WARPS * EAPW - 1) / (WARPS * EAPW);
 #define LAUNCH(S, E, U)                                                                                             \
   pair_eval_kernel<S, E, U><<<blocks, TPB, 0, h->stream>>>(n, h->d_xq.p, h->d_type.p, h->d_neigh.p, h->d_numspec.p, \
-                                                           h->d_neigh2.p, h->d_numneigh2.p, h->rowcap, nt1,        \
+                                                           h->d_neigh2.p, h->d_numneigh2.p, h->rowcap, h->nall, nt1, \
                                                            h->d_coef4.p, h->d_cut2.p, h->d_type_has_lj.p,          \
                                                            h->d_f.p, h->d_evdwl.p, h->d_phi.p, h->d_eatom.p,       \
                                                            h->pp.c_self)
