@@ -272,6 +272,7 @@ def main():
     for s in range(W):
         step_dev(s)
     builds0 = eng.get_counts()["builds"]
+    launch0, prune0 = eng.profile_get(8)[1], eng.profile_get(9)[1]
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -280,6 +281,8 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     builds1 = eng.get_counts()["builds"]
     rebuilds = builds1 - builds0
+    launches_timed = eng.profile_get(8)[1] - launch0
+    prunes = eng.profile_get(9)[1] - prune0
 
     # ---- e2e: host buffers through the C ABI -------------------------------------------------
     e2e = None
@@ -298,7 +301,7 @@ def main():
     for s in range(W, W + K):
         step_dev(s)
     eng.sync()
-    names = ["pair", "special", "site_reduce", "integrate", "charge_force_update", "halo_allreduce", "list_build",
+    names = ["pair", "prune", "site_reduce", "integrate", "charge_force_update", "halo_allreduce", "list_build",
              "set_x_check"]
     prof = {nm: eng.profile_get(i) for i, nm in enumerate(names)}
     eng.profile(False)
@@ -320,9 +323,7 @@ def main():
                 "kernel_share_of_step": pair_ms / max(sum(v[0] for v in prof.values()), 1e-9),
                 "note": "declared bound is HBM (north_star); the kernel is instruction-issue bound (about 57 fp64 "
                         "instructions per in-range pair, 27 % of issued instructions are fp64 math); see DESIGN.md"}
-    # kernels launched per step (counted from the launchers): set_x/check 3, forward 1, pair 1,
-    # partition 3 (+1 memset), integrate 2, apply charges 1  -> 11 + rebuild steps
-    launches = K * 11 + rebuilds * 22
+    launches = launches_timed       # counted by the library's launchers during the timed `value` loop
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline and nranks == 1:
@@ -336,7 +337,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": nranks, "steps": K, "warmup": W,
                 "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": dict(config, parallelism="spatial %dx%dx%d" % grid,
-                                                                      rebuilds_in_timed_region=rebuilds),
+                                                                      rebuilds_in_timed_region=rebuilds, prunes_in_timed_region=prunes),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                 "kernels_ms_per_step": {k: v[0] / K for k, v in prof.items()}, "wall_ms_per_step": wall_dev / K,
                 "step_ms_profiled": step_ms_prof}

@@ -677,6 +677,16 @@ int cph_profile(cph_handle *h, int enable) {
   return CPH_OK;
 }
 int cph_profile_get(cph_handle *h, int which, double *ms_total, int64_t *launches) {
+  if (which == 8) {          // total kernel launches of this library (always counted)
+    *ms_total = 0.0;
+    *launches = h->nlaunch;
+    return CPH_OK;
+  }
+  if (which == 9) {          // inner-list prunes so far
+    *ms_total = 0.0;
+    *launches = h->nprunes;
+    return CPH_OK;
+  }
   if (which < 0 || which >= 8) return cph_fail(h, CPH_ERR_ARG, "profile slot %d out of range", which);
   *ms_total = h->prof[which].ms;
   *launches = h->prof[which].launches;

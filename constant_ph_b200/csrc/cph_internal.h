@@ -178,11 +178,12 @@ struct cph_handle {
   // inner rows (rolling prune): pairs within rc + inner_skin, entry = j | type_j<<28
   DevBuf<int> d_neigh2, d_numneigh2;
   DevBuf<double> d_xinner;           // positions at the last prune
-  double inner_skin = 0.5;
+  double inner_skin = 0.4;           // measured best of 0.3..0.8 at config 3 (CPH_INNER_SKIN overrides)
   bool inner_valid = false, fused_pair = false;
   int64_t nprunes = 0;
   int rowcap = 0;
   int64_t nbuilds = 0, stored_neigh = 0, special_pairs = 0;
+  int64_t nlaunch = 0;               // kernels of this library launched so far
   int maxneigh = 0;
   DevBuf<unsigned int> d_flags;  // [0] max displacement^2 as float bits, [1] overflow, [2] drift...
   // scalars mirrored on host after site_reduce / integrate

@@ -512,6 +512,7 @@ int cph_forward_ghosts(cph_handle *h) {
     CPH_TRY(halo_exchange(h, gd, false));
   }
   if (h->nghost)
+    h->nlaunch += 1 + (h->nranks > 1 && h->nsend ? 1 : 0);
     ghost_copy_kernel<<<nblk(h->nghost), TPB, 0, st>>>(h->nghost, h->nlocal, h->d_ghost_src.p, h->d_ghost_code.p, gd,
                                                       h->d_recvx.p, nullptr, h->d_xq.p, nullptr, nullptr, nullptr,
                                                       nullptr, 0);
@@ -830,6 +831,7 @@ int cph_rebuild(cph_handle *h) {
   CPH_CUDA(h, h->d_eatom.reserve(n + 1));
   CPH_CUDA(h, cudaGetLastError());
   tr.mark("sites");
+  h->nlaunch += 27;          // this file's kernels per rebuild (cub sort/scan kernels not counted)
   h->inner_valid = false;    // the inner (pruned) rows are rebuilt from the new Verlet rows
   h->nbuilds++;
   return 0;

@@ -172,11 +172,11 @@ __device__ __forceinline__ void eval_pair(const double4 *s_coef, const double2 *
     poly = fma(t, poly, kc.a2);
     poly = fma(t, poly, kc.a1);
     const double erfcc = t * poly * erfcd;
-    const double pre = kc.qqrd2e * rinv;               // prefactor / (qi qj)
+    const double u = (kc.qqrd2e * rinv) * qj;          // prefactor / qi, shared by force and potential
     // forcecoul*r2inv = prefactor*(erfcc/r + 2a/sqrt(pi)*erfcd + r*f_shift)*r * r2inv
     const double fc = fma(erfcc, rinv, fma(kc.two_alpha_pis, erfcd, r * kc.f_shift));
-    fcoul = qi * qj * pre * (fc * rinv);
-    if (EFLAG) ph = qj * pre * fma(-rsq, kc.f_shift, fma(-r, kc.e_shift, erfcc));
+    fcoul = (qi * u) * (fc * rinv);
+    if (EFLAG) ph = u * fma(-rsq, kc.f_shift, fma(-r, kc.e_shift, erfcc));
   }
   if (!UNI) {
     fcoul = coul_on ? fcoul : 0.0;
@@ -523,7 +523,10 @@ prune_kernel(int nlocal, const float4 *__restrict__ xt, const int *__restrict__ 
 #ifndef CPH_EVAL_MINBLOCKS
 #define CPH_EVAL_MINBLOCKS 3
 #endif
-constexpr int EAPW = 8;   // atoms per warp in the evaluation kernel
+#ifndef CPH_EAPW
+#define CPH_EAPW 8
+#endif
+constexpr int EAPW = CPH_EAPW;   // atoms per warp in the evaluation kernel
 
 // K2b: one warp per atom over the pruned inner row.  Every lane evaluates one pair per
 // iteration with the next entry already loaded; no queue, no ballots: all issue slots go to the
@@ -676,6 +679,7 @@ int cph_launch_xt(cph_handle *h) {
   ProfScope ps(h, 1);
   const double3 origin = make_double3(h->grid.lo[0], h->grid.lo[1], h->grid.lo[2]);
   CPH_CUDA(h, h->d_xt.reserve((size_t)h->nall + 2));
+  h->nlaunch++;
   xt_kernel<<<(h->nall + 256) / 256, 256, 0, h->stream>>>(h->nall, h->d_xq.p, h->d_type.p, origin, h->d_xt.p);
   CPH_CUDA(h, cudaGetLastError());
   return 0;
@@ -701,6 +705,7 @@ int cph_launch_prune(cph_handle *h) {
   CPH_CUDA(h, h->d_xinner.reserve(3 * (size_t)n + 3));
   if (h->rowcap / CH * APW > MAXTILES)
     return cph_fail(h, CPH_ERR_OVERFLOW, "neighbour rows of %d entries exceed the prune kernel's tile schedule", h->rowcap);
+  h->nlaunch += 2;
   prune_kernel<<<(n + APB - 1) / APB, TPB, 0, h->stream>>>(n, h->d_xt.p, h->d_neigh.p, h->d_numneigh.p, h->rowcap, cutf,
                                                           h->nall, h->d_neigh2.p, h->d_numneigh2.p);
   snapshot_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(n, h->d_xq.p, h->d_xinner.p);
@@ -722,6 +727,7 @@ int cph_launch_pair(cph_handle *h, int eflag) {
   ProfScope ps(h, 0);
   const int nt1 = h->pp.ntypes + 1;
   const int blocks = (n + WARPS * EAPW - 1) / (WARPS * EAPW);
+  h->nlaunch++;
 #define LAUNCH(S, E, U)                                                                                             \
   pair_eval_kernel<S, E, U><<<blocks, TPB, 0, h->stream>>>(n, h->d_xq.p, h->d_type.p, h->d_neigh.p, h->d_numspec.p, \
                                                            h->d_neigh2.p, h->d_numneigh2.p, h->rowcap, h->nall, nt1, \
@@ -759,6 +765,7 @@ int cph_launch_pair_fused(cph_handle *h, int eflag) {
   const int blocks = (n + APB - 1) / APB;
   if (h->rowcap / CH * APW > MAXTILES)
     return cph_fail(h, CPH_ERR_OVERFLOW, "neighbour rows of %d entries exceed the pair kernel's tile schedule", h->rowcap);
+  h->nlaunch++;
   const int nt1 = h->pp.ntypes + 1;
 #define LAUNCH(S, E, U)                                                                                           \
   pair_fused_kernel<S, E, U><<<blocks, TPB, 0, h->stream>>>(n, h->d_xq.p, h->d_xt.p, h->d_neigh.p, h->d_numneigh.p,    \

@@ -307,6 +307,7 @@ int cph_launch_partition(cph_handle *h) {
     site_sum_kernel<<<nblk(h->ntitr), TPB, 0, st>>>(h->ntitr, h->d_titr_site.p, h->d_titr_local.p, h->d_titr_dq.p,
                                                     h->d_phi.p, h->d_eatom.p, h->d_mask.p, h->fix.Hbit, S,
                                                     h->fix.implicit_site, h->d_red.p);
+  h->nlaunch += h->ntitr ? 3 : 2;
   CPH_CUDA(h, cudaGetLastError());
   return 0;
 }
@@ -322,6 +323,7 @@ int cph_launch_integrate(cph_handle *h, double dt, int phase) {
                                        h->d_part.p);
   if (phase != 1)
     integrate_final_kernel<<<1, 96, 0, st>>>(nb, h->d_part.p, h->d_red.p, h->fix.dudl_mode, h->d_scal.p);
+  h->nlaunch += phase != 1 ? 2 : 1;
   CPH_CUDA(h, cudaGetLastError());
   return 0;
 }
@@ -329,6 +331,7 @@ int cph_launch_integrate(cph_handle *h, double dt, int phase) {
 int cph_launch_apply_charges(cph_handle *h) {
   if (h->ntitr == 0) return 0;
   ProfScope ps(h, 4);
+  h->nlaunch++;
   apply_charges_kernel<<<nblk(h->ntitr), TPB, 0, h->stream>>>(h->ntitr, h->d_titr_site.p, h->d_titr_local.p,
                                                              h->d_titr_qA.p, h->d_titr_dq.p, h->d_lam.p, h->d_xq.p);
   CPH_CUDA(h, cudaGetLastError());
@@ -338,6 +341,7 @@ int cph_launch_apply_charges(cph_handle *h) {
 int cph_launch_set_force(cph_handle *h) {
   if (h->nh == 0) return 0;
   ProfScope ps(h, 4);
+  h->nlaunch++;
   set_force_kernel<<<nblk(h->nh), TPB, 0, h->stream>>>(h->nh, h->d_hlist.p, h->d_site_of.p, h->d_lam.p,
                                                       h->fix.fscale_mode, h->d_f.p);
   CPH_CUDA(h, cudaGetLastError());
@@ -354,6 +358,7 @@ int cph_launch_set_x(cph_handle *h, const double *xc) {
   const double thresh2_in = 0.25 * h->inner_skin * h->inner_skin;
   const double *xin = h->inner_valid ? h->d_xinner.p : nullptr;
   if (n) {
+    h->nlaunch++;
     if (xc) set_x_kernel<<<nblk(n), TPB, 0, st>>>(n, xc, h->d_perm.p, h->d_xbuild.p, thresh2, xin, thresh2_in, h->d_xq.p,
                                                  h->d_flags.p);
     else check_kernel<<<nblk(n), TPB, 0, st>>>(n, h->d_xbuild.p, thresh2, xin, thresh2_in, h->d_xq.p, h->d_flags.p);
@@ -366,6 +371,7 @@ int cph_launch_gather_out(cph_handle *h, int what, double *out) {
   const int n = h->nlocal;
   if (n == 0) return 0;
   const double *src = what == 0 ? h->d_f.p : what == 1 ? h->d_eatom.p : h->d_phi.p;
+  h->nlaunch++;
   gather_out_kernel<<<nblk(n), TPB, 0, h->stream>>>(n, what == 0 ? 3 : 1, h->d_inv.p, src,
                                                    what == 3 ? h->d_xq.p : nullptr, out);
   CPH_CUDA(h, cudaGetLastError());
@@ -382,6 +388,7 @@ __global__ void pack_xq_kernel(int n, const double *__restrict__ x, const double
 // device-resident caller arrays -> packed {x,y,z,q} (cph_set_atoms with CPH_DEVICE)
 int cph_launch_pack_xq(cph_handle *h, int n, const double *x, const double *q) {
   if (n == 0) return 0;
+  h->nlaunch++;
   pack_xq_kernel<<<nblk(n), TPB, 0, h->stream>>>(n, x, q, h->d_xq.p);
   CPH_CUDA(h, cudaGetLastError());
   return 0;

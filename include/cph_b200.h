@@ -188,8 +188,10 @@ int cph_stream(cph_handle *h, void **stream);
 /* CUDA-event stopwatch on the library stream: whole region ... */
 int cph_timer_start(cph_handle *h);
 int cph_timer_stop(cph_handle *h, double *ms);
-/* ... and per kernel class while enabled.  which: 0 pair, 1 special pairs, 2 site reduce,
- * 3 lambda integrator, 4 charge update, 5 halo, 6 list build (all stages), 7 displacement check. */
+/* ... and per kernel class while enabled.  which: 0 pair evaluation, 1 inner-list prune (+ fp32 record
+ * refresh), 2 site reduce, 3 lambda integrator, 4 charge / force update, 5 halo + allreduce, 6 list build
+ * (all stages), 7 new positions + displacement check.  Always available: 8 -> launches = kernels of this
+ * library launched so far, 9 -> launches = inner-list prunes so far. */
 int cph_profile(cph_handle *h, int enable);
 int cph_profile_get(cph_handle *h, int which, double *ms_total, int64_t *launches);
 
