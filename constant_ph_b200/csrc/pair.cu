@@ -520,6 +520,9 @@ prune_kernel(int nlocal, const float4 *__restrict__ xt, const int *__restrict__ 
   }
 }
 
+#ifndef CPH_EVAL_ILP2
+#define CPH_EVAL_ILP2 0
+#endif
 #ifndef CPH_EVAL_MINBLOCKS
 #define CPH_EVAL_MINBLOCKS 3
 #endif
@@ -531,8 +534,24 @@ constexpr int EAPW = CPH_EAPW;   // atoms per warp in the evaluation kernel
 // K2b: one warp per atom over the pruned inner row.  Every lane evaluates one pair per
 // iteration with the next entry already loaded; no queue, no ballots: all issue slots go to the
 // fp64 evaluation.
+// launch shape measured on B200 (profiles/r1_scaling_and_bench.md): 64-thread CTAs capped at 72
+// registers (28 resident warps/SM, no spills) beat 256-thread CTAs at 80 registers by 8 %
+#ifndef CPH_EVAL_WARPS
+#define CPH_EVAL_WARPS 2
+#endif
+#ifndef CPH_EVAL_MAXNREG
+#define CPH_EVAL_MAXNREG 72
+#endif
+constexpr int EWARPS = CPH_EVAL_WARPS;
+constexpr int ETPB = EWARPS * 32;
+#ifdef CPH_EVAL_MAXNREG
+#define CPH_EVAL_BOUNDS __maxnreg__(CPH_EVAL_MAXNREG)
+#else
+#define CPH_EVAL_BOUNDS __launch_bounds__(ETPB, CPH_EVAL_MINBLOCKS)
+#endif
+
 template <int STYLE, int EFLAG, int UNI>
-__global__ void __launch_bounds__(TPB, CPH_EVAL_MINBLOCKS)
+__global__ void CPH_EVAL_BOUNDS
 pair_eval_kernel(int nlocal, const double4 *__restrict__ xq, const int *__restrict__ type,
                  const int *__restrict__ neigh, const int *__restrict__ numspec, const int *__restrict__ neigh2,
                  const int *__restrict__ numneigh2, int rowcap, int dummy, int nt1, const double4 *__restrict__ coef,
@@ -541,16 +560,16 @@ pair_eval_kernel(int nlocal, const double4 *__restrict__ xq, const int *__restri
   __shared__ double4 s_coef[CPH_MAXNT1 * CPH_MAXNT1];
   __shared__ double2 s_cut[CPH_MAXNT1 * CPH_MAXNT1];
   __shared__ double s_exp2[32];
-  for (int k = threadIdx.x; k < nt1 * nt1; k += TPB) {
+  for (int k = threadIdx.x; k < nt1 * nt1; k += ETPB) {
     s_coef[k] = coef[k];
     s_cut[k] = cuts[k];
   }
   if (threadIdx.x < 32) s_exp2[threadIdx.x] = kexp2[threadIdx.x];
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int base = blockIdx.x * (WARPS * EAPW) + w;
+  const int base = blockIdx.x * (EWARPS * EAPW) + w;
   for (int n = 0; n < EAPW; n++) {
-    const int i = base + n * WARPS;
+    const int i = base + n * EWARPS;
     if (i >= nlocal) break;
     const double4 pi = xq[i];
     const int ti = type[i];
@@ -580,6 +599,32 @@ pair_eval_kernel(int nlocal, const double4 *__restrict__ xq, const int *__restri
       }
       __syncwarp();
     }
+#if CPH_EVAL_ILP2
+    // two independent pairs per lane per iteration (entries k and k+32): the dependent fp64
+    // chains of the two evaluations interleave
+    for (int k0 = 0; k0 < n2; k0 += 64) {
+      const double4 p1 = ld256(xq + (e1 & CPH_JMASK));
+      const int ka = k0 + 64 + lane, kb = k0 + 96 + lane;
+      const int e2 = ka < n2 ? row2[ka] : dummy;
+      const int e3 = kb < n2 ? row2[kb] : dummy;
+      const double dx0 = pi.x - p0.x, dy0 = pi.y - p0.y, dz0 = pi.z - p0.z;
+      const double dx1 = pi.x - p1.x, dy1 = pi.y - p1.y, dz1 = pi.z - p1.z;
+      const double rs0 = fma(dz0, dz0, fma(dy0, dy0, dx0 * dx0));
+      const double rs1 = fma(dz1, dz1, fma(dy1, dy1, dx1 * dx1));
+      double f0, f1, v0, v1, h0, h1;
+      eval_pair<STYLE, EFLAG, UNI>(s_coef, s_cut, tbase + ((e0 >> CPH_TYPESHIFT) & 15), rs0, pi.w, p0.w, s_exp2,
+                                   has_lj, f0, v0, h0);
+      eval_pair<STYLE, EFLAG, UNI>(s_coef, s_cut, tbase + ((e1 >> CPH_TYPESHIFT) & 15), rs1, pi.w, p1.w, s_exp2,
+                                   has_lj, f1, v1, h1);
+      if (k0 + lane >= n2) { f0 = 0.0; v0 = 0.0; h0 = 0.0; }
+      if (k0 + 32 + lane >= n2) { f1 = 0.0; v1 = 0.0; h1 = 0.0; }
+      a.fx = fma(dx0, f0, a.fx); a.fy = fma(dy0, f0, a.fy); a.fz = fma(dz0, f0, a.fz);
+      a.fx = fma(dx1, f1, a.fx); a.fy = fma(dy1, f1, a.fy); a.fz = fma(dz1, f1, a.fz);
+      if (EFLAG) { a.ev += v0 + v1; a.phi += h0 + h1; }
+      e0 = e2; e1 = e3;
+      p0 = ld256(xq + (e0 & CPH_JMASK));
+    }
+#else
     for (int k0 = 0; k0 < n2; k0 += 32) {
       const double4 p1 = ld256(xq + (e1 & CPH_JMASK));
       const int kn = k0 + 64 + lane;
@@ -595,6 +640,7 @@ pair_eval_kernel(int nlocal, const double4 *__restrict__ xq, const int *__restri
       }
       e0 = e1; p0 = p1; e1 = e2;
     }
+#endif
     for (int o = 16; o; o >>= 1) {
       a.fx += __shfl_xor_sync(0xffffffffu, a.fx, o);
       a.fy += __shfl_xor_sync(0xffffffffu, a.fy, o);
@@ -726,10 +772,10 @@ int cph_launch_pair(cph_handle *h, int eflag) {
   if (!h->inner_valid) CPH_TRY(cph_launch_prune(h));
   ProfScope ps(h, 0);
   const int nt1 = h->pp.ntypes + 1;
-  const int blocks = (n + WARPS * EAPW - 1) / (WARPS * EAPW);
+  const int blocks = (n + EWARPS * EAPW - 1) / (EWARPS * EAPW);
   h->nlaunch++;
 #define LAUNCH(S, E, U)                                                                                             \
-  pair_eval_kernel<S, E, U><<<blocks, TPB, 0, h->stream>>>(n, h->d_xq.p, h->d_type.p, h->d_neigh.p, h->d_numspec.p, \
+  pair_eval_kernel<S, E, U><<<blocks, ETPB, 0, h->stream>>>(n, h->d_xq.p, h->d_type.p, h->d_neigh.p, h->d_numspec.p, \
                                                            h->d_neigh2.p, h->d_numneigh2.p, h->rowcap, h->nall, nt1, \
                                                            h->d_coef4.p, h->d_cut2.p, h->d_type_has_lj.p,          \
                                                            h->d_f.p, h->d_evdwl.p, h->d_phi.p, h->d_eatom.p,       \
