@@ -161,6 +161,9 @@ class Engine:
     def set_mode(self, dudl=DUDL_CHARGE, integrator=INTEGRATE_REFERENCE, fscale=FSCALE_LAMBDA):
         self._call("set_mode", C.c_int(dudl), C.c_int(integrator), C.c_int(fscale))
 
+    def set_water_buffer(self, enable=True):
+        self._call("set_water_buffer", C.c_int(1 if enable else 0))
+
     def set_sites(self, nsites, pK, titr_tag, titr_site, qA, qB):
         pK, qA, qB = _f64(pK), _f64(qA), _f64(qB)
         tt, ts = _i32(titr_tag), _i32(titr_site)
@@ -355,7 +358,8 @@ class Engine:
 
 def configure(eng, box, nevery=1, dudl=DUDL_CHARGE, integrator=INTEGRATE_REFERENCE,
               fscale=FSCALE_LAMBDA, bias_mode=BIAS_EXACT, implicit_site=False, ftm2v=None,
-              sublo=None, subhi=None, procgrid=(1, 1, 1), myloc=(0, 0, 0), owned=None, bias=None):
+              sublo=None, subhi=None, procgrid=(1, 1, 1), myloc=(0, 0, 0), owned=None, bias=None,
+              water_buffer=False):
     """Push a synth.Box into an engine: the calls FixConstantPH's constructor/init/setup make.
 
     implicit_site=True reproduces the reference's single global lambda over the hydrogen
@@ -371,6 +375,8 @@ def configure(eng, box, nevery=1, dudl=DUDL_CHARGE, integrator=INTEGRATE_REFEREN
     eng.set_fix(nevery, synth.GROUP_H_BIT, synth.GROUP_W_BIT, pK0, box.pH, box.T)
     eng.set_bias(bias_mode, **(bias or {}))
     eng.set_mode(dudl, integrator, fscale)
+    if water_buffer:
+        eng.set_water_buffer(True)
     if implicit_site:
         eng.set_sites(0, None, None, None, None, None)
         eng.set_lambda(box.lambda0[:1], box.v0[:1])

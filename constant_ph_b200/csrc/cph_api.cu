@@ -56,8 +56,8 @@ int size_sites(cph_handle *h) {
     CPH_CUDA(h, b->reserve(S + 1));
     CPH_CUDA(h, cudaMemsetAsync(b->p, 0, (S + 1) * sizeof(double), h->stream));
   }
-  CPH_CUDA(h, h->d_red.reserve(4 + 2 * S + 4));
-  CPH_CUDA(h, cudaMemsetAsync(h->d_red.p, 0, (4 + 2 * S + 4) * sizeof(double), h->stream));
+  CPH_CUDA(h, h->d_red.reserve(4 + 2 * S + 8));
+  CPH_CUDA(h, cudaMemsetAsync(h->d_red.p, 0, (4 + 2 * S + 8) * sizeof(double), h->stream));
   CPH_CUDA(h, h->d_scal.reserve(16));
   CPH_CUDA(h, cudaMemsetAsync(h->d_scal.p, 0, 16 * sizeof(double), h->stream));
   std::vector<double> half(S, 0.5);
@@ -129,12 +129,13 @@ int cph_destroy(cph_handle *h) {
   cph_pair_forget(h);
   DevBuf<double> *db[] = {&h->d_pK, &h->d_lam, &h->d_vlam, &h->d_alam, &h->d_flam, &h->d_fs, &h->d_dfs, &h->d_Us,
                           &h->d_dUs, &h->d_red, &h->d_titr_qA, &h->d_titr_dq, &h->d_scal, &h->d_part, &h->d_xbuild,
-                          &h->d_f, &h->d_evdwl, &h->d_phi, &h->d_eatom, &h->d_stage};
+                          &h->d_f, &h->d_evdwl, &h->d_phi, &h->d_eatom, &h->d_stage, &h->d_wq, &h->d_dQ};
   for (auto *b : db) b->release();
   DevBuf<int> *ib[] = {&h->d_titr_tag_sorted, &h->d_titr_entry_of_sorted, &h->d_titr_site, &h->d_titr_local, &h->d_type,
                        &h->d_tag, &h->d_mask, &h->d_perm, &h->d_inv, &h->d_site_of, &h->d_titr_of, &h->d_nspecial,
                        &h->d_special, &h->d_ghost_src, &h->d_ghost_code, &h->d_hlist, &h->d_istage, &h->d_vals,
-                       &h->d_vals2, &h->d_tmpi, &h->d_cell_start_o, &h->d_cell_start_g, &h->d_neigh, &h->d_numneigh, &h->d_numspec, &h->d_neigh2, &h->d_numneigh2, &h->d_scr_i, &h->d_scr_src, &h->d_scr_code, &h->d_scr_off, &h->d_mol, &h->d_rec_src, &h->d_rec_dir};
+                       &h->d_vals2, &h->d_tmpi, &h->d_cell_start_o, &h->d_cell_start_g, &h->d_neigh, &h->d_numneigh, &h->d_numspec, &h->d_neigh2, &h->d_numneigh2, &h->d_scr_i, &h->d_scr_src, &h->d_scr_code, &h->d_scr_off, &h->d_mol, &h->d_rec_src, &h->d_rec_dir,
+                       &h->d_wtag, &h->d_wlocal};
   for (auto *b : ib) b->release();
   h->d_xb.release(); h->d_molecule.release(); h->d_coef.release(); h->d_coef4.release(); h->d_cut2.release(); h->d_type_has_lj.release(); h->d_xt.release(); h->d_xq.release(); h->d_xq2.release(); h->d_keys.release(); h->d_keys2.release();
   h->d_xinner.release(); h->d_cubtmp.release(); h->d_flags.release(); h->d_scr_stats.release();
@@ -270,6 +271,13 @@ int cph_set_mode(cph_handle *h, int dudl_mode, int integrator_mode, int fscale_m
   return CPH_OK;
 }
 
+int cph_set_water_buffer(cph_handle *h, int enable) {
+  if (enable < 0) return cph_fail(h, CPH_ERR_ARG, "water buffer: negative atom count");
+  // `enable` is the number of atoms in the water group (the fix insists on 3, cpp:44-45); 1 is read as 3
+  h->water_n = enable == 1 ? 3 : enable;
+  return CPH_OK;
+}
+
 int cph_set_sites(cph_handle *h, int nsites, const double *pK, int ntitr, const int *titr_tag, const int *titr_site,
                   const double *qA, const double *qB) {
   if (nsites < 0 || ntitr < 0) return cph_fail(h, CPH_ERR_ARG, "negative site/atom count");
@@ -310,6 +318,11 @@ int cph_set_sites(cph_handle *h, int nsites, const double *pK, int ntitr, const 
   CPH_TRY(upload(h, h->d_titr_dq, dq.data(), ntitr));
   CPH_TRY(upload(h, h->d_titr_tag_sorted, h->titr_tag_sorted_h.data(), ntitr));
   CPH_TRY(upload(h, h->d_titr_entry_of_sorted, h->titr_entry_of_sorted_h.data(), ntitr));
+  {
+    std::vector<double> dQ(h->S, 0.0);
+    for (int t = 0; t < ntitr; t++) dQ[titr_site[t]] += qB[t] - qA[t];
+    CPH_TRY(upload(h, h->d_dQ, dQ.data(), dQ.size()));
+  }
   CPH_TRY(upload(h, h->d_pK, pK, nsites));
   CPH_CUDA(h, cudaStreamSynchronize(h->stream));
   CPH_TRY(size_sites(h));
@@ -363,6 +376,20 @@ int cph_set_atoms(cph_handle *h, int where, int nlocal, const double *x, const d
     CPH_TRY(upload(h, h->d_nspecial, nspecial, 3 * n, where));
     CPH_TRY(upload(h, h->d_special, special, n * maxspecial, where));
   }
+  // modify_water: remember the owned buffer atoms and the charge they were given (lambda = 0 state)
+  h->wtag_h.clear();
+  h->wq_h.clear();
+  if (h->water_n > 0) {
+    if (where != CPH_HOST) return cph_fail(h, CPH_ERR_ARG, "the water buffer needs host-resident mask/tag/q in cph_set_atoms");
+    for (size_t i = 0; i < n; i++)
+      if (mask[i] & h->fix.Wbit) { h->wtag_h.push_back(tag[i]); h->wq_h.push_back(q[i]); }
+    if ((int)h->wtag_h.size() > h->water_n || h->wtag_h.size() > 64)
+      return cph_fail(h, CPH_ERR_ARG, "the water group has %zu atoms on this rank, expected at most %d", h->wtag_h.size(), h->water_n);
+  }
+  h->nw_local = (int)h->wtag_h.size();
+  CPH_TRY(upload(h, h->d_wtag, h->wtag_h.data(), h->wtag_h.size()));
+  CPH_TRY(upload(h, h->d_wq, h->wq_h.data(), h->wq_h.size()));
+  CPH_CUDA(h, h->d_wlocal.reserve(h->wtag_h.size() + 1));
   std::vector<int> ident(n);
   std::iota(ident.begin(), ident.end(), 0);
   CPH_TRY(upload(h, h->d_perm, ident.data(), n));
@@ -433,7 +460,9 @@ int cph_site_reduce(cph_handle *h) {
   CPH_TRY(need(h, h->have_pass, "cph_pair_pass (with eflag) first"));
   cudaSetDevice(h->device);
   CPH_TRY(cph_launch_partition(h));
-  CPH_TRY(cph_comm_allreduce(h, h->d_red.p, 4 + 2 * h->S));   // cpp:274
+  CPH_TRY(cph_launch_water_phi(h));
+  CPH_TRY(cph_comm_allreduce(h, h->d_red.p, 4 + 2 * h->S + 1));   // cpp:274
+  if (h->fix.dudl_mode == CPH_DUDL_CHARGE) CPH_TRY(cph_launch_water_dudl(h));
   return CPH_OK;
 }
 

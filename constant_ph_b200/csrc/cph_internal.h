@@ -118,8 +118,16 @@ struct cph_handle {
   DevBuf<double> d_pK, d_lam, d_vlam, d_alam, d_flam, d_fs, d_dfs, d_Us, d_dUs;
   // one contiguous reduction buffer so a single allreduce covers everything (cpp:274):
   // [0]=HA [1]=HB [2]=E_vdwl [3]=E_coul [4..4+S)=dU/dlambda_s [4+S..4+2S)=HB_s-HA_s
+  // [4+2S]=sum of dE/dq over the owned water-buffer atoms (modify_water)
   DevBuf<double> d_red;
   DevBuf<PairCoef> d_coef;
+  // modify_water (h:58): charge buffer on the water group
+  int water_n = 0;                   // atoms in the water group (0 = buffer off)
+  int nw_local = 0;                  // of which this rank owns
+  std::vector<int> wtag_h;           // tags of the owned buffer atoms
+  std::vector<double> wq_h;          // their charges as supplied (lambda = 0 state)
+  DevBuf<int> d_wtag, d_wlocal;
+  DevBuf<double> d_wq, d_dQ;         // d_dQ[s] = sum_{t in s} (qB - qA)
   DevBuf<double4> d_coef4;      // {12 lj3, 6 lj4, lj3, lj4} per type pair
   DevBuf<double2> d_cut2;       // {cut_ljsq, cutsq} per type pair
   DevBuf<int> d_type_has_lj;    // type i has a non-zero LJ partner
@@ -214,6 +222,8 @@ void cph_pair_forget(cph_handle *h);
 int cph_launch_partition(cph_handle *h);        // HA, HB, E_vdwl, E_coul + per-site sums
 int cph_launch_integrate(cph_handle *h, double dt, int phase);
 int cph_launch_apply_charges(cph_handle *h);
+int cph_launch_water_phi(cph_handle *h);      // red[4+2S] = sum of dE/dq over owned buffer atoms
+int cph_launch_water_dudl(cph_handle *h);     // dU/dlambda_s -= dQ_s / n_W * red[4+2S] (after the allreduce)
 int cph_launch_set_force(cph_handle *h);
 int cph_launch_set_x(cph_handle *h, const double *x_dev_caller_order);
 int cph_launch_gather_out(cph_handle *h, int what, double *out_dev);  // 0 f, 1 eatom, 2 phi, 3 q

@@ -355,6 +355,15 @@ __global__ void xb_kernel(int nall, const double4 *__restrict__ xq, const int *_
   xb[k] = make_float4((float)(p.x - origin.x), (float)(p.y - origin.y), (float)(p.z - origin.z), __int_as_float(m));
 }
 
+// modify_water: where the owned buffer atoms sit in the internal order
+__global__ void water_map_kernel(int nlocal, const int *__restrict__ tag, const int *__restrict__ mask, int Wbit,
+                                 int nw, const int *__restrict__ wtag, int *wlocal) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nlocal || !(mask[k] & Wbit)) return;
+  for (int s = 0; s < nw; s++)
+    if (wtag[s] == tag[k]) wlocal[s] = k;
+}
+
 // site bookkeeping: owned atom -> titration entry by binary search of its tag
 __global__ void site_map_kernel(int nlocal, const int *__restrict__ tag, const int *__restrict__ mask, int ntitr,
                                 const int *__restrict__ tsorted, const int *__restrict__ entry_of_sorted,
@@ -809,6 +818,11 @@ int cph_rebuild(cph_handle *h) {
   CPH_CUDA(h, h->d_titr_local.reserve(h->ntitr + 1));
   if (h->ntitr) fill_int_kernel<<<nblk(h->ntitr), TPB, 0, st>>>(h->ntitr, h->d_titr_local.p, -1);
   h->nh = 0;
+  if (h->nw_local > 0 && n) {
+    fill_int_kernel<<<1, TPB, 0, st>>>(h->nw_local, h->d_wlocal.p, -1);
+    water_map_kernel<<<nblk(n), TPB, 0, st>>>(n, h->d_tag.p, h->d_mask.p, h->fix.Wbit, h->nw_local, h->d_wtag.p,
+                                              h->d_wlocal.p);
+  }
   if (n) {
     site_map_kernel<<<nblk(n), TPB, 0, st>>>(n, h->d_tag.p, h->d_mask.p, h->ntitr, h->d_titr_tag_sorted.p,
                                              h->d_titr_entry_of_sorted.p, h->d_titr_site.p, h->fix.implicit_site,

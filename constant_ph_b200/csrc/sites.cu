@@ -213,6 +213,36 @@ __global__ void apply_charges_kernel(int ntitr, const int *__restrict__ titr_sit
   xq[k].w = qA[t] + lam[titr_site[t]] * dq[t];
 }
 
+// modify_water (h:58, TODO at cpp:268): sum of dE/dq over the buffer atoms this rank owns
+__global__ void water_phi_kernel(int nw, const int *__restrict__ wlocal, const double *__restrict__ phi, double *out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double s = 0;
+  for (int k = 0; k < nw; k++)
+    if (wlocal[k] >= 0) s += phi[wlocal[k]];
+  *out = s;
+}
+// every buffer atom carries -(1/n_W) sum_s lambda_s dQ_s: dE/dlambda_s gains -(dQ_s/n_W) * sum_W dE/dq
+__global__ void water_dudl_kernel(int S, const double *__restrict__ dQ, double inv_nw, double *red) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < S) red[4 + s] -= dQ[s] * inv_nw * red[4 + 2 * S];
+}
+// one block: tot = sum_s lambda_s dQ_s in a fixed order, then the owned buffer atoms get q_base - tot/n_W
+__global__ void __launch_bounds__(TPB)
+water_apply_kernel(int S, const double *__restrict__ lam, const double *__restrict__ dQ, double inv_nw, int nw,
+                   const int *__restrict__ wlocal, const double *__restrict__ wq, double4 *xq) {
+  __shared__ double sm[TPB];
+  double v = 0;
+  for (int s = threadIdx.x; s < S; s += TPB) v += lam[s] * dQ[s];
+  sm[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = TPB / 2; o; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  const double tot = sm[0];
+  if (threadIdx.x < nw && wlocal[threadIdx.x] >= 0) xq[wlocal[threadIdx.x]].w = wq[threadIdx.x] - tot * inv_nw;
+}
+
 // set_force (cpp:149-171) over the compact hydrogen-group list instead of a scan of mask[]
 __global__ void set_force_kernel(int nh, const int *__restrict__ hlist, const int *__restrict__ site_of,
                                  const double *__restrict__ lam, int fscale_mode, double *f) {
@@ -299,7 +329,7 @@ int cph_launch_partition(cph_handle *h) {
   const int n = h->nlocal, S = h->S;
   cudaStream_t st = h->stream;
   CPH_CUDA(h, h->d_part.reserve((size_t)MAXPART * 4));
-  CPH_CUDA(h, cudaMemsetAsync(h->d_red.p, 0, (4 + 2 * (size_t)S) * sizeof(double), st));
+  CPH_CUDA(h, cudaMemsetAsync(h->d_red.p, 0, (4 + 2 * (size_t)S + 1) * sizeof(double), st));
   int nb = std::max(1, std::min(MAXPART, nblk(n)));
   partition_kernel<<<nb, TPB, 0, st>>>(n, h->d_eatom.p, h->d_evdwl.p, h->d_mask.p, h->fix.Hbit, h->d_part.p);
   partition_final_kernel<<<1, 128, 0, st>>>(nb, h->d_part.p, h->d_red.p, h->fix.implicit_site, S);
@@ -334,6 +364,27 @@ int cph_launch_apply_charges(cph_handle *h) {
   h->nlaunch++;
   apply_charges_kernel<<<nblk(h->ntitr), TPB, 0, h->stream>>>(h->ntitr, h->d_titr_site.p, h->d_titr_local.p,
                                                              h->d_titr_qA.p, h->d_titr_dq.p, h->d_lam.p, h->d_xq.p);
+  if (h->water_n > 0 && h->nw_local > 0) {
+    h->nlaunch++;
+    water_apply_kernel<<<1, TPB, 0, h->stream>>>(h->S, h->d_lam.p, h->d_dQ.p, 1.0 / h->water_n, h->nw_local,
+                                                 h->d_wlocal.p, h->d_wq.p, h->d_xq.p);
+  }
+  CPH_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+int cph_launch_water_phi(cph_handle *h) {
+  if (h->water_n <= 0) return 0;
+  h->nlaunch++;
+  water_phi_kernel<<<1, 32, 0, h->stream>>>(h->nw_local, h->d_wlocal.p, h->d_phi.p, h->d_red.p + 4 + 2 * (size_t)h->S);
+  CPH_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+int cph_launch_water_dudl(cph_handle *h) {
+  if (h->water_n <= 0) return 0;
+  h->nlaunch++;
+  water_dudl_kernel<<<nblk(h->S), TPB, 0, h->stream>>>(h->S, h->d_dQ.p, 1.0 / h->water_n, h->d_red.p);
   CPH_CUDA(h, cudaGetLastError());
   return 0;
 }

@@ -98,6 +98,11 @@ int cph_set_fix(cph_handle *h, int nevery, int groupHbit, int groupWbit, double 
 int cph_set_bias(cph_handle *h, double w, double s, double hbar, double k, double a, double b,
                  double r, double m, double d, double m_lambda, int bias_mode);
 int cph_set_mode(cph_handle *h, int dudl_mode, int integrator_mode, int fscale_mode);
+/* modify_water() (h:58: declared, never defined nor called; TODO at cpp:268; the constructor insists on a
+ * 3-atom water group, cpp:44-45).  When enabled (charge mode), every atom of the water group carries
+ * q_base - (1/n_W) sum_s lambda_s dQ_s, dQ_s = sum_{t in s}(qB_t - qA_t), so the box keeps the total charge
+ * it has at lambda = 0, and dU/dlambda_s gains -(dQ_s/n_W) sum_{a in W} dE/dq_a.  Off by default. */
+int cph_set_water_buffer(cph_handle *h, int enable);
 /* north_star multi-site tables.  Site s has pK[s]; titratable atom t (global tag titr_tag[t])
  * belongs to site titr_site[t] and has end-state charges qA[t], qB[t].  With nsites == 0 the
  * reference's single global lambda (one site = the whole hydrogen group, pK from cph_set_fix) is used. */

@@ -74,6 +74,8 @@ struct Oracle {
   double bw = 200.0, bs = 0.3, bh = 4.0, bk = 2.533, ba = 0.034041, bb = 0.005238, br = 16.458,
          bm = 0.1507, bd = 2.0, m_lambda = 20.0;
   int bias_mode = 0, dudl_mode = 1, integ_mode = 0, fscale_mode = 0;
+  int water_buffer = 0;           // modify_water(): keep the box charge constant through the 3-atom water group
+  std::vector<double> qbase;      // charges as supplied by the host (the lambda = 0 state of the buffer atoms)
   // sites
   int S = 1;
   bool implicit_site = true;  // nsites==0: one global lambda over the hydrogen group (reference)
@@ -407,6 +409,18 @@ void site_reduce(Oracle *o) {
     int t = o->titr_of[i];
     if (t >= 0) d[s] += (long double)(o->qB[t] - o->qA[t]) * o->phi[i];  // Appendix B (phi holds dE/dq_i)
   }
+  if (o->water_buffer && o->dudl_mode == 1) {
+    // modify_water (h:58; TODO at cpp:268): the buffer atoms carry -(1/nW) sum_s lambda_s dQ_s each,
+    // so dE/dlambda_s gains -(dQ_s/nW) * sum_{a in W} dE/dq_a
+    long double phiw = 0;
+    int nw = 0;
+    for (int i = 0; i < o->n; i++) if (o->mask[i] & o->Wbit) { phiw += o->phi[i]; nw++; }
+    if (nw) {
+      std::vector<long double> dQ(o->S, 0.0L);
+      for (size_t t = 0; t < o->qA.size(); t++) dQ[o->titr_site[t]] += (long double)(o->qB[t] - o->qA[t]);
+      for (int s = 0; s < o->S; s++) d[s] -= dQ[s] / nw * phiw;
+    }
+  }
   for (int s = 0; s < o->S; s++) { o->dudl[s] = (double)d[s]; o->hdiff[s] = (double)hd[s]; }
 }
 
@@ -487,6 +501,15 @@ void apply_charges(Oracle *o) {
     if (t < 0) continue;
     double l = o->lam[o->titr_site[t]];
     o->q[i] = o->qA[t] + l * (o->qB[t] - o->qA[t]);   // q(lambda) = (1-lambda) qA + lambda qB
+  }
+  if (o->water_buffer) {
+    // modify_water: total charge stays what it is at lambda = 0
+    long double tot = 0;
+    for (size_t t = 0; t < o->qA.size(); t++) tot += (long double)o->lam[o->titr_site[t]] * (o->qB[t] - o->qA[t]);
+    int nw = 0;
+    for (int i = 0; i < o->n; i++) nw += (o->mask[i] & o->Wbit) ? 1 : 0;
+    for (int i = 0; i < o->n; i++)
+      if (o->mask[i] & o->Wbit) o->q[i] = o->qbase[i] - (double)(tot / nw);
   }
 }
 
@@ -592,6 +615,8 @@ int orc_set_bias(void *h, double w, double s, double hbar, double k, double a, d
   return 0;
 }
 
+int orc_set_water_buffer(void *h, int enable) { ORC->water_buffer = enable ? 1 : 0; return 0; }
+
 int orc_set_mode(void *h, int dudl, int integ, int fscale) {
   ORC->dudl_mode = dudl; ORC->integ_mode = integ; ORC->fscale_mode = fscale; return 0;
 }
@@ -625,7 +650,7 @@ int orc_set_atoms(void *h, int, int n, const double *x, const double *q, const i
   for (int k = 0; k < 3; k++)
     if (o->periodic[k] && o->hi[k] - o->lo[k] < 2 * rlist) return fail(o, -6, "oracle needs box >= 2*(cut+skin)");
   o->n = n;
-  o->x.assign(x, x + 3 * (size_t)n); o->q.assign(q, q + n);
+  o->x.assign(x, x + 3 * (size_t)n); o->q.assign(q, q + n); o->qbase.assign(q, q + n);
   o->type.assign(type, type + n); o->tag.assign(tag, tag + n); o->mask.assign(mask, mask + n);
   for (int c = 0; c < 3; c++) o->spec[c].assign(n, {});
   if (nspecial && special)
@@ -652,6 +677,7 @@ int orc_set_atoms(void *h, int, int n, const double *x, const double *q, const i
   o->f.assign(3 * (size_t)n, 0); o->eatom.assign(n, 0); o->phi.assign(n, 0);
   build_list(o);
   o->have_atoms = true;
+  if (o->dudl_mode == 1 && !o->qA.empty()) apply_charges(o);   // charges follow lambda from the first pass on
   return 0;
 }
 

@@ -11,6 +11,7 @@
        bias exact|aswritten      exact derivatives (D13-D16) or cpp:123, 137-141 verbatim
        mlambda VALUE         lambda mass (cpp:96 hard-codes 20)
        lambda0 VALUE         initial lambda when no site file is given (never set in the reference)
+       buffer yes|no         modify_water() (h:58): keep the box charge constant through groupW
 
    The host side stays a LAMMPS Fix; every per-timestep loop of the reference (cpp:149-171,
    cpp:212-267) and the pair arithmetic north_star pulls into the path run in libcph_b200.so.
@@ -67,6 +68,7 @@ FixConstantPH::FixConstantPH(LAMMPS *lmp, int narg, char **arg) :
   fscale_mode = CPH_FSCALE_LAMBDA;
   bias_mode = CPH_BIAS_EXACT;
   m_lambda = 20.0;                                                                     // cpp:96
+  water_buffer = 0;
   lambda_host = 0.5;
   nsites = ntitr = 0;
   restart_n = 0;
@@ -101,6 +103,10 @@ FixConstantPH::FixConstantPH(LAMMPS *lmp, int narg, char **arg) :
     } else if (strcmp(key, "mlambda") == 0) {
       m_lambda = utils::numeric(FLERR, val, false, lmp);
       if (m_lambda <= 0.0) error->all(FLERR, "Illegal fix constant_pH mlambda value {}", m_lambda);
+    } else if (strcmp(key, "buffer") == 0) {
+      if (strcmp(val, "yes") == 0) water_buffer = 1;
+      else if (strcmp(val, "no") == 0) water_buffer = 0;
+      else error->all(FLERR, "Illegal fix constant_pH buffer value {}", val);
     } else if (strcmp(key, "lambda0") == 0) {
       lambda_host = utils::numeric(FLERR, val, false, lmp);
     } else {
@@ -249,6 +255,7 @@ void FixConstantPH::init()
   check(cph_set_fix(cph, nevery, groupHbit, groupWbit, pK, pH, T), "cph_set_fix");
   check(cph_set_bias(cph, w, s, h, k, a, b, r, m, d, m_lambda, bias_mode), "cph_set_bias");   // cpp:86-96
   check(cph_set_mode(cph, dudl_mode, integrator_mode, fscale_mode), "cph_set_mode");
+  check(cph_set_water_buffer(cph, water_buffer ? (int) group->count(igroupW) : 0), "cph_set_water_buffer");
   check(cph_set_sites(cph, nsites, site_pK, ntitr, titr_tag, titr_site, titr_qA, titr_qB), "cph_set_sites");
   if (restart_buf) {
     check(cph_unpack_restart(cph, restart_buf, restart_n), "cph_unpack_restart");
@@ -399,8 +406,10 @@ void FixConstantPH::integrate_lambda()
 
 void FixConstantPH::modify_water()
 {
-  // h:58: declared, never defined nor called in the reference (TODO at cpp:268).  Charge-neutrality
-  // buffering on the 3-atom water group is SURVEY.md §8(f1), the next row after this path.
+  // h:58: declared, never defined nor called in the reference (TODO at cpp:268).  With `buffer yes`
+  // the library moves -(1/3) sum_s lambda_s dQ_s onto each atom of the water group whenever it
+  // applies q(lambda) (cph_apply_charges inside cph_post_force), so the box charge stays constant.
+  check(cph_apply_charges(cph), "cph_apply_charges");
 }
 
 /* ---------------------------------------------------------------------- */

@@ -345,3 +345,18 @@ def test_config4_scaled_many_solutes(built):
     ng, kg = gpu.get_neighbors()
     no, ko = orc.get_neighbors()
     assert np.array_equal(ng, no) and np.array_equal(kg, ko)
+
+
+def test_water_buffer_modify_water(built):
+    """charge buffer on the 3-atom water group, CUDA path against the oracle."""
+    box = synth.config(2, scale=0.25)
+    gpu, orc = engines(box, bias=HEAVY, water_buffer=True)
+    q0 = gpu.get_q().sum()
+    lg = run_traj(gpu, box, 60)
+    lo = run_traj(orc, box, 60)
+    assert np.abs(lg - lo).max() <= 1e-8
+    close(gpu.get_q(), orc.get_q(), rtol=1e-9)
+    assert abs(gpu.get_q().sum() - q0) < 1e-10            # the box charge did not move with lambda
+    close(gpu.get_sites()["dudl"], orc.get_sites()["dudl"])
+    W = (box.mask & synth.GROUP_W_BIT) != 0
+    assert not np.allclose(gpu.get_q()[W], box.q[W])

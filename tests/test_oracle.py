@@ -179,3 +179,26 @@ def test_oracle_matches_golden_fixtures():
         assert abs(np.abs(f).sum() - case["f_abs_sum"]) <= 1e-11 * case["f_abs_sum"]
         c = o.get_counts()
         assert c["neighbors"] == case["neighbors"] and c["special_pairs"] == case["special_pairs"]
+
+
+def test_water_buffer_keeps_total_charge_and_dudl_consistent():
+    """modify_water (h:58, TODO at cpp:268): with the buffer on, the box charge is independent of
+    lambda and the analytic dU/dlambda (including the buffer term) equals the re-evaluated energy."""
+    box = synth.config(2, scale=0.2)
+    o = capi.configure(capi.Engine("orc"), box, water_buffer=True)
+    totals = []
+    for v in (0.0, 0.3, 1.0):
+        o.set_lambda(np.full(box.nsites, v)); o.apply_charges()
+        totals.append(o.get_q().sum())
+    assert max(totals) - min(totals) < 1e-12
+    W = (box.mask & synth.GROUP_W_BIT) != 0
+    assert W.sum() == 3 and not np.allclose(o.get_q()[W], box.q[W])
+    o.set_lambda(box.lambda0); o.apply_charges(); o.pair_pass(1); o.site_reduce()
+    dudl = o.get_sites()["dudl"].copy()
+    for site in range(3):
+        es = []
+        for sign in (+1, -1):
+            lam = box.lambda0.copy(); lam[site] += sign * 0.05
+            o.set_lambda(lam); o.apply_charges(); o.pair_pass(1); o.site_reduce()
+            sc = o.get_scalars(); es.append(sc["evdwl"] + sc["ecoul"])
+        assert abs((es[0] - es[1]) / 0.1 - dudl[site]) < 1e-8 * max(1.0, abs(dudl[site]))
