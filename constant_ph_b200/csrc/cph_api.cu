@@ -111,6 +111,9 @@ int cph_create(int device, cph_handle **out) {
     return cph_fail(nullptr, CPH_ERR_CUDA, "cannot create a stream on device %d", device);
   }
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->pev0); cudaEventCreate(&h->pev1);
+  cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&h->ev_flags, cudaEventDisableTiming);
+  cudaMallocHost((void **)&h->h_flags, 16 * sizeof(unsigned int));
   h->d_flags.reserve(96);
   cudaMemsetAsync(h->d_flags.p, 0, 8 * sizeof(unsigned int), h->stream);
   if (const char *e = getenv("CPH_INNER_SKIN")) h->inner_skin = std::max(0.0, atof(e));   // tuning knobs
@@ -142,6 +145,9 @@ int cph_destroy(cph_handle *h) {
   h->d_sendx.release(); h->d_recvx.release(); h->d_sendmeta.release(); h->d_recvmeta.release();
   if (h->h_pin) cudaFreeHost(h->h_pin);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->pev0); cudaEventDestroy(h->pev1);
+  cudaEventDestroy(h->ev_flags);
+  cudaStreamDestroy(h->stream2);
+  cudaFreeHost(h->h_flags);
   cudaStreamDestroy(h->stream);
   delete h;
   return CPH_OK;
@@ -507,16 +513,21 @@ int cph_post_force(cph_handle *h, int64_t ntimestep, double dt, int where, const
   // new positions + neighbor->decide()
   if (x) CPH_TRY(cph_set_x(h, where, x));
   else CPH_TRY(cph_launch_set_x(h, nullptr));
-  unsigned int fl[8];
   CPH_TRY(cph_comm_allreduce_max_u32_dev(h, h->d_flags.p, 6));   // global decision, one host sync
-  CPH_TRY(read_flags(h, fl));
+  // The decision flags travel to the host on a side stream while the main stream already
+  // refreshes the ghosts (speculatively: a rebuild redoes them, which costs nothing extra).
+  CPH_CUDA(h, cudaEventRecord(h->ev_flags, h->stream));
+  CPH_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_flags, 0));
+  CPH_CUDA(h, cudaMemcpyAsync(h->h_flags, h->d_flags.p, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream2));
+  CPH_TRY(cph_forward_ghosts(h));
+  CPH_CUDA(h, cudaStreamSynchronize(h->stream2));
+  const unsigned int *fl = h->h_flags;
   unsigned int any = fl[4];
   if (fl[5]) h->inner_valid = false;      // someone moved more than inner_skin/2 since the last prune
   float md;
   memcpy(&md, &fl[0], 4);
   h->scal_h[6] = md;
   if (any) CPH_TRY(cph_rebuild(h));
-  else CPH_TRY(cph_forward_ghosts(h));
   const bool active = (ntimestep % h->fix.nevery) == 0;                 // cpp:69
   CPH_TRY(cph_launch_pair(h, active ? 1 : 0));
   h->have_pass = true;

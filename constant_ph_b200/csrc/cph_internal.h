@@ -99,6 +99,9 @@ struct NcclApi;  // comm.cu
 struct cph_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;    // side stream: decision flags to the host while the halo runs
+  cudaEvent_t ev_flags = nullptr;
+  unsigned int *h_flags = nullptr;   // pinned
   std::string err;
   // configuration
   PairParams pp{};
