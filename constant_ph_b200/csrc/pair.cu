@@ -93,10 +93,21 @@ __device__ __forceinline__ double fast_exp_neg(double x, const double *s_exp2) {
   return __hiloint2double(__double2hiint(v) + ((ni >> 5) << 20), __double2loint(v));
 }
 
-// one 32-byte request per lane (LDG.E.256 on sm_100a)
+// the fp64 record {x,y,z,q} of one atom.  CPH_LD256=1: one 32-byte request per lane
+// (LDG.E.ENL2.256 on sm_100a; measured to be served from L2, L1 hit rate 27 %);
+// CPH_LD256=0: two 16-byte read-only loads that allocate in L1.
+#ifndef CPH_LD256
+#define CPH_LD256 1
+#endif
 __device__ __forceinline__ double4 ld256(const double4 *p) {
   double4 v;
+#if CPH_LD256
   asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+#else
+  const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
+  const double2 b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+  v = make_double4(a.x, a.y, b.x, b.y);
+#endif
   return v;
 }
 
