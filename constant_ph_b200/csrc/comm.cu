@@ -26,6 +26,7 @@ struct Nccl {
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -39,10 +40,10 @@ Nccl &nccl() {
   if (!n.lib) return n;
 #define BIND(name) *(void **)(&n.name) = dlsym(n.lib, "nccl" #name)
   BIND(GetUniqueId); BIND(CommInitRank); BIND(CommDestroy); BIND(AllReduce); BIND(Send); BIND(Recv);
-  BIND(GroupStart); BIND(GroupEnd); BIND(GetErrorString);
+  BIND(GroupStart); BIND(GroupEnd); BIND(GetErrorString); BIND(AllGather);
 #undef BIND
   n.ok = n.GetUniqueId && n.CommInitRank && n.CommDestroy && n.AllReduce && n.Send && n.Recv && n.GroupStart &&
-         n.GroupEnd && n.GetErrorString;
+         n.GroupEnd && n.GetErrorString && n.AllGather;
   return n;
 }
 
@@ -141,5 +142,10 @@ int cph_comm_exchange_counts(cph_handle *h, const int *active, const int *peer, 
   CPH_NCCL(h, n.GroupEnd());
   CPH_CUDA(h, cudaMemcpyAsync(recv_count, d + 27, 27 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CPH_OK;
+}
+
+int cph_comm_allgather(cph_handle *h, const void *sendbuf, void *recvbuf, size_t bytes_per_rank) {
+  CPH_NCCL(h, nccl().AllGather(sendbuf, recvbuf, bytes_per_rank, ncclUint8, (ncclComm_t)h->nccl_comm, h->stream));
   return CPH_OK;
 }

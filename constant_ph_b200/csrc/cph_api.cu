@@ -118,6 +118,7 @@ int cph_create(int device, cph_handle **out) {
   cudaMemsetAsync(h->d_flags.p, 0, 8 * sizeof(unsigned int), h->stream);
   if (const char *e = getenv("CPH_INNER_SKIN")) h->inner_skin = std::max(0.0, atof(e));   // tuning knobs
   if (const char *e = getenv("CPH_PAIR_FUSED")) h->fused_pair = atoi(e) != 0;
+  if (const char *e = getenv("CPH_HALO")) h->peer_halo_wanted = strcmp(e, "nccl") != 0;   // "nccl" forces ncclSend/Recv
   int rc = size_sites(h);
   if (rc) { g_create_error = h->err; delete h; return rc; }
   *out = h;
@@ -128,6 +129,7 @@ int cph_destroy(cph_handle *h) {
   if (!h) return CPH_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  cph_halo_close(h);
   cph_comm_destroy(h);
   cph_pair_forget(h);
   DevBuf<double> *db[] = {&h->d_pK, &h->d_lam, &h->d_vlam, &h->d_alam, &h->d_flam, &h->d_fs, &h->d_dfs, &h->d_Us,
@@ -141,7 +143,7 @@ int cph_destroy(cph_handle *h) {
                        &h->d_wtag, &h->d_wlocal};
   for (auto *b : ib) b->release();
   h->d_xb.release(); h->d_molecule.release(); h->d_coef.release(); h->d_coef4.release(); h->d_cut2.release(); h->d_type_has_lj.release(); h->d_xt.release(); h->d_xq.release(); h->d_xq2.release(); h->d_keys.release(); h->d_keys2.release();
-  h->d_xinner.release(); h->d_cubtmp.release(); h->d_flags.release(); h->d_scr_stats.release();
+  h->d_xinner.release(); h->d_cubtmp.release(); h->d_flags.release(); h->d_scr_stats.release(); h->d_ipc_stage.release();
   h->d_sendx.release(); h->d_recvx.release(); h->d_sendmeta.release(); h->d_recvmeta.release();
   if (h->h_pin) cudaFreeHost(h->h_pin);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->pev0); cudaEventDestroy(h->pev1);
@@ -513,13 +515,16 @@ int cph_post_force(cph_handle *h, int64_t ntimestep, double dt, int where, const
   // new positions + neighbor->decide()
   if (x) CPH_TRY(cph_set_x(h, where, x));
   else CPH_TRY(cph_launch_set_x(h, nullptr));
+  // Halo first (speculatively: a rebuild redoes it, which costs nothing extra).  In peer mode the
+  // pack kernel has stored this rank's copies into the neighbours' buffers; the all-reduce of the
+  // decision flags that follows is also the barrier after which every rank may read its own buffer.
+  CPH_TRY(cph_halo_send(h));
   CPH_TRY(cph_comm_allreduce_max_u32_dev(h, h->d_flags.p, 6));   // global decision, one host sync
-  // The decision flags travel to the host on a side stream while the main stream already
-  // refreshes the ghosts (speculatively: a rebuild redoes them, which costs nothing extra).
+  // the flags travel to the host on a side stream while the main stream builds the ghost atoms
   CPH_CUDA(h, cudaEventRecord(h->ev_flags, h->stream));
   CPH_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_flags, 0));
   CPH_CUDA(h, cudaMemcpyAsync(h->h_flags, h->d_flags.p, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream2));
-  CPH_TRY(cph_forward_ghosts(h));
+  CPH_TRY(cph_halo_finish(h));
   CPH_CUDA(h, cudaStreamSynchronize(h->stream2));
   const unsigned int *fl = h->h_flags;
   unsigned int any = fl[4];

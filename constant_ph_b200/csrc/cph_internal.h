@@ -163,7 +163,16 @@ struct cph_handle {
   int rec_start[28]{}, send_count[27]{}, send_off[27]{}, recv_count[27]{}, recv_off[27]{};
   DevBuf<int> d_rec_src, d_rec_dir;
   std::vector<int> peer_rank, peer_soff, peer_scnt, peer_roff, peer_rcnt;   // one message per neighbour rank
-  DevBuf<double4> d_sendx, d_recvx;
+  DevBuf<double4> d_sendx, d_recvx;   // d_recvx holds TWO halves of recv_half records (alternating per step)
+  size_t recv_half = 0;
+  int halo_parity = 0;
+  // peer-memory halo: neighbours' receive buffers mapped through CUDA IPC; the pack kernel stores
+  // {x,y,z,q} straight into them over NVLink (no ncclSend/ncclRecv on the per-step path)
+  bool peer_halo = false, peer_halo_wanted = true;
+  std::vector<void *> peer_base;                 // [nranks] mapped base of every neighbour's d_recvx
+  std::vector<unsigned char> peer_handle_cache;  // [nranks * 64] handle each mapping was opened from
+  std::vector<int> peer_table;                   // [nranks * 28] recv_off[27] + recv_half of every rank
+  DevBuf<unsigned char> d_ipc_stage;
   DevBuf<int4> d_sendmeta, d_recvmeta;
   DevBuf<double> d_f, d_evdwl, d_phi, d_eatom;  // [3*nlocal], [nlocal]...
   DevBuf<int> d_hlist;      // owned atoms in the hydrogen group
@@ -212,7 +221,10 @@ struct cph_handle {
 // ---- kernels (launchers) ----------------------------------------------------------------
 // neigh.cu
 int cph_rebuild(cph_handle *h);                 // sort, ghosts, cells, list, site map
-int cph_forward_ghosts(cph_handle *h);          // refresh ghost x and q
+int cph_forward_ghosts(cph_handle *h);          // refresh ghost x and q (send + barrier if needed + finish)
+int cph_halo_send(cph_handle *h);               // pack + ship the copies (peer stores over NVLink, or NCCL p2p)
+int cph_halo_finish(cph_handle *h);             // ghost atoms from self images + received copies
+void cph_halo_close(cph_handle *h);
 int cph_neighbors_to_host(cph_handle *h, int *numneigh, int64_t *keys, int64_t cap);
 // pair.cu
 int cph_launch_pair(cph_handle *h, int eflag);
@@ -237,6 +249,7 @@ int cph_comm_allreduce_max_u32(cph_handle *h, unsigned int *buf, int n);
 int cph_comm_allreduce_max_u32_dev(cph_handle *h, unsigned int *dbuf, int n);   // in place, on the stream
 int cph_comm_exchange(cph_handle *h, int npeers, const int *peers, const void *const *sendbuf, const size_t *sendbytes,
                       void *const *recvbuf, const size_t *recvbytes);
+int cph_comm_allgather(cph_handle *h, const void *sendbuf, void *recvbuf, size_t bytes_per_rank);
 int cph_comm_exchange_counts(cph_handle *h, const int *active, const int *peer, const int *from, const int *send_count,
                              int *recv_count);
 void cph_comm_destroy(cph_handle *h);

@@ -166,6 +166,28 @@ __global__ void halo_pack_kernel(int nrec, const int *__restrict__ rsrc, const i
   if (sendmeta) sendmeta[o] = make_int4(type[s] | (gd.imgcode[d] << 8), tag[s], mask[s], mol ? mol[s] : 0);
 }
 
+struct PeerTab {
+  double4 *dst[27];      // dst[d][r - start[d]]: where record r of direction d lands in the neighbour's buffer
+};
+
+// K6 fused pack + NVLink store: every copy that belongs to another rank is shifted across the
+// periodic boundary and stored straight into that rank's receive buffer (mapped peer memory).
+__global__ void halo_pack_peer_kernel(int nrec, const int *__restrict__ rsrc, const int *__restrict__ rdir,
+                                      DirTable tab, GhostDirs gd, const double4 *__restrict__ xq, PeerTab pt) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < nrec) {
+    const int d = rdir[r];
+    if (gd.active[d] == 2) {
+      double4 p = xq[rsrc[r]];
+      p.x += gd.shift[d][0];
+      p.y += gd.shift[d][1];
+      p.z += gd.shift[d][2];
+      pt.dst[d][r - tab.start[d]] = p;
+    }
+  }
+  __threadfence_system();   // the stores must have landed before this rank joins the next collective
+}
+
 // unsorted ghost candidates: local self images first (direction order), then received copies
 __global__ void ghost_candidates_kernel(int nrec, const int *__restrict__ rsrc, const int *__restrict__ rdir,
                                         DirTable tab, GhostDirs gd, int nloc, int nrecv,
@@ -487,7 +509,7 @@ static int halo_exchange(cph_handle *h, const GhostDirs &, bool with_meta) {
       }
     }
     if (h->peer_rcnt[k]) {
-      peers[np] = h->peer_rank[k]; rb[np] = h->d_recvx.p + h->peer_roff[k]; rn[np] = (size_t)h->peer_rcnt[k] * sizeof(double4);
+      peers[np] = h->peer_rank[k]; rb[np] = h->d_recvx.p + (size_t)h->halo_parity * h->recv_half + h->peer_roff[k]; rn[np] = (size_t)h->peer_rcnt[k] * sizeof(double4);
       sb[np] = nullptr; sn[np] = 0; np++;
       if (with_meta) {
         peers[np] = h->peer_rank[k]; rb[np] = h->d_recvmeta.p + h->peer_roff[k]; rn[np] = (size_t)h->peer_rcnt[k] * sizeof(int4);
@@ -506,26 +528,118 @@ static DirTable send_table(const cph_handle *h) {
   return t;
 }
 
-// comm->forward_comm(): refresh ghost x and q (every step)
-int cph_forward_ghosts(cph_handle *h) {
-  if (h->nghost == 0 && h->nsend == 0) return 0;
+// comm->forward_comm(), first half: ship the copies that belong to other ranks.  Peer mode: one
+// kernel packs AND stores them into the neighbours' receive buffers over NVLink; the caller's
+// next collective (the decision-flag all-reduce) is the barrier that makes them visible.
+// NCCL mode: pack + one ncclSend/ncclRecv per neighbour rank.
+int cph_halo_send(cph_handle *h) {
+  if (h->nranks == 1) return 0;
   ProfScope ps(h, 5);
   GhostDirs gd;
   make_ghost_dirs(h, gd);
   cudaStream_t st = h->stream;
-  if (h->nranks > 1) {
-    if (h->nsend)
+  h->halo_parity ^= 1;     // every rank toggles in lockstep: writers never touch the half being read
+  if (h->peer_halo) {
+    if (h->nsend) {
+      PeerTab pt;
+      for (int d = 0; d < 27; d++) {
+        pt.dst[d] = nullptr;
+        if (gd.active[d] != 2) continue;
+        const int p = gd.peer[d];
+        const int *row = h->peer_table.data() + (size_t)p * 28;
+        pt.dst[d] = (double4 *)h->peer_base[p] + (size_t)h->halo_parity * (size_t)row[27] + row[d];
+      }
+      h->nlaunch++;
+      halo_pack_peer_kernel<<<nblk(h->nrec), TPB, 0, st>>>(h->nrec, h->d_rec_src.p, h->d_rec_dir.p, send_table(h), gd,
+                                                          h->d_xq.p, pt);
+    }
+  } else {
+    if (h->nsend) {
+      h->nlaunch++;
       halo_pack_kernel<<<nblk(h->nrec), TPB, 0, st>>>(h->nrec, h->d_rec_src.p, h->d_rec_dir.p, send_table(h), gd,
                                                      h->d_xq.p, nullptr, nullptr, nullptr, nullptr, h->d_sendx.p,
                                                      nullptr);
+    }
     CPH_TRY(halo_exchange(h, gd, false));
   }
-  if (h->nghost)
-    h->nlaunch += 1 + (h->nranks > 1 && h->nsend ? 1 : 0);
-    ghost_copy_kernel<<<nblk(h->nghost), TPB, 0, st>>>(h->nghost, h->nlocal, h->d_ghost_src.p, h->d_ghost_code.p, gd,
-                                                      h->d_recvx.p, nullptr, h->d_xq.p, nullptr, nullptr, nullptr,
-                                                      nullptr, 0);
   CPH_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+// second half: self images and received copies -> ghost atoms
+int cph_halo_finish(cph_handle *h) {
+  if (h->nghost == 0) return 0;
+  ProfScope ps(h, 5);
+  GhostDirs gd;
+  make_ghost_dirs(h, gd);
+  h->nlaunch++;
+  ghost_copy_kernel<<<nblk(h->nghost), TPB, 0, h->stream>>>(h->nghost, h->nlocal, h->d_ghost_src.p, h->d_ghost_code.p, gd,
+                                                           h->d_recvx.p + (size_t)h->halo_parity * h->recv_half, nullptr,
+                                                           h->d_xq.p, nullptr, nullptr, nullptr, nullptr, 0);
+  CPH_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+int cph_forward_ghosts(cph_handle *h) {
+  CPH_TRY(cph_halo_send(h));
+  if (h->nranks > 1 && h->peer_halo) {
+    // stand-alone call: a (tiny) collective orders the peer stores before the reads
+    CPH_TRY(cph_comm_allreduce_max_u32_dev(h, h->d_flags.p + 8, 1));
+  }
+  return cph_halo_finish(h);
+}
+
+void cph_halo_close(cph_handle *h) {
+  for (size_t p = 0; p < h->peer_base.size(); p++)
+    if (h->peer_base[p]) cudaIpcCloseMemHandle(h->peer_base[p]);
+  h->peer_base.clear();
+  h->peer_handle_cache.clear();
+  h->peer_halo = false;
+}
+
+// Map the neighbours' receive buffers (CUDA IPC).  Called at every list build: handles and
+// layouts are all-gathered, mappings are reopened only when a neighbour's buffer moved.
+static int halo_map_peers(cph_handle *h, const GhostDirs &gd) {
+  const int P = h->nranks;
+  h->peer_halo = false;
+  if (P == 1 || !h->peer_halo_wanted) return 0;
+  const size_t rec = 64 + 28 * sizeof(int);   // IPC handle + recv_off[27] + recv_half
+  CPH_CUDA(h, h->d_ipc_stage.reserve(rec * (P + 1)));
+  std::vector<unsigned char> mine(rec, 0), all(rec * P, 0);
+  cudaIpcMemHandle_t hd;
+  unsigned int ok = cudaIpcGetMemHandle(&hd, h->d_recvx.p) == cudaSuccess ? 1u : 0u;
+  if (!ok) cudaGetLastError();
+  memcpy(mine.data(), &hd, 64);
+  int tab[28];
+  for (int d = 0; d < 27; d++) tab[d] = h->recv_off[d];
+  tab[27] = (int)h->recv_half;
+  memcpy(mine.data() + 64, tab, sizeof(tab));
+  CPH_CUDA(h, cudaMemcpyAsync(h->d_ipc_stage.p, mine.data(), rec, cudaMemcpyHostToDevice, h->stream));
+  CPH_TRY(cph_comm_allgather(h, h->d_ipc_stage.p, h->d_ipc_stage.p + rec, rec));
+  CPH_CUDA(h, cudaMemcpyAsync(all.data(), h->d_ipc_stage.p + rec, rec * P, cudaMemcpyDeviceToHost, h->stream));
+  CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->peer_base.resize(P, nullptr);
+  h->peer_handle_cache.resize((size_t)P * 64, 0);
+  h->peer_table.assign((size_t)P * 28, 0);
+  for (int p = 0; p < P; p++) memcpy(h->peer_table.data() + (size_t)p * 28, all.data() + rec * p + 64, 28 * sizeof(int));
+  for (int d = 0; d < 27 && ok; d++) {
+    if (gd.active[d] != 2) continue;
+    const int p = gd.peer[d];
+    if (p == h->rank) continue;
+    const unsigned char *hp = all.data() + rec * p;
+    if (h->peer_base[p] && memcmp(hp, h->peer_handle_cache.data() + (size_t)p * 64, 64) == 0) continue;
+    if (h->peer_base[p]) { cudaIpcCloseMemHandle(h->peer_base[p]); h->peer_base[p] = nullptr; }
+    cudaIpcMemHandle_t ph;
+    memcpy(&ph, hp, 64);
+    void *ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, ph, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+    h->peer_base[p] = ptr;
+    memcpy(h->peer_handle_cache.data() + (size_t)p * 64, hp, 64);
+  }
+  // every rank must agree: one failure anywhere falls back to NCCL everywhere
+  unsigned int bad = ok ? 0u : 1u;
+  CPH_TRY(cph_comm_allreduce_max_u32(h, &bad, 1));
+  h->peer_halo = bad == 0;
   return 0;
 }
 
@@ -715,13 +829,33 @@ int cph_rebuild(cph_handle *h) {
     h->nsend = nsend;
     CPH_CUDA(h, h->d_sendx.reserve(nsend + 1));
     CPH_CUDA(h, h->d_sendmeta.reserve(nsend + 1));
-    CPH_CUDA(h, h->d_recvx.reserve(nrecv + 1));
+    {
+      // two halves (alternating per step) so that a neighbour's next write never lands in the
+      // half this rank is still reading.  The buffer is exported through CUDA IPC, so it may only
+      // be reallocated after EVERY rank has closed its mappings: agree on "someone must grow",
+      // close, synchronise, then grow (with head room, so this is rare).
+      unsigned int grow = ((size_t)nrecv + 1 > h->recv_half) ? 1u : 0u;
+      unsigned int any_grow = grow;
+      CPH_TRY(cph_comm_allreduce_max_u32(h, &any_grow, 1));
+      if (any_grow) {
+        cph_halo_close(h);
+        unsigned int closed = 1;
+        CPH_TRY(cph_comm_allreduce_max_u32(h, &closed, 1));   // barrier: nobody maps anybody any more
+        if (grow) {
+          const size_t half = (size_t)nrecv + 1;
+          h->recv_half = half + half / 4 + 256;
+          h->d_recvx.release();
+          CPH_CUDA(h, h->d_recvx.reserve_exact(2 * h->recv_half));
+        }
+      }
+    }
     CPH_CUDA(h, h->d_recvmeta.reserve(nrecv + 1));
     if (nsend)
       halo_pack_kernel<<<nblk(nrec), TPB, 0, st>>>(nrec, h->d_rec_src.p, h->d_rec_dir.p, send_table(h), gd, h->d_xq.p,
                                                   h->d_type.p, h->d_tag.p, h->d_mask.p,
                                                   h->have_mol ? h->d_mol.p : nullptr, h->d_sendx.p, h->d_sendmeta.p);
     CPH_TRY(halo_exchange(h, gd, true));
+    CPH_TRY(halo_map_peers(h, gd));
   }
   h->nrecv = nrecv;
   const int nghost = nloc + nrecv;
@@ -731,12 +865,15 @@ int cph_rebuild(cph_handle *h) {
   if (nghost) {
     const int nthreads = std::max(nrec, nrecv);
     ghost_candidates_kernel<<<nblk(nthreads), TPB, 0, st>>>(nrec, h->d_rec_src.p, h->d_rec_dir.p, ltab, gd, nloc, nrecv,
-                                                           h->d_xq.p, h->d_tag.p, h->d_recvx.p, h->d_recvmeta.p, g,
+                                                           h->d_xq.p, h->d_tag.p,
+                                                           h->d_recvx.p + (size_t)h->halo_parity * h->recv_half,
+                                                           h->d_recvmeta.p, g,
                                                            h->d_scr_src.p, h->d_scr_code.p, h->d_keys.p, h->d_vals.p);
     CPH_TRY(sort_pairs(h, nghost, h->d_keys, h->d_keys2, h->d_vals, h->d_vals2, 64));
     gather_kernel<int><<<nblk(nghost), TPB, 0, st>>>(nghost, h->d_vals2.p, h->d_scr_src.p, h->d_ghost_src.p);
     gather_kernel<int><<<nblk(nghost), TPB, 0, st>>>(nghost, h->d_vals2.p, h->d_scr_code.p, h->d_ghost_code.p);
-    ghost_copy_kernel<<<nblk(nghost), TPB, 0, st>>>(nghost, n, h->d_ghost_src.p, h->d_ghost_code.p, gd, h->d_recvx.p,
+    ghost_copy_kernel<<<nblk(nghost), TPB, 0, st>>>(nghost, n, h->d_ghost_src.p, h->d_ghost_code.p, gd,
+                                                    h->d_recvx.p + (size_t)h->halo_parity * h->recv_half,
                                                     h->d_recvmeta.p, h->d_xq.p, h->d_type.p, h->d_tag.p, h->d_mask.p,
                                                     h->have_mol ? h->d_mol.p : nullptr, 1);
     after_sort_kernel<<<nblk(nghost), TPB, 0, st>>>(nghost, h->d_keys2.p, nullptr, nullptr, nullptr, nullptr,

@@ -537,10 +537,8 @@ prune_kernel(int nlocal, const float4 *__restrict__ xt, const int *__restrict__ 
 #ifndef CPH_EVAL_MINBLOCKS
 #define CPH_EVAL_MINBLOCKS 3
 #endif
-#ifndef CPH_EAPW
-#define CPH_EAPW 8
-#endif
-constexpr int EAPW = CPH_EAPW;   // atoms per warp in the evaluation kernel
+// atoms per warp in the evaluation kernel: 8 amortises the per-CTA table load best at 1M atoms,
+// 2 gives the finer work granularity that wins below ~300k atoms per rank (both measured)
 
 // K2b: one warp per atom over the pruned inner row.  Every lane evaluates one pair per
 // iteration with the next entry already loaded; no queue, no ballots: all issue slots go to the
@@ -561,7 +559,7 @@ constexpr int ETPB = EWARPS * 32;
 #define CPH_EVAL_BOUNDS __launch_bounds__(ETPB, CPH_EVAL_MINBLOCKS)
 #endif
 
-template <int STYLE, int EFLAG, int UNI>
+template <int STYLE, int EFLAG, int UNI, int EAPW>
 __global__ void CPH_EVAL_BOUNDS
 pair_eval_kernel(int nlocal, const double4 *__restrict__ xq, const int *__restrict__ type,
                  const int *__restrict__ neigh, const int *__restrict__ numspec, const int *__restrict__ neigh2,
@@ -783,10 +781,13 @@ int cph_launch_pair(cph_handle *h, int eflag) {
   if (!h->inner_valid) CPH_TRY(cph_launch_prune(h));
   ProfScope ps(h, 0);
   const int nt1 = h->pp.ntypes + 1;
-  const int blocks = (n + EWARPS * EAPW - 1) / (EWARPS * EAPW);
+  const bool small = n < 300000;
+  const int eapw = small ? 2 : 8;
+  const int blocks = (n + EWARPS * eapw - 1) / (EWARPS * eapw);
   h->nlaunch++;
-#define LAUNCH(S, E, U)                                                                                             \
-  pair_eval_kernel<S, E, U><<<blocks, ETPB, 0, h->stream>>>(n, h->d_xq.p, h->d_type.p, h->d_neigh.p, h->d_numspec.p, \
+#define LAUNCH(S, E, U) do { if (small) LAUNCH_A(S, E, U, 2); else LAUNCH_A(S, E, U, 8); } while (0)
+#define LAUNCH_A(S, E, U, A)                                                                                        \
+  pair_eval_kernel<S, E, U, A><<<blocks, ETPB, 0, h->stream>>>(n, h->d_xq.p, h->d_type.p, h->d_neigh.p, h->d_numspec.p, \
                                                            h->d_neigh2.p, h->d_numneigh2.p, h->rowcap, h->nall, nt1, \
                                                            h->d_coef4.p, h->d_cut2.p, h->d_type_has_lj.p,          \
                                                            h->d_f.p, h->d_evdwl.p, h->d_phi.p, h->d_eatom.p,       \
@@ -799,6 +800,7 @@ int cph_launch_pair(cph_handle *h, int eflag) {
   }
 #undef LAUNCH_E
 #undef LAUNCH
+#undef LAUNCH_A
   CPH_CUDA(h, cudaGetLastError());
   return 0;
 }
