@@ -161,6 +161,9 @@ class Engine:
     def set_mode(self, dudl=DUDL_CHARGE, integrator=INTEGRATE_REFERENCE, fscale=FSCALE_LAMBDA):
         self._call("set_mode", C.c_int(dudl), C.c_int(integrator), C.c_int(fscale))
 
+    def set_coordinate(self, theta=True):
+        self._call("set_coordinate", C.c_int(1 if theta else 0))
+
     def set_water_buffer(self, enable=True):
         self._call("set_water_buffer", C.c_int(1 if enable else 0))
 
@@ -359,7 +362,7 @@ class Engine:
 def configure(eng, box, nevery=1, dudl=DUDL_CHARGE, integrator=INTEGRATE_REFERENCE,
               fscale=FSCALE_LAMBDA, bias_mode=BIAS_EXACT, implicit_site=False, ftm2v=None,
               sublo=None, subhi=None, procgrid=(1, 1, 1), myloc=(0, 0, 0), owned=None, bias=None,
-              water_buffer=False):
+              water_buffer=False, theta=False):
     """Push a synth.Box into an engine: the calls FixConstantPH's constructor/init/setup make.
 
     implicit_site=True reproduces the reference's single global lambda over the hydrogen
@@ -377,6 +380,8 @@ def configure(eng, box, nevery=1, dudl=DUDL_CHARGE, integrator=INTEGRATE_REFEREN
     eng.set_mode(dudl, integrator, fscale)
     if water_buffer:
         eng.set_water_buffer(True)
+    if theta:
+        eng.set_coordinate(True)
     if implicit_site:
         eng.set_sites(0, None, None, None, None, None)
         eng.set_lambda(box.lambda0[:1], box.v0[:1])

@@ -51,7 +51,8 @@ int upload(cph_handle *h, DevBuf<T> &buf, const T *src, size_t n, int where = CP
 
 int size_sites(cph_handle *h) {
   size_t S = (size_t)h->S;
-  DevBuf<double> *bufs[] = {&h->d_lam, &h->d_vlam, &h->d_alam, &h->d_flam, &h->d_fs, &h->d_dfs, &h->d_Us, &h->d_dUs};
+  DevBuf<double> *bufs[] = {&h->d_lam, &h->d_vlam, &h->d_alam, &h->d_flam, &h->d_fs, &h->d_dfs, &h->d_Us, &h->d_dUs,
+                            &h->d_theta};
   for (auto *b : bufs) {
     CPH_CUDA(h, b->reserve(S + 1));
     CPH_CUDA(h, cudaMemsetAsync(b->p, 0, (S + 1) * sizeof(double), h->stream));
@@ -60,8 +61,9 @@ int size_sites(cph_handle *h) {
   CPH_CUDA(h, cudaMemsetAsync(h->d_red.p, 0, (4 + 2 * S + 8) * sizeof(double), h->stream));
   CPH_CUDA(h, h->d_scal.reserve(16));
   CPH_CUDA(h, cudaMemsetAsync(h->d_scal.p, 0, 16 * sizeof(double), h->stream));
-  std::vector<double> half(S, 0.5);
+  std::vector<double> half(S, 0.5), quarter_pi(S, 0.78539816339744830962);   // lambda = 1/2 <=> theta = pi/4
   CPH_CUDA(h, cudaMemcpyAsync(h->d_lam.p, half.data(), S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CPH_CUDA(h, cudaMemcpyAsync(h->d_theta.p, quarter_pi.data(), S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CPH_CUDA(h, cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -133,7 +135,7 @@ int cph_destroy(cph_handle *h) {
   cph_comm_destroy(h);
   cph_pair_forget(h);
   DevBuf<double> *db[] = {&h->d_pK, &h->d_lam, &h->d_vlam, &h->d_alam, &h->d_flam, &h->d_fs, &h->d_dfs, &h->d_Us,
-                          &h->d_dUs, &h->d_red, &h->d_titr_qA, &h->d_titr_dq, &h->d_scal, &h->d_part, &h->d_xbuild,
+                          &h->d_dUs, &h->d_theta, &h->d_red, &h->d_titr_qA, &h->d_titr_dq, &h->d_scal, &h->d_part, &h->d_xbuild,
                           &h->d_f, &h->d_evdwl, &h->d_phi, &h->d_eatom, &h->d_stage, &h->d_wq, &h->d_dQ};
   for (auto *b : db) b->release();
   DevBuf<int> *ib[] = {&h->d_titr_tag_sorted, &h->d_titr_entry_of_sorted, &h->d_titr_site, &h->d_titr_local, &h->d_type,
@@ -279,6 +281,12 @@ int cph_set_mode(cph_handle *h, int dudl_mode, int integrator_mode, int fscale_m
   return CPH_OK;
 }
 
+int cph_set_coordinate(cph_handle *h, int coordinate) {
+  if (coordinate != CPH_COORD_LAMBDA && coordinate != CPH_COORD_THETA) return cph_fail(h, CPH_ERR_ARG, "bad coordinate");
+  h->coord_theta = coordinate == CPH_COORD_THETA;
+  return CPH_OK;
+}
+
 int cph_set_water_buffer(cph_handle *h, int enable) {
   if (enable < 0) return cph_fail(h, CPH_ERR_ARG, "water buffer: negative atom count");
   // `enable` is the number of atoms in the water group (the fix insists on 3, cpp:44-45); 1 is read as 3
@@ -342,6 +350,12 @@ int cph_set_lambda(cph_handle *h, const double *lambda, const double *v_lambda) 
   cudaSetDevice(h->device);
   size_t b = (size_t)h->S * sizeof(double);
   if (lambda) CPH_CUDA(h, cudaMemcpyAsync(h->d_lam.p, lambda, b, cudaMemcpyHostToDevice, h->stream));
+  std::vector<double> th;
+  if (lambda) {   // theta = asin(sqrt(lambda)) on [0, pi/2]; kept in step with lambda in either mode
+    th.resize(h->S);
+    for (int s = 0; s < h->S; s++) th[s] = std::asin(std::sqrt(std::min(1.0, std::max(0.0, lambda[s]))));
+    CPH_CUDA(h, cudaMemcpyAsync(h->d_theta.p, th.data(), b, cudaMemcpyHostToDevice, h->stream));
+  }
   if (v_lambda) CPH_CUDA(h, cudaMemcpyAsync(h->d_vlam.p, v_lambda, b, cudaMemcpyHostToDevice, h->stream));
   CPH_CUDA(h, cudaStreamSynchronize(h->stream));
   if (h->have_atoms && h->fix.dudl_mode == CPH_DUDL_CHARGE) {
@@ -668,11 +682,12 @@ int cph_pack_restart(cph_handle *h, double *buf) {
   cudaSetDevice(h->device);
   const int S = h->S;
   std::vector<double> l(S), v(S), a(S);
-  CPH_CUDA(h, cudaMemcpyAsync(l.data(), h->d_lam.p, S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  // version 1: the coordinate is lambda; version 2: the coordinate is theta (lambda = sin^2 theta)
+  CPH_CUDA(h, cudaMemcpyAsync(l.data(), h->coord_theta ? h->d_theta.p : h->d_lam.p, S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CPH_CUDA(h, cudaMemcpyAsync(v.data(), h->d_vlam.p, S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CPH_CUDA(h, cudaMemcpyAsync(a.data(), h->d_alam.p, S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CPH_CUDA(h, cudaStreamSynchronize(h->stream));
-  buf[0] = 1.0; buf[1] = S;
+  buf[0] = h->coord_theta ? 2.0 : 1.0; buf[1] = S;
   for (int s = 0; s < S; s++) { buf[2 + 3 * s] = l[s]; buf[3 + 3 * s] = v[s]; buf[4 + 3 * s] = a[s]; }
   return CPH_OK;
 }
@@ -682,8 +697,17 @@ int cph_unpack_restart(cph_handle *h, const double *buf, int nd) {
   const int S = h->S;
   if (!buf || nd < 2 || (int)buf[1] != S || nd != 2 + 3 * S)
     return cph_fail(h, CPH_ERR_ARG, "restart record does not match the site table (%d sites)", S);
-  std::vector<double> l(S), v(S), a(S);
+  if ((buf[0] == 2.0) != h->coord_theta)
+    return cph_fail(h, CPH_ERR_ARG, "restart record was written with the other lambda coordinate");
+  std::vector<double> l(S), v(S), a(S), th(S);
   for (int s = 0; s < S; s++) { l[s] = buf[2 + 3 * s]; v[s] = buf[3 + 3 * s]; a[s] = buf[4 + 3 * s]; }
+  if (h->coord_theta) {
+    th = l;
+    for (int s = 0; s < S; s++) { const double sn = std::sin(th[s]); l[s] = sn * sn; }
+  } else {
+    for (int s = 0; s < S; s++) th[s] = std::asin(std::sqrt(std::min(1.0, std::max(0.0, l[s]))));
+  }
+  CPH_CUDA(h, cudaMemcpyAsync(h->d_theta.p, th.data(), S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CPH_CUDA(h, cudaMemcpyAsync(h->d_lam.p, l.data(), S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CPH_CUDA(h, cudaMemcpyAsync(h->d_vlam.p, v.data(), S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CPH_CUDA(h, cudaMemcpyAsync(h->d_alam.p, a.data(), S * sizeof(double), cudaMemcpyHostToDevice, h->stream));

@@ -147,18 +147,25 @@ __device__ __forceinline__ BiasOut bias_terms(const BiasParams &bp, double lambd
 // phase 2: VV force evaluation (a <- F/m)           phase 3: VV second kick + H_lambda
 __global__ void __launch_bounds__(TPB)
 integrate_kernel(int S, double dt, int phase, BiasParams bp, FixParams fx, const double *__restrict__ pK,
-                 const double *__restrict__ red, double *lam, double *vlam, double *alam, double *flam, double *fs,
-                 double *dfs, double *Us, double *dUs, double *partials) {
+                 const double *__restrict__ red, double *lam, double *theta, double *vlam, double *alam, double *flam,
+                 double *fs, double *dfs, double *Us, double *dUs, double *partials) {
+  // theta != NULL: the dynamical coordinate is theta with lambda = sin^2(theta) (north_star's lambda/theta
+  // variables; absent from the reference, which integrates lambda itself and confines it with U4/U5);
+  // velocity, acceleration and mass then refer to theta and F_theta = F_lambda * sin(2 theta).
   double v[3] = {0, 0, 0};   // sum of site terms of H_lambda, sum lambda*(HB_s-HA_s), kinetic
   for (int s = blockIdx.x * TPB + threadIdx.x; s < S; s += gridDim.x * TPB) {
-    double lambda = lam[s], vel = vlam[s], acc = alam[s];
+    double cq = theta ? theta[s] : lam[s];
+    double vel = vlam[s], acc = alam[s];
     if (phase == 1) {
       vel += 0.5 * acc * dt;
-      lambda += vel * dt;
-      lam[s] = lambda;
+      cq += vel * dt;
+      if (theta) { theta[s] = cq; const double sn = sin(cq); lam[s] = sn * sn; }
+      else lam[s] = cq;
       vlam[s] = vel;
       continue;
     }
+    double lambda = cq, chain = 1.0;
+    if (theta) { const double sn = sin(cq); lambda = sn * sn; chain = sin(2.0 * cq); }
     if (phase == 3) vel += 0.5 * acc * dt;
     BiasOut b = bias_terms(bp, lambda);
     const double pk = fx.implicit_site ? fx.pK : pK[s];
@@ -166,17 +173,18 @@ integrate_kernel(int S, double dt, int phase, BiasParams bp, FixParams fx, const
     const double dE = (fx.dudl_mode == CPH_DUDL_REFERENCE) ? hd : red[4 + s];
     const double ph = fx.boltz * fx.T * log(10.0) * (pk - fx.pH);
     const double f_lambda = -(dE + b.df * ph + b.dU);                 // cpp:111
-    const double a_lambda = f_lambda / bp.m_lambda * fx.ftm2v;        // cpp:112 (+ SURVEY D9)
+    const double a_lambda = f_lambda * chain / bp.m_lambda * fx.ftm2v;   // cpp:112 (+ SURVEY D9)
     const double kin = 0.5 * bp.m_lambda * vel * vel / fx.ftm2v;
     v[0] += b.f * ph + b.U + kin;                                     // cpp:114 site terms
     v[1] += lambda * hd;                                              // cpp:114 lambda*(HB-HA)
     v[2] += kin;
     fs[s] = b.f; dfs[s] = b.df; Us[s] = b.U; dUs[s] = b.dU; flam[s] = f_lambda;
     if (phase == 0) {
-      lambda = 0.5 * a_lambda * dt * dt + vel * dt + lambda;          // cpp:115
+      cq = 0.5 * a_lambda * dt * dt + vel * dt + cq;                  // cpp:115
       vel = a_lambda * dt + vel;                                      // cpp:116
     }
-    lam[s] = lambda;
+    if (theta) { theta[s] = cq; const double sn = sin(cq); lam[s] = sn * sn; }
+    else lam[s] = cq;
     vlam[s] = vel;
     alam[s] = a_lambda;
   }
@@ -348,7 +356,8 @@ int cph_launch_integrate(cph_handle *h, double dt, int phase) {
   cudaStream_t st = h->stream;
   CPH_CUDA(h, h->d_part.reserve((size_t)MAXPART * 4));
   int nb = std::max(1, std::min(MAXPART, nblk(S)));
-  integrate_kernel<<<nb, TPB, 0, st>>>(S, dt, phase, h->bias, h->fix, h->d_pK.p, h->d_red.p, h->d_lam.p, h->d_vlam.p,
+  integrate_kernel<<<nb, TPB, 0, st>>>(S, dt, phase, h->bias, h->fix, h->d_pK.p, h->d_red.p, h->d_lam.p,
+                                       h->coord_theta ? h->d_theta.p : nullptr, h->d_vlam.p,
                                        h->d_alam.p, h->d_flam.p, h->d_fs.p, h->d_dfs.p, h->d_Us.p, h->d_dUs.p,
                                        h->d_part.p);
   if (phase != 1)

@@ -98,6 +98,13 @@ int cph_set_fix(cph_handle *h, int nevery, int groupHbit, int groupWbit, double 
 int cph_set_bias(cph_handle *h, double w, double s, double hbar, double k, double a, double b,
                  double r, double m, double d, double m_lambda, int bias_mode);
 int cph_set_mode(cph_handle *h, int dudl_mode, int integrator_mode, int fscale_mode);
+/* north_star's lambda/theta variables (absent from the reference, which integrates lambda itself and
+ * confines it with the wall terms U4/U5 of cpp:135-136).  CPH_COORD_THETA: the dynamical coordinate is theta
+ * with lambda = sin^2(theta); v_lambda, the mass and the restart record then refer to theta and
+ * F_theta = F_lambda * sin(2 theta).  cph_set_lambda still takes lambda (theta = asin(sqrt(lambda))). */
+#define CPH_COORD_LAMBDA 0
+#define CPH_COORD_THETA  1
+int cph_set_coordinate(cph_handle *h, int coordinate);
 /* modify_water() (h:58: declared, never defined nor called; TODO at cpp:268; the constructor insists on a
  * 3-atom water group, cpp:44-45).  When enabled (charge mode), every atom of the water group carries
  * q_base - (1/n_W) sum_s lambda_s dQ_s, dQ_s = sum_{t in s}(qB_t - qA_t), so the box keeps the total charge

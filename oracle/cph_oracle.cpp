@@ -74,6 +74,8 @@ struct Oracle {
   double bw = 200.0, bs = 0.3, bh = 4.0, bk = 2.533, ba = 0.034041, bb = 0.005238, br = 16.458,
          bm = 0.1507, bd = 2.0, m_lambda = 20.0;
   int bias_mode = 0, dudl_mode = 1, integ_mode = 0, fscale_mode = 0;
+  int coord_theta = 0;            // 1: the dynamical coordinate is theta, lambda = sin^2 theta
+  std::vector<double> theta;
   int water_buffer = 0;           // modify_water(): keep the box charge constant through the 3-atom water group
   std::vector<double> qbase;      // charges as supplied by the host (the lambda = 0 state of the buffer atoms)
   // sites
@@ -462,29 +464,34 @@ void integrate(Oracle *o, double dt, int phase) {
   const double ln10 = std::log(10.0);
   long double hsum = 0, ke = 0, eff_ref = 0;
   for (int s = 0; s < o->S; s++) {
-    double &lambda = o->lam[s], &v = o->vlam[s], &acc = o->alam[s];
+    double &cq = o->coord_theta ? o->theta[s] : o->lam[s];
+    double &v = o->vlam[s], &acc = o->alam[s];
     if (phase == 1) {
       v += 0.5 * acc * dt;
-      lambda += v * dt;
+      cq += v * dt;
+      if (o->coord_theta) { double sn = std::sin(cq); o->lam[s] = sn * sn; }
       continue;
     }
     if (phase == 3) v += 0.5 * acc * dt;
+    double lambda = cq, chain = 1.0;
+    if (o->coord_theta) { double sn = std::sin(cq); lambda = sn * sn; chain = std::sin(2.0 * cq); }
     double f, df, U, dU;
     bias_terms(o, lambda, f, df, U, dU);
     const double pK = o->implicit_site ? o->pK0 : o->pK[s];
     const double dE = (o->dudl_mode == 0) ? o->hdiff[s] : o->dudl[s];
     const double ph = o->boltz * o->T * ln10 * (pK - o->pH);
     double f_lambda = -(dE + df * ph + dU);                                 // cpp:111
-    double a_lambda = f_lambda / o->m_lambda * o->ftm2v;                    // cpp:112 (+ D9)
+    double a_lambda = f_lambda * chain / o->m_lambda * o->ftm2v;            // cpp:112 (+ D9); theta: F_theta = F_lambda sin 2theta
     o->fs[s] = f; o->dfs[s] = df; o->Us[s] = U; o->dUs[s] = dU; o->flam[s] = f_lambda;
     double kin = 0.5 * o->m_lambda * v * v / o->ftm2v;
     hsum += f * ph + U + kin;                                               // cpp:114 site terms
     eff_ref += lambda * o->hdiff[s];                                        // cpp:114 lambda*(HB-HA)
     ke += kin;
     if (phase == 0) {
-      lambda = 0.5 * a_lambda * dt * dt + v * dt + lambda;                  // cpp:115
+      cq = 0.5 * a_lambda * dt * dt + v * dt + cq;                          // cpp:115
       v = a_lambda * dt + v;                                                // cpp:116
     }
+    if (o->coord_theta) { double sn = std::sin(cq); o->lam[s] = sn * sn; }
     acc = a_lambda;
   }
   if (phase == 1) return;
@@ -525,7 +532,7 @@ void set_force(Oracle *o) {
 
 void size_sites(Oracle *o) {
   int S = o->S;
-  o->lam.resize(S, 0.5); o->vlam.resize(S, 0.0); o->alam.resize(S, 0.0);
+  o->lam.resize(S, 0.5); o->vlam.resize(S, 0.0); o->alam.resize(S, 0.0); o->theta.resize(S, 0.78539816339744830962);
   o->dudl.assign(S, 0); o->hdiff.assign(S, 0); o->flam.assign(S, 0); o->fs.assign(S, 0);
   o->dfs.assign(S, 0); o->Us.assign(S, 0); o->dUs.assign(S, 0);
 }
@@ -615,6 +622,7 @@ int orc_set_bias(void *h, double w, double s, double hbar, double k, double a, d
   return 0;
 }
 
+int orc_set_coordinate(void *h, int c) { ORC->coord_theta = c == 1; return 0; }
 int orc_set_water_buffer(void *h, int enable) { ORC->water_buffer = enable ? 1 : 0; return 0; }
 
 int orc_set_mode(void *h, int dudl, int integ, int fscale) {
@@ -631,14 +639,17 @@ int orc_set_sites(void *h, int nsites, const double *pK, int ntitr, const int *t
   o->titr_tag.assign(ttag, ttag + ntitr); o->titr_site.assign(tsite, tsite + ntitr);
   o->qA.assign(qA, qA + ntitr); o->qB.assign(qB, qB + ntitr);
   for (int t = 0; t < ntitr; t++) if (tsite[t] < 0 || tsite[t] >= o->S) return fail(o, -1, "site index out of range");
-  o->lam.clear(); o->vlam.clear(); o->alam.clear();
+  o->lam.clear(); o->vlam.clear(); o->alam.clear(); o->theta.clear();
   size_sites(o);
   return 0;
 }
 
 int orc_set_lambda(void *h, const double *l, const double *v) {
   Oracle *o = ORC;
-  for (int s = 0; s < o->S; s++) { if (l) o->lam[s] = l[s]; if (v) o->vlam[s] = v[s]; }
+  for (int s = 0; s < o->S; s++) {
+    if (l) { o->lam[s] = l[s]; o->theta[s] = std::asin(std::sqrt(std::min(1.0, std::max(0.0, l[s])))); }
+    if (v) o->vlam[s] = v[s];
+  }
   return 0;
 }
 
@@ -808,14 +819,19 @@ int orc_get_neighbors(void *h, int *numneigh, int64_t *keys, int64_t cap) {
 int orc_restart_size(void *h, int *nd) { *nd = 2 + 3 * ORC->S; return 0; }
 int orc_pack_restart(void *h, double *buf) {
   Oracle *o = ORC;
-  buf[0] = 1.0; buf[1] = o->S;
-  for (int s = 0; s < o->S; s++) { buf[2 + 3 * s] = o->lam[s]; buf[3 + 3 * s] = o->vlam[s]; buf[4 + 3 * s] = o->alam[s]; }
+  buf[0] = o->coord_theta ? 2.0 : 1.0; buf[1] = o->S;
+  for (int s = 0; s < o->S; s++) { buf[2 + 3 * s] = o->coord_theta ? o->theta[s] : o->lam[s]; buf[3 + 3 * s] = o->vlam[s]; buf[4 + 3 * s] = o->alam[s]; }
   return 0;
 }
 int orc_unpack_restart(void *h, const double *buf, int nd) {
   Oracle *o = ORC;
   if (nd < 2 || (int)buf[1] != o->S || nd != 2 + 3 * o->S) return fail(o, -1, "restart does not match the site table");
-  for (int s = 0; s < o->S; s++) { o->lam[s] = buf[2 + 3 * s]; o->vlam[s] = buf[3 + 3 * s]; o->alam[s] = buf[4 + 3 * s]; }
+  if ((buf[0] == 2.0) != (o->coord_theta != 0)) return fail(o, -1, "restart record was written with the other lambda coordinate");
+  for (int s = 0; s < o->S; s++) {
+    if (o->coord_theta) { o->theta[s] = buf[2 + 3 * s]; double sn = std::sin(o->theta[s]); o->lam[s] = sn * sn; }
+    else { o->lam[s] = buf[2 + 3 * s]; o->theta[s] = std::asin(std::sqrt(std::min(1.0, std::max(0.0, o->lam[s])))); }
+    o->vlam[s] = buf[3 + 3 * s]; o->alam[s] = buf[4 + 3 * s];
+  }
   if (o->dudl_mode == 1 && o->have_atoms) apply_charges(o);
   return 0;
 }

@@ -12,6 +12,7 @@
        mlambda VALUE         lambda mass (cpp:96 hard-codes 20)
        lambda0 VALUE         initial lambda when no site file is given (never set in the reference)
        buffer yes|no         modify_water() (h:58): keep the box charge constant through groupW
+       coordinate lambda|theta   integrate lambda itself (reference) or theta with lambda = sin^2(theta)
 
    The host side stays a LAMMPS Fix; every per-timestep loop of the reference (cpp:149-171,
    cpp:212-267) and the pair arithmetic north_star pulls into the path run in libcph_b200.so.
@@ -69,6 +70,7 @@ FixConstantPH::FixConstantPH(LAMMPS *lmp, int narg, char **arg) :
   bias_mode = CPH_BIAS_EXACT;
   m_lambda = 20.0;                                                                     // cpp:96
   water_buffer = 0;
+  coord_theta = 0;
   lambda_host = 0.5;
   nsites = ntitr = 0;
   restart_n = 0;
@@ -103,6 +105,10 @@ FixConstantPH::FixConstantPH(LAMMPS *lmp, int narg, char **arg) :
     } else if (strcmp(key, "mlambda") == 0) {
       m_lambda = utils::numeric(FLERR, val, false, lmp);
       if (m_lambda <= 0.0) error->all(FLERR, "Illegal fix constant_pH mlambda value {}", m_lambda);
+    } else if (strcmp(key, "coordinate") == 0) {
+      if (strcmp(val, "theta") == 0) coord_theta = 1;
+      else if (strcmp(val, "lambda") == 0) coord_theta = 0;
+      else error->all(FLERR, "Illegal fix constant_pH coordinate value {}", val);
     } else if (strcmp(key, "buffer") == 0) {
       if (strcmp(val, "yes") == 0) water_buffer = 1;
       else if (strcmp(val, "no") == 0) water_buffer = 0;
@@ -255,6 +261,7 @@ void FixConstantPH::init()
   check(cph_set_fix(cph, nevery, groupHbit, groupWbit, pK, pH, T), "cph_set_fix");
   check(cph_set_bias(cph, w, s, h, k, a, b, r, m, d, m_lambda, bias_mode), "cph_set_bias");   // cpp:86-96
   check(cph_set_mode(cph, dudl_mode, integrator_mode, fscale_mode), "cph_set_mode");
+  check(cph_set_coordinate(cph, coord_theta ? CPH_COORD_THETA : CPH_COORD_LAMBDA), "cph_set_coordinate");
   check(cph_set_water_buffer(cph, water_buffer ? (int) group->count(igroupW) : 0), "cph_set_water_buffer");
   check(cph_set_sites(cph, nsites, site_pK, ntitr, titr_tag, titr_site, titr_qA, titr_qB), "cph_set_sites");
   if (restart_buf) {

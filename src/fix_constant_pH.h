@@ -59,7 +59,7 @@ class FixConstantPH : public Fix {
 
   // additions
   cph_handle *cph;
-  int dudl_mode, integrator_mode, fscale_mode, bias_mode, water_buffer;
+  int dudl_mode, integrator_mode, fscale_mode, bias_mode, water_buffer, coord_theta;
   char *sitefile;
   int nsites, ntitr;
   double *site_pK, *site_lambda0, *titr_qA, *titr_qB;

@@ -72,13 +72,16 @@ def parse(out):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["charge", "reference", "vv", "buffer"])
+@pytest.mark.parametrize("mode", ["charge", "reference", "vv", "buffer", "theta"])
 def test_fix_trajectory_matches_oracle(box_files, mode):
     box, b, s = box_files
     nsteps = 120
     if mode == "charge":
         args = ["sites", s, "mlambda", 2000]
         kw = dict(bias=dict(m_lambda=2000.0))
+    elif mode == "theta":
+        args = ["sites", s, "mlambda", 2000, "coordinate", "theta"]
+        kw = dict(bias=dict(m_lambda=2000.0), theta=True)
     elif mode == "buffer":
         args = ["sites", s, "mlambda", 2000, "buffer", "yes"]
         kw = dict(bias=dict(m_lambda=2000.0), water_buffer=True)

@@ -360,3 +360,24 @@ def test_water_buffer_modify_water(built):
     close(gpu.get_sites()["dudl"], orc.get_sites()["dudl"])
     W = (box.mask & synth.GROUP_W_BIT) != 0
     assert not np.allclose(gpu.get_q()[W], box.q[W])
+
+
+@pytest.mark.parametrize("integrator", [capi.INTEGRATE_REFERENCE, capi.INTEGRATE_VV])
+def test_theta_coordinate(built, integrator):
+    """lambda = sin^2(theta) dynamics (north_star lambda/theta variables), CUDA path against the oracle."""
+    box = synth.config(2, scale=0.25)
+    gpu, orc = engines(box, bias=HEAVY, theta=True, integrator=integrator)
+    for eng in (gpu, orc):
+        eng.post_force(0, box.dt, box.x, None)
+        eng.final_integrate(0.0)
+        for step in range(1, 150):
+            eng.initial_integrate(box.dt)
+            eng.post_force(step, box.dt, box.x, None)
+            eng.final_integrate(box.dt)
+    tg, to = gpu.get_sites(), orc.get_sites()
+    assert np.abs(tg["lambda"] - to["lambda"]).max() <= 1e-8
+    assert np.abs(tg["v_lambda"] - to["v_lambda"]).max() <= 1e-8
+    assert tg["lambda"].min() >= 0.0 and tg["lambda"].max() <= 1.0
+    assert abs(gpu.compute_scalar() - orc.compute_scalar()) <= 1e-8 * abs(orc.compute_scalar())
+    buf = gpu.pack_restart()
+    assert buf[0] == 2.0 and np.allclose(buf, orc.pack_restart(), rtol=0, atol=1e-8)

@@ -202,3 +202,24 @@ def test_water_buffer_keeps_total_charge_and_dudl_consistent():
             o.set_lambda(lam); o.apply_charges(); o.pair_pass(1); o.site_reduce()
             sc = o.get_scalars(); es.append(sc["evdwl"] + sc["ecoul"])
         assert abs((es[0] - es[1]) / 0.1 - dudl[site]) < 1e-8 * max(1.0, abs(dudl[site]))
+
+
+def test_theta_coordinate_keeps_lambda_in_range_and_conserves_energy():
+    """north_star's lambda/theta variables: with lambda = sin^2(theta) the site coordinate cannot leave
+    [0, 1]; velocity-Verlet on theta conserves the extended energy with frozen atoms."""
+    box = synth.config(2, scale=0.2)
+    o = capi.configure(capi.Engine("orc"), box, theta=True, integrator=capi.INTEGRATE_VV, bias=dict(m_lambda=2000.0))
+    o.post_force(0, box.dt, box.x, None); o.final_integrate(0.0)
+    H, lam = [], []
+    for step in range(1, 300):
+        o.initial_integrate(box.dt); o.post_force(step, box.dt, box.x, None); o.final_integrate(box.dt)
+        H.append(o.compute_scalar()); lam.append(o.get_sites()["lambda"].copy())
+    lam, H = np.array(lam), np.array(H)
+    assert lam.min() >= 0.0 and lam.max() <= 1.0 and lam.max() - lam.min() > 0.5
+    assert np.abs(H - H[0]).max() < 1e-2 * max(1.0, o.get_scalars()["ke"])
+    # restart carries theta (version 2) and refuses the other coordinate
+    buf = o.pack_restart()
+    assert buf[0] == 2.0
+    p = capi.configure(capi.Engine("orc"), box, bias=dict(m_lambda=2000.0))
+    with pytest.raises(capi.CphError):
+        p.unpack_restart(buf)
