@@ -381,3 +381,31 @@ def test_theta_coordinate(built, integrator):
     assert abs(gpu.compute_scalar() - orc.compute_scalar()) <= 1e-8 * abs(orc.compute_scalar())
     buf = gpu.pack_restart()
     assert buf[0] == 2.0 and np.allclose(buf, orc.pack_restart(), rtol=0, atol=1e-8)
+
+
+def test_pair_paths_agree_for_any_inner_skin(built, monkeypatch):
+    """The two-level list only prunes: forces, energies and potentials must not depend on the inner
+    skin (0 = prune every step ... 1.5 A) nor on whether the fused single-kernel path is used."""
+    box = synth.config(2, scale=0.25)
+    params = synth.jiggle_params(box, amp=0.9, period_lo=40.0, period_hi=90.0)
+    results = []
+    for env in ({"CPH_INNER_SKIN": "0.0"}, {"CPH_INNER_SKIN": "0.4"}, {"CPH_INNER_SKIN": "1.5"},
+                {"CPH_PAIR_FUSED": "1"}):
+        for k in ("CPH_INNER_SKIN", "CPH_PAIR_FUSED"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        eng = capi.configure(capi.Engine("cph", device=0), box, bias=HEAVY)
+        f = np.zeros((box.n, 3))
+        for step in range(30):
+            eng.post_force(step, box.dt, synth.jiggle_positions(box, params, step * box.dt), f)
+        results.append((f.copy(), eng.get_phi(), eng.get_sites()["lambda"].copy(), eng.get_scalars(),
+                        eng.profile_get(9)[1]))
+    f0, p0, l0, s0, _ = results[0]
+    for f, p, l, s, _ in results[1:]:
+        close(f, f0, rtol=1e-11)
+        close(p, p0, rtol=1e-11)
+        assert np.abs(l - l0).max() <= 1e-11
+        assert abs(s["ecoul"] - s0["ecoul"]) <= 1e-11 * abs(s0["ecoul"])
+    prunes = [r[4] for r in results]
+    assert prunes[0] >= 30 and prunes[2] < prunes[1] < prunes[0] and prunes[3] == 0
