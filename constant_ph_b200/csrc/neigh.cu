@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(TPB)
 list_build_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__restrict__ xt,
                   const int *__restrict__ tag, const int *__restrict__ perm, const int *__restrict__ nspecial,
                   const int *__restrict__ special, int maxspecial, Grid g, const int *__restrict__ start_o,
-                  const int *__restrict__ start_g, double rlist2, float margin, int dropmask,
+                  const int *__restrict__ start_g, int3 gl, double rlist2, float margin, int dropmask,
                   int rowcap, int dummy, int *neigh, int *numneigh,
                   int *numspec, unsigned int *flags, unsigned long long *stats) {
   const int lane = threadIdx.x & 31;
@@ -296,7 +296,13 @@ list_build_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__re
   int cnt = 0, nsp = 0;
   const float rl2 = (float)rlist2;
   const float lo2 = rl2 - margin, hi2 = rl2 + margin;
-  const float wx = (float)(1.0 / g.inv[0]), wy = (float)(1.0 / g.inv[1]), wz = (float)(1.0 / g.inv[2]);
+  const float wy = (float)(1.0 / g.inv[1]), wz = (float)(1.0 / g.inv[2]);
+  const float ivx = (float)g.inv[0];
+  // ghost cells live in the outer `gl` cell layers of the grid (everything outside the sub-box);
+  // an atom whose +-2 stencil stays inside the interior never meets a ghost: skip that half of the loops
+  const bool near_ghost = cx < gl.x + 2 || cx >= g.n[0] - gl.x - 2 || cy < gl.y + 2 || cy >= g.n[1] - gl.y - 2 ||
+                          cz < gl.z + 2 || cz >= g.n[2] - gl.z - 2;
+  const int nsets = near_ghost ? 2 : 1;
   for (int dz = -2; dz <= 2; dz++) {
     const int z = cz + dz;
     if (z < 0 || z >= g.n[2]) continue;
@@ -309,10 +315,10 @@ list_build_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__re
       const float rem = hi2 - fmaxf(gz, 0.f) * fmaxf(gz, 0.f) - fmaxf(gy, 0.f) * fmaxf(gy, 0.f);
       if (rem < 0.f) continue;
       const float xr = sqrtf(rem) * 1.0001f + 1e-3f;
-      const int x0 = max((int)floorf((pti.x - xr) / wx), 0), x1 = min((int)floorf((pti.x + xr) / wx), g.n[0] - 1);
+      const int x0 = max((int)floorf((pti.x - xr) * ivx), 0), x1 = min((int)floorf((pti.x + xr) * ivx), g.n[0] - 1);
       if (x1 < x0) continue;
       const int c0 = (z * g.n[1] + y) * g.n[0];
-      for (int set = 0; set < 2; set++) {
+      for (int set = 0; set < nsets; set++) {
         const int *st = set ? start_g : start_o;
         const int base = set ? nlocal : 0;
         const int s = st[c0 + x0], e = st[c0 + x1 + 1];
@@ -320,7 +326,7 @@ list_build_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__re
           const int p = p0 + lane;
           bool ok = p < e;
           const int j = base + p;
-          int sb = 0;
+          bool spc = false;    // candidate for a special-bond partner (same molecule): rare
           if (ok) {
             const float4 pj = xt[j];
             const float fx = pti.x - pj.x, fy = pti.y - pj.y, fz = pti.z - pj.z;
@@ -331,22 +337,29 @@ list_build_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__re
               const double dx = pi.x - qj.x, dy_ = pi.y - qj.y, dz_ = pi.z - qj.z;
               ok = dx * dx + dy_ * dy_ + dz_ * dz_ < rlist2;
             }
-            if (ok && ns3 && __float_as_int(pj.w) == moli) {
+            spc = ok && ns3 && __float_as_int(pj.w) == moli;
+          }
+          if (__any_sync(0xffffffffu, spc)) {
+            // slow path (a few chunks per atom): look the tag up in special[i]; special-bond partners
+            // fill the row from the back, the rest of the chunk goes on to the fast path below
+            int sb = 0;
+            if (spc) {
               const int tj = tag[j];
               for (int k = 0; k < ns3; k++)
                 if (sp[k] == tj) { sb = k < ns1 ? 1 : (k < ns2 ? 2 : 3); break; }
-              if ((dropmask >> sb) & 1) ok = false;   // both weights zero (and not dsf): not stored
+              if ((dropmask >> sb) & 1) { ok = false; sb = 0; }   // both weights zero (and not dsf): not stored
             }
+            const unsigned int ms = __ballot_sync(0xffffffffu, ok && sb);
+            const int poss = nsp + __popc(ms & ((1u << lane) - 1));
+            if (ok && sb && poss < rowcap) row[rowcap - 1 - poss] = j | (sb << CPH_SBSHIFT);
+            nsp += __popc(ms);
+            if (sb) ok = false;
           }
-          // ordinary neighbours fill the row from the front, special-bond partners from the back
-          const unsigned int m = __ballot_sync(0xffffffffu, ok && !sb);
-          const unsigned int ms = __ballot_sync(0xffffffffu, ok && sb);
+          // ordinary neighbours fill the row from the front
+          const unsigned int m = __ballot_sync(0xffffffffu, ok);
           const int pos = cnt + __popc(m & ((1u << lane) - 1));
-          const int poss = nsp + __popc(ms & ((1u << lane) - 1));
-          if (ok && !sb && pos < rowcap) row[pos] = j;
-          if (ok && sb && poss < rowcap) row[rowcap - 1 - poss] = j | (sb << CPH_SBSHIFT);
+          if (ok && pos < rowcap) row[pos] = j;
           cnt += __popc(m);
-          nsp += __popc(ms);
         }
       }
     }
@@ -920,6 +933,17 @@ int cph_rebuild(cph_handle *h) {
   double extent = 0;
   for (int k = 0; k < 3; k++) extent = std::max(extent, g.n[k] / g.inv[k]);
   const float fmargin = (float)(32.0 * rlist * extent * 5.97e-8 + 1e-5 * rlist * rlist);
+  // grid layers (from each face of the grid) that can hold ghost atoms: a ghost is a copy of an atom
+  // some rank owns, so it sits outside this sub-box or at most `skin` inside it (drifted owners)
+  int3 ghost_layers;
+  {
+    int gl[3];
+    for (int k = 0; k < 3; k++) {
+      const double w = 1.0 / g.inv[k];
+      gl[k] = (int)std::floor((h->sublo[k] + h->skin - g.lo[k]) / w) + 1;
+    }
+    ghost_layers = make_int3(gl[0], gl[1], gl[2]);
+  }
   for (int attempt = 0; attempt < 4 && n; attempt++) {
     CPH_CUDA(h, h->d_neigh.reserve((size_t)n * h->rowcap));
     CPH_CUDA(h, cudaMemsetAsync(stats.p, 0, 2 * sizeof(unsigned long long), st));
@@ -930,7 +954,7 @@ int cph_rebuild(cph_handle *h) {
     list_build_kernel<<<blocks, TPB, 0, st>>>(
         n, h->d_xq.p, h->d_xb.p, h->d_tag.p, h->d_perm.p, h->maxspecial ? h->d_nspecial.p : nullptr,
         h->maxspecial ? h->d_special.p : nullptr, h->maxspecial, g, h->d_cell_start_o.p, h->d_cell_start_g.p,
-        rlist * rlist, fmargin, dropmask, h->rowcap, h->nall, h->d_neigh.p,
+        ghost_layers, rlist * rlist, fmargin, dropmask, h->rowcap, h->nall, h->d_neigh.p,
         h->d_numneigh.p, h->d_numspec.p, h->d_flags.p, stats.p);
     CPH_CUDA(h, cudaGetLastError());
     unsigned long long stats_h[2];
