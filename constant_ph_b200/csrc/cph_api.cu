@@ -252,8 +252,15 @@ int cph_set_domain(cph_handle *h, const double *boxlo, const double *boxhi, cons
       return cph_fail(h, CPH_ERR_ARG, "bad processor grid in dim %d", k);
   }
   int np = h->procgrid[0] * h->procgrid[1] * h->procgrid[2];
-  if (np != h->nranks && !(np > 1 && h->nranks == 1 && false))
-    if (np != h->nranks) return cph_fail(h, CPH_ERR_ARG, "procgrid has %d ranks but the rank group has %d", np, h->nranks);
+  if (np != h->nranks)
+    return cph_fail(h, CPH_ERR_ARG, "procgrid has %d ranks but the rank group has %d (call cph_comm_init_nccl first)", np,
+                    h->nranks);
+  {
+    const int me = (h->myloc[2] * h->procgrid[1] + h->myloc[1]) * h->procgrid[0] + h->myloc[0];
+    if (h->nranks > 1 && me != h->rank)
+      return cph_fail(h, CPH_ERR_ARG, "myloc maps to rank %d but this handle is rank %d (x-fastest brick order expected)", me,
+                      h->rank);
+  }
   h->skin = skin;
   h->have_domain = true;
   h->rowcap = 0;

@@ -247,12 +247,6 @@ struct WarpSmem {
   int sched[MAXTILES];                // tile schedule: tile index (row offset / CH) of each tile of this warp
 };
 
-#ifndef CPH_DRAIN64
-#define CPH_DRAIN64 0
-#endif
-#ifndef CPH_PREFETCH
-#define CPH_PREFETCH 0
-#endif
 #ifndef CPH_PAIR_MINBLOCKS
 #define CPH_PAIR_MINBLOCKS 3
 #endif
@@ -362,23 +356,6 @@ pair_fused_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__re
       }
       head += count;
     };
-    // evaluate 64 queued pairs, two independent ones per lane (ILP 2 on the dependent fp64 chains)
-    auto drain64 = [&]() {
-      const int2 e0 = sm.queue[(head + lane) & (QCAP - 1)];
-      const int2 e1 = sm.queue[(head + 32 + lane) & (QCAP - 1)];
-      const double4 p0 = ld256(xq + e0.x), p1 = ld256(xq + e1.x);
-      const double dx0 = pi.x - p0.x, dy0 = pi.y - p0.y, dz0 = pi.z - p0.z;
-      const double dx1 = pi.x - p1.x, dy1 = pi.y - p1.y, dz1 = pi.z - p1.z;
-      const double rs0 = fma(dz0, dz0, fma(dy0, dy0, dx0 * dx0));
-      const double rs1 = fma(dz1, dz1, fma(dy1, dy1, dx1 * dx1));
-      double f0, f1, v0, v1, h0, h1;
-      eval_pair<STYLE, EFLAG, UNI>(s_coef, s_cut, e0.y, rs0, pi.w, p0.w, s_exp2, has_lj, f0, v0, h0);
-      eval_pair<STYLE, EFLAG, UNI>(s_coef, s_cut, e1.y, rs1, pi.w, p1.w, s_exp2, has_lj, f1, v1, h1);
-      a.fx = fma(dx0, f0, a.fx); a.fy = fma(dy0, f0, a.fy); a.fz = fma(dz0, f0, a.fz);
-      a.fx = fma(dx1, f1, a.fx); a.fy = fma(dy1, f1, a.fy); a.fz = fma(dz1, f1, a.fz);
-      if (EFLAG) { a.ev += v0 + v1; a.phi += h0 + h1; }
-      head += 64;
-    };
     // two candidates per lane: fp32 test, ballot-compact into the queue
     auto push2 = [&](int ra, const float4 &pa, int rb, const float4 &pb) {
       const float dxa = pti.x - pa.x, dya = pti.y - pa.y, dza = pti.z - pa.z;
@@ -390,18 +367,9 @@ pair_fused_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__re
       const int ca = __popc(ma);
       if (ina) sm.queue[(tail + __popc(ma & ltmask)) & (QCAP - 1)] = make_int2(ra, tbase + __float_as_int(pa.w));
       if (inb) sm.queue[(tail + ca + __popc(mb & ltmask)) & (QCAP - 1)] = make_int2(rb, tbase + __float_as_int(pb.w));
-#if CPH_PREFETCH
-      // pull the fp64 records of the survivors towards L1 while the filter keeps going
-      if (ina) asm volatile("prefetch.global.L1 [%0];" ::"l"(xq + ra));
-      if (inb) asm volatile("prefetch.global.L1 [%0];" ::"l"(xq + rb));
-#endif
       tail += ca + __popc(mb);
       __syncwarp();
-#if CPH_DRAIN64
-      if (tail - head >= 64) drain64();
-#else
       while (tail - head >= 32) drain(32);
-#endif
     };
 
     for (int t = 0; t < ntile; t++) {
