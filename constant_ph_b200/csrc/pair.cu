@@ -539,7 +539,7 @@ pair_eval_kernel(int nlocal, const double4 *__restrict__ xq, const int *__restri
   __shared__ double s_exp2[32];
   for (int k = threadIdx.x; k < nt1 * nt1; k += ETPB) {
     s_coef[k] = coef[k];
-    s_cut[k] = cuts[k];
+    if (!UNI) s_cut[k] = cuts[k];     // per-pair cutoffs are only read when they differ from the global one
   }
   if (threadIdx.x < 32) s_exp2[threadIdx.x] = kexp2[threadIdx.x];
   __syncthreads();
@@ -570,7 +570,7 @@ pair_eval_kernel(int nlocal, const double4 *__restrict__ xq, const int *__restri
         const double delx = pi.x - pq.x, dely = pi.y - pq.y, delz = pi.z - pq.z;
         const double rsq = fma(delz, delz, fma(dely, dely, delx * delx));
         double o5[5];
-        eval_special<STYLE, EFLAG>(s_coef, s_cut, tt, delx, dely, delz, rsq, pi.w, pq.w, sb, o5);
+        eval_special<STYLE, EFLAG>(s_coef, cuts /* global: rare path */, tt, delx, dely, delz, rsq, pi.w, pq.w, sb, o5);
         a.fx = o5[0]; a.fy = o5[1]; a.fz = o5[2];
         if (EFLAG) { a.ev = o5[3]; a.phi = o5[4]; }
       }
