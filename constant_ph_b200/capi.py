@@ -362,7 +362,7 @@ class Engine:
 def configure(eng, box, nevery=1, dudl=DUDL_CHARGE, integrator=INTEGRATE_REFERENCE,
               fscale=FSCALE_LAMBDA, bias_mode=BIAS_EXACT, implicit_site=False, ftm2v=None,
               sublo=None, subhi=None, procgrid=(1, 1, 1), myloc=(0, 0, 0), owned=None, bias=None,
-              water_buffer=False, theta=False):
+              water_buffer=False, theta=False, cut_lj=None, cut_coul=None):
     """Push a synth.Box into an engine: the calls FixConstantPH's constructor/init/setup make.
 
     implicit_site=True reproduces the reference's single global lambda over the hydrogen
@@ -371,8 +371,9 @@ def configure(eng, box, nevery=1, dudl=DUDL_CHARGE, integrator=INTEGRATE_REFEREN
     bias: overrides of the init() constants (fix_constant_pH.cpp:86-96), e.g. m_lambda."""
     from . import synth
     eng.set_units(synth.QQRD2E, synth.BOLTZ, synth.FTM2V if ftm2v is None else ftm2v)
-    eng.set_pair(box.style, box.ntypes, box.epsilon, box.sigma, None, box.cut_lj, box.cut_coul,
-                 box.alpha, box.special_lj, box.special_coul)
+    # cut_lj: optional (ntypes+1)^2 table of per-type-pair LJ cutoffs (pair_coeff ... cut_lj); cut_coul: override
+    eng.set_pair(box.style, box.ntypes, box.epsilon, box.sigma, cut_lj, box.cut_lj,
+                 box.cut_coul if cut_coul is None else cut_coul, box.alpha, box.special_lj, box.special_coul)
     eng.set_domain(box.boxlo, box.boxhi, (1, 1, 1), sublo, subhi, procgrid, myloc, box.skin)
     pK0 = float(box.pK[0]) if box.nsites else 0.0
     eng.set_fix(nevery, synth.GROUP_H_BIT, synth.GROUP_W_BIT, pK0, box.pH, box.T)

@@ -409,3 +409,27 @@ def test_pair_paths_agree_for_any_inner_skin(built, monkeypatch):
         assert abs(s["ecoul"] - s0["ecoul"]) <= 1e-11 * abs(s0["ecoul"])
     prunes = [r[4] for r in results]
     assert prunes[0] >= 30 and prunes[2] < prunes[1] < prunes[0] and prunes[3] == 0
+
+
+@pytest.mark.parametrize("cfg,scale", [(1, 1.0), (2, 0.25)])
+def test_per_type_pair_cutoffs(built, cfg, scale):
+    """pair_coeff-style per-type-pair LJ cutoffs and cut_lj != cut_coul: the non-uniform-cutoff kernels
+    (three separate fp64 cutoff decisions per pair) against the oracle, both pair styles."""
+    box = synth.config(cfg, scale=scale)
+    nt1 = box.ntypes + 1
+    cut_lj = np.full((nt1, nt1), 9.0)
+    cut_lj[1, 1] = 8.5                       # O-O shorter than everything else
+    cut_lj[1, 3:] = cut_lj[3:, 1] = 9.5      # water O - solute atoms longer
+    kw = dict(cut_lj=cut_lj, cut_coul=10.0, bias=HEAVY)
+    gpu, orc = engines(box, **kw)
+    check_pass(gpu, orc)
+    ng, kg = gpu.get_neighbors()
+    no, ko = orc.get_neighbors()
+    assert np.array_equal(ng, no) and np.array_equal(kg, ko)
+    lg = run_traj(gpu, box, 20)
+    lo = run_traj(orc, box, 20)
+    assert np.abs(lg - lo).max() <= 1e-9
+    # and with the Coulomb cutoff shorter than the LJ one
+    kw = dict(cut_lj=np.full((nt1, nt1), 10.0), cut_coul=9.0, bias=HEAVY)
+    gpu, orc = engines(box, **kw)
+    check_pass(gpu, orc)
