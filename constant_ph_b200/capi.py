@@ -161,6 +161,9 @@ class Engine:
     def set_mode(self, dudl=DUDL_CHARGE, integrator=INTEGRATE_REFERENCE, fscale=FSCALE_LAMBDA):
         self._call("set_mode", C.c_int(dudl), C.c_int(integrator), C.c_int(fscale))
 
+    def set_extra_partition(self, dHA, dHB):
+        self._call("set_extra_partition", C.c_double(dHA), C.c_double(dHB))
+
     def set_coordinate(self, theta=True):
         self._call("set_coordinate", C.c_int(1 if theta else 0))
 

@@ -288,6 +288,12 @@ int cph_set_mode(cph_handle *h, int dudl_mode, int integrator_mode, int fscale_m
   return CPH_OK;
 }
 
+int cph_set_extra_partition(cph_handle *h, double dHA, double dHB) {
+  h->extra_HA = dHA;
+  h->extra_HB = dHB;
+  return CPH_OK;
+}
+
 int cph_set_coordinate(cph_handle *h, int coordinate) {
   if (coordinate != CPH_COORD_LAMBDA && coordinate != CPH_COORD_THETA) return cph_fail(h, CPH_ERR_ARG, "bad coordinate");
   h->coord_theta = coordinate == CPH_COORD_THETA;

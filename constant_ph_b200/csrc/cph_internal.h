@@ -113,6 +113,7 @@ struct cph_handle {
   BiasParams bias{200.0, 0.3, 4.0, 2.533, 0.034041, 0.005238, 16.458, 0.1507, 2.0, 20.0, 0};
   FixParams fix{1, 0, 0, 0.0, 7.0, 300.0, 0.0019872067, 1.0, 1, 0, 0, 1};
   double qqrd2e = 332.06371;
+  double extra_HA = 0.0, extra_HB = 0.0;   // host-tallied energy sources for the next site reduce (cpp:221-244)
   // sites (host copies, site-major order)
   int S = 1, ntitr = 0;
   std::vector<int> titr_tag_sorted_h;  // titr tags sorted ascending (for the device binary search)

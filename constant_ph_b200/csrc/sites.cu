@@ -63,14 +63,21 @@ partition_kernel(int n, const double *__restrict__ eatom, const double *__restri
 }
 
 __global__ void partition_final_kernel(int nb, const double *__restrict__ partials, double *red, int implicit_site,
-                                       int S) {
+                                       int S, double extra_HA, double extra_HB) {
   const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
   __shared__ double out[4];
   if (c < 4) {
     double s = 0;
     for (int b = lane; b < nb; b += 32) s += partials[(size_t)b * 4 + c];
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) { out[c] = s; red[c] = s; }
+    // extra_HA/HB: this rank's share of the per-atom energies LAMMPS tallied on the host (bonded styles,
+    // KSpace: cpp:221-244), already partitioned by the fix exactly as cpp:264-267 does
+    if (lane == 0) {
+      if (c == 0) s += extra_HA;
+      if (c == 1) s += extra_HB;
+      out[c] = s;
+      red[c] = s;
+    }
   }
   __syncthreads();
   // reference single site: HB - HA of the whole hydrogen group (cpp:111)
@@ -340,7 +347,9 @@ int cph_launch_partition(cph_handle *h) {
   CPH_CUDA(h, cudaMemsetAsync(h->d_red.p, 0, (4 + 2 * (size_t)S + 1) * sizeof(double), st));
   int nb = std::max(1, std::min(MAXPART, nblk(n)));
   partition_kernel<<<nb, TPB, 0, st>>>(n, h->d_eatom.p, h->d_evdwl.p, h->d_mask.p, h->fix.Hbit, h->d_part.p);
-  partition_final_kernel<<<1, 128, 0, st>>>(nb, h->d_part.p, h->d_red.p, h->fix.implicit_site, S);
+  partition_final_kernel<<<1, 128, 0, st>>>(nb, h->d_part.p, h->d_red.p, h->fix.implicit_site, S, h->extra_HA,
+                                            h->extra_HB);
+  h->extra_HA = h->extra_HB = 0.0;   // consumed
   if (h->ntitr)
     site_sum_kernel<<<nblk(h->ntitr), TPB, 0, st>>>(h->ntitr, h->d_titr_site.p, h->d_titr_local.p, h->d_titr_dq.p,
                                                     h->d_phi.p, h->d_eatom.p, h->d_mask.p, h->fix.Hbit, S,

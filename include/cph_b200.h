@@ -146,6 +146,11 @@ int cph_forward(cph_handle *h);
 int cph_pair_pass(cph_handle *h, int eflag);
 /* compute_Hs() (cpp:177-280): HA, HB, per-site HB_s-HA_s and dU/dlambda_s, summed over ranks. */
 int cph_site_reduce(cph_handle *h);
+/* The other energy sources compute_Hs adds to H_atom (cpp:221-249: bond, angle, dihedral, improper, kspace,
+ * fix energies) stay with LAMMPS on the host.  The fix folds their ghost shares (cpp:253, 287-308), partitions
+ * them as cpp:264-267 does and hands this rank's two sums over; they enter HA and HB (and HB-HA of the
+ * reference's single site) at the next site reduce and are then cleared. */
+int cph_set_extra_partition(cph_handle *h, double dHA, double dHB);
 /* calculate_df + calculate_dU + integrate_lambda (cpp:109-145), dt = nevery*update->dt. */
 int cph_integrate_lambda(cph_handle *h, double dt);
 /* north_star hooks absent from the reference. */

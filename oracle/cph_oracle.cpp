@@ -76,6 +76,7 @@ struct Oracle {
   int bias_mode = 0, dudl_mode = 1, integ_mode = 0, fscale_mode = 0;
   int coord_theta = 0;            // 1: the dynamical coordinate is theta, lambda = sin^2 theta
   std::vector<double> theta;
+  double extra_HA = 0, extra_HB = 0;   // host-tallied sources of compute_Hs (cpp:221-249)
   int water_buffer = 0;           // modify_water(): keep the box charge constant through the 3-atom water group
   std::vector<double> qbase;      // charges as supplied by the host (the lambda = 0 state of the buffer atoms)
   // sites
@@ -401,6 +402,8 @@ void site_reduce(Oracle *o) {
     HA += o->eatom[i];                                   // cpp:265
     if (!(o->mask[i] & o->Hbit)) HB += o->eatom[i];      // cpp:266
   }
+  HA += o->extra_HA;
+  HB += o->extra_HB;
   o->HA = (double)HA;
   o->HB = (double)HB;
   std::vector<long double> d(o->S, 0.0L), hd(o->S, 0.0L);
@@ -423,6 +426,8 @@ void site_reduce(Oracle *o) {
       for (int s = 0; s < o->S; s++) d[s] -= dQ[s] / nw * phiw;
     }
   }
+  if (o->implicit_site) hd[0] += (long double)o->extra_HB - (long double)o->extra_HA;
+  o->extra_HA = o->extra_HB = 0;
   for (int s = 0; s < o->S; s++) { o->dudl[s] = (double)d[s]; o->hdiff[s] = (double)hd[s]; }
 }
 
@@ -622,6 +627,7 @@ int orc_set_bias(void *h, double w, double s, double hbar, double k, double a, d
   return 0;
 }
 
+int orc_set_extra_partition(void *h, double a, double b) { ORC->extra_HA = a; ORC->extra_HB = b; return 0; }
 int orc_set_coordinate(void *h, int c) { ORC->coord_theta = c == 1; return 0; }
 int orc_set_water_buffer(void *h, int enable) { ORC->water_buffer = enable ? 1 : 0; return 0; }
 

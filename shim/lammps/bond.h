@@ -1,0 +1,2 @@
+// forwarding header: in a real LAMMPS tree the upstream "bond.h" is found instead (see lammps_shim.h)
+#include "lammps_shim.h"

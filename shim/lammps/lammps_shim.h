@@ -121,6 +121,19 @@ class Pair {
   }
 };
 
+// bonded styles and KSpace: only what compute_Hs touches (cpp:221-244)
+class EnergyStyle {
+ public:
+  double *eatom = nullptr;
+  int compute_flag = 1;
+  int tip4pflag = 0;
+};
+typedef EnergyStyle Bond;
+typedef EnergyStyle Angle;
+typedef EnergyStyle Dihedral;
+typedef EnergyStyle Improper;
+typedef EnergyStyle KSpace;
+
 class Force {
  public:
   double boltz = 0.0019872067, qqrd2e = 332.06371, ftm2v = 1.0 / 48.88821291 / 48.88821291;
@@ -128,7 +141,11 @@ class Force {
   int newton = 1, newton_pair = 1, newton_bond = 1;
   Pair *pair = nullptr;
   char *pair_style = nullptr;
-  void *bond = nullptr, *angle = nullptr, *dihedral = nullptr, *improper = nullptr, *kspace = nullptr;
+  Bond *bond = nullptr;
+  Angle *angle = nullptr;
+  Dihedral *dihedral = nullptr;
+  Improper *improper = nullptr;
+  KSpace *kspace = nullptr;
   Pair *pair_match(const std::string &word, int exact, int = 0) {
     if (!pair) return nullptr;
     if (exact ? pair->style == word : pair->style.find(word) != std::string::npos) return pair;

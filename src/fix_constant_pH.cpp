@@ -21,12 +21,17 @@
 
 #include "fix_constant_pH.h"
 
+#include "angle.h"
 #include "atom.h"
+#include "bond.h"
 #include "comm.h"
+#include "dihedral.h"
 #include "domain.h"
 #include "error.h"
 #include "force.h"
 #include "group.h"
+#include "improper.h"
+#include "kspace.h"
 #include "memory.h"
 #include "neighbor.h"
 #include "pair.h"
@@ -335,6 +340,9 @@ void FixConstantPH::post_force(int /*vflag*/)
   const int nlocal = atom->nlocal;
   const double *x = nlocal ? &atom->x[0][0] : nullptr;
 
+  // cpp:221-253: energy sources that stay with LAMMPS on the host enter the HA/HB partition
+  if (update->ntimestep % nevery == 0) compute_Hs();
+
   // cpp:69-78: on nevery steps compute_Hs, calculate_df, calculate_dU, integrate_lambda;
   // set_force on every step.  One library call runs the whole sequence on the device.
   check(cph_post_force(cph, update->ntimestep, update->dt, CPH_HOST, x, fbuf), "cph_post_force");
@@ -399,8 +407,66 @@ void FixConstantPH::set_force()
 
 void FixConstantPH::compute_Hs()
 {
-  check(cph_pair_pass(cph, 1), "cph_pair_pass");            // the eatom of cpp:216-219
-  check(cph_site_reduce(cph), "cph_site_reduce");           // cpp:259-277
+  // The pair part of H_atom (cpp:216-219) is produced and partitioned on the device.  What follows is
+  // the rest of the reference routine (cpp:200-267, "taken from src/compute_pe_atom.cpp") for the
+  // sources LAMMPS keeps on the host: bonded styles and KSpace.  Their two partition sums are handed
+  // to the library, which adds them to HA/HB before the all-reduce that replaces cpp:274.
+  const bool any = (force->bond && force->bond->eatom) || (force->angle && force->angle->eatom) ||
+                   (force->dihedral && force->dihedral->eatom) || (force->improper && force->improper->eatom) ||
+                   (force->kspace && force->kspace->compute_flag && force->kspace->eatom);
+  if (!any) return;
+  if (update->eflag_atom != update->ntimestep)                                         // cpp:181-183
+    error->all(FLERR, "Per-atom energy was not tallied on needed timestep");
+
+  if (atom->nmax > nmax) {                                                             // cpp:188-192
+    memory->destroy(H_atom);
+    nmax = atom->nmax;
+    memory->create(H_atom, nmax, "constant_pH:H_atom");
+  }
+
+  int i;
+  int nlocal = atom->nlocal;                                                           // cpp:200-208
+  int nbond = nlocal;
+  int ntotal = nlocal;
+  int nkspace = nlocal;
+  if (force->newton_bond) nbond += atom->nghost;
+  if (force->newton) ntotal += atom->nghost;
+  if (force->kspace && force->kspace->tip4pflag) nkspace += atom->nghost;
+
+  for (i = 0; i < ntotal; i++) H_atom[i] = 0.0;                                        // cpp:212
+
+  if (force->bond && force->bond->eatom) {                                             // cpp:221-224
+    double *eatom = force->bond->eatom;
+    for (i = 0; i < nbond; i++) H_atom[i] += eatom[i];
+  }
+  if (force->angle && force->angle->eatom) {                                           // cpp:226-229
+    double *eatom = force->angle->eatom;
+    for (i = 0; i < nbond; i++) H_atom[i] += eatom[i];
+  }
+  if (force->dihedral && force->dihedral->eatom) {                                     // cpp:231-234
+    double *eatom = force->dihedral->eatom;
+    for (i = 0; i < nbond; i++) H_atom[i] += eatom[i];
+  }
+  if (force->improper && force->improper->eatom) {                                     // cpp:236-239
+    double *eatom = force->improper->eatom;
+    for (i = 0; i < nbond; i++) H_atom[i] += eatom[i];
+  }
+  if (force->kspace && force->kspace->compute_flag && force->kspace->eatom) {          // cpp:241-244
+    double *eatom = force->kspace->eatom;
+    for (i = 0; i < nkspace; i++) H_atom[i] += eatom[i];
+  }
+
+  // communicate ghost energy between neighbor procs                                    cpp:251-253
+  if (force->newton || (force->kspace && force->kspace->tip4pflag)) comm->reverse_comm(this);
+
+  int *mask = atom->mask;                                                              // cpp:257-267
+  double HA_local = 0.0;
+  double HB_local = 0.0;
+  for (i = 0; i < nlocal; i++) {
+    HA_local += H_atom[i];
+    if (!(mask[i] & groupHbit)) HB_local += H_atom[i];
+  }
+  check(cph_set_extra_partition(cph, HA_local, HB_local), "cph_set_extra_partition");
 }
 
 void FixConstantPH::calculate_df() {}                       // cpp:120-124: fused into the integrator kernel
@@ -481,17 +547,29 @@ void FixConstantPH::restart(char *buf)
 }
 
 /* ----------------------------------------------------------------------
-   cpp:287-308.  With the library's full neighbour list every owned atom's energy is complete
-   on its owner, so there is nothing to fold; the hooks stay for interface parity.
+   cpp:287-308.  The pair energies live on the device (full neighbour list: nothing to fold); H_atom
+   carries the host-side sources of compute_Hs, whose ghost shares are folded exactly as in the reference.
 ------------------------------------------------------------------------- */
 
 int FixConstantPH::pack_reverse_comm(int n, int first, double *buf)
 {
   int i, m, last;
+
   m = 0;
   last = first + n;
-  for (i = first; i < last; i++) buf[m++] = 0.0;
+  for (i = first; i < last; i++) buf[m++] = H_atom[i];                                 // cpp:293
   return m;
 }
 
-void FixConstantPH::unpack_reverse_comm(int /*n*/, int * /*list*/, double * /*buf*/) {}
+/* ---------------------------------------------------------------------- */
+
+void FixConstantPH::unpack_reverse_comm(int n, int *list, double *buf)
+{
+  int i, j, m;
+
+  m = 0;
+  for (i = 0; i < n; i++) {                                                            // cpp:304-307
+    j = list[i];
+    H_atom[j] += buf[m++];
+  }
+}

@@ -83,6 +83,18 @@ int main(int argc, char **argv) {
                                 std::to_string(hd[21]), std::to_string(hd[18]), std::to_string(hd[19])};
   int first_kw = 3;
   if (argc > 4 && !strcmp(argv[3], "nevery")) { a[3] = argv[4]; first_kw = 5; }
+  // "bonded SCALE": a synthetic bond style whose per-atom energy is SCALE*(1 + i % 7), to exercise the
+  // host-side sources of compute_Hs (cpp:221-253)
+  Bond bond;
+  std::vector<double> bond_eatom;
+  if (argc > first_kw + 1 && !strcmp(argv[first_kw], "bonded")) {
+    const double sc = atof(argv[first_kw + 1]);
+    bond_eatom.resize(n);
+    for (int i = 0; i < n; i++) bond_eatom[i] = sc * (1 + i % 7);
+    bond.eatom = bond_eatom.data();
+    lmp.force->bond = &bond;
+    first_kw += 2;
+  }
   for (int k = first_kw; k < argc; k++) a.push_back(argv[k]);
   std::vector<char *> av;
   for (auto &s : a) av.push_back((char *)s.c_str());
@@ -92,6 +104,7 @@ int main(int argc, char **argv) {
     const int mask_bits = fix.setmask();
     fix.init();
     lmp.update->ntimestep = 0;
+    lmp.update->eflag_atom = 0;
     fix.setup(0);
     const int S = fix.size_vector / 4;
     auto report = [&](long step) {
@@ -102,6 +115,7 @@ int main(int argc, char **argv) {
     report(0);
     for (int step = 1; step <= nsteps; step++) {
       lmp.update->ntimestep = step;
+      lmp.update->eflag_atom = step;
       if (mask_bits & FixConst::INITIAL_INTEGRATE) fix.initial_integrate(0);
       std::fill(f.begin(), f.end(), 0.0);                 // force_clear(); pair->compute is off
       fix.post_force(0);

@@ -31,8 +31,9 @@ def test_fix_builds_against_the_shim(built):
     # the fix source names only upstream LAMMPS headers and the C ABI
     src = open(os.path.join(ROOT, "src", "fix_constant_pH.cpp")).read()
     incs = [l.split('"')[1] for l in src.splitlines() if l.startswith('#include "')]
-    assert set(incs) <= {"fix_constant_pH.h", "atom.h", "comm.h", "domain.h", "error.h", "force.h", "group.h",
-                         "memory.h", "neighbor.h", "pair.h", "update.h", "cph_b200.h"}
+    assert set(incs) <= {"fix_constant_pH.h", "angle.h", "atom.h", "bond.h", "comm.h", "dihedral.h", "domain.h",
+                         "error.h", "force.h", "group.h", "improper.h", "kspace.h", "memory.h", "neighbor.h",
+                         "pair.h", "update.h", "cph_b200.h"}
     assert "lammps_shim" not in src
 
 
@@ -72,13 +73,17 @@ def parse(out):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["charge", "reference", "vv", "buffer", "theta"])
+@pytest.mark.parametrize("mode", ["charge", "reference", "vv", "buffer", "theta", "bonded"])
 def test_fix_trajectory_matches_oracle(box_files, mode):
     box, b, s = box_files
     nsteps = 120
     if mode == "charge":
         args = ["sites", s, "mlambda", 2000]
         kw = dict(bias=dict(m_lambda=2000.0))
+    elif mode == "bonded":
+        # reference mode + a host-side bonded energy source folded into HA/HB (cpp:221-253)
+        args = ["nevery", 2, "bonded", 0.01, "mlambda", 2000, "lambda0", 0.5]
+        kw = dict(bias=dict(m_lambda=2000.0), dudl=capi.DUDL_REFERENCE, implicit_site=True, nevery=2)
     elif mode == "theta":
         args = ["sites", s, "mlambda", 2000, "coordinate", "theta"]
         kw = dict(bias=dict(m_lambda=2000.0), theta=True)
@@ -100,12 +105,22 @@ def test_fix_trajectory_matches_oracle(box_files, mode):
     orc = capi.configure(capi.Engine("orc"), box, **kw)
     lam, H = [], []
     f = np.zeros((box.n, 3))
+    nev = kw.get("nevery", 1)
+
+    def extras(step):
+        if mode != "bonded" or step % nev:
+            return
+        e = 0.01 * (1 + np.arange(box.n) % 7)
+        Hm = (box.mask & synth.GROUP_H_BIT) != 0
+        orc.set_extra_partition(float(e.sum()), float(e[~Hm].sum()))
+
+    extras(0)
     orc.post_force(0, box.dt, box.x, f)                       # setup()
     lam.append(orc.get_sites()["lambda"].copy()); H.append(orc.compute_scalar())
-    nev = kw.get("nevery", 1)
     for step in range(1, nsteps + 1):
         if mode == "vv":
             orc.initial_integrate(box.dt * nev)
+        extras(step)
         orc.post_force(step, box.dt, box.x, f)
         if mode == "vv":
             orc.final_integrate(box.dt * nev)
