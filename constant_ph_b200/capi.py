@@ -161,6 +161,9 @@ class Engine:
     def set_mode(self, dudl=DUDL_CHARGE, integrator=INTEGRATE_REFERENCE, fscale=FSCALE_LAMBDA):
         self._call("set_mode", C.c_int(dudl), C.c_int(integrator), C.c_int(fscale))
 
+    def set_thermostat(self, tau):
+        self._call("set_thermostat", C.c_double(tau))
+
     def set_extra_partition(self, dHA, dHB):
         self._call("set_extra_partition", C.c_double(dHA), C.c_double(dHB))
 
@@ -273,7 +276,7 @@ class Engine:
         out = np.zeros(8)
         self._call("get_scalars", _d(out))
         return dict(HA=out[0], HB=out[1], evdwl=out[2], ecoul=out[3], H_lambda=out[4], ke=out[5],
-                    maxdisp2=out[6])
+                    maxdisp2=out[6], thermostat=out[7])
 
     def get_sites(self):
         S = self.nsites
@@ -365,7 +368,7 @@ class Engine:
 def configure(eng, box, nevery=1, dudl=DUDL_CHARGE, integrator=INTEGRATE_REFERENCE,
               fscale=FSCALE_LAMBDA, bias_mode=BIAS_EXACT, implicit_site=False, ftm2v=None,
               sublo=None, subhi=None, procgrid=(1, 1, 1), myloc=(0, 0, 0), owned=None, bias=None,
-              water_buffer=False, theta=False, cut_lj=None, cut_coul=None):
+              water_buffer=False, theta=False, cut_lj=None, cut_coul=None, thermostat=0.0):
     """Push a synth.Box into an engine: the calls FixConstantPH's constructor/init/setup make.
 
     implicit_site=True reproduces the reference's single global lambda over the hydrogen
@@ -386,6 +389,8 @@ def configure(eng, box, nevery=1, dudl=DUDL_CHARGE, integrator=INTEGRATE_REFEREN
         eng.set_water_buffer(True)
     if theta:
         eng.set_coordinate(True)
+    if thermostat:
+        eng.set_thermostat(thermostat)
     if implicit_site:
         eng.set_sites(0, None, None, None, None, None)
         eng.set_lambda(box.lambda0[:1], box.v0[:1])

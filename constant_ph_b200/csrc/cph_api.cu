@@ -288,6 +288,12 @@ int cph_set_mode(cph_handle *h, int dudl_mode, int integrator_mode, int fscale_m
   return CPH_OK;
 }
 
+int cph_set_thermostat(cph_handle *h, double tau) {
+  if (tau < 0) return cph_fail(h, CPH_ERR_ARG, "thermostat period must be >= 0");
+  h->nh_tau = tau;
+  return CPH_OK;
+}
+
 int cph_set_extra_partition(cph_handle *h, double dHA, double dHB) {
   h->extra_HA = dHA;
   h->extra_HB = dHB;
@@ -603,7 +609,10 @@ int cph_get_scalars(cph_handle *h, double *out8) {
   CPH_CUDA(h, cudaMemcpyAsync(sc, h->d_scal.p, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
   CPH_CUDA(h, cudaStreamSynchronize(h->stream));
   out8[0] = red[0]; out8[1] = red[1]; out8[2] = red[2]; out8[3] = red[3];
-  out8[4] = sc[4]; out8[5] = sc[5]; out8[6] = h->scal_h[6]; out8[7] = 0;
+  double nhe = 0;
+  CPH_CUDA(h, cudaMemcpyAsync(&nhe, h->d_scal.p + 11, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  out8[4] = sc[4]; out8[5] = sc[5]; out8[6] = h->scal_h[6]; out8[7] = nhe;
   return CPH_OK;
 }
 
@@ -689,7 +698,7 @@ int cph_get_neighbors(cph_handle *h, int *numneigh, int64_t *keys, int64_t keys_
 }
 
 // ---- restart: [version, S, (lambda, v, a) * S] as doubles (LAMMPS write_restart layout) ----------------------
-int cph_restart_size(cph_handle *h, int *ndoubles) { *ndoubles = 2 + 3 * h->S; return CPH_OK; }
+int cph_restart_size(cph_handle *h, int *ndoubles) { *ndoubles = 2 + 3 * h->S + (h->nh_tau > 0 ? 2 : 0); return CPH_OK; }
 
 int cph_pack_restart(cph_handle *h, double *buf) {
   cudaSetDevice(h->device);
@@ -702,13 +711,21 @@ int cph_pack_restart(cph_handle *h, double *buf) {
   CPH_CUDA(h, cudaStreamSynchronize(h->stream));
   buf[0] = h->coord_theta ? 2.0 : 1.0; buf[1] = S;
   for (int s = 0; s < S; s++) { buf[2 + 3 * s] = l[s]; buf[3 + 3 * s] = v[s]; buf[4 + 3 * s] = a[s]; }
+  if (h->nh_tau > 0) {   // thermostat state: xi, eta
+    double sc[12];
+    CPH_CUDA(h, cudaMemcpyAsync(sc, h->d_scal.p, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
+    CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+    buf[2 + 3 * S] = sc[8];
+    buf[3 + 3 * S] = sc[10];
+  }
   return CPH_OK;
 }
 
 int cph_unpack_restart(cph_handle *h, const double *buf, int nd) {
   cudaSetDevice(h->device);
   const int S = h->S;
-  if (!buf || nd < 2 || (int)buf[1] != S || nd != 2 + 3 * S)
+  const int extra = h->nh_tau > 0 ? 2 : 0;
+  if (!buf || nd < 2 || (int)buf[1] != S || nd != 2 + 3 * S + extra)
     return cph_fail(h, CPH_ERR_ARG, "restart record does not match the site table (%d sites)", S);
   if ((buf[0] == 2.0) != h->coord_theta)
     return cph_fail(h, CPH_ERR_ARG, "restart record was written with the other lambda coordinate");
@@ -724,6 +741,10 @@ int cph_unpack_restart(cph_handle *h, const double *buf, int nd) {
   CPH_CUDA(h, cudaMemcpyAsync(h->d_lam.p, l.data(), S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CPH_CUDA(h, cudaMemcpyAsync(h->d_vlam.p, v.data(), S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CPH_CUDA(h, cudaMemcpyAsync(h->d_alam.p, a.data(), S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (extra) {
+    CPH_CUDA(h, cudaMemcpyAsync(h->d_scal.p + 8, &buf[2 + 3 * S], sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CPH_CUDA(h, cudaMemcpyAsync(h->d_scal.p + 10, &buf[3 + 3 * S], sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
   CPH_CUDA(h, cudaStreamSynchronize(h->stream));
   if (h->have_atoms && h->fix.dudl_mode == CPH_DUDL_CHARGE) {
     CPH_TRY(cph_launch_apply_charges(h));

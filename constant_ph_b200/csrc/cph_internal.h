@@ -122,6 +122,7 @@ struct cph_handle {
   DevBuf<double> d_pK, d_lam, d_vlam, d_alam, d_flam, d_fs, d_dfs, d_Us, d_dUs;
   DevBuf<double> d_theta;            // dynamical coordinate when coord_theta (lambda = sin^2 theta)
   bool coord_theta = false;
+  double nh_tau = 0.0;               // Nose-Hoover period of the lambda thermostat (0 = off); xi, eta in d_scal[8], [10]
   // one contiguous reduction buffer so a single allreduce covers everything (cpp:274):
   // [0]=HA [1]=HB [2]=E_vdwl [3]=E_coul [4..4+S)=dU/dlambda_s [4+S..4+2S)=HB_s-HA_s
   // [4+2S]=sum of dE/dq over the owned water-buffer atoms (modify_water)

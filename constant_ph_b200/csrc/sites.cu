@@ -155,7 +155,10 @@ __device__ __forceinline__ BiasOut bias_terms(const BiasParams &bp, double lambd
 __global__ void __launch_bounds__(TPB)
 integrate_kernel(int S, double dt, int phase, BiasParams bp, FixParams fx, const double *__restrict__ pK,
                  const double *__restrict__ red, double *lam, double *theta, double *vlam, double *alam, double *flam,
-                 double *fs, double *dfs, double *Us, double *dUs, double *partials) {
+                 double *fs, double *dfs, double *Us, double *dUs, double *partials, const double *__restrict__ scal,
+                 int thermo) {
+  // thermo: Nose-Hoover on the site velocities (velocity-Verlet form only); scal[9] = exp(-xi dt/2)
+  const double nh = thermo ? scal[9] : 1.0;
   // theta != NULL: the dynamical coordinate is theta with lambda = sin^2(theta) (north_star's lambda/theta
   // variables; absent from the reference, which integrates lambda itself and confines it with U4/U5);
   // velocity, acceleration and mass then refer to theta and F_theta = F_lambda * sin(2 theta).
@@ -164,7 +167,7 @@ integrate_kernel(int S, double dt, int phase, BiasParams bp, FixParams fx, const
     double cq = theta ? theta[s] : lam[s];
     double vel = vlam[s], acc = alam[s];
     if (phase == 1) {
-      vel += 0.5 * acc * dt;
+      vel = vel * nh + 0.5 * acc * dt;
       cq += vel * dt;
       if (theta) { theta[s] = cq; const double sn = sin(cq); lam[s] = sn * sn; }
       else lam[s] = cq;
@@ -173,7 +176,7 @@ integrate_kernel(int S, double dt, int phase, BiasParams bp, FixParams fx, const
     }
     double lambda = cq, chain = 1.0;
     if (theta) { const double sn = sin(cq); lambda = sn * sn; chain = sin(2.0 * cq); }
-    if (phase == 3) vel += 0.5 * acc * dt;
+    if (phase == 3) vel = (vel + 0.5 * acc * dt) * nh;
     BiasOut b = bias_terms(bp, lambda);
     const double pk = fx.implicit_site ? fx.pK : pK[s];
     const double hd = red[4 + S + s];
@@ -198,8 +201,18 @@ integrate_kernel(int S, double dt, int phase, BiasParams bp, FixParams fx, const
   if (phase != 1) block_reduce_store<3>(v, partials);
 }
 
+// Nose-Hoover half step before the first kick: xi += dt/2 (2K - S kT)/Q, eta += xi dt/2,
+// scal[9] = exp(-xi dt/2).  scal[5] = K of the previous step, scal[8] = xi, scal[10] = eta.
+__global__ void nh_pre_kernel(double *scal, double dt, double SkT, double Q) {
+  if (threadIdx.x || blockIdx.x) return;
+  double xi = scal[8] + 0.5 * dt * (2.0 * scal[5] - SkT) / Q;
+  scal[8] = xi;
+  scal[10] += 0.5 * dt * xi;
+  scal[9] = exp(-0.5 * dt * xi);
+}
+
 __global__ void integrate_final_kernel(int nb, const double *__restrict__ partials, const double *__restrict__ red,
-                                       int dudl_mode, double *scal) {
+                                       int dudl_mode, double *scal, int thermo_post, double dt, double SkT, double Q) {
   const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
   __shared__ double out[3];
   if (c < 3) {
@@ -214,6 +227,11 @@ __global__ void integrate_final_kernel(int nb, const double *__restrict__ partia
     double eff = (dudl_mode == CPH_DUDL_REFERENCE) ? red[0] + out[1] : red[2] + red[3];
     scal[4] = eff + out[0];
     scal[5] = out[2];
+    if (thermo_post) {   // second Nose-Hoover half step, with the kinetic energy after the scaled final kick
+      scal[10] += 0.5 * dt * scal[8];
+      scal[8] += 0.5 * dt * (2.0 * out[2] - SkT) / Q;
+      scal[11] = 0.5 * Q * scal[8] * scal[8] + SkT * scal[10];    // thermostat energy (conserved with H_lambda)
+    }
   }
 }
 
@@ -365,12 +383,19 @@ int cph_launch_integrate(cph_handle *h, double dt, int phase) {
   cudaStream_t st = h->stream;
   CPH_CUDA(h, h->d_part.reserve((size_t)MAXPART * 4));
   int nb = std::max(1, std::min(MAXPART, nblk(S)));
+  const int thermo = (h->nh_tau > 0 && h->fix.integ_mode == CPH_INTEGRATE_VV && (phase == 1 || phase == 3)) ? 1 : 0;
+  const double SkT = S * h->fix.boltz * h->fix.T, Q = SkT * h->nh_tau * h->nh_tau;
+  if (thermo && phase == 1) {
+    h->nlaunch++;
+    nh_pre_kernel<<<1, 32, 0, st>>>(h->d_scal.p, dt, SkT, Q);
+  }
   integrate_kernel<<<nb, TPB, 0, st>>>(S, dt, phase, h->bias, h->fix, h->d_pK.p, h->d_red.p, h->d_lam.p,
                                        h->coord_theta ? h->d_theta.p : nullptr, h->d_vlam.p,
                                        h->d_alam.p, h->d_flam.p, h->d_fs.p, h->d_dfs.p, h->d_Us.p, h->d_dUs.p,
-                                       h->d_part.p);
+                                       h->d_part.p, h->d_scal.p, thermo);
   if (phase != 1)
-    integrate_final_kernel<<<1, 96, 0, st>>>(nb, h->d_part.p, h->d_red.p, h->fix.dudl_mode, h->d_scal.p);
+    integrate_final_kernel<<<1, 96, 0, st>>>(nb, h->d_part.p, h->d_red.p, h->fix.dudl_mode, h->d_scal.p,
+                                             thermo && phase == 3 && dt > 0, dt, SkT, Q);
   h->nlaunch += phase != 1 ? 2 : 1;
   CPH_CUDA(h, cudaGetLastError());
   return 0;

@@ -102,6 +102,11 @@ int cph_set_mode(cph_handle *h, int dudl_mode, int integrator_mode, int fscale_m
  * confines it with the wall terms U4/U5 of cpp:135-136).  CPH_COORD_THETA: the dynamical coordinate is theta
  * with lambda = sin^2(theta); v_lambda, the mass and the restart record then refer to theta and
  * F_theta = F_lambda * sin(2 theta).  cph_set_lambda still takes lambda (theta = asin(sqrt(lambda))). */
+/* Nose-Hoover thermostat on the site velocities at the fix's temperature T (velocity-Verlet form only;
+ * absent from the reference): tau = period in time units, 0 = off.  The restart record then also carries
+ * the thermostat state, and out8[7] of cph_get_scalars is the thermostat energy Q xi^2/2 + S k T eta,
+ * which together with H_lambda is conserved for frozen atoms. */
+int cph_set_thermostat(cph_handle *h, double tau);
 #define CPH_COORD_LAMBDA 0
 #define CPH_COORD_THETA  1
 int cph_set_coordinate(cph_handle *h, int coordinate);
@@ -172,7 +177,7 @@ int cph_get_eatom(cph_handle *h, int where, double *eatom);  /* nlocal; pair eat
 int cph_get_phi(cph_handle *h, int where, double *phi);      /* nlocal; d E_coul / d q_i */
 int cph_get_q(cph_handle *h, int where, double *q);          /* nlocal; current charges */
 /* out[0]=HA out[1]=HB (cpp:276-277) out[2]=E_vdwl out[3]=E_coul out[4]=H_lambda (cpp:114)
- * out[5]=sum of site kinetic energies out[6]=max displacement^2 at the last check out[7]=reserved */
+ * out[5]=sum of site kinetic energies out[6]=max displacement^2 at the last check out[7]=thermostat energy */
 int cph_get_scalars(cph_handle *h, double *out8);
 /* per-site arrays, each nsites long or NULL: lambda, v_lambda, dU/dlambda (charge), HB_s-HA_s,
  * F_lambda (cpp:111), f, df (cpp:122-123), U, dU (cpp:143-144). */

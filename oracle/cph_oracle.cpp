@@ -74,6 +74,7 @@ struct Oracle {
   double bw = 200.0, bs = 0.3, bh = 4.0, bk = 2.533, ba = 0.034041, bb = 0.005238, br = 16.458,
          bm = 0.1507, bd = 2.0, m_lambda = 20.0;
   int bias_mode = 0, dudl_mode = 1, integ_mode = 0, fscale_mode = 0;
+  double nh_tau = 0, nh_xi = 0, nh_eta = 0, nh_energy = 0;   // Nose-Hoover thermostat on the site velocities
   int coord_theta = 0;            // 1: the dynamical coordinate is theta, lambda = sin^2 theta
   std::vector<double> theta;
   double extra_HA = 0, extra_HB = 0;   // host-tallied sources of compute_Hs (cpp:221-249)
@@ -468,16 +469,24 @@ void bias_terms(const Oracle *o, double lambda, double &f, double &df, double &U
 void integrate(Oracle *o, double dt, int phase) {
   const double ln10 = std::log(10.0);
   long double hsum = 0, ke = 0, eff_ref = 0;
+  const bool thermo = o->nh_tau > 0 && o->integ_mode == 1 && (phase == 1 || phase == 3);
+  const double SkT = o->S * o->boltz * o->T, Q = SkT * o->nh_tau * o->nh_tau;
+  double nh = 1.0;
+  if (thermo && phase == 1) {          // first Nose-Hoover half step (K of the previous step)
+    o->nh_xi += 0.5 * dt * (2.0 * o->ke_sites - SkT) / Q;
+    o->nh_eta += 0.5 * dt * o->nh_xi;
+  }
+  if (thermo) nh = std::exp(-0.5 * dt * o->nh_xi);
   for (int s = 0; s < o->S; s++) {
     double &cq = o->coord_theta ? o->theta[s] : o->lam[s];
     double &v = o->vlam[s], &acc = o->alam[s];
     if (phase == 1) {
-      v += 0.5 * acc * dt;
+      v = v * nh + 0.5 * acc * dt;
       cq += v * dt;
       if (o->coord_theta) { double sn = std::sin(cq); o->lam[s] = sn * sn; }
       continue;
     }
-    if (phase == 3) v += 0.5 * acc * dt;
+    if (phase == 3) v = (v + 0.5 * acc * dt) * nh;
     double lambda = cq, chain = 1.0;
     if (o->coord_theta) { double sn = std::sin(cq); lambda = sn * sn; chain = std::sin(2.0 * cq); }
     double f, df, U, dU;
@@ -505,6 +514,11 @@ void integrate(Oracle *o, double dt, int phase) {
   double eff = (o->dudl_mode == 0) ? o->HA + (double)eff_ref : o->evdwl + o->ecoul;
   o->Hlambda = eff + (double)hsum;
   o->ke_sites = (double)ke;
+  if (thermo && phase == 3 && dt > 0) {   // second Nose-Hoover half step
+    o->nh_eta += 0.5 * dt * o->nh_xi;
+    o->nh_xi += 0.5 * dt * (2.0 * o->ke_sites - SkT) / Q;
+    o->nh_energy = 0.5 * Q * o->nh_xi * o->nh_xi + SkT * o->nh_eta;
+  }
 }
 
 void apply_charges(Oracle *o) {
@@ -627,6 +641,7 @@ int orc_set_bias(void *h, double w, double s, double hbar, double k, double a, d
   return 0;
 }
 
+int orc_set_thermostat(void *h, double tau) { ORC->nh_tau = tau; return 0; }
 int orc_set_extra_partition(void *h, double a, double b) { ORC->extra_HA = a; ORC->extra_HB = b; return 0; }
 int orc_set_coordinate(void *h, int c) { ORC->coord_theta = c == 1; return 0; }
 int orc_set_water_buffer(void *h, int enable) { ORC->water_buffer = enable ? 1 : 0; return 0; }
@@ -756,7 +771,7 @@ int orc_get_q(void *h, int, double *q) { std::memcpy(q, ORC->q.data(), sizeof(do
 int orc_get_scalars(void *h, double *out) {
   Oracle *o = ORC;
   out[0] = o->HA; out[1] = o->HB; out[2] = o->evdwl; out[3] = o->ecoul; out[4] = o->Hlambda;
-  out[5] = o->ke_sites; out[6] = o->maxdisp2; out[7] = 0;
+  out[5] = o->ke_sites; out[6] = o->maxdisp2; out[7] = o->nh_energy;
   return 0;
 }
 int orc_get_sites(void *h, double *lambda, double *v, double *dudl, double *hdiff, double *flam, double *f,
@@ -822,16 +837,19 @@ int orc_get_neighbors(void *h, int *numneigh, int64_t *keys, int64_t cap) {
   return 0;
 }
 
-int orc_restart_size(void *h, int *nd) { *nd = 2 + 3 * ORC->S; return 0; }
+int orc_restart_size(void *h, int *nd) { *nd = 2 + 3 * ORC->S + (ORC->nh_tau > 0 ? 2 : 0); return 0; }
 int orc_pack_restart(void *h, double *buf) {
   Oracle *o = ORC;
   buf[0] = o->coord_theta ? 2.0 : 1.0; buf[1] = o->S;
   for (int s = 0; s < o->S; s++) { buf[2 + 3 * s] = o->coord_theta ? o->theta[s] : o->lam[s]; buf[3 + 3 * s] = o->vlam[s]; buf[4 + 3 * s] = o->alam[s]; }
+  if (o->nh_tau > 0) { buf[2 + 3 * o->S] = o->nh_xi; buf[3 + 3 * o->S] = o->nh_eta; }
   return 0;
 }
 int orc_unpack_restart(void *h, const double *buf, int nd) {
   Oracle *o = ORC;
-  if (nd < 2 || (int)buf[1] != o->S || nd != 2 + 3 * o->S) return fail(o, -1, "restart does not match the site table");
+  const int extra = o->nh_tau > 0 ? 2 : 0;
+  if (nd < 2 || (int)buf[1] != o->S || nd != 2 + 3 * o->S + extra) return fail(o, -1, "restart does not match the site table");
+  if (extra) { o->nh_xi = buf[2 + 3 * o->S]; o->nh_eta = buf[3 + 3 * o->S]; }
   if ((buf[0] == 2.0) != (o->coord_theta != 0)) return fail(o, -1, "restart record was written with the other lambda coordinate");
   for (int s = 0; s < o->S; s++) {
     if (o->coord_theta) { o->theta[s] = buf[2 + 3 * s]; double sn = std::sin(o->theta[s]); o->lam[s] = sn * sn; }

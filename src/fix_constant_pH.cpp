@@ -13,6 +13,7 @@
        lambda0 VALUE         initial lambda when no site file is given (never set in the reference)
        buffer yes|no         modify_water() (h:58): keep the box charge constant through groupW
        coordinate lambda|theta   integrate lambda itself (reference) or theta with lambda = sin^2(theta)
+       tlambda TAU           Nose-Hoover thermostat (period TAU) on the site velocities at T; needs integrator vv
 
    The host side stays a LAMMPS Fix; every per-timestep loop of the reference (cpp:149-171,
    cpp:212-267) and the pair arithmetic north_star pulls into the path run in libcph_b200.so.
@@ -76,6 +77,7 @@ FixConstantPH::FixConstantPH(LAMMPS *lmp, int narg, char **arg) :
   m_lambda = 20.0;                                                                     // cpp:96
   water_buffer = 0;
   coord_theta = 0;
+  t_lambda_period = 0.0;
   lambda_host = 0.5;
   nsites = ntitr = 0;
   restart_n = 0;
@@ -110,6 +112,9 @@ FixConstantPH::FixConstantPH(LAMMPS *lmp, int narg, char **arg) :
     } else if (strcmp(key, "mlambda") == 0) {
       m_lambda = utils::numeric(FLERR, val, false, lmp);
       if (m_lambda <= 0.0) error->all(FLERR, "Illegal fix constant_pH mlambda value {}", m_lambda);
+    } else if (strcmp(key, "tlambda") == 0) {
+      t_lambda_period = utils::numeric(FLERR, val, false, lmp);
+      if (t_lambda_period < 0.0) error->all(FLERR, "Illegal fix constant_pH tlambda value {}", t_lambda_period);
     } else if (strcmp(key, "coordinate") == 0) {
       if (strcmp(val, "theta") == 0) coord_theta = 1;
       else if (strcmp(val, "lambda") == 0) coord_theta = 0;
@@ -266,6 +271,9 @@ void FixConstantPH::init()
   check(cph_set_fix(cph, nevery, groupHbit, groupWbit, pK, pH, T), "cph_set_fix");
   check(cph_set_bias(cph, w, s, h, k, a, b, r, m, d, m_lambda, bias_mode), "cph_set_bias");   // cpp:86-96
   check(cph_set_mode(cph, dudl_mode, integrator_mode, fscale_mode), "cph_set_mode");
+  if (t_lambda_period > 0.0 && integrator_mode != CPH_INTEGRATE_VV)
+    error->all(FLERR, "fix constant_pH tlambda requires integrator vv");
+  check(cph_set_thermostat(cph, t_lambda_period), "cph_set_thermostat");
   check(cph_set_coordinate(cph, coord_theta ? CPH_COORD_THETA : CPH_COORD_LAMBDA), "cph_set_coordinate");
   check(cph_set_water_buffer(cph, water_buffer ? (int) group->count(igroupW) : 0), "cph_set_water_buffer");
   check(cph_set_sites(cph, nsites, site_pK, ntitr, titr_tag, titr_site, titr_qA, titr_qB), "cph_set_sites");
@@ -514,7 +522,7 @@ double FixConstantPH::memory_usage()
 }
 
 /* ----------------------------------------------------------------------
-   restart: [version, S, (lambda, v, a) * S] as doubles, LAMMPS global-restart layout
+   restart: [version, S, (lambda|theta, v, a) * S, (xi, eta if tlambda)] as doubles, LAMMPS global-restart layout
 ------------------------------------------------------------------------- */
 
 void FixConstantPH::write_restart(FILE *fp)
@@ -535,7 +543,7 @@ void FixConstantPH::restart(char *buf)
 {
   double *list = (double *) buf;
   const int S = (int) list[1];
-  restart_n = 2 + 3 * S;
+  restart_n = 2 + 3 * S + (t_lambda_period > 0.0 ? 2 : 0);     // + thermostat state (xi, eta)
   free(restart_buf);
   restart_buf = (double *) malloc(sizeof(double) * restart_n);
   memcpy(restart_buf, list, sizeof(double) * restart_n);

@@ -53,6 +53,7 @@ class FixConstantPH : public Fix {
   double pK, pH, T;
   double a, b, s, m, w, r, d, h, k;      // h and k are used at cpp:88-89 but undeclared in the reference
   double m_lambda;
+  double t_lambda_period;                // Nose-Hoover period of the lambda thermostat (0 = off)
   double HA, HB;
   int nmax;
   double *H_atom;                        // kept for interface parity; energies live on the device

@@ -73,13 +73,16 @@ def parse(out):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["charge", "reference", "vv", "buffer", "theta", "bonded"])
+@pytest.mark.parametrize("mode", ["charge", "reference", "vv", "buffer", "theta", "bonded", "thermostat"])
 def test_fix_trajectory_matches_oracle(box_files, mode):
     box, b, s = box_files
     nsteps = 120
     if mode == "charge":
         args = ["sites", s, "mlambda", 2000]
         kw = dict(bias=dict(m_lambda=2000.0))
+    elif mode == "thermostat":
+        args = ["sites", s, "mlambda", 2000, "integrator", "vv", "coordinate", "theta", "tlambda", 40]
+        kw = dict(bias=dict(m_lambda=2000.0), integrator=capi.INTEGRATE_VV, theta=True, thermostat=40.0)
     elif mode == "bonded":
         # reference mode + a host-side bonded energy source folded into HA/HB (cpp:221-253)
         args = ["nevery", 2, "bonded", 0.01, "mlambda", 2000, "lambda0", 0.5]
@@ -118,16 +121,16 @@ def test_fix_trajectory_matches_oracle(box_files, mode):
     orc.post_force(0, box.dt, box.x, f)                       # setup()
     lam.append(orc.get_sites()["lambda"].copy()); H.append(orc.compute_scalar())
     for step in range(1, nsteps + 1):
-        if mode == "vv":
+        if mode in ("vv", "thermostat"):
             orc.initial_integrate(box.dt * nev)
         extras(step)
         orc.post_force(step, box.dt, box.x, f)
-        if mode == "vv":
+        if mode in ("vv", "thermostat"):
             orc.final_integrate(box.dt * nev)
         lam.append(orc.get_sites()["lambda"].copy()); H.append(orc.compute_scalar())
     lam, H = np.array(lam), np.array(H)
     assert np.abs(rows[:, 2:] - lam).max() <= 1e-8
     assert np.abs(rows[:, 1] - H).max() <= 1e-8 * np.abs(H).max()
     assert abs(extra["FORCES_ABS_SUM"] - np.abs(f).sum()) <= 1e-9 * np.abs(f).sum()
-    assert extra["RESTART_BYTES"] == 8 * (2 + 3 * max(1, lam.shape[1]))
+    assert extra["RESTART_BYTES"] == 8 * (2 + 3 * max(1, lam.shape[1]) + (2 if mode == "thermostat" else 0))
     assert extra["MEMORY_USAGE"] > 1e6

@@ -433,3 +433,32 @@ def test_per_type_pair_cutoffs(built, cfg, scale):
     kw = dict(cut_lj=np.full((nt1, nt1), 10.0), cut_coul=9.0, bias=HEAVY)
     gpu, orc = engines(box, **kw)
     check_pass(gpu, orc)
+
+
+def test_nose_hoover_thermostat(built):
+    """lambda thermostat (f3): CUDA path against the oracle, including the thermostat state in the restart."""
+    box = synth.config(2, scale=0.25)
+    gpu, orc = engines(box, bias=HEAVY, theta=True, integrator=capi.INTEGRATE_VV, thermostat=40.0)
+    for eng in (gpu, orc):
+        eng.post_force(0, box.dt, box.x, None)
+        eng.final_integrate(0.0)
+        for step in range(1, 200):
+            eng.initial_integrate(box.dt)
+            eng.post_force(step, box.dt, box.x, None)
+            eng.final_integrate(box.dt)
+    tg, to = gpu.get_sites(), orc.get_sites()
+    assert np.abs(tg["lambda"] - to["lambda"]).max() <= 1e-8
+    assert np.abs(tg["v_lambda"] - to["v_lambda"]).max() <= 1e-8
+    sg, so = gpu.get_scalars(), orc.get_scalars()
+    assert abs(sg["thermostat"] - so["thermostat"]) <= 1e-8 * max(1.0, abs(so["thermostat"]))
+    assert abs(sg["ke"] - so["ke"]) <= 1e-8 * max(1.0, so["ke"])
+    bg, bo = gpu.pack_restart(), orc.pack_restart()
+    assert bg.size == 4 + 3 * box.nsites and np.allclose(bg, bo, rtol=0, atol=1e-8)
+    # restart into a fresh engine continues identically
+    g2 = capi.configure(capi.Engine("cph", device=0), box, bias=HEAVY, theta=True, integrator=capi.INTEGRATE_VV,
+                        thermostat=40.0)
+    g2.post_force(199, box.dt, box.x, None)
+    g2.unpack_restart(bg)
+    for eng in (gpu, g2):
+        eng.initial_integrate(box.dt); eng.post_force(200, box.dt, box.x, None); eng.final_integrate(box.dt)
+    assert np.abs(gpu.get_sites()["lambda"] - g2.get_sites()["lambda"]).max() <= 1e-12

@@ -223,3 +223,22 @@ def test_theta_coordinate_keeps_lambda_in_range_and_conserves_energy():
     p = capi.configure(capi.Engine("orc"), box, bias=dict(m_lambda=2000.0))
     with pytest.raises(capi.CphError):
         p.unpack_restart(buf)
+
+
+def test_nose_hoover_lambda_thermostat():
+    """f3: Nose-Hoover on the site velocities (velocity-Verlet form).  The site kinetic energy settles at
+    kT/2 per site and H_lambda + thermostat energy is conserved with frozen atoms."""
+    box = synth.config(2, scale=0.2)
+    o = capi.configure(capi.Engine("orc"), box, integrator=capi.INTEGRATE_VV, bias=dict(m_lambda=2000.0),
+                       thermostat=50.0, theta=True)
+    o.post_force(0, box.dt, box.x, None); o.final_integrate(0.0)
+    H, K = [], []
+    for step in range(1, 2500):
+        o.initial_integrate(box.dt); o.post_force(step, box.dt, box.x, None); o.final_integrate(box.dt)
+        s = o.get_scalars(); H.append(s["H_lambda"] + s["thermostat"]); K.append(s["ke"])
+    H, K = np.array(H), np.array(K)
+    kT = synth.BOLTZ * box.T
+    assert abs(K[800:].mean() / box.nsites - 0.5 * kT) < 0.15 * 0.5 * kT
+    assert np.abs(H - H[0]).max() < 5e-3
+    buf = o.pack_restart()
+    assert buf.size == 4 + 3 * box.nsites and buf[-2] != 0.0
