@@ -698,7 +698,7 @@ int cph_get_neighbors(cph_handle *h, int *numneigh, int64_t *keys, int64_t keys_
 }
 
 // ---- restart: [version, S, (lambda, v, a) * S] as doubles (LAMMPS write_restart layout) ----------------------
-int cph_restart_size(cph_handle *h, int *ndoubles) { *ndoubles = 2 + 3 * h->S + (h->nh_tau > 0 ? 2 : 0); return CPH_OK; }
+int cph_restart_size(cph_handle *h, int *ndoubles) { *ndoubles = 2 + 3 * h->S + (h->nh_tau > 0 ? 3 : 0); return CPH_OK; }
 
 int cph_pack_restart(cph_handle *h, double *buf) {
   cudaSetDevice(h->device);
@@ -711,12 +711,13 @@ int cph_pack_restart(cph_handle *h, double *buf) {
   CPH_CUDA(h, cudaStreamSynchronize(h->stream));
   buf[0] = h->coord_theta ? 2.0 : 1.0; buf[1] = S;
   for (int s = 0; s < S; s++) { buf[2 + 3 * s] = l[s]; buf[3 + 3 * s] = v[s]; buf[4 + 3 * s] = a[s]; }
-  if (h->nh_tau > 0) {   // thermostat state: xi, eta
+  if (h->nh_tau > 0) {   // thermostat state: xi, eta and the kinetic energy its next half step starts from
     double sc[12];
     CPH_CUDA(h, cudaMemcpyAsync(sc, h->d_scal.p, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
     CPH_CUDA(h, cudaStreamSynchronize(h->stream));
     buf[2 + 3 * S] = sc[8];
     buf[3 + 3 * S] = sc[10];
+    buf[4 + 3 * S] = sc[5];
   }
   return CPH_OK;
 }
@@ -724,7 +725,7 @@ int cph_pack_restart(cph_handle *h, double *buf) {
 int cph_unpack_restart(cph_handle *h, const double *buf, int nd) {
   cudaSetDevice(h->device);
   const int S = h->S;
-  const int extra = h->nh_tau > 0 ? 2 : 0;
+  const int extra = h->nh_tau > 0 ? 3 : 0;
   if (!buf || nd < 2 || (int)buf[1] != S || nd != 2 + 3 * S + extra)
     return cph_fail(h, CPH_ERR_ARG, "restart record does not match the site table (%d sites)", S);
   if ((buf[0] == 2.0) != h->coord_theta)
@@ -744,6 +745,7 @@ int cph_unpack_restart(cph_handle *h, const double *buf, int nd) {
   if (extra) {
     CPH_CUDA(h, cudaMemcpyAsync(h->d_scal.p + 8, &buf[2 + 3 * S], sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CPH_CUDA(h, cudaMemcpyAsync(h->d_scal.p + 10, &buf[3 + 3 * S], sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CPH_CUDA(h, cudaMemcpyAsync(h->d_scal.p + 5, &buf[4 + 3 * S], sizeof(double), cudaMemcpyHostToDevice, h->stream));
   }
   CPH_CUDA(h, cudaStreamSynchronize(h->stream));
   if (h->have_atoms && h->fix.dudl_mode == CPH_DUDL_CHARGE) {

@@ -104,7 +104,7 @@ int cph_set_mode(cph_handle *h, int dudl_mode, int integrator_mode, int fscale_m
  * F_theta = F_lambda * sin(2 theta).  cph_set_lambda still takes lambda (theta = asin(sqrt(lambda))). */
 /* Nose-Hoover thermostat on the site velocities at the fix's temperature T (velocity-Verlet form only;
  * absent from the reference): tau = period in time units, 0 = off.  The restart record then also carries
- * the thermostat state, and out8[7] of cph_get_scalars is the thermostat energy Q xi^2/2 + S k T eta,
+ * the thermostat state (xi, eta, K), and out8[7] of cph_get_scalars is the thermostat energy Q xi^2/2 + S k T eta,
  * which together with H_lambda is conserved for frozen atoms. */
 int cph_set_thermostat(cph_handle *h, double tau);
 #define CPH_COORD_LAMBDA 0

@@ -837,19 +837,19 @@ int orc_get_neighbors(void *h, int *numneigh, int64_t *keys, int64_t cap) {
   return 0;
 }
 
-int orc_restart_size(void *h, int *nd) { *nd = 2 + 3 * ORC->S + (ORC->nh_tau > 0 ? 2 : 0); return 0; }
+int orc_restart_size(void *h, int *nd) { *nd = 2 + 3 * ORC->S + (ORC->nh_tau > 0 ? 3 : 0); return 0; }
 int orc_pack_restart(void *h, double *buf) {
   Oracle *o = ORC;
   buf[0] = o->coord_theta ? 2.0 : 1.0; buf[1] = o->S;
   for (int s = 0; s < o->S; s++) { buf[2 + 3 * s] = o->coord_theta ? o->theta[s] : o->lam[s]; buf[3 + 3 * s] = o->vlam[s]; buf[4 + 3 * s] = o->alam[s]; }
-  if (o->nh_tau > 0) { buf[2 + 3 * o->S] = o->nh_xi; buf[3 + 3 * o->S] = o->nh_eta; }
+  if (o->nh_tau > 0) { buf[2 + 3 * o->S] = o->nh_xi; buf[3 + 3 * o->S] = o->nh_eta; buf[4 + 3 * o->S] = o->ke_sites; }
   return 0;
 }
 int orc_unpack_restart(void *h, const double *buf, int nd) {
   Oracle *o = ORC;
-  const int extra = o->nh_tau > 0 ? 2 : 0;
+  const int extra = o->nh_tau > 0 ? 3 : 0;
   if (nd < 2 || (int)buf[1] != o->S || nd != 2 + 3 * o->S + extra) return fail(o, -1, "restart does not match the site table");
-  if (extra) { o->nh_xi = buf[2 + 3 * o->S]; o->nh_eta = buf[3 + 3 * o->S]; }
+  if (extra) { o->nh_xi = buf[2 + 3 * o->S]; o->nh_eta = buf[3 + 3 * o->S]; o->ke_sites = buf[4 + 3 * o->S]; }
   if ((buf[0] == 2.0) != (o->coord_theta != 0)) return fail(o, -1, "restart record was written with the other lambda coordinate");
   for (int s = 0; s < o->S; s++) {
     if (o->coord_theta) { o->theta[s] = buf[2 + 3 * s]; double sn = std::sin(o->theta[s]); o->lam[s] = sn * sn; }

@@ -522,7 +522,7 @@ double FixConstantPH::memory_usage()
 }
 
 /* ----------------------------------------------------------------------
-   restart: [version, S, (lambda|theta, v, a) * S, (xi, eta if tlambda)] as doubles, LAMMPS global-restart layout
+   restart: [version, S, (lambda|theta, v, a) * S, (xi, eta, K if tlambda)] as doubles, LAMMPS global-restart layout
 ------------------------------------------------------------------------- */
 
 void FixConstantPH::write_restart(FILE *fp)
@@ -543,7 +543,7 @@ void FixConstantPH::restart(char *buf)
 {
   double *list = (double *) buf;
   const int S = (int) list[1];
-  restart_n = 2 + 3 * S + (t_lambda_period > 0.0 ? 2 : 0);     // + thermostat state (xi, eta)
+  restart_n = 2 + 3 * S + (t_lambda_period > 0.0 ? 3 : 0);     // + thermostat state (xi, eta, K)
   free(restart_buf);
   restart_buf = (double *) malloc(sizeof(double) * restart_n);
   memcpy(restart_buf, list, sizeof(double) * restart_n);

@@ -132,5 +132,5 @@ def test_fix_trajectory_matches_oracle(box_files, mode):
     assert np.abs(rows[:, 2:] - lam).max() <= 1e-8
     assert np.abs(rows[:, 1] - H).max() <= 1e-8 * np.abs(H).max()
     assert abs(extra["FORCES_ABS_SUM"] - np.abs(f).sum()) <= 1e-9 * np.abs(f).sum()
-    assert extra["RESTART_BYTES"] == 8 * (2 + 3 * max(1, lam.shape[1]) + (2 if mode == "thermostat" else 0))
+    assert extra["RESTART_BYTES"] == 8 * (2 + 3 * max(1, lam.shape[1]) + (3 if mode == "thermostat" else 0))
     assert extra["MEMORY_USAGE"] > 1e6

@@ -453,7 +453,7 @@ def test_nose_hoover_thermostat(built):
     assert abs(sg["thermostat"] - so["thermostat"]) <= 1e-8 * max(1.0, abs(so["thermostat"]))
     assert abs(sg["ke"] - so["ke"]) <= 1e-8 * max(1.0, so["ke"])
     bg, bo = gpu.pack_restart(), orc.pack_restart()
-    assert bg.size == 4 + 3 * box.nsites and np.allclose(bg, bo, rtol=0, atol=1e-8)
+    assert bg.size == 5 + 3 * box.nsites and np.allclose(bg, bo, rtol=0, atol=1e-8)
     # restart into a fresh engine continues identically
     g2 = capi.configure(capi.Engine("cph", device=0), box, bias=HEAVY, theta=True, integrator=capi.INTEGRATE_VV,
                         thermostat=40.0)

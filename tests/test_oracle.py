@@ -241,4 +241,4 @@ def test_nose_hoover_lambda_thermostat():
     assert abs(K[800:].mean() / box.nsites - 0.5 * kT) < 0.15 * 0.5 * kT
     assert np.abs(H - H[0]).max() < 5e-3
     buf = o.pack_restart()
-    assert buf.size == 4 + 3 * box.nsites and buf[-2] != 0.0
+    assert buf.size == 5 + 3 * box.nsites and buf[-3] != 0.0
