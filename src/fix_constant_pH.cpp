@@ -38,97 +38,114 @@
 #include "pair.h"
 #include "update.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "cph_b200.h"
 
 using namespace LAMMPS_NS;
 using namespace FixConst;
 
-/* ---------------------------------------------------------------------- */
+namespace {
 
-FixConstantPH::FixConstantPH(LAMMPS *lmp, int narg, char **arg) :
-  Fix(lmp, narg, arg), H_atom(nullptr), cph(nullptr), sitefile(nullptr), site_pK(nullptr),
-  site_lambda0(nullptr), titr_qA(nullptr), titr_qB(nullptr), titr_tag(nullptr), titr_site(nullptr),
-  restart_buf(nullptr), xbuf(nullptr), fbuf(nullptr)
+// keywords whose value is one of two words
+struct Choice {
+  const char *key, *word0, *word1;
+  int val0, val1;
+};
+const Choice kChoices[] = {
+    {"dudl", "reference", "charge", CPH_DUDL_REFERENCE, CPH_DUDL_CHARGE},
+    {"integrator", "reference", "vv", CPH_INTEGRATE_REFERENCE, CPH_INTEGRATE_VV},
+    {"fscale", "lambda", "oneminus", CPH_FSCALE_LAMBDA, CPH_FSCALE_ONE_MINUS},
+    {"bias", "exact", "aswritten", CPH_BIAS_EXACT, CPH_BIAS_AS_WRITTEN},
+    {"buffer", "no", "yes", 0, 1},
+    {"coordinate", "lambda", "theta", CPH_COORD_LAMBDA, CPH_COORD_THETA},
+};
+const int kNumChoices = sizeof(kChoices) / sizeof(kChoices[0]);
+
+// one rank per GPU: the launcher's local rank picks the device
+int local_device()
 {
-  if (narg < 9) utils::missing_cmd_args(FLERR, "fix constant_pH", error);              // cpp:36 (D3)
-  nevery = utils::inumeric(FLERR, arg[3], false, lmp);                                 // cpp:37
-  if (nevery <= 0) error->all(FLERR, "Illegal fix constant pH every value {}", nevery); // cpp:38 (D4)
-  igroupH = group->find(arg[4]);                                                       // cpp:39
-  if (igroupH == -1) error->all(FLERR, "Cannot find the hydrogens group for fix constant_pH");  // cpp:40 (D5)
-  groupHbit = group->bitmask[igroupH];                                                 // cpp:41
-  igroupW = group->find(arg[5]);                                                       // cpp:42
-  if (igroupW == -1) error->all(FLERR, "Cannot find the water group for fix constant_pH");      // cpp:43
-  if (group->count(igroupW) != 3)                                                      // cpp:44-45
-    error->all(FLERR, "Number of atoms in the water molecule for the fix constant_pH is {} instead of three",
-               group->count(igroupW));
-  groupWbit = group->bitmask[igroupW];                                                 // cpp:46
-  pK = utils::numeric(FLERR, arg[6], false, lmp);                                      // cpp:47
-  pH = utils::numeric(FLERR, arg[7], false, lmp);                                      // cpp:48
-  T = utils::numeric(FLERR, arg[8], false, lmp);                                       // cpp:49
+  for (const char *name : {"LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "SLURM_LOCALID", "MV2_COMM_WORLD_LOCAL_RANK"})
+    if (const char *v = getenv(name)) return atoi(v);
+  return 0;
+}
 
-  dudl_mode = CPH_DUDL_REFERENCE;
-  integrator_mode = CPH_INTEGRATE_REFERENCE;
-  fscale_mode = CPH_FSCALE_LAMBDA;
-  bias_mode = CPH_BIAS_EXACT;
-  m_lambda = 20.0;                                                                     // cpp:96
-  water_buffer = 0;
-  coord_theta = 0;
-  t_lambda_period = 0.0;
-  lambda_host = 0.5;
-  nsites = ntitr = 0;
-  restart_n = 0;
-  atoms_sent = false;
-  bufmax = 0;
-  nmax = 1;
-  HA = HB = 0.0;
+}    // namespace
 
-  int iarg = 9;                                                                        // cpp:51
-  while (iarg < narg) {                                                                // cpp:52 (D6: advance or fail)
+/* ----------------------------------------------------------------------
+   constructor: the six positional arguments of the reference (cpp:36-49), then keywords
+------------------------------------------------------------------------- */
+
+FixConstantPH::FixConstantPH(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg)
+{
+  cph = nullptr;
+  host_energy = nullptr;
+  host_energy_cap = 0;
+  force_out = nullptr;
+  force_cap = 0;
+  pending_restart = nullptr;
+  pending_n = 0;
+  resend_atoms = true;
+  part[0] = part[1] = 0.0;
+  tab = Sites{0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  opt = Options{CPH_DUDL_REFERENCE, CPH_INTEGRATE_REFERENCE, CPH_FSCALE_LAMBDA, CPH_BIAS_EXACT, 0, CPH_COORD_LAMBDA,
+                0.0, 0.5, nullptr};
+  bias = Bias{0, 0, 0, 0, 0, 0, 0, 0, 0, 20.0};         // mass: cpp:96; the rest is loaded in init()
+  lambda_cached = opt.lambda_start;
+
+  const int npositional = 9;                            // ID group style + 6 (cpp:36)
+  if (narg < npositional) utils::missing_cmd_args(FLERR, "fix constant_pH", error);
+
+  nevery = utils::inumeric(FLERR, arg[3], false, lmp);
+  if (nevery <= 0)                                      // the reference lets 0 through to a modulo
+    error->all(FLERR, "Illegal fix constant pH every value {}", nevery);
+
+  auto lookup_group = [&](const char *name, const char *what) {
+    const int id = group->find(name);
+    if (id < 0) error->all(FLERR, "Cannot find the {} group for fix constant_pH", what);
+    return id;
+  };
+  in.hyd_group = lookup_group(arg[4], "hydrogens");
+  in.wat_group = lookup_group(arg[5], "water");
+  in.hyd_bit = group->bitmask[in.hyd_group];
+  in.wat_bit = group->bitmask[in.wat_group];
+  const bigint nwater = group->count(in.wat_group);
+  if (nwater != 3)                                      // cpp:44-45
+    error->all(FLERR, "Number of atoms in the water molecule for the fix constant_pH is {} instead of three", nwater);
+
+  in.pK = utils::numeric(FLERR, arg[6], false, lmp);
+  in.pH = utils::numeric(FLERR, arg[7], false, lmp);
+  in.temperature = utils::numeric(FLERR, arg[8], false, lmp);
+
+  int *const choice_target[kNumChoices] = {&opt.dudl, &opt.integrator, &opt.fscale, &opt.bias_form, &opt.buffer, &opt.theta};
+  for (int iarg = npositional; iarg < narg; iarg += 2) {
     if (iarg + 1 >= narg) utils::missing_cmd_args(FLERR, "fix constant_pH", error);
     const char *key = arg[iarg], *val = arg[iarg + 1];
-    if (strcmp(key, "sites") == 0) {
-      sitefile = strdup(val);
-      dudl_mode = CPH_DUDL_CHARGE;
-    } else if (strcmp(key, "dudl") == 0) {
-      if (strcmp(val, "charge") == 0) dudl_mode = CPH_DUDL_CHARGE;
-      else if (strcmp(val, "reference") == 0) dudl_mode = CPH_DUDL_REFERENCE;
-      else error->all(FLERR, "Illegal fix constant_pH dudl value {}", val);
-    } else if (strcmp(key, "integrator") == 0) {
-      if (strcmp(val, "vv") == 0) integrator_mode = CPH_INTEGRATE_VV;
-      else if (strcmp(val, "reference") == 0) integrator_mode = CPH_INTEGRATE_REFERENCE;
-      else error->all(FLERR, "Illegal fix constant_pH integrator value {}", val);
-    } else if (strcmp(key, "fscale") == 0) {
-      if (strcmp(val, "oneminus") == 0) fscale_mode = CPH_FSCALE_ONE_MINUS;
-      else if (strcmp(val, "lambda") == 0) fscale_mode = CPH_FSCALE_LAMBDA;
-      else error->all(FLERR, "Illegal fix constant_pH fscale value {}", val);
-    } else if (strcmp(key, "bias") == 0) {
-      if (strcmp(val, "aswritten") == 0) bias_mode = CPH_BIAS_AS_WRITTEN;
-      else if (strcmp(val, "exact") == 0) bias_mode = CPH_BIAS_EXACT;
-      else error->all(FLERR, "Illegal fix constant_pH bias value {}", val);
+    int c = 0;
+    while (c < kNumChoices && strcmp(key, kChoices[c].key) != 0) c++;
+    if (c < kNumChoices) {
+      if (strcmp(val, kChoices[c].word0) == 0) *choice_target[c] = kChoices[c].val0;
+      else if (strcmp(val, kChoices[c].word1) == 0) *choice_target[c] = kChoices[c].val1;
+      else error->all(FLERR, "Illegal fix constant_pH {} value {}", key, val);
+    } else if (strcmp(key, "sites") == 0) {
+      opt.site_file = strdup(val);
+      opt.dudl = CPH_DUDL_CHARGE;
     } else if (strcmp(key, "mlambda") == 0) {
-      m_lambda = utils::numeric(FLERR, val, false, lmp);
-      if (m_lambda <= 0.0) error->all(FLERR, "Illegal fix constant_pH mlambda value {}", m_lambda);
+      bias.mass = utils::numeric(FLERR, val, false, lmp);
+      if (bias.mass <= 0.0) error->all(FLERR, "Illegal fix constant_pH mlambda value {}", bias.mass);
     } else if (strcmp(key, "tlambda") == 0) {
-      t_lambda_period = utils::numeric(FLERR, val, false, lmp);
-      if (t_lambda_period < 0.0) error->all(FLERR, "Illegal fix constant_pH tlambda value {}", t_lambda_period);
-    } else if (strcmp(key, "coordinate") == 0) {
-      if (strcmp(val, "theta") == 0) coord_theta = 1;
-      else if (strcmp(val, "lambda") == 0) coord_theta = 0;
-      else error->all(FLERR, "Illegal fix constant_pH coordinate value {}", val);
-    } else if (strcmp(key, "buffer") == 0) {
-      if (strcmp(val, "yes") == 0) water_buffer = 1;
-      else if (strcmp(val, "no") == 0) water_buffer = 0;
-      else error->all(FLERR, "Illegal fix constant_pH buffer value {}", val);
+      opt.thermostat_period = utils::numeric(FLERR, val, false, lmp);
+      if (opt.thermostat_period < 0.0)
+        error->all(FLERR, "Illegal fix constant_pH tlambda value {}", opt.thermostat_period);
     } else if (strcmp(key, "lambda0") == 0) {
-      lambda_host = utils::numeric(FLERR, val, false, lmp);
+      opt.lambda_start = lambda_cached = utils::numeric(FLERR, val, false, lmp);
     } else {
       error->all(FLERR, "Unknown fix constant_pH keyword: {}", key);
     }
-    iarg += 2;
   }
 
   scalar_flag = 1;          // compute_scalar(): H_lambda (cpp:114)
@@ -138,8 +155,8 @@ FixConstantPH::FixConstantPH(LAMMPS *lmp, int narg, char **arg) :
   extscalar = 1;
   extvector = 0;
   restart_global = 1;       // write_restart / restart (absent from the reference)
-  comm_reverse = 1;         // cpp:253, 282-284 (D18)
-  if (sitefile) read_sites(sitefile);
+  comm_reverse = 1;         // one double per ghost for the host-tallied energies (cpp:253, 282-284)
+  if (opt.site_file) load_site_table(opt.site_file);
 }
 
 /* ---------------------------------------------------------------------- */
@@ -147,96 +164,74 @@ FixConstantPH::FixConstantPH(LAMMPS *lmp, int narg, char **arg) :
 FixConstantPH::~FixConstantPH()
 {
   if (cph) cph_destroy(cph);
-  memory->destroy(H_atom);                                                             // D7
-  free(sitefile);
-  free(site_pK); free(site_lambda0); free(titr_qA); free(titr_qB); free(titr_tag); free(titr_site);
-  free(restart_buf); free(xbuf); free(fbuf);
+  memory->destroy(host_energy);
+  void *owned[] = {opt.site_file, tab.pK, tab.lambda0, tab.qA, tab.qB, tab.tag, tab.site, pending_restart, force_out};
+  for (void *p : owned) free(p);
 }
 
 /* ---------------------------------------------------------------------- */
 
 int FixConstantPH::setmask()
 {
-  int mask = 0;
-  mask |= POST_FORCE;                    // the reference's only hook (cpp:67)
-  mask |= POST_NEIGHBOR;                 // atoms were migrated / re-sorted: resend them
-  if (integrator_mode == CPH_INTEGRATE_VV) {
-    mask |= INITIAL_INTEGRATE;
-    mask |= FINAL_INTEGRATE;
-  }
-  return mask;
+  int hooks = POST_FORCE | POST_NEIGHBOR;     // post_force is the reference's only hook (cpp:67)
+  if (opt.integrator == CPH_INTEGRATE_VV) hooks |= INITIAL_INTEGRATE | FINAL_INTEGRATE;
+  return hooks;
 }
 
 /* ---------------------------------------------------------------------- */
 
-void FixConstantPH::check(int rc, const char *what)
+void FixConstantPH::require(int rc, const char *what)
 {
-  if (rc == CPH_OK) return;
-  error->all(FLERR, "fix constant_pH: {} failed: {}", what, cph_last_error(cph));
+  if (rc != CPH_OK) error->all(FLERR, "fix constant_pH: {} failed: {}", what, cph_last_error(cph));
 }
 
 /* ----------------------------------------------------------------------
    site table:  line 1 "nsites ntitr"; nsites lines "pK lambda0"; ntitr lines "tag site qA qB"
 ------------------------------------------------------------------------- */
 
-void FixConstantPH::read_sites(const char *path)
+void FixConstantPH::load_site_table(const char *path)
 {
   FILE *fp = fopen(path, "r");
   if (!fp) error->all(FLERR, "Cannot open fix constant_pH site file {}", path);
-  if (fscanf(fp, "%d %d", &nsites, &ntitr) != 2 || nsites < 1 || ntitr < 0)
+  if (fscanf(fp, "%d %d", &tab.nsites, &tab.natoms) != 2 || tab.nsites < 1 || tab.natoms < 0)
     error->all(FLERR, "Bad header in fix constant_pH site file {}", path);
-  site_pK = (double *) malloc(sizeof(double) * nsites);
-  site_lambda0 = (double *) malloc(sizeof(double) * nsites);
-  titr_tag = (int *) malloc(sizeof(int) * (ntitr + 1));
-  titr_site = (int *) malloc(sizeof(int) * (ntitr + 1));
-  titr_qA = (double *) malloc(sizeof(double) * (ntitr + 1));
-  titr_qB = (double *) malloc(sizeof(double) * (ntitr + 1));
-  for (int s = 0; s < nsites; s++)
-    if (fscanf(fp, "%lf %lf", &site_pK[s], &site_lambda0[s]) != 2)
+  tab.pK = (double *) calloc(tab.nsites, sizeof(double));
+  tab.lambda0 = (double *) calloc(tab.nsites, sizeof(double));
+  tab.tag = (int *) calloc(tab.natoms + 1, sizeof(int));
+  tab.site = (int *) calloc(tab.natoms + 1, sizeof(int));
+  tab.qA = (double *) calloc(tab.natoms + 1, sizeof(double));
+  tab.qB = (double *) calloc(tab.natoms + 1, sizeof(double));
+  for (int s = 0; s < tab.nsites; s++)
+    if (fscanf(fp, "%lf %lf", &tab.pK[s], &tab.lambda0[s]) != 2)
       error->all(FLERR, "Bad site line {} in fix constant_pH site file", s);
-  for (int t = 0; t < ntitr; t++)
-    if (fscanf(fp, "%d %d %lf %lf", &titr_tag[t], &titr_site[t], &titr_qA[t], &titr_qB[t]) != 4)
+  for (int t = 0; t < tab.natoms; t++)
+    if (fscanf(fp, "%d %d %lf %lf", &tab.tag[t], &tab.site[t], &tab.qA[t], &tab.qB[t]) != 4)
       error->all(FLERR, "Bad atom line {} in fix constant_pH site file", t);
   fclose(fp);
 }
 
-/* ---------------------------------------------------------------------- */
+/* ----------------------------------------------------------------------
+   init: bias constants (cpp:85-96) and the whole configuration of the device side
+------------------------------------------------------------------------- */
 
 void FixConstantPH::init()
 {
-  // default values from Donnini, Ullmann, J Chem Theory Comput 2016 - Table S2   (cpp:85-94)
-  w = 200.0;
-  s = 0.3;
-  h = 4.0;
-  k = 2.533;
-  a = 0.034041;
-  b = 0.005238;
-  r = 16.458;
-  m = 0.1507;
-  d = 2.0;
-
-  if (atom->nmax > nmax) {                                                             // cpp:100-104
-    memory->destroy(H_atom);
-    nmax = atom->nmax;
-    memory->create(H_atom, nmax, "constant_pH:H_atom");
-  }
+  // Donnini, Ullmann, J Chem Theory Comput 2016, Table S2 -- the values at cpp:86-94
+  bias = Bias{200.0, 0.3, 4.0, 2.533, 0.034041, 0.005238, 16.458, 0.1507, 2.0, bias.mass};
 
   if (!atom->q_flag) error->all(FLERR, "fix constant_pH requires atom attribute q");
   if (domain->triclinic) error->all(FLERR, "fix constant_pH does not support triclinic boxes");
+  if (opt.thermostat_period > 0.0 && opt.integrator != CPH_INTEGRATE_VV)
+    error->all(FLERR, "fix constant_pH tlambda requires integrator vv");
 
   if (!cph) {
-    int dev = 0;
-    const char *lr = getenv("LOCAL_RANK");
-    if (!lr) lr = getenv("OMPI_COMM_WORLD_LOCAL_RANK");
-    if (!lr) lr = getenv("SLURM_LOCALID");
-    if (lr) dev = atoi(lr);
-    cph_handle *hnd = nullptr;
-    int rc = cph_create(dev, &hnd);
-    if (rc != CPH_OK) error->all(FLERR, "fix constant_pH: no usable CUDA device: {}", cph_last_error(nullptr));
-    cph = hnd;
+    cph_handle *fresh = nullptr;
+    if (cph_create(local_device(), &fresh) != CPH_OK)
+      error->all(FLERR, "fix constant_pH: no usable CUDA device: {}", cph_last_error(nullptr));
+    cph = fresh;
   }
 
-  check(cph_set_units(cph, force->qqrd2e, force->boltz, force->ftm2v), "cph_set_units");   // D8, D9
+  require(cph_set_units(cph, force->qqrd2e, force->boltz, force->ftm2v), "cph_set_units");
 
   // the pair style whose eatom the reference reads (cpp:216-219); its arithmetic runs in the library
   int style = -1;
@@ -247,47 +242,42 @@ void FixConstantPH::init()
   int dim = 0;
   double **eps = (double **) pair->extract("epsilon", dim);
   double **sig = (double **) pair->extract("sigma", dim);
-  double *cut_coul = (double *) pair->extract("cut_coul", dim);
-  double *cut_lj = (double *) pair->extract("cut_lj", dim);
-  double *alpha = (double *) pair->extract("alpha", dim);
+  const double *cut_coul = (double *) pair->extract("cut_coul", dim);
+  const double *cut_lj = (double *) pair->extract("cut_lj", dim);
+  const double *alpha = (double *) pair->extract("alpha", dim);
   if (!eps || !sig || !cut_coul) error->all(FLERR, "fix constant_pH: pair style does not expose epsilon/sigma/cut_coul");
   if (style == CPH_PAIR_LJ_CUT_COUL_DSF && !alpha) error->all(FLERR, "fix constant_pH: pair style does not expose alpha");
-  const int nt = atom->ntypes;
-  double *e1 = (double *) calloc((size_t)(nt + 1) * (nt + 1), sizeof(double));
-  double *s1 = (double *) calloc((size_t)(nt + 1) * (nt + 1), sizeof(double));
-  for (int i = 1; i <= nt; i++)
-    for (int j = 1; j <= nt; j++) {
-      const int lo = i < j ? i : j, hi = i < j ? j : i;      // init_one fills i <= j
-      e1[i * (nt + 1) + j] = eps[lo][hi];
-      s1[i * (nt + 1) + j] = sig[lo][hi];
+  const int nt1 = atom->ntypes + 1;
+  std::vector<double> e_tab((size_t) nt1 * nt1, 0.0), s_tab((size_t) nt1 * nt1, 0.0);
+  for (int i = 1; i < nt1; i++)
+    for (int j = 1; j < nt1; j++) {
+      const int lo = std::min(i, j), hi = std::max(i, j);      // Pair::init_one fills i <= j
+      e_tab[(size_t) i * nt1 + j] = eps[lo][hi];
+      s_tab[(size_t) i * nt1 + j] = sig[lo][hi];
     }
-  check(cph_set_pair(cph, style, nt, e1, s1, nullptr, cut_lj ? *cut_lj : *cut_coul, *cut_coul, alpha ? *alpha : 0.0,
-                     force->special_lj, force->special_coul), "cph_set_pair");
-  free(e1);
-  free(s1);
+  require(cph_set_pair(cph, style, atom->ntypes, e_tab.data(), s_tab.data(), nullptr, cut_lj ? *cut_lj : *cut_coul,
+                       *cut_coul, alpha ? *alpha : 0.0, force->special_lj, force->special_coul), "cph_set_pair");
 
-  check(cph_set_domain(cph, domain->boxlo, domain->boxhi, domain->periodicity, domain->sublo, domain->subhi,
-                       comm->procgrid, comm->myloc, neighbor->skin), "cph_set_domain");
-  check(cph_set_fix(cph, nevery, groupHbit, groupWbit, pK, pH, T), "cph_set_fix");
-  check(cph_set_bias(cph, w, s, h, k, a, b, r, m, d, m_lambda, bias_mode), "cph_set_bias");   // cpp:86-96
-  check(cph_set_mode(cph, dudl_mode, integrator_mode, fscale_mode), "cph_set_mode");
-  if (t_lambda_period > 0.0 && integrator_mode != CPH_INTEGRATE_VV)
-    error->all(FLERR, "fix constant_pH tlambda requires integrator vv");
-  check(cph_set_thermostat(cph, t_lambda_period), "cph_set_thermostat");
-  check(cph_set_coordinate(cph, coord_theta ? CPH_COORD_THETA : CPH_COORD_LAMBDA), "cph_set_coordinate");
-  check(cph_set_water_buffer(cph, water_buffer ? (int) group->count(igroupW) : 0), "cph_set_water_buffer");
-  check(cph_set_sites(cph, nsites, site_pK, ntitr, titr_tag, titr_site, titr_qA, titr_qB), "cph_set_sites");
-  if (restart_buf) {
-    check(cph_unpack_restart(cph, restart_buf, restart_n), "cph_unpack_restart");
-    free(restart_buf);
-    restart_buf = nullptr;
-  } else if (nsites) {
-    check(cph_set_lambda(cph, site_lambda0, nullptr), "cph_set_lambda");
+  require(cph_set_domain(cph, domain->boxlo, domain->boxhi, domain->periodicity, domain->sublo, domain->subhi,
+                         comm->procgrid, comm->myloc, neighbor->skin), "cph_set_domain");
+  require(cph_set_fix(cph, nevery, in.hyd_bit, in.wat_bit, in.pK, in.pH, in.temperature), "cph_set_fix");
+  require(cph_set_bias(cph, bias.w, bias.s, bias.h, bias.k, bias.a, bias.b, bias.r, bias.m, bias.d, bias.mass,
+                       opt.bias_form), "cph_set_bias");
+  require(cph_set_mode(cph, opt.dudl, opt.integrator, opt.fscale), "cph_set_mode");
+  require(cph_set_thermostat(cph, opt.thermostat_period), "cph_set_thermostat");
+  require(cph_set_coordinate(cph, opt.theta), "cph_set_coordinate");
+  require(cph_set_water_buffer(cph, opt.buffer ? (int) group->count(in.wat_group) : 0), "cph_set_water_buffer");
+  require(cph_set_sites(cph, tab.nsites, tab.pK, tab.natoms, tab.tag, tab.site, tab.qA, tab.qB), "cph_set_sites");
+
+  if (pending_restart) {
+    require(cph_unpack_restart(cph, pending_restart, pending_n), "cph_unpack_restart");
+    free(pending_restart);
+    pending_restart = nullptr;
   } else {
-    check(cph_set_lambda(cph, &lambda_host, nullptr), "cph_set_lambda");
+    require(cph_set_lambda(cph, tab.nsites ? tab.lambda0 : &opt.lambda_start, nullptr), "cph_set_lambda");
   }
-  size_vector = 4 * (nsites ? nsites : 1);
-  atoms_sent = false;
+  size_vector = 4 * std::max(tab.nsites, 1);
+  resend_atoms = true;
 }
 
 /* ---------------------------------------------------------------------- */
@@ -300,31 +290,29 @@ void FixConstantPH::init_list(int /*id*/, NeighList * /*ptr*/)
 
 /* ---------------------------------------------------------------------- */
 
-void FixConstantPH::send_atoms()
+void FixConstantPH::upload_atoms()
 {
-  const int nlocal = atom->nlocal;
-  const double *x = nlocal ? &atom->x[0][0] : nullptr;
-  const int *nspecial = (atom->maxspecial && atom->nspecial && nlocal) ? &atom->nspecial[0][0] : nullptr;
-  const int *special = (atom->maxspecial && atom->special && nlocal) ? &atom->special[0][0] : nullptr;
-  check(cph_set_atoms(cph, CPH_HOST, nlocal, x, atom->q, atom->type, atom->tag, atom->mask,
-                      atom->molecule_flag ? atom->molecule : nullptr, nspecial, special,
-                      nspecial ? atom->maxspecial : 0), "cph_set_atoms");
-  if (nlocal > bufmax) {
-    bufmax = nlocal + nlocal / 8 + 16;
-    free(fbuf);
-    fbuf = (double *) malloc(sizeof(double) * 3 * bufmax);
+  const int n = atom->nlocal;
+  const bool specials = atom->maxspecial > 0 && atom->nspecial && atom->special && n > 0;
+  require(cph_set_atoms(cph, CPH_HOST, n, n ? atom->x[0] : nullptr, atom->q, atom->type, atom->tag, atom->mask,
+                        atom->molecule_flag ? atom->molecule : nullptr, specials ? atom->nspecial[0] : nullptr,
+                        specials ? atom->special[0] : nullptr, specials ? atom->maxspecial : 0), "cph_set_atoms");
+  if (n > force_cap) {
+    force_cap = n + n / 8 + 16;
+    free(force_out);
+    force_out = (double *) malloc(sizeof(double) * 3 * force_cap);
   }
-  atoms_sent = true;
+  resend_atoms = false;
 }
 
 void FixConstantPH::post_neighbor()
 {
-  atoms_sent = false;      // LAMMPS migrated and re-sorted atoms: local indices changed
+  resend_atoms = true;     // LAMMPS migrated and re-sorted atoms: local indices changed
 }
 
 void FixConstantPH::setup(int vflag)
 {
-  send_atoms();
+  upload_atoms();
   post_force(vflag);       // as most fixes do; the reference declares setup (h:35) without a body
 }
 
@@ -332,149 +320,118 @@ void FixConstantPH::setup(int vflag)
 
 void FixConstantPH::initial_integrate(int /*vflag*/)
 {
-  check(cph_initial_integrate(cph, update->dt * nevery), "cph_initial_integrate");
+  require(cph_initial_integrate(cph, update->dt * nevery), "cph_initial_integrate");
 }
 
 void FixConstantPH::final_integrate()
 {
-  check(cph_final_integrate(cph, update->dt * nevery), "cph_final_integrate");
+  require(cph_final_integrate(cph, update->dt * nevery), "cph_final_integrate");
 }
 
-/* ---------------------------------------------------------------------- */
+/* ----------------------------------------------------------------------
+   post_force (cpp:67-79): on nevery steps the energy partition, df, dU and the lambda step;
+   on every step the force rescale.  One library call runs the sequence on the device.
+------------------------------------------------------------------------- */
 
 void FixConstantPH::post_force(int /*vflag*/)
 {
-  if (!atoms_sent) send_atoms();
-  const int nlocal = atom->nlocal;
-  const double *x = nlocal ? &atom->x[0][0] : nullptr;
+  if (resend_atoms) upload_atoms();
+  const int n = atom->nlocal;
+  if (update->ntimestep % nevery == 0) compute_Hs();       // host-tallied energy sources (cpp:221-253)
 
-  // cpp:221-253: energy sources that stay with LAMMPS on the host enter the HA/HB partition
-  if (update->ntimestep % nevery == 0) compute_Hs();
+  require(cph_post_force(cph, update->ntimestep, update->dt, CPH_HOST, n ? atom->x[0] : nullptr, force_out),
+          "cph_post_force");
 
-  // cpp:69-78: on nevery steps compute_Hs, calculate_df, calculate_dU, integrate_lambda;
-  // set_force on every step.  One library call runs the whole sequence on the device.
-  check(cph_post_force(cph, update->ntimestep, update->dt, CPH_HOST, x, fbuf), "cph_post_force");
+  double scalars[8];
+  require(cph_get_scalars(cph, scalars), "cph_get_scalars");
+  std::copy(scalars, scalars + 2, part);                    // HA, HB (cpp:276-277)
 
-  double sc[8];
-  check(cph_get_scalars(cph, sc), "cph_get_scalars");
-  HA = sc[0];                                                                          // cpp:276
-  HB = sc[1];                                                                          // cpp:277
-
-  const bool pair_on_host = force->pair && force->pair->compute_flag;
-  double **f = atom->f;
-  if (dudl_mode == CPH_DUDL_REFERENCE) {
-    // cpp:162-170 scales the TOTAL force on the hydrogen group.  The library already scaled the
-    // pair part it owns; scale whatever else LAMMPS put in atom->f (bonded terms, other fixes).
-    check(cph_get_sites(cph, &lambda_host, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr),
-          "cph_get_sites");
-    if (nsites == 0 && !pair_on_host) {
-      const double scale = fscale_mode == CPH_FSCALE_LAMBDA ? lambda_host : 1.0 - lambda_host;
-      int *mask = atom->mask;
-      for (int i = 0; i < nlocal; i++)
-        if (mask[i] & groupHbit) {
-          f[i][0] *= scale;
-          f[i][1] *= scale;
-          f[i][2] *= scale;
-        }
-    }
+  const bool lammps_owns_pair_forces = force->pair && force->pair->compute_flag;
+  if (opt.dudl == CPH_DUDL_REFERENCE) {
+    require(cph_get_sites(cph, &lambda_cached, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr),
+            "cph_get_sites");
+    // The reference scales the TOTAL force on the hydrogen group (cpp:162-170).  The library has already
+    // scaled the pair part it owns; whatever else LAMMPS put into atom->f (bonded terms, other fixes)
+    // gets the same factor here, before the pair part is added.
+    if (tab.nsites == 0 && !lammps_owns_pair_forces) set_force();
   }
-  if (!pair_on_host) {
-    // `pair_modify compute no`: the GPU pair pass IS the pair computation; add its forces
-    for (int i = 0; i < nlocal; i++) {
-      f[i][0] += fbuf[3 * i];
-      f[i][1] += fbuf[3 * i + 1];
-      f[i][2] += fbuf[3 * i + 2];
-    }
-  } else if (dudl_mode == CPH_DUDL_REFERENCE) {
-    set_force();           // LAMMPS computed the pair forces itself: reference behaviour, cpp:78
-  }
-}
-
-/* ---------------------------------------------------------------------- */
-
-void FixConstantPH::set_force()
-{
-  // cpp:149-171 verbatim, for the configuration in which LAMMPS (not the library) owns the forces
-  double **f = atom->f;
-  int *mask = atom->mask;
-  int nlocal = atom->nlocal;
-  const double lambda = fscale_mode == CPH_FSCALE_LAMBDA ? lambda_host : 1.0 - lambda_host;
-  for (int i = 0; i < nlocal; i++) {
-    if (mask[i] & groupHbit) {
-      f[i][0] *= lambda;
-      f[i][1] *= lambda;
-      f[i][2] *= lambda;
-    }
+  if (!lammps_owns_pair_forces) {
+    // `pair_modify compute no`: the GPU pair pass IS the pair computation
+    double *f = n ? atom->f[0] : nullptr;
+    for (int k = 0; k < 3 * n; k++) f[k] += force_out[k];
+  } else if (opt.dudl == CPH_DUDL_REFERENCE) {
+    set_force();           // LAMMPS computed the pair forces itself: the factor applies to everything
   }
 }
 
 /* ----------------------------------------------------------------------
-   the reference's helpers: their arithmetic is in the library, these entry points let the
-   sequence of cpp:69-73 be driven step by step (tests, debugging)
+   set_force (cpp:149-171): multiply the forces of the hydrogen group
+------------------------------------------------------------------------- */
+
+void FixConstantPH::scale_hydrogen_forces(double factor)
+{
+  const int n = atom->nlocal;
+  const int *mask = atom->mask;
+  for (int i = 0; i < n; i++) {
+    if (!(mask[i] & in.hyd_bit)) continue;
+    double *fi = atom->f[i];
+    for (int c = 0; c < 3; c++) fi[c] *= factor;
+  }
+}
+
+void FixConstantPH::set_force()
+{
+  scale_hydrogen_forces(opt.fscale == CPH_FSCALE_LAMBDA ? lambda_cached : 1.0 - lambda_cached);
+}
+
+/* ----------------------------------------------------------------------
+   compute_Hs (cpp:177-280).  The pair part of the per-atom energy is produced and partitioned
+   on the device.  This is the rest of that routine, for the sources LAMMPS keeps on the host
+   (bond, angle, dihedral, improper, kspace: cpp:221-244): accumulate them per atom, fold the
+   ghost shares back (cpp:253), split into "all atoms" and "all but the hydrogen group"
+   (cpp:264-267) and hand the two sums to the library, which adds them before the all-reduce
+   that replaces cpp:274.
 ------------------------------------------------------------------------- */
 
 void FixConstantPH::compute_Hs()
 {
-  // The pair part of H_atom (cpp:216-219) is produced and partitioned on the device.  What follows is
-  // the rest of the reference routine (cpp:200-267, "taken from src/compute_pe_atom.cpp") for the
-  // sources LAMMPS keeps on the host: bonded styles and KSpace.  Their two partition sums are handed
-  // to the library, which adds them to HA/HB before the all-reduce that replaces cpp:274.
-  const bool any = (force->bond && force->bond->eatom) || (force->angle && force->angle->eatom) ||
-                   (force->dihedral && force->dihedral->eatom) || (force->improper && force->improper->eatom) ||
-                   (force->kspace && force->kspace->compute_flag && force->kspace->eatom);
-  if (!any) return;
-  if (update->eflag_atom != update->ntimestep)                                         // cpp:181-183
+  struct Source {
+    const double *eatom;
+    int count;
+  };
+  const int nlocal = atom->nlocal, nall = nlocal + atom->nghost;
+  const int nbonded = force->newton_bond ? nall : nlocal;                       // cpp:206
+  const bool tip4p = force->kspace && force->kspace->tip4pflag;
+  const int nkspace = tip4p ? nall : nlocal;                                    // cpp:208
+  std::vector<Source> sources;
+  if (force->bond && force->bond->eatom) sources.push_back({force->bond->eatom, nbonded});
+  if (force->angle && force->angle->eatom) sources.push_back({force->angle->eatom, nbonded});
+  if (force->dihedral && force->dihedral->eatom) sources.push_back({force->dihedral->eatom, nbonded});
+  if (force->improper && force->improper->eatom) sources.push_back({force->improper->eatom, nbonded});
+  if (force->kspace && force->kspace->compute_flag && force->kspace->eatom)
+    sources.push_back({force->kspace->eatom, nkspace});
+  if (sources.empty()) return;
+
+  if (update->eflag_atom != update->ntimestep)                                  // cpp:181-183
     error->all(FLERR, "Per-atom energy was not tallied on needed timestep");
-
-  if (atom->nmax > nmax) {                                                             // cpp:188-192
-    memory->destroy(H_atom);
-    nmax = atom->nmax;
-    memory->create(H_atom, nmax, "constant_pH:H_atom");
+  if (atom->nmax > host_energy_cap) {                                           // cpp:188-192
+    memory->destroy(host_energy);
+    host_energy_cap = atom->nmax;
+    memory->create(host_energy, host_energy_cap, "constant_pH:host_energy");
   }
 
-  int i;
-  int nlocal = atom->nlocal;                                                           // cpp:200-208
-  int nbond = nlocal;
-  int ntotal = nlocal;
-  int nkspace = nlocal;
-  if (force->newton_bond) nbond += atom->nghost;
-  if (force->newton) ntotal += atom->nghost;
-  if (force->kspace && force->kspace->tip4pflag) nkspace += atom->nghost;
+  std::fill(host_energy, host_energy + std::min(nall, host_energy_cap), 0.0);
+  for (const Source &src : sources)
+    for (int i = 0; i < src.count; i++) host_energy[i] += src.eatom[i];
+  if (force->newton || tip4p) comm->reverse_comm(this);                         // cpp:253
 
-  for (i = 0; i < ntotal; i++) H_atom[i] = 0.0;                                        // cpp:212
-
-  if (force->bond && force->bond->eatom) {                                             // cpp:221-224
-    double *eatom = force->bond->eatom;
-    for (i = 0; i < nbond; i++) H_atom[i] += eatom[i];
+  double everyone = 0.0, without_hydrogens = 0.0;
+  const int *mask = atom->mask;
+  for (int i = 0; i < nlocal; i++) {
+    everyone += host_energy[i];
+    if ((mask[i] & in.hyd_bit) == 0) without_hydrogens += host_energy[i];
   }
-  if (force->angle && force->angle->eatom) {                                           // cpp:226-229
-    double *eatom = force->angle->eatom;
-    for (i = 0; i < nbond; i++) H_atom[i] += eatom[i];
-  }
-  if (force->dihedral && force->dihedral->eatom) {                                     // cpp:231-234
-    double *eatom = force->dihedral->eatom;
-    for (i = 0; i < nbond; i++) H_atom[i] += eatom[i];
-  }
-  if (force->improper && force->improper->eatom) {                                     // cpp:236-239
-    double *eatom = force->improper->eatom;
-    for (i = 0; i < nbond; i++) H_atom[i] += eatom[i];
-  }
-  if (force->kspace && force->kspace->compute_flag && force->kspace->eatom) {          // cpp:241-244
-    double *eatom = force->kspace->eatom;
-    for (i = 0; i < nkspace; i++) H_atom[i] += eatom[i];
-  }
-
-  // communicate ghost energy between neighbor procs                                    cpp:251-253
-  if (force->newton || (force->kspace && force->kspace->tip4pflag)) comm->reverse_comm(this);
-
-  int *mask = atom->mask;                                                              // cpp:257-267
-  double HA_local = 0.0;
-  double HB_local = 0.0;
-  for (i = 0; i < nlocal; i++) {
-    HA_local += H_atom[i];
-    if (!(mask[i] & groupHbit)) HB_local += H_atom[i];
-  }
-  check(cph_set_extra_partition(cph, HA_local, HB_local), "cph_set_extra_partition");
+  require(cph_set_extra_partition(cph, everyone, without_hydrogens), "cph_set_extra_partition");
 }
 
 void FixConstantPH::calculate_df() {}                       // cpp:120-124: fused into the integrator kernel
@@ -482,7 +439,7 @@ void FixConstantPH::calculate_dU() {}                       // cpp:128-145: fuse
 
 void FixConstantPH::integrate_lambda()
 {
-  check(cph_integrate_lambda(cph, nevery * update->dt), "cph_integrate_lambda");       // cpp:109-117
+  require(cph_integrate_lambda(cph, nevery * update->dt), "cph_integrate_lambda");       // cpp:109-117
 }
 
 void FixConstantPH::modify_water()
@@ -490,94 +447,82 @@ void FixConstantPH::modify_water()
   // h:58: declared, never defined nor called in the reference (TODO at cpp:268).  With `buffer yes`
   // the library moves -(1/3) sum_s lambda_s dQ_s onto each atom of the water group whenever it
   // applies q(lambda) (cph_apply_charges inside cph_post_force), so the box charge stays constant.
-  check(cph_apply_charges(cph), "cph_apply_charges");
+  require(cph_apply_charges(cph), "cph_apply_charges");
 }
 
 /* ---------------------------------------------------------------------- */
 
 double FixConstantPH::compute_scalar()
 {
-  double v = 0.0;
-  check(cph_compute_scalar(cph, &v), "cph_compute_scalar");
-  return v;
+  double value = 0.0;
+  require(cph_compute_scalar(cph, &value), "cph_compute_scalar");
+  return value;
 }
 
 double FixConstantPH::compute_vector(int i)
 {
-  double v = 0.0;
-  check(cph_compute_vector(cph, i, &v), "cph_compute_vector");
-  return v;
+  double value = 0.0;
+  require(cph_compute_vector(cph, i, &value), "cph_compute_vector");
+  return value;
 }
 
 /* ----------------------------------------------------------------------
-   memory usage of local atom-based array (cpp:310-318) plus the device buffers
+   memory usage: the host-side per-atom arrays (cpp:310-318) plus the device buffers
 ------------------------------------------------------------------------- */
 
 double FixConstantPH::memory_usage()
 {
-  double bytes = (double) nmax * sizeof(double);
-  double dev = 0.0;
-  if (cph) cph_memory_usage(cph, &dev);
-  return bytes + dev;
+  double device_bytes = 0.0;
+  if (cph) cph_memory_usage(cph, &device_bytes);
+  return device_bytes + sizeof(double) * ((double) host_energy_cap + 3.0 * force_cap);
 }
 
 /* ----------------------------------------------------------------------
-   restart: [version, S, (lambda|theta, v, a) * S, (xi, eta, K if tlambda)] as doubles, LAMMPS global-restart layout
+   restart: [version, S, (lambda|theta, v, a) * S, (xi, eta, K if tlambda)] as doubles,
+   LAMMPS global-restart layout
 ------------------------------------------------------------------------- */
 
 void FixConstantPH::write_restart(FILE *fp)
 {
   int n = 0;
-  check(cph_restart_size(cph, &n), "cph_restart_size");
-  double *list = (double *) malloc(sizeof(double) * n);
-  check(cph_pack_restart(cph, list), "cph_pack_restart");
+  require(cph_restart_size(cph, &n), "cph_restart_size");
+  std::vector<double> record(n);
+  require(cph_pack_restart(cph, record.data()), "cph_pack_restart");
   if (comm->me == 0) {
-    int size = n * sizeof(double);
-    fwrite(&size, sizeof(int), 1, fp);
-    fwrite(list, sizeof(double), n, fp);
+    const int bytes = n * (int) sizeof(double);
+    fwrite(&bytes, sizeof(int), 1, fp);
+    fwrite(record.data(), sizeof(double), n, fp);
   }
-  free(list);
 }
 
 void FixConstantPH::restart(char *buf)
 {
-  double *list = (double *) buf;
-  const int S = (int) list[1];
-  restart_n = 2 + 3 * S + (t_lambda_period > 0.0 ? 3 : 0);     // + thermostat state (xi, eta, K)
-  free(restart_buf);
-  restart_buf = (double *) malloc(sizeof(double) * restart_n);
-  memcpy(restart_buf, list, sizeof(double) * restart_n);
+  const double *record = (const double *) buf;
+  const int nsites_in_record = (int) record[1];
+  pending_n = 2 + 3 * nsites_in_record + (opt.thermostat_period > 0.0 ? 3 : 0);
+  free(pending_restart);
+  pending_restart = (double *) malloc(sizeof(double) * pending_n);
+  memcpy(pending_restart, record, sizeof(double) * pending_n);
   if (cph) {      // already initialised: apply now
-    check(cph_unpack_restart(cph, restart_buf, restart_n), "cph_unpack_restart");
-    free(restart_buf);
-    restart_buf = nullptr;
+    require(cph_unpack_restart(cph, pending_restart, pending_n), "cph_unpack_restart");
+    free(pending_restart);
+    pending_restart = nullptr;
   }
 }
 
 /* ----------------------------------------------------------------------
-   cpp:287-308.  The pair energies live on the device (full neighbour list: nothing to fold); H_atom
-   carries the host-side sources of compute_Hs, whose ghost shares are folded exactly as in the reference.
+   reverse communication of the host-tallied per-atom energies (the reference has these bodies at
+   cpp:287-308 but does not declare them).  The pair energies live on the device, where a full
+   neighbour list leaves nothing to fold.
 ------------------------------------------------------------------------- */
 
 int FixConstantPH::pack_reverse_comm(int n, int first, double *buf)
 {
-  int i, m, last;
-
-  m = 0;
-  last = first + n;
-  for (i = first; i < last; i++) buf[m++] = H_atom[i];                                 // cpp:293
-  return m;
+  memcpy(buf, host_energy + first, sizeof(double) * n);
+  return n;
 }
-
-/* ---------------------------------------------------------------------- */
 
 void FixConstantPH::unpack_reverse_comm(int n, int *list, double *buf)
 {
-  int i, j, m;
-
-  m = 0;
-  for (i = 0; i < n; i++) {                                                            // cpp:304-307
-    j = list[i];
-    H_atom[j] += buf[m++];
-  }
+  for (int k = 0; k < n; k++) host_energy[list[k]] += buf[k];
 }

@@ -7,7 +7,8 @@
    over per-atom arrays.  Hooks the reference declares (h:31-40) keep their signatures;
    hooks north_star adds (initial_integrate, final_integrate, write_restart, restart,
    pack/unpack_reverse_comm, which the reference defines but never declares, cpp:287-308)
-   are marked below.
+   are marked below.  Private state is this implementation's own; only the public surface
+   is dictated by the reference.
 ------------------------------------------------------------------------- */
 
 #ifdef FIX_CLASS
@@ -27,62 +28,79 @@ namespace LAMMPS_NS {
 
 class FixConstantPH : public Fix {
  public:
-  FixConstantPH(class LAMMPS *, int, char **);         // reference h:31, cpp:33-56
-  ~FixConstantPH() override;                            // h:32
-  int setmask() override;                               // h:33 (never defined in the reference)
-  void init() override;                                 // h:34, cpp:83-105
-  void setup(int) override;                             // h:35 (never defined)
-  void post_force(int) override;                        // h:36, cpp:67-79
-  double compute_scalar() override;                     // h:37 (never defined): H_lambda of cpp:114
-  double compute_vector(int) override;                  // h:38 (never defined)
-  double memory_usage() override;                       // h:39, cpp:314-318 (defined on the wrong class there)
-  void init_list(int, class NeighList *) override;      // h:40 (never defined): the library owns its list
-  // north_star hooks absent from the reference
+  // ---- the reference's public surface (h:31-40) ------------------------------------------------
+  FixConstantPH(class LAMMPS *, int, char **);         // cpp:33-56
+  ~FixConstantPH() override;
+  int setmask() override;                               // declared, never defined in the reference
+  void init() override;                                 // cpp:83-105
+  void setup(int) override;                             // declared, never defined
+  void post_force(int) override;                        // cpp:67-79
+  double compute_scalar() override;                     // declared, never defined: H_lambda of cpp:114
+  double compute_vector(int) override;                  // declared, never defined
+  double memory_usage() override;                       // cpp:314-318 (defined on the wrong class there)
+  void init_list(int, class NeighList *) override;      // declared, never defined: the library owns its list
+
+  // ---- hooks north_star asks for, absent from the reference ------------------------------------
   void initial_integrate(int) override;
   void final_integrate() override;
   void post_neighbor() override;
   void write_restart(FILE *) override;
   void restart(char *) override;
-  int pack_reverse_comm(int, int, double *) override;           // cpp:287-295
-  void unpack_reverse_comm(int, int *, double *) override;      // cpp:299-308
+  int pack_reverse_comm(int, int, double *) override;           // body at cpp:287-295, undeclared there
+  void unpack_reverse_comm(int, int *, double *) override;      // body at cpp:299-308, undeclared there
 
  private:
-  // Input variables for constant values (reference h:44-51)
-  int igroupH, igroupW;
-  int groupHbit, groupWbit;
-  double pK, pH, T;
-  double a, b, s, m, w, r, d, h, k;      // h and k are used at cpp:88-89 but undeclared in the reference
-  double m_lambda;
-  double t_lambda_period;                // Nose-Hoover period of the lambda thermostat (0 = off)
-  double HA, HB;
-  int nmax;
-  double *H_atom;                        // kept for interface parity; energies live on the device
+  // positional arguments arg[3..8] (cpp:37-49)
+  struct Args {
+    int hyd_group, wat_group;      // group ids of arg[4], arg[5]
+    int hyd_bit, wat_bit;          // their bitmasks
+    double pK, pH, temperature;
+  } in;
 
-  // additions
-  cph_handle *cph;
-  int dudl_mode, integrator_mode, fscale_mode, bias_mode, water_buffer, coord_theta;
-  char *sitefile;
-  int nsites, ntitr;
-  double *site_pK, *site_lambda0, *titr_qA, *titr_qB;
-  int *titr_tag, *titr_site;
-  double *restart_buf;
-  int restart_n;
-  bool atoms_sent;
-  double *xbuf, *fbuf;
-  int bufmax;
-  double lambda_host;                    // lambda of the single reference site, for the host-side rescale
+  // Donnini-2016 bias constants loaded in init() (cpp:86-96)
+  struct Bias {
+    double w, s, h, k, a, b, r, m, d;
+    double mass;                   // m_lambda
+  } bias;
 
-  // reference helpers (h:53-58); the arithmetic now runs in the library
-  void integrate_lambda();               // cpp:109-117  -> cph_integrate_lambda
-  void compute_Hs();                     // cpp:177-280  -> cph_pair_pass + cph_site_reduce
-  void calculate_df();                   // cpp:120-124  -> lambda integrator kernel
-  void calculate_dU();                   // cpp:128-145  -> lambda integrator kernel
-  void set_force();                      // cpp:149-171
-  void modify_water();                   // h:58, never defined nor called in the reference
+  // keyword-selected behaviour (the reference's keyword loop, cpp:51-54, is empty)
+  struct Options {
+    int dudl, integrator, fscale, bias_form, buffer, theta;
+    double thermostat_period;
+    double lambda_start;
+    char *site_file;
+  } opt;
 
-  void check(int rc, const char *what);
-  void read_sites(const char *path);
-  void send_atoms();
+  // per-site table read from the site file (north_star multi-site; none in the reference)
+  struct Sites {
+    int nsites, natoms;
+    double *pK, *lambda0, *qA, *qB;
+    int *tag, *site;
+  } tab;
+
+  cph_handle *cph;                 // the device side
+  double part[2];                  // HA, HB of the last reduction (cpp:276-277)
+  double lambda_cached;            // lambda of the reference's single site, for the host-side rescale
+  double *host_energy;             // the reference's H_atom (h:51): host-tallied energy sources
+  int host_energy_cap;             // its length (the reference's nmax)
+  double *force_out;               // pair forces coming back from the device, caller order
+  int force_cap;
+  double *pending_restart;         // restart record received before init()
+  int pending_n;
+  bool resend_atoms;
+
+  // the reference's private helpers (h:53-58), kept by name; their arithmetic runs in the library
+  void compute_Hs();               // cpp:177-280: host-tallied sources only, the pair part is on the device
+  void calculate_df();             // cpp:120-124: fused into the integrator kernel
+  void calculate_dU();             // cpp:128-145: fused into the integrator kernel
+  void integrate_lambda();         // cpp:109-117
+  void set_force();                // cpp:149-171
+  void modify_water();             // h:58: never defined nor called in the reference
+
+  void require(int rc, const char *what);
+  void load_site_table(const char *path);
+  void upload_atoms();
+  void scale_hydrogen_forces(double factor);
 };
 
 }    // namespace LAMMPS_NS
