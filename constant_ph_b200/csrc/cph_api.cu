@@ -120,6 +120,7 @@ int cph_create(int device, cph_handle **out) {
   cudaMemsetAsync(h->d_flags.p, 0, 8 * sizeof(unsigned int), h->stream);
   if (const char *e = getenv("CPH_INNER_SKIN")) h->inner_skin = std::max(0.0, atof(e));   // tuning knobs
   if (const char *e = getenv("CPH_PAIR_FUSED")) h->fused_pair = atoi(e) != 0;
+  if (const char *e = getenv("CPH_SPECULATE")) h->speculate = atoi(e) != 0;
   if (const char *e = getenv("CPH_HALO")) h->peer_halo_wanted = strcmp(e, "nccl") != 0;   // "nccl" forces ncclSend/Recv
   int rc = size_sites(h);
   if (rc) { g_create_error = h->err; delete h; return rc; }
@@ -558,6 +559,12 @@ int cph_post_force(cph_handle *h, int64_t ntimestep, double dt, int where, const
   CPH_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_flags, 0));
   CPH_CUDA(h, cudaMemcpyAsync(h->h_flags, h->d_flags.p, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream2));
   CPH_TRY(cph_halo_finish(h));
+  const bool active = (ntimestep % h->fix.nevery) == 0;                 // cpp:69
+  // Most steps need neither a re-neighbouring nor a prune.  Enqueue the pair pass on that assumption,
+  // gated on the device copy of the flags, so the GPU has work while the host waits for its copy;
+  // when the guess is wrong the gated grid retires at once and the pass is launched again below.
+  const bool guessed = h->speculate && h->inner_valid && !h->fused_pair && !h->profiling && h->nlocal > 0;
+  if (guessed) CPH_TRY(cph_launch_pair(h, active ? 1 : 0, h->d_flags.p));
   CPH_CUDA(h, cudaStreamSynchronize(h->stream2));
   const unsigned int *fl = h->h_flags;
   unsigned int any = fl[4];
@@ -566,8 +573,7 @@ int cph_post_force(cph_handle *h, int64_t ntimestep, double dt, int where, const
   memcpy(&md, &fl[0], 4);
   h->scal_h[6] = md;
   if (any) CPH_TRY(cph_rebuild(h));
-  const bool active = (ntimestep % h->fix.nevery) == 0;                 // cpp:69
-  CPH_TRY(cph_launch_pair(h, active ? 1 : 0));
+  if (!guessed || any || fl[5]) CPH_TRY(cph_launch_pair(h, active ? 1 : 0));
   h->have_pass = true;
   if (active) {
     CPH_TRY(cph_site_reduce(h));                                        // cpp:70

@@ -204,6 +204,7 @@ struct cph_handle {
   DevBuf<double> d_xinner;           // positions at the last prune
   double inner_skin = 0.4;           // measured best of 0.3..0.8 at config 3 (CPH_INNER_SKIN overrides)
   bool inner_valid = false, fused_pair = false;
+  bool speculate = true;        // enqueue the pair pass before the host has read the list flags (CPH_SPECULATE=0: off)
   int64_t nprunes = 0;
   int rowcap = 0;
   int64_t nbuilds = 0, stored_neigh = 0, special_pairs = 0;
@@ -231,7 +232,7 @@ int cph_halo_finish(cph_handle *h);             // ghost atoms from self images 
 void cph_halo_close(cph_handle *h);
 int cph_neighbors_to_host(cph_handle *h, int *numneigh, int64_t *keys, int64_t cap);
 // pair.cu
-int cph_launch_pair(cph_handle *h, int eflag);
+int cph_launch_pair(cph_handle *h, int eflag, const unsigned int *gate = nullptr);
 int cph_launch_pair_fused(cph_handle *h, int eflag);
 int cph_launch_prune(cph_handle *h);
 int cph_pair_upload_constants(cph_handle *h);

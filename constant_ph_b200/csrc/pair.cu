@@ -533,7 +533,12 @@ pair_eval_kernel(int nlocal, const double4 *__restrict__ xq, const int *__restri
                  const int *__restrict__ neigh, const int *__restrict__ numspec, const int *__restrict__ neigh2,
                  const int *__restrict__ numneigh2, int rowcap, int dummy, int nt1, const double4 *__restrict__ coef,
                  const double2 *__restrict__ cuts, const int *__restrict__ type_has_lj, double *__restrict__ f,
-                 double *__restrict__ evdwl, double *__restrict__ phi, double *__restrict__ eatom, double c_self) {
+                 double *__restrict__ evdwl, double *__restrict__ phi, double *__restrict__ eatom, double c_self,
+                 const unsigned int *__restrict__ gate) {
+  // speculative launch (cph_post_force): enqueued before the host has seen this step's list flags;
+  // if a re-neighbouring or a prune turns out to be due, the whole grid retires and the host
+  // launches the pass again behind the rebuilt rows
+  if (gate != nullptr && (gate[4] | gate[5]) != 0u) return;
   __shared__ double4 s_coef[CPH_MAXNT1 * CPH_MAXNT1];
   __shared__ double2 s_cut[CPH_MAXNT1 * CPH_MAXNT1];
   __shared__ double s_exp2[32];
@@ -738,9 +743,11 @@ int cph_launch_prune(cph_handle *h) {
   return 0;
 }
 
-int cph_launch_pair(cph_handle *h, int eflag) {
+int cph_launch_pair(cph_handle *h, int eflag, const unsigned int *gate) {
   const int n = h->nlocal;
   if (n == 0) return 0;
+  if (gate && (h->fused_pair || !h->inner_valid))
+    return cph_fail(h, CPH_ERR_STATE, "a gated pair pass needs valid inner rows");
   if (h->device < 0 || h->device >= 64 || g_kc_owner[h->device] != h || h->kc_dirty) {
     CPH_TRY(cph_pair_upload_constants(h));
     h->kc_dirty = false;
@@ -759,7 +766,7 @@ int cph_launch_pair(cph_handle *h, int eflag) {
                                                            h->d_neigh2.p, h->d_numneigh2.p, h->rowcap, h->nall, nt1, \
                                                            h->d_coef4.p, h->d_cut2.p, h->d_type_has_lj.p,          \
                                                            h->d_f.p, h->d_evdwl.p, h->d_phi.p, h->d_eatom.p,       \
-                                                           h->pp.c_self)
+                                                           h->pp.c_self, gate)
 #define LAUNCH_E(S, U) do { if (eflag) LAUNCH(S, 1, U); else LAUNCH(S, 0, U); } while (0)
   if (h->pp.style == CPH_PAIR_LJ_CUT_COUL_CUT) {
     if (h->uniform_cut) LAUNCH_E(CPH_PAIR_LJ_CUT_COUL_CUT, 1); else LAUNCH_E(CPH_PAIR_LJ_CUT_COUL_CUT, 0);
