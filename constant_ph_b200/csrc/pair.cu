@@ -757,10 +757,18 @@ int cph_launch_pair(cph_handle *h, int eflag, const unsigned int *gate) {
   ProfScope ps(h, 0);
   const int nt1 = h->pp.ntypes + 1;
   const bool small = n < 300000;
-  const int eapw = small ? 2 : 8;
+  // atoms per warp: fewer on small boxes so the grid still covers the 148 SMs several times over
+  static const int eapw_env = getenv("CPH_EAPW") ? atoi(getenv("CPH_EAPW")) : 0;
+  // measured on B200 (profiles/r1_scaling_and_bench.md): 2 and 4 tie at 125k atoms, 4 wins by 1 % at 250k
+  const int eapw = (eapw_env == 1 || eapw_env == 2 || eapw_env == 4 || eapw_env == 8) ? eapw_env
+                   : n < 200000 ? 2 : small ? 4 : 8;
   const int blocks = (n + EWARPS * eapw - 1) / (EWARPS * eapw);
   h->nlaunch++;
-#define LAUNCH(S, E, U) do { if (small) LAUNCH_A(S, E, U, 2); else LAUNCH_A(S, E, U, 8); } while (0)
+#define LAUNCH(S, E, U)                                                                 \
+  do {                                                                                  \
+    if (eapw == 1) LAUNCH_A(S, E, U, 1); else if (eapw == 2) LAUNCH_A(S, E, U, 2);      \
+    else if (eapw == 4) LAUNCH_A(S, E, U, 4); else LAUNCH_A(S, E, U, 8);                \
+  } while (0)
 #define LAUNCH_A(S, E, U, A)                                                                                        \
   pair_eval_kernel<S, E, U, A><<<blocks, ETPB, 0, h->stream>>>(n, h->d_xq.p, h->d_type.p, h->d_neigh.p, h->d_numspec.p, \
                                                            h->d_neigh2.p, h->d_numneigh2.p, h->rowcap, h->nall, nt1, \

@@ -455,3 +455,155 @@ def write_harness_input(box, path_bin, path_sites=None):
                 fh.write("%.17g %.17g\n" % (box.pK[s], box.lambda0[s]))
             for t in range(box.titr_tag.size):
                 fh.write("%d %d %.17g %.17g\n" % (box.titr_tag[t], box.titr_site[t], box.qA[t], box.qB[t]))
+
+
+# ---- flexible molecules: bonded topology and masses -----------------------
+_MASS = {1: 15.9994, 2: 1.008, 3: 12.011, 4: 12.011, 5: 15.9994, 6: 15.9994, 7: 1.008, 8: 1.008,
+         9: 14.0067, 10: 1.008}
+# SPC/Fw flexible water in LAMMPS' E = K (r - r0)^2 convention; every other bond / angle type takes
+# its equilibrium value from the solute template and a generic stiffness
+_WATER_BOND = (529.581, 1.012)
+_WATER_ANGLE = (37.95, np.deg2rad(113.24))
+_SOLUTE_BOND_K = 300.0
+_SOLUTE_ANGLE_K = 50.0
+
+
+@dataclass
+class Topology:
+    """Per-atom incident bond / angle lists in LAMMPS' `newton_bond off` layout: every bond is stored
+    with both of its atoms and every angle with all three (atom->num_bond, bond_type, bond_atom,
+    num_angle, angle_type, angle_atom1/2/3), partner ids are tags."""
+    bond_k: np.ndarray         # (nbondtypes+1,)
+    bond_r0: np.ndarray
+    angle_k: np.ndarray        # (nangletypes+1,)
+    angle_theta0: np.ndarray   # radians
+    maxbond: int
+    num_bond: np.ndarray       # (n,)
+    bond_type: np.ndarray      # (n,maxbond)
+    bond_atom: np.ndarray      # (n,maxbond) partner tag
+    maxangle: int
+    num_angle: np.ndarray
+    angle_type: np.ndarray     # (n,maxangle)
+    angle_atom1: np.ndarray
+    angle_atom2: np.ndarray    # centre
+    angle_atom3: np.ndarray
+    mass: np.ndarray           # (ntypes+1,)
+
+    @property
+    def nbondtypes(self):
+        return self.bond_k.size - 1
+
+    @property
+    def nangletypes(self):
+        return self.angle_k.size - 1
+
+
+def _type_tables():
+    """Bond types keyed on the unordered atom-type pair, angle types on (end, centre, end)."""
+    bonds, angles = {}, {}
+    for local, types, blist in ((_WATER_LOCAL, _WATER_TYPE, _WATER_BONDS), (_ACID_LOCAL, _ACID_TYPE, _ACID_BONDS),
+                                (_AMINE_LOCAL, _AMINE_TYPE, _AMINE_BONDS)):
+        water = local is _WATER_LOCAL
+        adj = [[] for _ in range(len(types))]
+        for a, b in blist:
+            adj[a].append(b)
+            adj[b].append(a)
+            key = (min(types[a], types[b]), max(types[a], types[b]))
+            if key not in bonds:
+                r0 = float(np.linalg.norm(local[a] - local[b]))
+                bonds[key] = _WATER_BOND if water else (_SOLUTE_BOND_K, r0)
+        for c, nb in enumerate(adj):
+            for u in range(len(nb)):
+                for w in range(u + 1, len(nb)):
+                    a, b = nb[u], nb[w]
+                    key = (min(types[a], types[b]), int(types[c]), max(types[a], types[b]))
+                    if key not in angles:
+                        d1, d2 = local[a] - local[c], local[b] - local[c]
+                        th = float(np.arccos(np.dot(d1, d2) / np.linalg.norm(d1) / np.linalg.norm(d2)))
+                        angles[key] = _WATER_ANGLE if water else (_SOLUTE_ANGLE_K, th)
+    return bonds, angles
+
+
+def topology(box):
+    """Bonded topology of `box`, derived from its 1-2 special lists (a 1-2 partner IS a bond)."""
+    n = box.n
+    t2i = box.meta["tag_to_index"]
+    btab, atab = _type_tables()
+    bkeys, akeys = sorted(btab), sorted(atab)
+    bond_k = np.array([0.0] + [btab[k][0] for k in bkeys])
+    bond_r0 = np.array([0.0] + [btab[k][1] for k in bkeys])
+    angle_k = np.array([0.0] + [atab[k][0] for k in akeys])
+    angle_t0 = np.array([0.0] + [atab[k][1] for k in akeys])
+    blook = np.zeros((NTYPES + 1, NTYPES + 1), dtype=np.int32)
+    for idx, (a, b) in enumerate(bkeys):
+        blook[a, b] = blook[b, a] = idx + 1
+    alook = np.zeros((NTYPES + 1, NTYPES + 1, NTYPES + 1), dtype=np.int32)
+    for idx, (a, c, b) in enumerate(akeys):
+        alook[a, c, b] = alook[b, c, a] = idx + 1
+
+    num_bond = box.nspecial[:, 0].astype(np.int32).copy()
+    maxbond = max(1, int(num_bond.max()) if n else 1)
+    bond_atom = np.zeros((n, maxbond), dtype=np.int32)
+    bond_type = np.zeros((n, maxbond), dtype=np.int32)
+    pidx = np.zeros((n, maxbond), dtype=np.int64)
+    for m in range(maxbond):
+        rows = np.nonzero(num_bond > m)[0]
+        tg = box.special[rows, m]
+        bond_atom[rows, m] = tg
+        pidx[rows, m] = t2i[tg]
+        bond_type[rows, m] = blook[box.type[rows], box.type[pidx[rows, m]]]
+    assert (bond_type[np.arange(maxbond)[None, :] < num_bond[:, None]] > 0).all(), "bond without a type"
+
+    # incident angles: centred on the atom (pairs of its partners), or through a partner (atom is an end)
+    triples = []                                     # (rows, a1, a2, a3) tag arrays
+    for m1 in range(maxbond):
+        for m2 in range(m1 + 1, maxbond):
+            rows = np.nonzero(num_bond > m2)[0]
+            triples.append((rows, bond_atom[rows, m1], box.tag[rows], bond_atom[rows, m2]))
+    for m in range(maxbond):
+        rows_m = np.nonzero(num_bond > m)[0]
+        c = pidx[rows_m, m]
+        for m2 in range(maxbond):
+            ok = (num_bond[c] > m2)
+            far = np.where(ok, bond_atom[c, np.minimum(m2, maxbond - 1)], 0)
+            ok &= far != box.tag[rows_m]
+            rows = rows_m[ok]
+            triples.append((rows, box.tag[rows], box.tag[c[ok]], far[ok]))
+    num_angle = np.zeros(n, dtype=np.int32)
+    for rows, _, _, _ in triples:
+        np.add.at(num_angle, rows, 1)
+    maxangle = max(1, int(num_angle.max()) if n else 1)
+    a1 = np.zeros((n, maxangle), dtype=np.int32)
+    a2 = np.zeros((n, maxangle), dtype=np.int32)
+    a3 = np.zeros((n, maxangle), dtype=np.int32)
+    at = np.zeros((n, maxangle), dtype=np.int32)
+    cnt = np.zeros(n, dtype=np.int64)
+    for rows, t1, t2, t3 in triples:
+        if rows.size == 0:
+            continue
+        k = cnt[rows]
+        a1[rows, k], a2[rows, k], a3[rows, k] = t1, t2, t3
+        at[rows, k] = alook[box.type[t2i[t1]], box.type[t2i[t2]], box.type[t2i[t3]]]
+        cnt[rows] += 1
+    assert (cnt == num_angle).all()
+    assert (at[np.arange(maxangle)[None, :] < num_angle[:, None]] > 0).all(), "angle without a type"
+    mass = np.zeros(NTYPES + 1)
+    for t, mval in _MASS.items():
+        mass[t] = mval
+    return Topology(bond_k=bond_k, bond_r0=bond_r0, angle_k=angle_k, angle_theta0=angle_t0, maxbond=maxbond,
+                    num_bond=num_bond, bond_type=np.ascontiguousarray(bond_type),
+                    bond_atom=np.ascontiguousarray(bond_atom), maxangle=maxangle, num_angle=num_angle,
+                    angle_type=np.ascontiguousarray(at), angle_atom1=np.ascontiguousarray(a1),
+                    angle_atom2=np.ascontiguousarray(a2), angle_atom3=np.ascontiguousarray(a3), mass=mass)
+
+
+def thermal_velocities(box, topo, T=None, seed=777):
+    """Maxwell-Boltzmann velocities [A/fs] at temperature T with the net momentum removed."""
+    T = box.T if T is None else T
+    rng = np.random.default_rng(seed)
+    m = topo.mass[box.type]
+    # (1/2) m v^2 mvv2e = (1/2) kB T per component;  mvv2e = 1 / ftm2v in `units real`
+    sd = np.sqrt(BOLTZ * T * FTM2V / m)
+    v = rng.normal(size=(box.n, 3)) * sd[:, None]
+    v -= (m[:, None] * v).sum(axis=0) / m.sum()
+    return np.ascontiguousarray(v)

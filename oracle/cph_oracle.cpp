@@ -106,6 +106,17 @@ struct Oracle {
   // results
   std::vector<double> f, eatom, phi;
   bool have_atoms = false, have_pass = false;
+  // f2: bonded terms (bond_style harmonic, angle_style harmonic) whose eatom cpp:221-229 adds to the partition;
+  // per-atom incident lists in LAMMPS' newton_bond-off layout (every bond with both atoms, every angle with all three)
+  std::vector<double> bond_k, bond_r0, angle_k, angle_t0;      // indexed by type, 1-based
+  int maxbond = 0, maxangle = 0;
+  std::vector<int> num_bond, bond_type, bond_atom, num_angle, angle_type, angle_a1, angle_a2, angle_a3;
+  std::vector<int> index_of_tag;
+  bool have_topology = false;
+  double e_bond = 0, e_angle = 0;
+  // f2: plain velocity-Verlet of the atoms (fix nve) so that boxes can run real dynamics
+  std::vector<double> mass, v;
+  bool md = false;
 };
 
 int fail(Oracle *o, int code, const char *msg) {
@@ -120,6 +131,13 @@ inline double cself(const Oracle *o) {
 
 void build_list(Oracle *o) {
   const int n = o->n;
+  if (o->md)   // self-propelled atoms: remap into the periodic box when re-neighbouring, as LAMMPS does
+    for (int i = 0; i < n; i++)
+      for (int k = 0; k < 3; k++)
+        if (o->periodic[k]) {
+          const double Lk = o->hi[k] - o->lo[k];
+          o->x[3 * i + k] -= std::floor((o->x[3 * i + k] - o->lo[k]) / Lk) * Lk;
+        }
   const double cutmax = std::max(o->cut_lj_max, o->cut_coul);
   const double rlist = cutmax + o->skin;
   const double rlist2 = rlist * rlist;
@@ -394,6 +412,85 @@ void pair_pass(Oracle *o, int eflag) {
     o->ecoul = (double)ec;
   }
   o->have_pass = true;
+}
+
+// f2 -- bond_style harmonic and angle_style harmonic as upstream LAMMPS writes them
+// [UPSTREAM-LAMMPS bond_harmonic.cpp / angle_harmonic.cpp, from memory]: E_bond = K (r - r0)^2,
+// E_angle = K (theta - theta0)^2, each term evaluated once, forces to all its atoms (Newton),
+// energy shared equally between them (ev_tally: 1/2 per bond atom, 1/3 per angle atom).
+// Runs after pair_pass and ADDS to f / eatom, so the partition of cpp:264-267 sees the bonded
+// energy the way cpp:221-229 adds bond->eatom and angle->eatom to H_atom.
+void bonded_pass(Oracle *o, int eflag) {
+  if (!o->have_topology) return;
+  const int n = o->n;
+  double L[3];
+  for (int k = 0; k < 3; k++) L[k] = o->hi[k] - o->lo[k];
+  auto delta = [&](int a, int b, double *d) {       // x_a - x_b, closest image
+    for (int k = 0; k < 3; k++) {
+      d[k] = o->x[3 * a + k] - o->x[3 * b + k];
+      if (o->periodic[k]) d[k] -= L[k] * std::nearbyint(d[k] / L[k]);
+    }
+  };
+  long double eb = 0, ea = 0;
+  for (int i = 0; i < n; i++) {
+    for (int m = 0; m < o->num_bond[i]; m++) {
+      const int tj = o->bond_atom[(size_t)i * o->maxbond + m];
+      if (o->tag[i] > tj) continue;                 // stored with both atoms: evaluate once
+      const int j = o->index_of_tag[tj], bt = o->bond_type[(size_t)i * o->maxbond + m];
+      double d[3];
+      delta(i, j, d);
+      const double rsq = d[0] * d[0] + d[1] * d[1] + d[2] * d[2], r = std::sqrt(rsq);
+      const double dr = r - o->bond_r0[bt], rk = o->bond_k[bt] * dr;
+      const double fbond = r > 0.0 ? -2.0 * rk / r : 0.0;
+      for (int k = 0; k < 3; k++) { o->f[3 * i + k] += d[k] * fbond; o->f[3 * j + k] -= d[k] * fbond; }
+      if (eflag) {
+        const double e = rk * dr;
+        o->eatom[i] += 0.5 * e; o->eatom[j] += 0.5 * e;
+        eb += e;
+      }
+    }
+    for (int m = 0; m < o->num_angle[i]; m++) {
+      const size_t am = (size_t)i * o->maxangle + m;
+      if (o->angle_a2[am] != o->tag[i]) continue;   // stored with all three atoms: evaluate at the centre
+      const int i1 = o->index_of_tag[o->angle_a1[am]], i2 = i, i3 = o->index_of_tag[o->angle_a3[am]];
+      const int at = o->angle_type[am];
+      double d1[3], d2[3];
+      delta(i1, i2, d1);
+      delta(i3, i2, d2);
+      const double rsq1 = d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2], r1 = std::sqrt(rsq1);
+      const double rsq2 = d2[0] * d2[0] + d2[1] * d2[1] + d2[2] * d2[2], r2 = std::sqrt(rsq2);
+      double c = (d1[0] * d2[0] + d1[1] * d2[1] + d1[2] * d2[2]) / (r1 * r2);
+      c = std::min(1.0, std::max(-1.0, c));
+      double sn = std::sqrt(1.0 - c * c);
+      if (sn < 0.001) sn = 0.001;
+      sn = 1.0 / sn;
+      const double dtheta = std::acos(c) - o->angle_t0[at], tk = o->angle_k[at] * dtheta;
+      const double a = -2.0 * tk * sn, a11 = a * c / rsq1, a12 = -a / (r1 * r2), a22 = a * c / rsq2;
+      for (int k = 0; k < 3; k++) {
+        const double f1 = a11 * d1[k] + a12 * d2[k], f3 = a22 * d2[k] + a12 * d1[k];
+        o->f[3 * i1 + k] += f1; o->f[3 * i2 + k] -= f1 + f3; o->f[3 * i3 + k] += f3;
+      }
+      if (eflag) {
+        const double e = tk * dtheta;
+        o->eatom[i1] += e / 3.0; o->eatom[i2] += e / 3.0; o->eatom[i3] += e / 3.0;
+        ea += e;
+      }
+    }
+  }
+  if (eflag) { o->e_bond = (double)eb; o->e_angle = (double)ea; }
+}
+
+// f2 -- fix nve [UPSTREAM-LAMMPS fix_nve.cpp, from memory]: dtf = dt/2 * ftm2v;
+// initial: v += dtf f/m, x += dt v;  final: v += dtf f/m
+void md_kick(Oracle *o, double dt, bool drift) {
+  const double dtf = 0.5 * dt * o->ftm2v;
+  for (int i = 0; i < o->n; i++) {
+    const double dtfm = dtf / o->mass[o->type[i]];
+    for (int k = 0; k < 3; k++) {
+      o->v[3 * i + k] += dtfm * o->f[3 * i + k];
+      if (drift) o->x[3 * i + k] += dt * o->v[3 * i + k];
+    }
+  }
 }
 
 // compute_Hs tail (cpp:259-277) plus the per-site sums.
@@ -707,6 +804,8 @@ int orc_set_atoms(void *h, int, int n, const double *x, const double *q, const i
     else if (o->implicit_site && (mask[i] & o->Hbit)) o->site_of[i] = 0;
   }
   o->f.assign(3 * (size_t)n, 0); o->eatom.assign(n, 0); o->phi.assign(n, 0);
+  o->have_topology = false;   // per-atom lists follow the atom order: resend after every set_atoms
+  o->md = false;
   build_list(o);
   o->have_atoms = true;
   if (o->dudl_mode == 1 && !o->qA.empty()) apply_charges(o);   // charges follow lambda from the first pass on
@@ -726,7 +825,7 @@ int orc_rebuild(void *h) { build_list(ORC); return 0; }
 int orc_forward(void *) { return 0; }
 int orc_pair_pass(void *h, int eflag) {
   if (!ORC->have_atoms) return fail(ORC, -2, "set_atoms first");
-  pair_pass(ORC, eflag); return 0;
+  pair_pass(ORC, eflag); bonded_pass(ORC, eflag); return 0;
 }
 int orc_site_reduce(void *h) {
   if (!ORC->have_pass) return fail(ORC, -2, "pair pass first");
@@ -754,6 +853,7 @@ int orc_post_force(void *h, int64_t ntimestep, double dt, int, const double *x, 
   if (max_disp2(o) > 0.25 * o->skin * o->skin) build_list(o);
   bool active = (ntimestep % o->nevery) == 0;   // cpp:69
   pair_pass(o, active ? 1 : 0);
+  bonded_pass(o, active ? 1 : 0);               // cpp:221-229: bonded eatom joins the partition
   if (active) {
     site_reduce(o);                             // cpp:70
     integrate(o, dt * o->nevery, o->integ_mode == 0 ? 0 : 2);   // cpp:71-73, t_lambda = nevery*dt (cpp:113)
@@ -864,6 +964,57 @@ int orc_unpack_restart(void *h, const double *buf, int nd) {
 int orc_bias_terms(void *h, double lambda, double *out4) {
   bias_terms(ORC, lambda, out4[0], out4[1], out4[2], out4[3]);
   return 0;
+}
+// ---- f2: bonded terms and atom dynamics ----------------------------------------------------------
+int orc_set_bonded(void *h, int nbondtypes, const double *k, const double *r0, int nangletypes, const double *ak,
+                   const double *theta0) {
+  Oracle *o = ORC;
+  o->bond_k.assign(k, k + nbondtypes + 1); o->bond_r0.assign(r0, r0 + nbondtypes + 1);
+  o->angle_k.assign(ak, ak + nangletypes + 1); o->angle_t0.assign(theta0, theta0 + nangletypes + 1);
+  return 0;
+}
+int orc_set_topology(void *h, int n, int maxbond, const int *num_bond, const int *bond_type, const int *bond_atom,
+                     int maxangle, const int *num_angle, const int *angle_type, const int *a1, const int *a2,
+                     const int *a3) {
+  Oracle *o = ORC;
+  if (!o->have_atoms || n != o->n) return fail(o, -2, "set_topology after set_atoms, same atom count");
+  o->maxbond = maxbond; o->maxangle = maxangle;
+  o->num_bond.assign(num_bond, num_bond + n);
+  o->bond_type.assign(bond_type, bond_type + (size_t)n * maxbond);
+  o->bond_atom.assign(bond_atom, bond_atom + (size_t)n * maxbond);
+  o->num_angle.assign(num_angle, num_angle + n);
+  o->angle_type.assign(angle_type, angle_type + (size_t)n * maxangle);
+  o->angle_a1.assign(a1, a1 + (size_t)n * maxangle);
+  o->angle_a2.assign(a2, a2 + (size_t)n * maxangle);
+  o->angle_a3.assign(a3, a3 + (size_t)n * maxangle);
+  int maxtag = 0;
+  for (int i = 0; i < n; i++) maxtag = std::max(maxtag, o->tag[i]);
+  o->index_of_tag.assign(maxtag + 1, -1);
+  for (int i = 0; i < n; i++) o->index_of_tag[o->tag[i]] = i;
+  o->have_topology = true;
+  return 0;
+}
+int orc_get_bonded_energy(void *h, double *out2) { out2[0] = ORC->e_bond; out2[1] = ORC->e_angle; return 0; }
+int orc_set_mass(void *h, int ntypes, const double *mass) { ORC->mass.assign(mass, mass + ntypes + 1); return 0; }
+int orc_set_v(void *h, int, const double *v) {
+  Oracle *o = ORC;
+  if (!o->have_atoms || o->mass.empty()) return fail(o, -2, "set_atoms and set_mass before set_v");
+  o->v.assign(v, v + 3 * (size_t)o->n);
+  o->md = true;
+  return 0;
+}
+int orc_md_initial_integrate(void *h, double dt) {
+  if (!ORC->md || !ORC->have_pass) return fail(ORC, -2, "set_v and a force pass first");
+  md_kick(ORC, dt, true); return 0;
+}
+int orc_md_final_integrate(void *h, double dt) {
+  if (!ORC->md || !ORC->have_pass) return fail(ORC, -2, "set_v and a force pass first");
+  md_kick(ORC, dt, false); return 0;
+}
+int orc_get_x(void *h, int, double *x) { std::memcpy(x, ORC->x.data(), sizeof(double) * 3 * (size_t)ORC->n); return 0; }
+int orc_get_v(void *h, int, double *v) {
+  if (!ORC->md) return fail(ORC, -2, "set_v first");
+  std::memcpy(v, ORC->v.data(), sizeof(double) * 3 * (size_t)ORC->n); return 0;
 }
 int orc_sync(void *) { return 0; }
 
