@@ -272,6 +272,45 @@ class Engine:
     def get_q(self):
         return self._get_atoms("get_q", 1)
 
+    # -- f2: bonded terms and atom dynamics ----------------------------------------------
+    def set_bonded(self, bond_k, bond_r0, angle_k, angle_theta0):
+        bk, br, ak, at = _f64(bond_k), _f64(bond_r0), _f64(angle_k), _f64(angle_theta0)
+        self._call("set_bonded", C.c_int(bk.size - 1), _d(bk), _d(br), C.c_int(ak.size - 1), _d(ak), _d(at))
+
+    def set_topology(self, topo, rows=None):
+        """`topo` is a synth.Topology; `rows` selects the owned atoms (same selection and order as set_atoms)."""
+        pick = (lambda a: a) if rows is None else (lambda a: a[rows])
+        arrs = [_i32(pick(a)) for a in (topo.num_bond, topo.bond_type, topo.bond_atom, topo.num_angle,
+                                        topo.angle_type, topo.angle_atom1, topo.angle_atom2, topo.angle_atom3)]
+        nb, bt, ba, na, at, a1, a2, a3 = arrs
+        self._call("set_topology", C.c_int(nb.shape[0]), C.c_int(topo.maxbond), _i(nb), _i(bt), _i(ba),
+                   C.c_int(topo.maxangle), _i(na), _i(at), _i(a1), _i(a2), _i(a3))
+
+    def get_bonded_energy(self):
+        out = np.zeros(2)
+        self._call("get_bonded_energy", _d(out))
+        return out
+
+    def set_mass(self, mass):
+        m = _f64(mass)
+        self._call("set_mass", C.c_int(m.size - 1), _d(m))
+
+    def set_v(self, v):
+        v = _f64(v)
+        self._call("set_v", C.c_int(HOST), _d(v))
+
+    def md_initial_integrate(self, dt):
+        self._call("md_initial_integrate", C.c_double(dt))
+
+    def md_final_integrate(self, dt):
+        self._call("md_final_integrate", C.c_double(dt))
+
+    def get_x(self):
+        return self._get_atoms("get_x", 3)
+
+    def get_v(self):
+        return self._get_atoms("get_v", 3)
+
     def get_scalars(self):
         out = np.zeros(8)
         self._call("get_scalars", _d(out))
@@ -368,13 +407,15 @@ class Engine:
 def configure(eng, box, nevery=1, dudl=DUDL_CHARGE, integrator=INTEGRATE_REFERENCE,
               fscale=FSCALE_LAMBDA, bias_mode=BIAS_EXACT, implicit_site=False, ftm2v=None,
               sublo=None, subhi=None, procgrid=(1, 1, 1), myloc=(0, 0, 0), owned=None, bias=None,
-              water_buffer=False, theta=False, cut_lj=None, cut_coul=None, thermostat=0.0):
+              water_buffer=False, theta=False, cut_lj=None, cut_coul=None, thermostat=0.0,
+              topology=None, velocities=None):
     """Push a synth.Box into an engine: the calls FixConstantPH's constructor/init/setup make.
 
     implicit_site=True reproduces the reference's single global lambda over the hydrogen
     group (nsites = 0, pK from the fix arguments, fix_constant_pH.cpp:47).
     owned: index array of the atoms this rank owns (None = all).
-    bias: overrides of the init() constants (fix_constant_pH.cpp:86-96), e.g. m_lambda."""
+    bias: overrides of the init() constants (fix_constant_pH.cpp:86-96), e.g. m_lambda.
+    topology: a synth.Topology -> bonded terms on; velocities: (n,3) -> fix-nve dynamics on."""
     from . import synth
     eng.set_units(synth.QQRD2E, synth.BOLTZ, synth.FTM2V if ftm2v is None else ftm2v)
     # cut_lj: optional (ntypes+1)^2 table of per-type-pair LJ cutoffs (pair_coeff ... cut_lj); cut_coul: override
@@ -400,4 +441,10 @@ def configure(eng, box, nevery=1, dudl=DUDL_CHARGE, integrator=INTEGRATE_REFEREN
     sel = slice(None) if owned is None else owned
     eng.set_atoms(box.x[sel], box.q[sel], box.type[sel], box.tag[sel], box.mask[sel], box.molecule[sel],
                   box.nspecial[sel], box.special[sel], box.maxspecial)
+    if topology is not None:
+        eng.set_bonded(topology.bond_k, topology.bond_r0, topology.angle_k, topology.angle_theta0)
+        eng.set_topology(topology, None if owned is None else owned)
+        if velocities is not None:
+            eng.set_mass(topology.mass)
+            eng.set_v(velocities[sel])
     return eng

@@ -135,6 +135,7 @@ int cph_destroy(cph_handle *h) {
   cph_halo_close(h);
   cph_comm_destroy(h);
   cph_pair_forget(h);
+  cph_bonded_release(h);
   DevBuf<double> *db[] = {&h->d_pK, &h->d_lam, &h->d_vlam, &h->d_alam, &h->d_flam, &h->d_fs, &h->d_dfs, &h->d_Us,
                           &h->d_dUs, &h->d_theta, &h->d_red, &h->d_titr_qA, &h->d_titr_dq, &h->d_scal, &h->d_part, &h->d_xbuild,
                           &h->d_f, &h->d_evdwl, &h->d_phi, &h->d_eatom, &h->d_stage, &h->d_wq, &h->d_dQ};
@@ -442,6 +443,8 @@ int cph_set_atoms(cph_handle *h, int where, int nlocal, const double *x, const d
       break;
     }
   h->have_atoms = false;
+  h->have_topology = false;   // per-atom lists and velocities follow the atom order: the host sends them again
+  h->md_on = false;
   CPH_TRY(cph_rebuild(h));
   h->have_atoms = true;
   h->have_pass = false;
@@ -494,6 +497,7 @@ int cph_pair_pass(cph_handle *h, int eflag) {
   CPH_TRY(need(h, h->have_atoms, "cph_set_atoms first"));
   cudaSetDevice(h->device);
   CPH_TRY(cph_launch_pair(h, eflag ? 1 : 0));
+  CPH_TRY(cph_launch_bonded(h, eflag ? 1 : 0));
   h->have_pass = true;
   return CPH_OK;
 }
@@ -574,6 +578,7 @@ int cph_post_force(cph_handle *h, int64_t ntimestep, double dt, int where, const
   h->scal_h[6] = md;
   if (any) CPH_TRY(cph_rebuild(h));
   if (!guessed || any || fl[5]) CPH_TRY(cph_launch_pair(h, active ? 1 : 0));
+  CPH_TRY(cph_launch_bonded(h, active ? 1 : 0));                        // cpp:221-229: bonded eatom joins the partition
   h->have_pass = true;
   if (active) {
     CPH_TRY(cph_site_reduce(h));                                        // cpp:70
@@ -606,6 +611,59 @@ int cph_get_q(cph_handle *h, int where, double *q) {
   CPH_TRY(need(h, h->have_atoms, "cph_set_atoms first"));
   cudaSetDevice(h->device);
   return fetch_atoms(h, 3, 1, where, q);
+}
+
+// ---- f2: bonded terms and atom dynamics ------------------------------------------------------------
+int cph_set_bonded(cph_handle *h, int nbondtypes, const double *bond_k, const double *bond_r0, int nangletypes,
+                   const double *angle_k, const double *angle_theta0) {
+  cudaSetDevice(h->device);
+  return cph_bonded_set_coef(h, nbondtypes, bond_k, bond_r0, nangletypes, angle_k, angle_theta0);
+}
+int cph_set_topology(cph_handle *h, int nlocal, int maxbond, const int *num_bond, const int *bond_type,
+                     const int *bond_atom, int maxangle, const int *num_angle, const int *angle_type,
+                     const int *angle_atom1, const int *angle_atom2, const int *angle_atom3) {
+  cudaSetDevice(h->device);
+  return cph_bonded_set_topology(h, nlocal, maxbond, num_bond, bond_type, bond_atom, maxangle, num_angle, angle_type,
+                                 angle_atom1, angle_atom2, angle_atom3);
+}
+int cph_get_bonded_energy(cph_handle *h, double *out2) {
+  CPH_TRY(need(h, h->have_pass, "no pair pass yet"));
+  cudaSetDevice(h->device);
+  return cph_bonded_energy(h, out2);
+}
+int cph_set_mass(cph_handle *h, int ntypes, const double *mass) {
+  if (ntypes < 1 || ntypes + 1 > CPH_MAXNT1 || !mass) return cph_fail(h, CPH_ERR_ARG, "cph_set_mass: ntypes %d outside [1,%d]", ntypes, CPH_MAXNT1 - 1);
+  for (int t = 1; t <= ntypes; t++) {
+    if (!(mass[t] > 0.0)) return cph_fail(h, CPH_ERR_ARG, "mass of type %d must be positive", t);
+    h->mass_h[t] = mass[t];
+  }
+  return CPH_OK;
+}
+int cph_set_v(cph_handle *h, int where, const double *v) {
+  CPH_TRY(need(h, h->have_atoms, "cph_set_atoms first"));
+  if (!v && h->nlocal) return cph_fail(h, CPH_ERR_ARG, "v is NULL");
+  cudaSetDevice(h->device);
+  return cph_md_set_v(h, where, v);
+}
+int cph_md_initial_integrate(cph_handle *h, double dt) {
+  CPH_TRY(need(h, h->md_on && h->have_pass, "cph_set_v and a force pass first"));
+  cudaSetDevice(h->device);
+  return cph_md_kick(h, dt, 1);
+}
+int cph_md_final_integrate(cph_handle *h, double dt) {
+  CPH_TRY(need(h, h->md_on && h->have_pass, "cph_set_v and a force pass first"));
+  cudaSetDevice(h->device);
+  return cph_md_kick(h, dt, 0);
+}
+int cph_get_x(cph_handle *h, int where, double *x) {
+  CPH_TRY(need(h, h->have_atoms, "cph_set_atoms first"));
+  cudaSetDevice(h->device);
+  return fetch_atoms(h, 4, 3, where, x);
+}
+int cph_get_v(cph_handle *h, int where, double *v) {
+  CPH_TRY(need(h, h->have_atoms && h->md_on, "cph_set_v first"));
+  cudaSetDevice(h->device);
+  return fetch_atoms(h, 5, 3, where, v);
 }
 
 int cph_get_scalars(cph_handle *h, double *out8) {
@@ -667,6 +725,11 @@ int cph_memory_usage(cph_handle *h, double *bytes) {
   b += h->d_keys.bytes() + h->d_keys2.bytes() + h->d_vals.bytes() + h->d_vals2.bytes() + h->d_tmpi.bytes();
   b += h->d_stage.bytes() + h->d_cubtmp.bytes() + h->d_cell_start_o.bytes() + h->d_cell_start_g.bytes();
   b += h->d_nspecial.bytes() + h->d_special.bytes() + h->d_ghost_src.bytes() + h->d_ghost_code.bytes();
+  b += h->d_neigh2.bytes() + h->d_numneigh2.bytes() + h->d_xinner.bytes() + h->d_xt.bytes() + h->d_xb.bytes();
+  b += h->d_bond_j.bytes() + h->d_bond_t.bytes() + h->d_angle_j.bytes() + h->d_angle_t.bytes() + h->d_bcount.bytes();
+  b += h->d_bond_type.bytes() + h->d_bond_atom.bytes() + h->d_angle_type.bytes() + h->d_angle_a1.bytes() +
+       h->d_angle_a2.bytes() + h->d_angle_a3.bytes() + h->d_num_bond.bytes() + h->d_num_angle.bytes();
+  b += h->d_v.bytes() + h->d_v2.bytes();
   *bytes = b;
   return CPH_OK;
 }

@@ -213,6 +213,20 @@ struct cph_handle {
   DevBuf<unsigned int> d_flags;  // [0] max displacement^2 as float bits, [1] overflow, [2] drift...
   // scalars mirrored on host after site_reduce / integrate
   double scal_h[16]{};
+  // f2: bonded terms of flexible molecules (bond_style harmonic, angle_style harmonic) + fix-nve atom dynamics
+  int nbondtypes = 0, nangletypes = 0, maxbond = 0, maxangle = 0;
+  bool have_bonded_coef = false, have_topology = false, md_on = false;
+  int last_dropmask = 0;             // special classes the last list build left out of the rows
+  DevBuf<double2> d_bond_coef, d_angle_coef;          // {K, r0} / {K, theta0} by type
+  DevBuf<int> d_num_bond, d_bond_type, d_bond_atom;   // caller order, as uploaded (partner ids are tags)
+  DevBuf<int> d_num_angle, d_angle_type, d_angle_a1, d_angle_a2, d_angle_a3;
+  DevBuf<int> d_bcount;              // internal order: bonds | angles << 8 of the atom
+  DevBuf<int> d_bond_j, d_bond_t;    // internal order [nlocal * maxbond]: partner index (owned or ghost), type
+  DevBuf<int> d_angle_j;             // internal order [nlocal * maxangle * 2]: indices of the other two atoms
+  DevBuf<int> d_angle_t;             // type | role << 16 (role 0/2: an end, 1: the centre)
+  DevBuf<double> d_bonded_e;         // [2] E_bond, E_angle of the owned shares
+  double mass_h[CPH_MAXNT1]{};
+  DevBuf<double3> d_v, d_v2;         // internal order velocities (owned atoms)
   // comm
   int nranks = 1, rank = 0;
   void *nccl_comm = nullptr;
@@ -246,8 +260,21 @@ int cph_launch_water_phi(cph_handle *h);      // red[4+2S] = sum of dE/dq over o
 int cph_launch_water_dudl(cph_handle *h);     // dU/dlambda_s -= dQ_s / n_W * red[4+2S] (after the allreduce)
 int cph_launch_set_force(cph_handle *h);
 int cph_launch_set_x(cph_handle *h, const double *x_dev_caller_order);
-int cph_launch_gather_out(cph_handle *h, int what, double *out_dev);  // 0 f, 1 eatom, 2 phi, 3 q
+int cph_launch_gather_out(cph_handle *h, int what, double *out_dev);  // 0 f, 1 eatom, 2 phi, 3 q, 4 x, 5 v
 int cph_launch_pack_xq(cph_handle *h, int n, const double *x, const double *q);
+// bonded.cu
+int cph_bonded_resolve(cph_handle *h);          // partner tags -> indices in the current internal order (after a list build)
+int cph_launch_bonded(cph_handle *h, int eflag);   // adds bond + angle forces / per-atom energy to the pair results
+int cph_md_wrap(cph_handle *h);                 // remap self-propelled atoms into the periodic box (before re-neighbouring)
+void cph_bonded_release(cph_handle *h);
+int cph_bonded_set_coef(cph_handle *h, int nbondtypes, const double *bk, const double *br0, int nangletypes,
+                        const double *ak, const double *at0);
+int cph_bonded_set_topology(cph_handle *h, int nlocal, int maxbond, const int *num_bond, const int *bond_type,
+                            const int *bond_atom, int maxangle, const int *num_angle, const int *angle_type,
+                            const int *a1, const int *a2, const int *a3);
+int cph_bonded_energy(cph_handle *h, double *out2);
+int cph_md_set_v(cph_handle *h, int where, const double *v_caller_order);
+int cph_md_kick(cph_handle *h, double dt, int drift);
 // comm.cu
 int cph_comm_allreduce(cph_handle *h, double *buf, int n);            // sum
 int cph_comm_allreduce_max_u32(cph_handle *h, unsigned int *buf, int n);

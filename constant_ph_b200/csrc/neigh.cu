@@ -725,6 +725,7 @@ int cph_rebuild(cph_handle *h) {
   }
   CPH_CUDA(h, h->d_flags.reserve(8));
   CPH_CUDA(h, cudaMemsetAsync(h->d_flags.p, 0, 8 * sizeof(unsigned int), st));
+  CPH_TRY(cph_md_wrap(h));   // device-side dynamics: remap into the periodic box, as LAMMPS does when re-neighbouring
 
   // ---- drift of owned atoms outside the sub-box -> ghost cutoff ---------------------------
   double3 slo = make_double3(h->sublo[0], h->sublo[1], h->sublo[2]);
@@ -766,6 +767,7 @@ int cph_rebuild(cph_handle *h) {
     CPH_TRY(sort_pairs(h, n, h->d_keys, h->d_keys2, h->d_vals, h->d_vals2, 64));
     // d_vals2 = old index of the atom now at position k
     CPH_TRY(permute_buf(h, n, h->d_vals2.p, h->d_xq, h->d_xq2, h->atom_cap));
+    if (h->md_on) CPH_TRY(permute_buf(h, n, h->d_vals2.p, h->d_v, h->d_v2, h->d_v.cap));
     // d_scr_i is a persistent scratch buffer; after each swap it holds the previous array
     DevBuf<int> &tmp = h->d_scr_i;
     const size_t icap = h->d_type.cap;   // == tag/mask/perm/scr_i capacity (ensure_atom_capacity)
@@ -927,9 +929,10 @@ int cph_rebuild(cph_handle *h) {
   xb_kernel<<<nblk(h->nall + 1), TPB, 0, st>>>(h->nall, h->d_xq.p, h->have_mol ? h->d_mol.p : nullptr,
                                               make_double3(g.lo[0], g.lo[1], g.lo[2]), h->d_xb.p);
   int dropmask = 0;   // special class c is not stored when both weights are zero, except under coul/dsf
-  if (h->pp.style != CPH_PAIR_LJ_CUT_COUL_DSF)
+  if (h->pp.style != CPH_PAIR_LJ_CUT_COUL_DSF && !h->have_topology)   // bonded partners are looked up among the specials
     for (int c = 1; c <= 3; c++)
       if (h->pp.special_lj[c] == 0.0 && h->pp.special_coul[c] == 0.0) dropmask |= 1 << c;
+  h->last_dropmask = dropmask;
   double extent = 0;
   for (int k = 0; k < 3; k++) extent = std::max(extent, g.n[k] / g.inv[k]);
   const float fmargin = (float)(32.0 * rlist * extent * 5.97e-8 + 1e-5 * rlist * rlist);
@@ -1009,6 +1012,7 @@ int cph_rebuild(cph_handle *h) {
   h->nlaunch += 27;          // this file's kernels per rebuild (cub sort/scan kernels not counted)
   h->inner_valid = false;    // the inner (pruned) rows are rebuilt from the new Verlet rows
   h->nbuilds++;
+  CPH_TRY(cph_bonded_resolve(h));   // bond / angle partners in the new internal order
   return 0;
 }
 

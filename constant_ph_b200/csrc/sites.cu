@@ -63,7 +63,7 @@ partition_kernel(int n, const double *__restrict__ eatom, const double *__restri
 }
 
 __global__ void partition_final_kernel(int nb, const double *__restrict__ partials, double *red, int implicit_site,
-                                       int S, double extra_HA, double extra_HB) {
+                                       int S, double extra_HA, double extra_HB, const double *__restrict__ bonded_e) {
   const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
   __shared__ double out[4];
   if (c < 4) {
@@ -75,6 +75,8 @@ __global__ void partition_final_kernel(int nb, const double *__restrict__ partia
     if (lane == 0) {
       if (c == 0) s += extra_HA;
       if (c == 1) s += extra_HB;
+      // E_coul is summed as eatom - evdwl; with bonded terms on the device (f2) eatom also holds their shares
+      if (c == 3 && bonded_e) s -= bonded_e[0] + bonded_e[1];
       out[c] = s;
       red[c] = s;
     }
@@ -351,7 +353,12 @@ __global__ void gather_out_kernel(int n, int width, const int *__restrict__ inv,
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n) return;
   int k = inv[c];
-  if (xq) { out[c] = xq[k].w; return; }
+  if (xq) {
+    const double4 p = xq[k];
+    if (width == 1) out[c] = p.w;                        // charges
+    else { out[3 * (size_t)c] = p.x; out[3 * (size_t)c + 1] = p.y; out[3 * (size_t)c + 2] = p.z; }   // positions
+    return;
+  }
   for (int d = 0; d < width; d++) out[(size_t)c * width + d] = src[(size_t)k * width + d];
 }
 
@@ -366,7 +373,7 @@ int cph_launch_partition(cph_handle *h) {
   int nb = std::max(1, std::min(MAXPART, nblk(n)));
   partition_kernel<<<nb, TPB, 0, st>>>(n, h->d_eatom.p, h->d_evdwl.p, h->d_mask.p, h->fix.Hbit, h->d_part.p);
   partition_final_kernel<<<1, 128, 0, st>>>(nb, h->d_part.p, h->d_red.p, h->fix.implicit_site, S, h->extra_HA,
-                                            h->extra_HB);
+                                            h->extra_HB, h->have_topology ? h->d_bonded_e.p : nullptr);
   h->extra_HA = h->extra_HB = 0.0;   // consumed
   if (h->ntitr)
     site_sum_kernel<<<nblk(h->ntitr), TPB, 0, st>>>(h->ntitr, h->d_titr_site.p, h->d_titr_local.p, h->d_titr_dq.p,
@@ -464,10 +471,11 @@ int cph_launch_set_x(cph_handle *h, const double *xc) {
 int cph_launch_gather_out(cph_handle *h, int what, double *out) {
   const int n = h->nlocal;
   if (n == 0) return 0;
-  const double *src = what == 0 ? h->d_f.p : what == 1 ? h->d_eatom.p : h->d_phi.p;
+  const double *src = what == 0 ? h->d_f.p : what == 1 ? h->d_eatom.p : what == 5 ? (const double *)h->d_v.p : h->d_phi.p;
+  const bool three = what == 0 || what == 4 || what == 5;
   h->nlaunch++;
-  gather_out_kernel<<<nblk(n), TPB, 0, h->stream>>>(n, what == 0 ? 3 : 1, h->d_inv.p, src,
-                                                   what == 3 ? h->d_xq.p : nullptr, out);
+  gather_out_kernel<<<nblk(n), TPB, 0, h->stream>>>(n, three ? 3 : 1, h->d_inv.p, src,
+                                                   (what == 3 || what == 4) ? h->d_xq.p : nullptr, out);
   CPH_CUDA(h, cudaGetLastError());
   return 0;
 }

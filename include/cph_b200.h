@@ -198,6 +198,40 @@ int cph_get_site_map(cph_handle *h, int *site_of_atom);
  * of the periodic shift of j.  Pass keys == NULL to get the counts only. */
 int cph_get_neighbors(cph_handle *h, int *numneigh, int64_t *keys, int64_t keys_capacity);
 
+/* ---- bonded terms and atom dynamics on the device ------------------ */
+/* The reference adds bond->eatom and angle->eatom to H_atom before the HA/HB partition (cpp:221-229).
+ * With a topology set, cph_pair_pass / cph_post_force evaluate bond_style harmonic, E = K (r - r0)^2, and
+ * angle_style harmonic, E = K (theta - theta0)^2, right behind the pair pass and ADD forces and per-atom
+ * energy (1/2 per bond atom, 1/3 per angle atom, LAMMPS' ev_tally) to the pair results, so cph_get_forces,
+ * cph_get_eatom and the partition of cph_site_reduce include them; cph_set_extra_partition then only
+ * carries what still lives on the host (dihedral, improper, kspace).
+ * Coefficient tables are indexed by type, 1-based, [0] unused (bond_coeff / angle_coeff; theta0 in radians). */
+int cph_set_bonded(cph_handle *h, int nbondtypes, const double *bond_k, const double *bond_r0,
+                   int nangletypes, const double *angle_k, const double *angle_theta0);
+/* atom->num_bond, bond_type, bond_atom, num_angle, angle_type, angle_atom1/2/3 of the owned atoms, in the
+ * order of the last cph_set_atoms (call it again after every cph_set_atoms), row-major [nlocal][maxbond] /
+ * [nlocal][maxangle], host pointers.  Layout of `newton_bond off`: every bond is listed with both of its
+ * atoms and every angle with all three, so each rank can evaluate its owned atoms' shares without a
+ * reverse exchange.  Partners are resolved through the special-bond tables given to cph_set_atoms. */
+int cph_set_topology(cph_handle *h, int nlocal, int maxbond, const int *num_bond, const int *bond_type,
+                     const int *bond_atom, int maxangle, const int *num_angle, const int *angle_type,
+                     const int *angle_atom1, const int *angle_atom2, const int *angle_atom3);
+/* out[0] = E_bond, out[1] = E_angle of the last pass with eflag, summed over ranks. */
+int cph_get_bonded_energy(cph_handle *h, double *out2);
+/* `fix nve` on the device, so a box can run real dynamics with positions resident in HBM:
+ * cph_md_initial_integrate: v += dt/2 ftm2v f/m, x += dt v;  cph_md_final_integrate: v += dt/2 ftm2v f/m.
+ * Step: cph_md_initial_integrate, cph_post_force(x = NULL), cph_md_final_integrate.  mass is per type,
+ * 1-based.  Velocities follow the atoms through list rebuilds; cph_set_atoms discards them (send them
+ * again).  Atoms are remapped into the periodic box at list rebuilds along dimensions the rank spans
+ * alone; an atom that drifts more than the skin out of a decomposed sub-box is the host's to migrate
+ * (CPH_ERR_DOMAIN, as with host-driven positions). */
+int cph_set_mass(cph_handle *h, int ntypes, const double *mass);
+int cph_set_v(cph_handle *h, int where, const double *v);    /* nlocal*3, caller order */
+int cph_md_initial_integrate(cph_handle *h, double dt);
+int cph_md_final_integrate(cph_handle *h, double dt);
+int cph_get_x(cph_handle *h, int where, double *x);          /* nlocal*3, caller order */
+int cph_get_v(cph_handle *h, int where, double *v);          /* nlocal*3, caller order */
+
 /* ---- restart (absent from the reference; LAMMPS write_restart/restart layout) ---------- */
 int cph_restart_size(cph_handle *h, int *ndoubles);
 int cph_pack_restart(cph_handle *h, double *buf);
