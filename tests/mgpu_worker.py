@@ -21,6 +21,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
     scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
     nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+    bonded = len(sys.argv) > 3 and sys.argv[3] == "bonded"
     box = synth.config(2, scale=scale, shuffle=True)
     params = synth.jiggle_params(box, amp=0.9, period_lo=40.0, period_hi=90.0)
     grid = bench.decompose(box, world)
@@ -33,6 +34,8 @@ def main():
     dist.broadcast(idbuf, 0)
     eng.comm_init_nccl(world, rank, bytes(idbuf.cpu().numpy().tobytes()))
     kw = dict(bias=dict(m_lambda=2000.0))
+    if bonded:   # bond / angle partners of atoms near a sub-box face are ghosts
+        kw["topology"] = synth.topology(box)
     capi.configure(eng, box, sublo=sublo, subhi=subhi, procgrid=grid, myloc=loc, owned=owned, **kw)
     ref = capi.configure(capi.Engine("cph", device=lrank), box, **kw) if rank == 0 else None
 
@@ -56,6 +59,10 @@ def main():
             worst["dudl"] = max(worst["dudl"], np.abs(t_m["dudl"] - t_r["dudl"]).max() / np.abs(t_r["dudl"]).max())
             for k in ("HA", "HB", "evdwl", "ecoul", "H_lambda"):
                 worst["e"] = max(worst["e"], abs(s_m[k] - s_r[k]) / abs(s_r[k]))
+        if bonded:
+            eb = eng.get_bonded_energy()          # collective: all ranks call it
+            if rank == 0:
+                worst["e"] = max(worst["e"], float(np.abs(eb - ref.get_bonded_energy()).max() / ref.get_bonded_energy().max()))
     counts = eng.get_counts()
     tot = torch.tensor([counts["nlocal"], counts["neighbors"], counts["titr_owned"], counts["builds"]],
                        dtype=torch.int64, device="cuda")

@@ -17,13 +17,13 @@ def ngpus():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_multi_rank_matches_single_rank(built, world):
+@pytest.mark.parametrize("world,mode", [(2, "pair"), (2, "bonded"), (4, "pair"), (8, "pair")])
+def test_multi_rank_matches_single_rank(built, world, mode):
     if ngpus() < world:
         pytest.skip("needs %d GPUs" % world)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
-           "--master-addr", "127.0.0.1", "--master-port", str(29600 + world),
-           os.path.join(ROOT, "tests", "mgpu_worker.py"), "1.0" if world <= 2 else "2.0", "40"]
+           "--master-addr", "127.0.0.1", "--master-port", str(29600 + world + (50 if mode == "bonded" else 0)),
+           os.path.join(ROOT, "tests", "mgpu_worker.py"), "1.0" if world <= 2 else "2.0", "40", mode]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     line = [l for l in r.stdout.splitlines() if l.startswith("MGPU_RESULT ")]
     assert r.returncode == 0 and line, (r.stdout[-2000:], r.stderr[-4000:])
