@@ -14,6 +14,8 @@
        buffer yes|no         modify_water() (h:58): keep the box charge constant through groupW
        coordinate lambda|theta   integrate lambda itself (reference) or theta with lambda = sin^2(theta)
        tlambda TAU           Nose-Hoover thermostat (period TAU) on the site velocities at T; needs integrator vv
+       bias_w|bias_s|bias_h|bias_k|bias_a|bias_b|bias_r|bias_m|bias_d VALUE
+                             override one constant of the bias potential (init() loads Donnini's table, cpp:86-94)
 
    The host side stays a LAMMPS Fix; every per-timestep loop of the reference (cpp:149-171,
    cpp:212-267) and the pair arithmetic north_star pulls into the path run in libcph_b200.so.
@@ -65,6 +67,7 @@ const Choice kChoices[] = {
     {"coordinate", "lambda", "theta", CPH_COORD_LAMBDA, CPH_COORD_THETA},
 };
 const int kNumChoices = sizeof(kChoices) / sizeof(kChoices[0]);
+const char kBiasNames[] = "wshkabrmd";      // bias_<letter> keywords, in the order of cpp:86-94
 
 // one rank per GPU: the launcher's local rank picks the device
 int local_device()
@@ -93,7 +96,8 @@ FixConstantPH::FixConstantPH(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg,
   part[0] = part[1] = 0.0;
   tab = Sites{0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   opt = Options{CPH_DUDL_REFERENCE, CPH_INTEGRATE_REFERENCE, CPH_FSCALE_LAMBDA, CPH_BIAS_EXACT, 0, CPH_COORD_LAMBDA,
-                0.0, 0.5, nullptr};
+                0.0, 0.5, nullptr, {}};
+  for (double &u : opt.bias_user) u = NAN;
   bias = Bias{0, 0, 0, 0, 0, 0, 0, 0, 0, 20.0};         // mass: cpp:96; the rest is loaded in init()
   lambda_cached = opt.lambda_start;
 
@@ -143,6 +147,8 @@ FixConstantPH::FixConstantPH(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg,
         error->all(FLERR, "Illegal fix constant_pH tlambda value {}", opt.thermostat_period);
     } else if (strcmp(key, "lambda0") == 0) {
       opt.lambda_start = lambda_cached = utils::numeric(FLERR, val, false, lmp);
+    } else if (strncmp(key, "bias_", 5) == 0 && key[5] && !key[6] && strchr(kBiasNames, key[5])) {
+      opt.bias_user[strchr(kBiasNames, key[5]) - kBiasNames] = utils::numeric(FLERR, val, false, lmp);
     } else {
       error->all(FLERR, "Unknown fix constant_pH keyword: {}", key);
     }
@@ -218,6 +224,9 @@ void FixConstantPH::init()
 {
   // Donnini, Ullmann, J Chem Theory Comput 2016, Table S2 -- the values at cpp:86-94
   bias = Bias{200.0, 0.3, 4.0, 2.533, 0.034041, 0.005238, 16.458, 0.1507, 2.0, bias.mass};
+  double *slot[9] = {&bias.w, &bias.s, &bias.h, &bias.k, &bias.a, &bias.b, &bias.r, &bias.m, &bias.d};
+  for (int c = 0; c < 9; c++)
+    if (!std::isnan(opt.bias_user[c])) *slot[c] = opt.bias_user[c];
 
   if (!atom->q_flag) error->all(FLERR, "fix constant_pH requires atom attribute q");
   if (domain->triclinic) error->all(FLERR, "fix constant_pH does not support triclinic boxes");

@@ -69,6 +69,7 @@ class FixConstantPH : public Fix {
     double thermostat_period;
     double lambda_start;
     char *site_file;
+    double bias_user[9];           // w s h k a b r m d given as keywords (bias_w ... bias_d); NaN = table value
   } opt;
 
   // per-site table read from the site file (north_star multi-site; none in the reference)

@@ -23,6 +23,10 @@ CASES = [
     dict(name="cfg1_reference_mode", config=1, scale=1.0, steps=3,
          kw=dict(dudl=capi.DUDL_REFERENCE, implicit_site=True, bias=dict(m_lambda=2000.0))),
     dict(name="cfg2_dsf_charge", config=2, scale=0.2, steps=3, kw=dict(bias=dict(m_lambda=2000.0))),
+    # SPC/Fw bonds and angles join the forces and the partitioned per-atom energy
+    dict(name="cfg1_reference_mode_bonded", config=1, scale=1.0, steps=3, bonded=True,
+         kw=dict(dudl=capi.DUDL_REFERENCE, implicit_site=True, bias=dict(m_lambda=2000.0))),
+    dict(name="cfg2_dsf_charge_bonded", config=2, scale=0.2, steps=3, bonded=True, kw=dict(bias=dict(m_lambda=2000.0))),
 ]
 
 
@@ -30,7 +34,8 @@ def main():
     out = {"generated_by": "tests/golden/make_golden.py", "cases": []}
     for case in CASES:
         box = synth.config(case["config"], scale=case["scale"])
-        o = capi.configure(capi.Engine("orc"), box, **case["kw"])
+        topo = synth.topology(box) if case.get("bonded") else None
+        o = capi.configure(capi.Engine("orc"), box, topology=topo, **case["kw"])
         for step in range(case["steps"]):
             o.post_force(step, box.dt, box.x, None)
         s, t, c = o.get_scalars(), o.get_sites(), o.get_counts()
@@ -39,6 +44,8 @@ def main():
         rec["lambda"] = [float(v) for v in t["lambda"]]
         rec["dudl"] = [float(v) for v in t["dudl"]]
         rec["f_abs_sum"] = float(np.abs(o.get_forces()).sum())
+        if topo is not None:
+            rec["bonded_energy"] = [float(v) for v in o.get_bonded_energy()]
         rec["neighbors"] = c["neighbors"]
         rec["special_pairs"] = c["special_pairs"]
         out["cases"].append(rec)

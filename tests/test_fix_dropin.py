@@ -73,13 +73,17 @@ def parse(out):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["charge", "reference", "vv", "buffer", "theta", "bonded", "thermostat"])
+@pytest.mark.parametrize("mode", ["charge", "reference", "vv", "buffer", "theta", "bonded", "thermostat", "biasconst"])
 def test_fix_trajectory_matches_oracle(box_files, mode):
     box, b, s = box_files
     nsteps = 120
     if mode == "charge":
         args = ["sites", s, "mlambda", 2000]
         kw = dict(bias=dict(m_lambda=2000.0))
+    elif mode == "biasconst":
+        # settable bias constants (the reference hard-codes Donnini's table in init(), cpp:86-94)
+        args = ["sites", s, "mlambda", 2000, "bias_h", 2.5, "bias_w", 150, "bias_d", 1.5]
+        kw = dict(bias=dict(m_lambda=2000.0, hbar=2.5, w=150.0, d=1.5))
     elif mode == "thermostat":
         args = ["sites", s, "mlambda", 2000, "integrator", "vv", "coordinate", "theta", "tlambda", 40]
         kw = dict(bias=dict(m_lambda=2000.0), integrator=capi.INTEGRATE_VV, theta=True, thermostat=40.0)

@@ -167,10 +167,13 @@ def test_oracle_matches_golden_fixtures():
     g = json.load(open(os.path.join(GOLDEN, "oracle_golden.json")))
     for case in g["cases"]:
         box = synth.config(case["config"], scale=case["scale"])
-        o = capi.configure(capi.Engine("orc"), box, **{k: v for k, v in case["kw"].items()})
+        topo = synth.topology(box) if case.get("bonded") else None
+        o = capi.configure(capi.Engine("orc"), box, topology=topo, **{k: v for k, v in case["kw"].items()})
         for step in range(case["steps"]):
             o.post_force(step, box.dt, box.x, None)
         s, t = o.get_scalars(), o.get_sites()
+        if topo is not None:
+            assert np.allclose(o.get_bonded_energy(), case["bonded_energy"], rtol=1e-12, atol=0)
         for k, v in case["scalars"].items():
             assert abs(s[k] - v) <= 1e-11 * max(1.0, abs(v)), (case["name"], k, s[k], v)
         assert np.allclose(t["lambda"], case["lambda"], rtol=0, atol=1e-12)
