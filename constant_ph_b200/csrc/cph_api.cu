@@ -115,6 +115,7 @@ int cph_create(int device, cph_handle **out) {
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->pev0); cudaEventCreate(&h->pev1);
   cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&h->ev_flags, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_force, cudaEventDisableTiming);
   cudaMallocHost((void **)&h->h_flags, 16 * sizeof(unsigned int));
   h->d_flags.reserve(96);
   cudaMemsetAsync(h->d_flags.p, 0, 8 * sizeof(unsigned int), h->stream);
@@ -152,6 +153,7 @@ int cph_destroy(cph_handle *h) {
   if (h->h_pin) cudaFreeHost(h->h_pin);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->pev0); cudaEventDestroy(h->pev1);
   cudaEventDestroy(h->ev_flags);
+  cudaEventDestroy(h->ev_force);
   cudaStreamDestroy(h->stream2);
   cudaFreeHost(h->h_flags);
   cudaStreamDestroy(h->stream);
@@ -580,6 +582,17 @@ int cph_post_force(cph_handle *h, int64_t ntimestep, double dt, int where, const
   if (!guessed || any || fl[5]) CPH_TRY(cph_launch_pair(h, active ? 1 : 0));
   CPH_TRY(cph_launch_bonded(h, active ? 1 : 0));                        // cpp:221-229: bonded eatom joins the partition
   h->have_pass = true;
+  // In charge mode nothing after this point touches the forces, so their way back to the host
+  // (gather to caller order + D2H) runs on the side stream under the site reduce / lambda update.
+  const bool early_f = f && where == CPH_HOST && h->fix.dudl_mode == CPH_DUDL_CHARGE && h->nlocal > 0 && !h->profiling;
+  if (early_f) {
+    const size_t n3 = 3 * (size_t)h->nlocal;
+    CPH_CUDA(h, h->d_stage.reserve(n3));
+    CPH_CUDA(h, cudaEventRecord(h->ev_force, h->stream));
+    CPH_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_force, 0));
+    CPH_TRY(cph_launch_gather_out(h, 0, h->d_stage.p, h->stream2));
+    CPH_CUDA(h, cudaMemcpyAsync(f, h->d_stage.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream2));
+  }
   if (active) {
     CPH_TRY(cph_site_reduce(h));                                        // cpp:70
     const int phase = h->fix.integ_mode == CPH_INTEGRATE_REFERENCE ? 0 : 2;
@@ -587,7 +600,12 @@ int cph_post_force(cph_handle *h, int64_t ntimestep, double dt, int where, const
     if (h->fix.dudl_mode == CPH_DUDL_CHARGE && phase == 0) CPH_TRY(cph_launch_apply_charges(h));
   }
   if (h->fix.dudl_mode == CPH_DUDL_REFERENCE) CPH_TRY(cph_launch_set_force(h));   // cpp:78, every step
-  if (f) CPH_TRY(fetch_atoms(h, 0, 3, where, f));
+  if (early_f) {
+    CPH_CUDA(h, cudaStreamSynchronize(h->stream2));
+    CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  } else if (f) {
+    CPH_TRY(fetch_atoms(h, 0, 3, where, f));
+  }
   return CPH_OK;
 }
 

@@ -101,6 +101,7 @@ struct cph_handle {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;    // side stream: decision flags to the host while the halo runs
   cudaEvent_t ev_flags = nullptr;
+  cudaEvent_t ev_force = nullptr;    // forces final: their copy to the host overlaps the lambda tail of the step
   unsigned int *h_flags = nullptr;   // pinned
   std::string err;
   // configuration
@@ -260,7 +261,7 @@ int cph_launch_water_phi(cph_handle *h);      // red[4+2S] = sum of dE/dq over o
 int cph_launch_water_dudl(cph_handle *h);     // dU/dlambda_s -= dQ_s / n_W * red[4+2S] (after the allreduce)
 int cph_launch_set_force(cph_handle *h);
 int cph_launch_set_x(cph_handle *h, const double *x_dev_caller_order);
-int cph_launch_gather_out(cph_handle *h, int what, double *out_dev);  // 0 f, 1 eatom, 2 phi, 3 q, 4 x, 5 v
+int cph_launch_gather_out(cph_handle *h, int what, double *out_dev, cudaStream_t on = nullptr);  // 0 f, 1 eatom, 2 phi, 3 q, 4 x, 5 v
 int cph_launch_pack_xq(cph_handle *h, int n, const double *x, const double *q);
 // bonded.cu
 int cph_bonded_resolve(cph_handle *h);          // partner tags -> indices in the current internal order (after a list build)

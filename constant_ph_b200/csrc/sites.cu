@@ -453,8 +453,9 @@ int cph_launch_set_x(cph_handle *h, const double *xc) {
   ProfScope ps(h, 7);
   const int n = h->nlocal;
   cudaStream_t st = h->stream;
-  CPH_CUDA(h, cudaMemsetAsync(h->d_flags.p, 0, sizeof(unsigned int), st));
-  CPH_CUDA(h, cudaMemsetAsync(h->d_flags.p + 4, 0, 2 * sizeof(unsigned int), st));
+  // words 0 (max displacement), 4 (re-neighbour) and 5 (prune) are this step's; 1..3 belong to the list
+  // build, which clears them itself before use, so one memset covers the lot
+  CPH_CUDA(h, cudaMemsetAsync(h->d_flags.p, 0, 6 * sizeof(unsigned int), st));
   const double thresh2 = 0.25 * h->skin * h->skin;
   const double thresh2_in = 0.25 * h->inner_skin * h->inner_skin;
   const double *xin = h->inner_valid ? h->d_xinner.p : nullptr;
@@ -468,13 +469,14 @@ int cph_launch_set_x(cph_handle *h, const double *xc) {
   return 0;
 }
 
-int cph_launch_gather_out(cph_handle *h, int what, double *out) {
+int cph_launch_gather_out(cph_handle *h, int what, double *out, cudaStream_t on) {
   const int n = h->nlocal;
   if (n == 0) return 0;
+  cudaStream_t st = on ? on : h->stream;
   const double *src = what == 0 ? h->d_f.p : what == 1 ? h->d_eatom.p : what == 5 ? (const double *)h->d_v.p : h->d_phi.p;
   const bool three = what == 0 || what == 4 || what == 5;
   h->nlaunch++;
-  gather_out_kernel<<<nblk(n), TPB, 0, h->stream>>>(n, three ? 3 : 1, h->d_inv.p, src,
+  gather_out_kernel<<<nblk(n), TPB, 0, st>>>(n, three ? 3 : 1, h->d_inv.p, src,
                                                    (what == 3 || what == 4) ? h->d_xq.p : nullptr, out);
   CPH_CUDA(h, cudaGetLastError());
   return 0;
