@@ -216,13 +216,18 @@ def _lattice_dims(n_atoms_target):
 
 def make_box(name="custom", n_atoms=3000, n_acid=1, n_amine=0, style=STYLE_COUL_CUT,
              seed=1, cut=10.0, skin=2.0, alpha=0.2, pH=4.8, T=300.0, dense_titr_frac=0.0,
-             jitter=0.3, shuffle=False, special_14=0.5):
+             jitter=0.3, shuffle=False, special_14=0.5, md_safe=False):
     """Build a water + solute box.
 
     n_acid / n_amine solutes each take three lattice slots along x (the solute
     sits in the middle one) so that no water overlaps them.  dense_titr_frac > 0
     additionally turns that fraction of *water* atoms into single-atom sites
     (BASELINE config 5).
+
+    md_safe: a start that real dynamics can run from.  The default placement lets
+    solutes sit in adjacent lattice rows, where their 8-atom bodies interpenetrate -- harmless for
+    prescribed motion, an LJ-core explosion within five steps of an integrator.  With md_safe solutes
+    are at least two lattice rows apart in y and z and the four water slots beside them are emptied too.
     """
     rng = np.random.default_rng(seed)
     spacing = (1.0 / 0.0334) ** (1.0 / 3.0)
@@ -234,7 +239,9 @@ def make_box(name="custom", n_atoms=3000, n_acid=1, n_amine=0, style=STYLE_COUL_
     occupied = np.zeros((nx, ny, nz), dtype=np.int8)    # 0 water, 1 solute centre, 2 emptied
     centres = []
     if nsol:
-        cand = [(i, j, k) for i in range(1, nx - 1, 3) for j in range(ny) for k in range(nz)]
+        stride = 2 if md_safe else 1
+        cand = [(i, j, k) for i in range(1, nx - 1, 3) for j in range(0, ny - stride + 1, stride)
+                for k in range(0, nz - stride + 1, stride)]
         if len(cand) < nsol:
             raise ValueError("box too small for %d solutes" % nsol)
         pick = rng.choice(len(cand), size=nsol, replace=False)
@@ -244,6 +251,9 @@ def make_box(name="custom", n_atoms=3000, n_acid=1, n_amine=0, style=STYLE_COUL_
             occupied[i, j, k] = 1
             occupied[i - 1, j, k] = 2
             occupied[i + 1, j, k] = 2
+            if md_safe:
+                for dj, dk in ((1, 0), (-1, 0), (0, 1), (0, -1)):
+                    occupied[i, (j + dj) % ny, (k + dk) % nz] = 2
             centres.append((i, j, k))
     wi, wj, wk = np.nonzero(occupied == 0)
     nwat = wi.size

@@ -64,7 +64,7 @@ def test_oracle_bonded_forces_are_the_energy_gradient(built):
 
 
 def test_oracle_dynamics_conserve_energy(built):
-    box = synth.config(2, scale=0.1)
+    box = synth.config(2, scale=0.1, md_safe=True)
     topo = synth.topology(box)
     v0 = synth.thermal_velocities(box, topo, T=100.0)
     orc = capi.configure(capi.Engine("orc"), box, bias=dict(m_lambda=1e12), topology=topo, velocities=v0)
@@ -146,7 +146,7 @@ def test_reference_mode_partition_with_bonded_energy(built):
 @pytest.mark.gpu
 def test_device_dynamics_follow_the_oracle(built):
     """fix nve on the device + lambda dynamics, positions resident in HBM, list rebuilds inside the run."""
-    box = synth.config(2, scale=0.25)
+    box = synth.config(2, scale=0.25, md_safe=True)          # a start with no interpenetrating solutes
     topo = synth.topology(box)
     v0 = synth.thermal_velocities(box, topo, T=300.0)
     cph, orc = _pair(box, topo, velocities=v0)
@@ -168,6 +168,7 @@ def test_device_dynamics_follow_the_oracle(built):
     assert cph.get_counts()["builds"] >= 3                            # the list was rebuilt along the way
     assert _rel(cph.get_forces(), orc.get_forces()) <= 1e-8
     assert _rel(cph.get_bonded_energy(), orc.get_bonded_energy()) <= 1e-9
+    assert np.abs(cph.get_v()).max() < 0.5                     # A/fs: nothing blew up
 
 
 @pytest.mark.gpu
