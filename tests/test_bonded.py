@@ -33,6 +33,30 @@ def test_topology_generator_is_consistent():
     assert topo.bond_k[1] == pytest.approx(529.581) and topo.bond_r0[1] == pytest.approx(1.012)
 
 
+def test_md_safe_start_has_no_interpenetrating_molecules():
+    """The headline boxes let neighbouring solutes overlap (harmless for prescribed motion, an LJ-core explosion
+    for an integrator: profiles/r1_scaling_and_bench.md).  md_safe keeps every pair of LJ-carrying atoms of
+    different molecules apart."""
+    from scipy.spatial import cKDTree
+    worst = {}
+    for safe in (False, True):
+        # a box crowded with solutes, so that the default placement certainly puts some in adjacent rows
+        box = synth.make_box("crowded", n_atoms=30000, n_acid=300, n_amine=300, style=synth.STYLE_COUL_DSF,
+                             seed=9, jitter=0.1, md_safe=safe)
+        L = box.boxhi - box.boxlo
+        x = box.x - np.floor(box.x / L) * L
+        x = np.minimum(x, np.nextafter(L, 0.0))
+        heavy = np.nonzero(np.diag(box.epsilon)[box.type] > 0.05)[0]          # atoms with a real LJ core
+        pairs = cKDTree(x[heavy], boxsize=L).query_pairs(2.6, output_type="ndarray")
+        a, b = heavy[pairs[:, 0]], heavy[pairs[:, 1]]
+        inter = box.molecule[a] != box.molecule[b]
+        d = x[a[inter]] - x[b[inter]]
+        d -= L * np.round(d / L)
+        worst[safe] = np.linalg.norm(d, axis=1).min() if inter.any() else np.inf
+    assert worst[False] < 1.6            # the default placement does produce overlapping solutes
+    assert worst[True] > 2.2             # nothing closer than a hydrogen-bonded O...O contact
+
+
 def test_oracle_bonded_forces_are_the_energy_gradient(built):
     box = synth.config(2, scale=0.1)
     topo = synth.topology(box)
