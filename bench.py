@@ -31,6 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from constant_ph_b200 import capi, synth  # noqa: E402
+import oracle.binding  # noqa: E402,F401  -- the CPU checker, for the cpu_baseline / --impl reference legs only
 
 METRIC = "timesteps_per_s_1M_atoms"
 UNIT = "timesteps/s"
@@ -138,7 +139,7 @@ def run_cpu(args, box, params, nthreads=None, steps=None, warmup=None):
         ncores = len(os.sched_getaffinity(0))
     except Exception:
         pass
-    eng = capi.Engine("orc", native_oracle=True)
+    eng = capi.Engine("orc", variant=True)        # -march=native build of the checker
     nt = eng.lib.orc_set_threads(int(nthreads or ncores))
     t0 = time.perf_counter()
     capi.configure(eng, box, bias=dict(m_lambda=M_LAMBDA))

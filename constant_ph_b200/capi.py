@@ -1,9 +1,11 @@
 """ctypes binding of the C ABI in include/cph_b200.h.
 
-`Engine("cph")` drives libcph_b200.so (the CUDA product).  `Engine("orc")` drives the
-CPU oracle with the same call table; it is for tests, smoke() and bench.py's CPU-baseline
-legs only -- nothing in the product path constructs it.  There is no fallback from one to
-the other: if libcph_b200.so is missing or no CUDA device is present, Engine("cph") raises.
+`Engine("cph")` drives libcph_b200.so (the CUDA product) and is the only engine this package
+knows how to load.  The call table is generic over the symbol prefix, so that test
+infrastructure can register a second implementation of the same ABI to check against
+(`register_library`; the checker's own loader does that when ITS module is imported by tests/,
+smoke() or bench.py -- nothing in this package imports, builds, loads or names it).  There is
+no fallback: if libcph_b200.so is missing or no CUDA device is present, Engine("cph") raises.
 
 Method names are the C names without the prefix; argument meaning follows the header
 (which cites the reference line each entry point stands in for).
@@ -12,7 +14,6 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-import subprocess
 
 import numpy as np
 
@@ -29,7 +30,6 @@ BIAS_DEFAULT = dict(w=200.0, s=0.3, hbar=4.0, k=2.533, a=0.034041, b=0.005238, r
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CUDA_LIB = os.path.join(_ROOT, "constant_ph_b200", "csrc", "libcph_b200.so")
-ORACLE_DIR = os.path.join(_ROOT, "oracle")
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -59,17 +59,19 @@ def _i32(a):
 
 
 _libs = {}
+_registered = {}     # prefix -> loader(variant) of another implementation of the same ABI (test infrastructure)
 
 
-def build_oracle(native=False):
-    """Compile the oracle with its own Makefile (checker infrastructure; gcc only)."""
-    target = "native" if native else "all"
-    subprocess.run(["make", "-C", ORACLE_DIR, target], check=True, capture_output=True)
-    return os.path.join(ORACLE_DIR, "libcph_oracle_native.so" if native else "libcph_oracle.so")
+def register_library(prefix, loader):
+    """Make Engine(prefix) available.  `loader(variant)` returns a ctypes library exporting the ABI of
+    include/cph_b200.h under `<prefix>_` names.  Called by checkers, never by this package."""
+    if prefix == "cph":
+        raise ValueError("the product library is not replaceable")
+    _registered[prefix] = loader
 
 
-def load_library(prefix, native_oracle=False):
-    key = (prefix, native_oracle)
+def load_library(prefix, variant=False):
+    key = (prefix, variant)
     if key in _libs:
         return _libs[key]
     if prefix == "cph":
@@ -77,14 +79,10 @@ def load_library(prefix, native_oracle=False):
             raise CphError(-3, "libcph_b200.so is not built (run __graft_entry__.build()); "
                                "there is no CPU fallback")
         lib = C.CDLL(CUDA_LIB, mode=C.RTLD_GLOBAL)
-    elif prefix == "orc":
-        path = os.path.join(ORACLE_DIR, "libcph_oracle_native.so" if native_oracle else "libcph_oracle.so")
-        src = os.path.join(ORACLE_DIR, "cph_oracle.cpp")
-        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
-            path = build_oracle(native_oracle)
-        lib = C.CDLL(path)
+    elif prefix in _registered:
+        lib = _registered[prefix](variant)
     else:
-        raise ValueError(prefix)
+        raise CphError(-1, "no engine %r: this package ships only the CUDA library" % (prefix,))
     lib_last = getattr(lib, prefix + "_last_error")
     lib_last.restype = C.c_char_p
     lib_last.argtypes = [C.c_void_p]
@@ -95,9 +93,9 @@ def load_library(prefix, native_oracle=False):
 class Engine:
     """One handle (one rank / one GPU)."""
 
-    def __init__(self, prefix="cph", device=0, native_oracle=False):
+    def __init__(self, prefix="cph", device=0, variant=False):
         self.prefix = prefix
-        self.lib = load_library(prefix, native_oracle)
+        self.lib = load_library(prefix, variant)
         self.h = C.c_void_p()
         self.nlocal = 0
         self.nsites = 1
@@ -397,7 +395,7 @@ class Engine:
         self._call("profile_get", C.c_int(which), C.byref(ms), C.byref(n))
         return ms.value, int(n.value)
 
-    # oracle-only helper (closed-form KATs)
+    # not part of include/cph_b200.h: exported only by checker implementations (closed-form known answers)
     def bias_terms(self, lam):
         out = np.zeros(4)
         self._call("bias_terms", C.c_double(lam), _d(out))

@@ -17,6 +17,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from constant_ph_b200 import capi, synth  # noqa: E402
+import oracle.binding  # noqa: E402,F401  -- registers capi.Engine("orc")
 
 CASES = [
     dict(name="cfg1_coul_cut_charge", config=1, scale=1.0, steps=3, kw=dict(bias=dict(m_lambda=2000.0))),

@@ -56,4 +56,25 @@ def test_product_sources_never_reference_the_oracle():
                 txt = open(os.path.join(d, fn)).read()
                 if "orc_" in txt or "cph_oracle" in txt:
                     bad.append(fn)
+    # the Python side of the package: no import of, path into, or symbol of the checker either
+    pkg = os.path.join(ROOT, "constant_ph_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            txt = open(os.path.join(pkg, fn)).read()
+            if "import oracle" in txt or "oracle/" in txt or "libcph_oracle" in txt or "orc_" in txt or '"oracle"' in txt:
+                bad.append(fn)
     assert not bad, bad
+
+
+def test_only_the_cuda_engine_ships_with_the_package():
+    """capi.Engine knows one library; a second engine exists only after test infrastructure registers it."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from constant_ph_b200 import capi\n"
+            "try:\n"
+            "    capi.Engine('orc')\n"
+            "except capi.CphError as e:\n"
+            "    print('refused', e.code)\n" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.stdout.strip() == "refused -1", (r.stdout, r.stderr[-500:])
