@@ -33,6 +33,8 @@ sys.path.insert(0, ROOT)
 from constant_ph_b200 import capi, synth  # noqa: E402
 import oracle.binding  # noqa: E402,F401  -- the CPU checker, for the cpu_baseline / --impl reference legs only
 
+# fp64 instructions (DADD/DMUL/DFMA/DSETP) per 32-pair trip of pair_eval_kernel's row loop, from cuobjdump -sass
+FP64_PER_TRIP = {"dsf": 40, "dsf_lj": 49}
 METRIC = "timesteps_per_s_1M_atoms"
 UNIT = "timesteps/s"
 M_LAMBDA = 2000.0     # see tests/test_gpu_parity.py: Donnini's 20 u nm^2 in Angstrom^2
@@ -44,6 +46,46 @@ def peaks():
         d = json.load(open(p))
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+GOLDEN_CFG3 = os.path.join(ROOT, "tests", "golden", "cfg3_full_golden.json")
+
+
+def host_cores():
+    """(threads the process may run on, nproc of the box)."""
+    total = os.cpu_count() or 1
+    try:
+        return len(os.sched_getaffinity(0)), total
+    except Exception:
+        return total, total
+
+
+def parity_check(eng, box, frame, golden, allsum):
+    """Steps 0..3 of the workload trajectory on a freshly configured engine, compared with the committed
+    oracle values (tests/golden/cfg3_full_golden.json).  Every rank calls this; site sums and energies are
+    already all-reduced by the library, forces / list totals are summed over ranks with `allsum`."""
+    worst = {"dudl_max_rel": 0.0, "energy_rel": 0.0, "lambda_max_abs": 0.0, "force_abs_sum_rel": 0.0}
+    neighbors_equal = True
+    for step in range(max(int(k) for k in golden["steps"]) + 1):
+        eng.post_force(step, box.dt, frame(step), None)
+        g = golden["steps"].get(str(step))
+        if g is None:
+            continue
+        s, t, c = eng.get_scalars(), eng.get_sites(), eng.get_counts()
+        tot = allsum([float(np.abs(eng.get_forces()).sum()), float(c["neighbors"]), float(c["special_pairs"]),
+                      float(c["nlocal"])])
+        gd = np.array(g["dudl"])
+        worst["dudl_max_rel"] = max(worst["dudl_max_rel"], float(np.abs(t["dudl"] - gd).max() / np.abs(gd).max()))
+        worst["lambda_max_abs"] = max(worst["lambda_max_abs"], float(np.abs(t["lambda"] - np.array(g["lambda"])).max()))
+        for k in ("HA", "HB", "evdwl", "ecoul", "H_lambda"):
+            worst["energy_rel"] = max(worst["energy_rel"], abs(s[k] - g["scalars"][k]) / abs(g["scalars"][k]))
+        worst["force_abs_sum_rel"] = max(worst["force_abs_sum_rel"], abs(tot[0] - g["f_abs_sum"]) / g["f_abs_sum"])
+        neighbors_equal = neighbors_equal and int(tot[1]) == g["neighbors"] and int(tot[2]) == g["special_pairs"] \
+            and int(tot[3]) == g["nlocal"]
+    ok = (worst["dudl_max_rel"] <= 1e-10 and worst["energy_rel"] <= 1e-10 and worst["lambda_max_abs"] <= 1e-8
+          and worst["force_abs_sum_rel"] <= 1e-10 and neighbors_equal)
+    return dict(worst, neighbors_equal=bool(neighbors_equal), ok=bool(ok), halo=eng.get_halo_mode(),
+                against="tests/golden/cfg3_full_golden.json (oracle, steps 0 and 3 of this trajectory)")
 
 
 class ClockSampler:
@@ -134,11 +176,7 @@ def algorithmic_bytes(c, ntitr_owned):
 
 def run_cpu(args, box, params, nthreads=None, steps=None, warmup=None):
     """The oracle (CPU restatement of the reference algorithm) on the host cores."""
-    ncores = os.cpu_count() or 1
-    try:
-        ncores = len(os.sched_getaffinity(0))
-    except Exception:
-        pass
+    ncores, _ = host_cores()
     eng = capi.Engine("orc", variant=True)        # -march=native build of the checker
     nt = eng.lib.orc_set_threads(int(nthreads or ncores))
     t0 = time.perf_counter()
@@ -149,13 +187,16 @@ def run_cpu(args, box, params, nthreads=None, steps=None, warmup=None):
     for s in range(warmup):
         eng.post_force(s, box.dt, synth.jiggle_positions(box, params, s * box.dt), None)
     f = np.zeros((box.n, 3))
-    xs = [synth.jiggle_positions(box, params, (warmup + s) * box.dt) for s in range(steps)]
-    t0 = time.perf_counter()
-    for s in range(steps):
-        eng.post_force(warmup + s, box.dt, xs[s], f)
-    dt = time.perf_counter() - t0
+    builds_before = eng.get_counts()["builds"]
+    dt = 0.0
+    for s in range(steps):       # the frame is produced outside the clock, as the GPU arm's frames are
+        x = synth.jiggle_positions(box, params, (warmup + s) * box.dt)
+        t1 = time.perf_counter()
+        eng.post_force(warmup + s, box.dt, x, f)
+        dt += time.perf_counter() - t1
     builds = eng.get_counts()["builds"]
-    return dict(steps_per_s=steps / dt, ms_per_step=1e3 * dt / steps, cores=nt, setup_s=t_setup, builds=builds)
+    return dict(steps_per_s=steps / dt, ms_per_step=1e3 * dt / steps, cores=nt, setup_s=t_setup, builds=builds,
+                builds_timed=builds - builds_before)
 
 
 def main():
@@ -167,6 +208,7 @@ def main():
     ap.add_argument("--atoms", type=int, default=1_000_000, help="atoms in the box (config 3 = 1M)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-check", action="store_true", help="skip the parity check against the committed golden values")
     ap.add_argument("--md-steps", type=int, default=100,
                     help="extra leg: flexible-water dynamics integrated on the device (0 = skip; 1 rank only)")
     args = ap.parse_args()
@@ -187,18 +229,19 @@ def main():
         if rank != 0:
             return 0
         box, params = workload(args)
-        steps = min(args.steps, 6)
-        warm = min(args.warmup, 1)
+        steps, warm = args.steps, args.warmup          # the same trajectory window as the CUDA arm, rebuilds included
         r = run_cpu(args, box, params, steps=steps, warmup=warm)
-        sample = ("full %d-atom workload, %d timed steps after %d warm-up on %d OpenMP threads; "
-                  "list build %.1f s not in the timed steps unless the jiggle triggered one (%d builds total)"
-                  % (box.n, steps, warm, r["cores"], r["setup_s"], r["builds"]))
+        aff, nproc = host_cores()
+        sample = ("full %d-atom workload, %d timed steps after %d warm-up on %d OpenMP threads (affinity %d of nproc %d); "
+                  "%d list rebuild(s) inside the timed steps, as in the CUDA arm's window; initial build %.1f s untimed"
+                  % (box.n, steps, warm, r["cores"], aff, nproc, r["builds_timed"], r["setup_s"]))
         line = {"impl": "reference", "metric": METRIC, "value": r["steps_per_s"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": r["steps_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                                 "sample": sample},
+                                 "sample": sample, "nproc": nproc, "affinity_cores": aff},
                 "e2e": {"value": r["steps_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "rebuilds_in_timed_region": r["builds_timed"],
                 "note": "restated CPU reference (oracle/cph_oracle.cpp, g++ -O3 -march=native -fopenmp); the upstream "
                         "fix does not compile and LAMMPS is not available, so this is a port, not an upstream binary"}
         print(json.dumps(line))
@@ -239,6 +282,22 @@ def main():
 
     def frame(s):
         return np.ascontiguousarray(synth.jiggle_positions(box, params, s * box.dt)[sel])
+
+    def allsum(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        if multi:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.cpu()]
+
+    # ---- parity of THIS engine on THIS workload against the committed oracle values, at every rank count ------
+    check = {"skipped": "golden values exist for the full-size workload only (--atoms 1000000)"}
+    if os.path.exists(GOLDEN_CFG3) and args.atoms == 1_000_000 and not args.no_check:
+        golden = json.load(open(GOLDEN_CFG3))
+        if golden["atoms"] == box.n:
+            check = parity_check(eng, box, frame, golden, allsum)
+            # back to the start of the trajectory for the measurement
+            capi.configure(eng, box, bias=dict(m_lambda=M_LAMBDA), sublo=sublo, subhi=subhi, procgrid=grid, myloc=loc,
+                           owned=owned)
 
     # device-resident frames for `value`; pinned host frames for `e2e`
     frames_h = torch.empty((nfr, nloc, 3), dtype=torch.float64).pin_memory()
@@ -314,30 +373,54 @@ def main():
     abytes, mbar = algorithmic_bytes(counts, counts["titr_owned"])
     peak, peak_src = peaks()
     achieved = abytes / (pair_avg_ms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1_pair_traffic.json")
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r2_pair_traffic.json")
     if os.path.exists(tp) and nranks == 1 and args.atoms == 1_000_000:
         tj = json.load(open(tp))
-        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]     # per launch, from the committed ncu capture
+        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]     # per launch
+        traffic_src = "profiles/r2_pair_traffic.json: dram__bytes_read+write of one `ncu --set full` capture of this kernel " \
+                      "on this workload (a committed profile value, not measured by this run)"
     step_ms_prof = sum(v[0] for v in prof.values()) / K
-    roofline = {"bound": "hbm", "kernel": "pair_eval_kernel<dsf,eflag=1> (K2b; the fp32 prune K2a runs every ~4 steps)",
+    roofline = {"bound": "hbm", "kernel": "pair_eval_kernel<dsf,eflag=1> (K2b; the fp32 prune K2a runs every few steps)",
                 "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": abytes, "mean_neighbors": mbar, "kernel_ms": pair_avg_ms,
+                "kernel_launches_profiled": pair_launches,
                 "kernel_share_of_step": pair_ms / max(sum(v[0] for v in prof.values()), 1e-9),
                 "prune_ms_per_launch": prof["prune"][0] / max(prof["prune"][1], 1),
+                "prune_launches_profiled": prof["prune"][1],
                 "note": "algorithmic bytes follow SURVEY 8(d) (Verlet list of M neighbours); the evaluation kernel "
                         "streams the pruned inner rows, so its measured DRAM traffic is below that figure. Declared "
-                        "bound is HBM (north_star); the kernel is fp64-issue bound (about 65 fp64 instructions per "
-                        "evaluated pair, fp64 pipe 55 % busy); see DESIGN.md"}
+                        "bound is HBM (north_star); the kernel is bound by the fp64 pipe, see roofline_fp64 and DESIGN.md"}
+    # fp64 roofline of the same kernel: fp64 instructions it must issue against the measured DFMA rate of this GPU
+    inner, inner_padded = eng.get_inner_counts()
+    trips = inner_padded / 32.0
+    has_lj = np.array([(box.epsilon[t, 1:] != 0).any() for t in range(box.ntypes + 1)])
+    frac_lj = float(has_lj[box.type[sel]].mean()) if nloc else 0.0
+    fp64_per_trip = FP64_PER_TRIP["dsf_lj"] * frac_lj + FP64_PER_TRIP["dsf"] * (1.0 - frac_lj)
+    peak_dfma, peak_tflops = capi.bench_fp64_peak(local_rank)
+    ach_fp64 = trips * fp64_per_trip / (pair_avg_ms * 1e-3)
+    roofline_fp64 = {"bound": "fp64 pipe", "unit": "fp64 warp instructions/s", "achieved": ach_fp64,
+                     "peak_measured": peak_dfma, "frac": ach_fp64 / peak_dfma, "peak_measured_tflops": peak_tflops,
+                     "fp64_instr_per_32_pairs": {"no_lj_partner": FP64_PER_TRIP["dsf"], "lj": FP64_PER_TRIP["dsf_lj"],
+                                                 "weighted": fp64_per_trip},
+                     "loop_trips_per_launch": trips, "inner_row_entries": inner,
+                     "note": "peak = cph_bench_fp64_peak (8 independent DFMA chains per thread on every SM, best of 5); "
+                             "fp64 instruction counts per 32-pair loop trip are counted from the SASS of the committed "
+                             "kernel (profiles/r2_eval_sass_counts.md) and cross-checked against ncu's "
+                             "smsp__inst_executed_pipe_fp64 in profiles/"}
     launches = launches_timed       # counted by the library's launchers during the timed `value` loop
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline and nranks == 1:
         r = run_cpu(args, box, params, steps=3, warmup=1)
-        cpu = {"value": r["steps_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-               "sample": "full %d-atom workload, 3 timed steps after 1 warm-up step (list build %.1f s excluded)"
-                         % (box.n, r["setup_s"])}
+        aff, nproc = host_cores()
+        cpu = {"value": r["steps_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "nproc": nproc,
+               "affinity_cores": aff,
+               "sample": "full %d-atom workload, 3 timed steps after 1 warm-up step on %d threads (list build %.1f s "
+                         "excluded; --impl reference times the whole window incl. rebuilds)"
+                         % (box.n, r["cores"], r["setup_s"])}
 
     # ---- extra leg: real dynamics, positions resident in HBM ------------------------
     # SPC/Fw bonds and angles on the device, fix-nve integration of the atoms, lambda dynamics on top.
@@ -379,10 +462,13 @@ def main():
         value = K / (ms_dev * 1e-3)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": nranks, "steps": K, "warmup": W,
                 "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "config": dict(config, parallelism="spatial %dx%dx%d" % grid,
-                                                                      rebuilds_in_timed_region=rebuilds, prunes_in_timed_region=prunes),
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+                "dtype": "f64", "data": "synthetic", "config": config,
+                "parallelism": "spatial %dx%dx%d" % grid, "rebuilds_in_timed_region": rebuilds,
+                "prunes_in_timed_region": prunes, "check": check,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+                "roofline_fp64": roofline_fp64, "cpu_baseline": cpu,
                 "kernels_ms_per_step": {k: v[0] / K for k, v in prof.items()}, "wall_ms_per_step": wall_dev / K,
+                "seed_error": capi.bench_seed_error(local_rank),
                 "step_ms_profiled": step_ms_prof, "md": md}
         print(json.dumps(line))
     if multi:

@@ -29,7 +29,8 @@ BIAS_DEFAULT = dict(w=200.0, s=0.3, hbar=4.0, k=2.533, a=0.034041, b=0.005238, r
                     m=0.1507, d=2.0, m_lambda=20.0)
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CUDA_LIB = os.path.join(_ROOT, "constant_ph_b200", "csrc", "libcph_b200.so")
+# CPH_B200_LIB selects another build of the SAME CUDA library (kernel tuning variants under constant_ph_b200/csrc/)
+CUDA_LIB = os.environ.get("CPH_B200_LIB") or os.path.join(_ROOT, "constant_ph_b200", "csrc", "libcph_b200.so")
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -343,6 +344,17 @@ class Engine:
         return dict(nlocal=int(out[0]), nghost=int(out[1]), neighbors=int(out[2]), maxneigh=int(out[3]),
                     special_pairs=int(out[4]), builds=int(out[5]), titr_owned=int(out[6]), nsites=int(out[7]))
 
+    def get_halo_mode(self):
+        m = C.c_int(0)
+        self._call("get_halo_mode", C.byref(m))
+        return ("none", "nccl", "peer")[m.value]
+
+    def get_inner_counts(self):
+        """(entries of the pruned inner rows, the same padded to 32 per row)."""
+        out = np.zeros(2, dtype=np.int64)
+        self._call("get_inner_counts", out.ctypes.data_as(_lp))
+        return int(out[0]), int(out[1])
+
     def get_site_map(self):
         out = np.empty(self.nlocal, dtype=np.int32)
         self._call("get_site_map", _i(out))
@@ -400,6 +412,26 @@ class Engine:
         out = np.zeros(4)
         self._call("bias_terms", C.c_double(lam), _d(out))
         return dict(f=out[0], df=out[1], U=out[2], dU=out[3])
+
+
+def bench_fp64_peak(device=0):
+    """Measured sustained DFMA rate of the device: (warp-level DFMA instructions / s, TFLOP/s)."""
+    lib = load_library("cph")
+    a, b = C.c_double(0), C.c_double(0)
+    rc = lib.cph_bench_fp64_peak(C.c_int(device), C.byref(a), C.byref(b))
+    if rc != 0:
+        raise CphError(rc, "cph_bench_fp64_peak failed")
+    return a.value, b.value
+
+
+def bench_seed_error(device=0):
+    """Worst relative error of the 1/sqrt and 1/x seeds and of their refined forms (fastmath.cuh)."""
+    lib = load_library("cph")
+    out = np.zeros(4)
+    rc = lib.cph_bench_seed_error(C.c_int(device), _d(out))
+    if rc != 0:
+        raise CphError(rc, "cph_bench_seed_error failed")
+    return dict(rsqrt_seed=out[0], rcp_seed=out[1], rsqrt=out[2], rcp=out[3], refine_order=int(lib.cph_refine_order()))
 
 
 def configure(eng, box, nevery=1, dudl=DUDL_CHARGE, integrator=INTEGRATE_REFERENCE,

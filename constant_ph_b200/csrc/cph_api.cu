@@ -108,6 +108,7 @@ int cph_create(int device, cph_handle **out) {
                     prop.major, prop.minor);
   cph_handle *h = new cph_handle();
   h->device = device;
+  h->num_sms = prop.multiProcessorCount;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete h;
     return cph_fail(nullptr, CPH_ERR_CUDA, "cannot create a stream on device %d", device);
@@ -120,7 +121,6 @@ int cph_create(int device, cph_handle **out) {
   h->d_flags.reserve(96);
   cudaMemsetAsync(h->d_flags.p, 0, 8 * sizeof(unsigned int), h->stream);
   if (const char *e = getenv("CPH_INNER_SKIN")) h->inner_skin = std::max(0.0, atof(e));   // tuning knobs
-  if (const char *e = getenv("CPH_PAIR_FUSED")) h->fused_pair = atoi(e) != 0;
   if (const char *e = getenv("CPH_SPECULATE")) h->speculate = atoi(e) != 0;
   if (const char *e = getenv("CPH_HALO")) h->peer_halo_wanted = strcmp(e, "nccl") != 0;   // "nccl" forces ncclSend/Recv
   int rc = size_sites(h);
@@ -135,7 +135,6 @@ int cph_destroy(cph_handle *h) {
   cudaStreamSynchronize(h->stream);
   cph_halo_close(h);
   cph_comm_destroy(h);
-  cph_pair_forget(h);
   cph_bonded_release(h);
   DevBuf<double> *db[] = {&h->d_pK, &h->d_lam, &h->d_vlam, &h->d_alam, &h->d_flam, &h->d_fs, &h->d_dfs, &h->d_Us,
                           &h->d_dUs, &h->d_theta, &h->d_red, &h->d_titr_qA, &h->d_titr_dq, &h->d_scal, &h->d_part, &h->d_xbuild,
@@ -148,7 +147,7 @@ int cph_destroy(cph_handle *h) {
                        &h->d_wtag, &h->d_wlocal};
   for (auto *b : ib) b->release();
   h->d_xb.release(); h->d_molecule.release(); h->d_coef.release(); h->d_coef4.release(); h->d_cut2.release(); h->d_type_has_lj.release(); h->d_xt.release(); h->d_xq.release(); h->d_xq2.release(); h->d_keys.release(); h->d_keys2.release();
-  h->d_xinner.release(); h->d_cubtmp.release(); h->d_flags.release(); h->d_scr_stats.release(); h->d_ipc_stage.release();
+  h->d_xinner.release(); h->d_exp2.release(); h->d_cubtmp.release(); h->d_flags.release(); h->d_scr_stats.release(); h->d_ipc_stage.release();
   h->d_sendx.release(); h->d_recvx.release(); h->d_sendmeta.release(); h->d_recvmeta.release();
   if (h->h_pin) cudaFreeHost(h->h_pin);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->pev0); cudaEventDestroy(h->pev1);
@@ -569,7 +568,7 @@ int cph_post_force(cph_handle *h, int64_t ntimestep, double dt, int where, const
   // Most steps need neither a re-neighbouring nor a prune.  Enqueue the pair pass on that assumption,
   // gated on the device copy of the flags, so the GPU has work while the host waits for its copy;
   // when the guess is wrong the gated grid retires at once and the pass is launched again below.
-  const bool guessed = h->speculate && h->inner_valid && !h->fused_pair && !h->profiling && h->nlocal > 0;
+  const bool guessed = h->speculate && h->inner_valid && !h->profiling && h->nlocal > 0;
   if (guessed) CPH_TRY(cph_launch_pair(h, active ? 1 : 0, h->d_flags.p));
   CPH_CUDA(h, cudaStreamSynchronize(h->stream2));
   const unsigned int *fl = h->h_flags;
@@ -764,6 +763,17 @@ int cph_get_counts(cph_handle *h, int64_t *out8) {
   out8[0] = h->nlocal; out8[1] = h->nghost; out8[2] = h->stored_neigh; out8[3] = h->maxneigh;
   out8[4] = h->special_pairs; out8[5] = h->nbuilds; out8[6] = nt; out8[7] = h->fix.implicit_site ? 0 : h->S;
   return CPH_OK;
+}
+
+int cph_get_halo_mode(cph_handle *h, int *mode) {
+  *mode = h->nranks == 1 ? 0 : (h->peer_halo ? 2 : 1);
+  return CPH_OK;
+}
+
+int cph_get_inner_counts(cph_handle *h, int64_t *out2) {
+  CPH_TRY(need(h, h->have_atoms, "cph_set_atoms first"));
+  cudaSetDevice(h->device);
+  return cph_inner_counts(h, out2);
 }
 
 int cph_get_site_map(cph_handle *h, int *site_of_atom) {

@@ -71,6 +71,30 @@ struct PairParams {
   double special_lj[4], special_coul[4];
 };
 
+// constants of the evaluation loop (pair.cu); passed to the kernel by value with every launch
+struct EvalConst {
+  double cutsq, cut_coulsq;            // global cutoff^2 (max over type pairs), Coulomb cutoff^2
+  double exp_scale, exp_magic, exp_c1s;   // -alpha^2 256/ln2, 2^52+2^51, ln2/(256 alpha^2)
+  double b1, b2, b3, b4;               // (-alpha^2)^k / k!
+  double pa, a1, a2, a3, a4, a5;       // EWALD_P alpha and LAMMPS' erfc polynomial
+  double cD, e_shift, f_shift;         // 2 alpha/sqrt(pi), dsf shifts
+  double qqrd2e, c_self;
+  double neg_alpha2;                   // slow path only
+  double one_m_fc[4], flj[4], fcoul[4];
+};
+
+struct EvalArgs {
+  EvalConst c;
+  int nlocal, nt1, rowcap, rowcap2, eapw;
+  const double4 *xq;
+  const int *type, *neigh, *numspec, *neigh2, *numneigh2, *type_has_lj;
+  const double4 *coef;
+  const double2 *cuts;
+  const double *exp2;
+  double *f, *evdwl, *phi, *eatom;
+  const unsigned int *gate;
+};
+
 struct BiasParams {
   double w, s, h, k, a, b, r, m, d, m_lambda;
   int mode;
@@ -204,7 +228,11 @@ struct cph_handle {
   DevBuf<int> d_neigh2, d_numneigh2;
   DevBuf<double> d_xinner;           // positions at the last prune
   double inner_skin = 0.4;           // measured best of 0.3..0.8 at config 3 (CPH_INNER_SKIN overrides)
-  bool inner_valid = false, fused_pair = false;
+  bool inner_valid = false;
+  int rowcap2 = 0;                   // pitch of the inner rows
+  EvalConst eval_const{};
+  DevBuf<double> d_exp2;             // 2^(j/256), staged into shared memory by the evaluation kernel
+  int num_sms = 148;
   bool speculate = true;        // enqueue the pair pass before the host has read the list flags (CPH_SPECULATE=0: off)
   int64_t nprunes = 0;
   int rowcap = 0;
@@ -248,11 +276,10 @@ void cph_halo_close(cph_handle *h);
 int cph_neighbors_to_host(cph_handle *h, int *numneigh, int64_t *keys, int64_t cap);
 // pair.cu
 int cph_launch_pair(cph_handle *h, int eflag, const unsigned int *gate = nullptr);
-int cph_launch_pair_fused(cph_handle *h, int eflag);
 int cph_launch_prune(cph_handle *h);
-int cph_pair_upload_constants(cph_handle *h);
+int cph_pair_fill_constants(cph_handle *h);
+int cph_inner_counts(cph_handle *h, int64_t *out2);
 int cph_launch_xt(cph_handle *h);
-void cph_pair_forget(cph_handle *h);
 // sites.cu
 int cph_launch_partition(cph_handle *h);        // HA, HB, E_vdwl, E_coul + per-site sums
 int cph_launch_integrate(cph_handle *h, double dt, int phase);

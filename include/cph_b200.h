@@ -191,6 +191,9 @@ int cph_memory_usage(cph_handle *h, double *bytes);
 /* out[0]=nlocal out[1]=nghost out[2]=stored neighbours (sum) out[3]=max per atom out[4]=special pairs
  * out[5]=list builds so far out[6]=titratable atoms owned out[7]=nsites */
 int cph_get_counts(cph_handle *h, int64_t *out8);
+/* how the per-step ghost refresh travels: 0 = single rank (periodic self images only), 1 = ncclSend/ncclRecv,
+ * 2 = stores into the neighbours' receive buffers over NVLink (CUDA IPC peer memory) */
+int cph_get_halo_mode(cph_handle *h, int *mode);
 /* bookkeeping checks (bit-exact parity): site index of every owned atom (-1 = none), caller order */
 int cph_get_site_map(cph_handle *h, int *site_of_atom);
 /* neighbour list as sets: numneigh[i] per owned atom (caller order), then keys
@@ -250,6 +253,21 @@ int cph_timer_stop(cph_handle *h, double *ms);
  * library launched so far, 9 -> launches = inner-list prunes so far. */
 int cph_profile(cph_handle *h, int enable);
 int cph_profile_get(cph_handle *h, int which, double *ms_total, int64_t *launches);
+
+/* out[0] = entries of the pruned inner rows the pair evaluation walks, out[1] = the same with every row padded
+ * to a multiple of 32 (= 32 x the loop trips of the evaluation kernel): the work count behind bench.py's
+ * fp64 roofline. */
+int cph_get_inner_counts(cph_handle *h, int64_t *out2);
+
+/* ---- device microbenchmarks (no handle): the measured fp64 peak SURVEY.md section 7 asks for, and the
+ * accuracy of the hardware-seeded 1/sqrt(x), 1/x the pair evaluation is built on ------------------------- */
+/* sustained DFMA rate of `device`: warp-level DFMA instructions per second, and 2 x thread-level DFMAs as TFLOP/s */
+int cph_bench_fp64_peak(int device, double *dfma_warp_instr_per_s, double *tflops);
+/* worst relative error over the argument ranges of the pair kernel: out[0] 1/sqrt seed, out[1] 1/x seed,
+ * out[2] refined 1/sqrt, out[3] refined 1/x */
+int cph_bench_seed_error(int device, double *out4);
+/* order of the Newton step behind the seeds this library was built with (2 or 3) */
+int cph_refine_order(void);
 
 #ifdef __cplusplus
 }

@@ -31,7 +31,52 @@ CASES = [
 ]
 
 
+# The configuration every BENCH / SCALE number is quoted on (BASELINE configs[2], full size), on the first frames of
+# bench.py's own trajectory; values after step 0 and after step 3.  bench.py checks its engines against this file
+# before the timed loop at every rank count, tests/test_gpu_parity.py does the same under pytest.
+CFG3_STEPS = (0, 3)
+CFG3_KW = dict(bias=dict(m_lambda=2000.0))
+
+
+def cfg3_workload(scale=1.0):
+    """Box + prescribed-motion parameters of bench.py's workload (same call, same seeds)."""
+    box = synth.config(3, scale=scale)
+    params = synth.jiggle_params(box, amp=0.45, period_lo=60.0, period_hi=140.0)
+    return box, params
+
+
+def snapshot(eng):
+    s, t, c = eng.get_scalars(), eng.get_sites(), eng.get_counts()
+    f = eng.get_forces()
+    return {"scalars": {k: float(s[k]) for k in ("HA", "HB", "evdwl", "ecoul", "H_lambda")},
+            "dudl": [float(v) for v in t["dudl"]], "lambda": [float(v) for v in t["lambda"]],
+            "f_abs_sum": float(np.abs(f).sum()), "f_max": float(np.abs(f).max()),
+            "neighbors": c["neighbors"], "special_pairs": c["special_pairs"], "nlocal": c["nlocal"]}
+
+
+def make_cfg3_full(path, scale=1.0):
+    box, params = cfg3_workload(scale)
+    o = capi.Engine("orc")
+    o.lib.orc_set_threads(os.cpu_count() or 1)
+    capi.configure(o, box, **CFG3_KW)
+    rec = {"generated_by": "tests/golden/make_golden.py (oracle output; the reference holds no vectors)",
+           "config": 3, "scale": scale, "atoms": int(box.n), "sites": int(box.nsites),
+           "kw": CFG3_KW, "jiggle": dict(amp=0.45, period_lo=60.0, period_hi=140.0), "steps": {}}
+    for step in range(max(CFG3_STEPS) + 1):
+        o.post_force(step, box.dt, synth.jiggle_positions(box, params, step * box.dt), None)
+        if step in CFG3_STEPS:
+            rec["steps"][str(step)] = snapshot(o)
+    with open(path, "w") as fh:
+        json.dump(rec, fh)
+    print("wrote", path)
+
+
 def main():
+    here = os.path.dirname(os.path.abspath(__file__))
+    if "--cfg3" in sys.argv or "--all" in sys.argv:
+        make_cfg3_full(os.path.join(here, "cfg3_full_golden.json"))
+        if "--cfg3" in sys.argv:
+            return
     out = {"generated_by": "tests/golden/make_golden.py", "cases": []}
     for case in CASES:
         box = synth.config(case["config"], scale=case["scale"])
