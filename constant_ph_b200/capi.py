@@ -163,6 +163,9 @@ class Engine:
     def set_thermostat(self, tau):
         self._call("set_thermostat", C.c_double(tau))
 
+    def set_excluded_policy(self, drop):
+        self._call("set_excluded_policy", C.c_int(1 if drop else 0))
+
     def set_extra_partition(self, dHA, dHB):
         self._call("set_extra_partition", C.c_double(dHA), C.c_double(dHB))
 
@@ -252,6 +255,21 @@ class Engine:
             xp = None if x is None else C.cast(C.c_void_p(int(x)), _dp)
             fp = None if f is None else C.cast(C.c_void_p(int(f)), _dp)
         self._call("post_force", C.c_int64(int(ntimestep)), C.c_double(dt), C.c_int(where), xp, fp)
+
+    def setup(self, ntimestep, x=None, f=None, where=HOST):
+        """setup(): post_force without the lambda step (see cph_setup)."""
+        if where == HOST:
+            x = _f64(x)
+            if f is not None:
+                assert f.dtype == np.float64 and f.flags.c_contiguous
+            xp, fp = _d(x), _d(f)
+        else:
+            xp = None if x is None else C.cast(C.c_void_p(int(x)), _dp)
+            fp = None if f is None else C.cast(C.c_void_p(int(f)), _dp)
+        self._call("setup", C.c_int64(int(ntimestep)), C.c_int(where), xp, fp)
+
+    def set_force_mode(self, accumulate):
+        self._call("set_force_mode", C.c_int(1 if accumulate else 0))
 
     # -- results -----------------------------------------------------------------------------
     def _get_atoms(self, name, width):
@@ -438,7 +456,7 @@ def configure(eng, box, nevery=1, dudl=DUDL_CHARGE, integrator=INTEGRATE_REFEREN
               fscale=FSCALE_LAMBDA, bias_mode=BIAS_EXACT, implicit_site=False, ftm2v=None,
               sublo=None, subhi=None, procgrid=(1, 1, 1), myloc=(0, 0, 0), owned=None, bias=None,
               water_buffer=False, theta=False, cut_lj=None, cut_coul=None, thermostat=0.0,
-              topology=None, velocities=None):
+              topology=None, velocities=None, drop_excluded=False):
     """Push a synth.Box into an engine: the calls FixConstantPH's constructor/init/setup make.
 
     implicit_site=True reproduces the reference's single global lambda over the hydrogen
@@ -456,6 +474,8 @@ def configure(eng, box, nevery=1, dudl=DUDL_CHARGE, integrator=INTEGRATE_REFEREN
     eng.set_fix(nevery, synth.GROUP_H_BIT, synth.GROUP_W_BIT, pK0, box.pH, box.T)
     eng.set_bias(bias_mode, **(bias or {}))
     eng.set_mode(dudl, integrator, fscale)
+    if drop_excluded:
+        eng.set_excluded_policy(True)
     if water_buffer:
         eng.set_water_buffer(True)
     if theta:

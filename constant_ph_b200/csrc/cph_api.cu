@@ -9,6 +9,8 @@
 #include <cstring>
 #include <numeric>
 
+#include <omp.h>
+
 #include "cph_internal.h"
 
 static thread_local std::string g_create_error;
@@ -80,6 +82,89 @@ int fetch_atoms(cph_handle *h, int what, int width, int where, double *out) {
   return 0;
 }
 
+// Is this host pointer page-locked (cudaMallocHost / cudaHostRegister)?  LAMMPS' atom->x and atom->f are not.
+bool is_pinned(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+constexpr int HCHUNKS = 4;   // host staging pipeline depth
+
+int host_threads() {
+  static const int nt = std::max(1, std::min(16, omp_get_max_threads()));
+  return nt;
+}
+
+// caller's host array -> device.  Page-locked memory goes straight through the copy engine; pageable memory
+// (LAMMPS' own arrays) is copied by the host cores into the library's page-locked staging in HCHUNKS pieces,
+// each shipped as soon as it is complete, so the DMA of one piece overlaps the copy of the next.
+int upload_host_array(cph_handle *h, double *dst_dev, const double *src, size_t n) {
+  if (n == 0) return 0;
+  if (is_pinned(src)) {
+    CPH_CUDA(h, cudaMemcpyAsync(dst_dev, src, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    return 0;
+  }
+  CPH_CUDA(h, cudaEventSynchronize(h->ev_xstage));          // the previous upload has left the staging buffer
+  CPH_TRY(ensure_pinned(h, n * sizeof(double) + 64));
+  double *stage = h->h_pin;
+  const int nt = host_threads();
+  for (int c = 0; c < HCHUNKS; c++) {
+    const size_t lo = n * c / HCHUNKS, hi = n * (c + 1) / HCHUNKS;
+    if (hi == lo) continue;
+#pragma omp parallel for num_threads(nt) schedule(static)
+    for (int t = 0; t < nt; t++) {
+      const size_t a = lo + (hi - lo) * t / nt, b = lo + (hi - lo) * (t + 1) / nt;
+      memcpy(stage + a, src + a, (b - a) * sizeof(double));
+    }
+    CPH_CUDA(h, cudaMemcpyAsync(dst_dev + lo, stage + lo, (hi - lo) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
+  CPH_CUDA(h, cudaEventRecord(h->ev_xstage, h->stream));
+  return 0;
+}
+
+// device forces (already gathered to caller order in d_stage on `st`) -> caller's host array: stored, or
+// ADDED to what the array holds (cph_set_force_mode: the fix under `pair_modify compute no`, cpp:149-171 keeps
+// the other force contributions LAMMPS put there).  Straight DMA when the destination is page-locked and the
+// mode is "store"; otherwise HCHUNKS pieces through page-locked staging, each added / copied by the host cores
+// while the next one is in flight.  Returns with the data in place.
+int deliver_forces(cph_handle *h, double *f, size_t n3, cudaStream_t st) {
+  if (n3 == 0) return 0;
+  if (!h->force_add && is_pinned(f)) {
+    CPH_CUDA(h, cudaMemcpyAsync(f, h->d_stage.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CPH_CUDA(h, cudaStreamSynchronize(st));
+    return 0;
+  }
+  if (n3 * sizeof(double) > h->h_fpin_bytes) {
+    if (h->h_fpin) cudaFreeHost(h->h_fpin);
+    h->h_fpin = nullptr;
+    h->h_fpin_bytes = 0;
+    const size_t want = n3 * sizeof(double) + n3 + 64;
+    CPH_CUDA(h, cudaMallocHost((void **)&h->h_fpin, want));
+    h->h_fpin_bytes = want;
+  }
+  double *stage = h->h_fpin;
+  for (int c = 0; c < HCHUNKS; c++) {
+    const size_t lo = n3 * c / HCHUNKS, hi = n3 * (c + 1) / HCHUNKS;
+    if (hi > lo)
+      CPH_CUDA(h, cudaMemcpyAsync(stage + lo, h->d_stage.p + lo, (hi - lo) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CPH_CUDA(h, cudaEventRecord(h->ev_fchunk[c], st));
+  }
+  const int nt = host_threads();
+  const bool add = h->force_add;
+  for (int c = 0; c < HCHUNKS; c++) {
+    const size_t lo = n3 * c / HCHUNKS, hi = n3 * (c + 1) / HCHUNKS;
+    CPH_CUDA(h, cudaEventSynchronize(h->ev_fchunk[c]));
+#pragma omp parallel for num_threads(nt) schedule(static)
+    for (int t = 0; t < nt; t++) {
+      const size_t a = lo + (hi - lo) * t / nt, b = lo + (hi - lo) * (t + 1) / nt;
+      if (add) for (size_t k = a; k < b; k++) f[k] += stage[k];
+      else memcpy(f + a, stage + a, (b - a) * sizeof(double));
+    }
+  }
+  return 0;
+}
+
 int read_flags(cph_handle *h, unsigned int *flags_h) {
   CPH_CUDA(h, cudaMemcpyAsync(flags_h, h->d_flags.p, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
   CPH_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -113,13 +198,26 @@ int cph_create(int device, cph_handle **out) {
     delete h;
     return cph_fail(nullptr, CPH_ERR_CUDA, "cannot create a stream on device %d", device);
   }
-  cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->pev0); cudaEventCreate(&h->pev1);
-  cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
-  cudaEventCreateWithFlags(&h->ev_flags, cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&h->ev_force, cudaEventDisableTiming);
-  cudaMallocHost((void **)&h->h_flags, 16 * sizeof(unsigned int));
-  h->d_flags.reserve(96);
-  cudaMemsetAsync(h->d_flags.p, 0, 8 * sizeof(unsigned int), h->stream);
+  {
+    cudaError_t rc = cudaSuccess;
+    auto keep = [&](cudaError_t e2) { if (rc == cudaSuccess && e2 != cudaSuccess) rc = e2; };
+    keep(cudaEventCreate(&h->ev0)); keep(cudaEventCreate(&h->ev1));
+    keep(cudaEventCreate(&h->pev0)); keep(cudaEventCreate(&h->pev1));
+    keep(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    keep(cudaEventCreateWithFlags(&h->ev_flags, cudaEventDisableTiming));
+    keep(cudaEventCreateWithFlags(&h->ev_force, cudaEventDisableTiming));
+    keep(cudaEventCreateWithFlags(&h->ev_xstage, cudaEventDisableTiming));
+    for (auto &ev : h->ev_fchunk) keep(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    keep(cudaMallocHost((void **)&h->h_flags, 16 * sizeof(unsigned int)));
+    keep(h->d_flags.reserve(96));
+    if (rc == cudaSuccess) keep(cudaMemsetAsync(h->d_flags.p, 0, 96 * sizeof(unsigned int), h->stream));
+    if (rc != cudaSuccess) {
+      cph_fail(nullptr, CPH_ERR_CUDA, "cph_create: %s while setting up streams, events and flag buffers on device %d",
+               cudaGetErrorString(rc), device);
+      cph_destroy(h);
+      return CPH_ERR_CUDA;
+    }
+  }
   if (const char *e = getenv("CPH_INNER_SKIN")) h->inner_skin = std::max(0.0, atof(e));   // tuning knobs
   if (const char *e = getenv("CPH_SPECULATE")) h->speculate = atoi(e) != 0;
   if (const char *e = getenv("CPH_HALO")) h->peer_halo_wanted = strcmp(e, "nccl") != 0;   // "nccl" forces ncclSend/Recv
@@ -140,19 +238,23 @@ int cph_destroy(cph_handle *h) {
                           &h->d_dUs, &h->d_theta, &h->d_red, &h->d_titr_qA, &h->d_titr_dq, &h->d_scal, &h->d_part, &h->d_xbuild,
                           &h->d_f, &h->d_evdwl, &h->d_phi, &h->d_eatom, &h->d_stage, &h->d_wq, &h->d_dQ};
   for (auto *b : db) b->release();
-  DevBuf<int> *ib[] = {&h->d_titr_tag_sorted, &h->d_titr_entry_of_sorted, &h->d_titr_site, &h->d_titr_local, &h->d_type,
+  DevBuf<int> *ib[] = {&h->d_titr_tag_sorted, &h->d_titr_entry_of_sorted, &h->d_titr_site, &h->d_titr_local, &h->d_site_start, &h->d_type,
                        &h->d_tag, &h->d_mask, &h->d_perm, &h->d_inv, &h->d_site_of, &h->d_titr_of, &h->d_nspecial,
                        &h->d_special, &h->d_ghost_src, &h->d_ghost_code, &h->d_hlist, &h->d_istage, &h->d_vals,
                        &h->d_vals2, &h->d_tmpi, &h->d_cell_start_o, &h->d_cell_start_g, &h->d_neigh, &h->d_numneigh, &h->d_numspec, &h->d_neigh2, &h->d_numneigh2, &h->d_scr_i, &h->d_scr_src, &h->d_scr_code, &h->d_scr_off, &h->d_mol, &h->d_rec_src, &h->d_rec_dir,
                        &h->d_wtag, &h->d_wlocal};
   for (auto *b : ib) b->release();
   h->d_xb.release(); h->d_molecule.release(); h->d_coef.release(); h->d_coef4.release(); h->d_cut2.release(); h->d_type_has_lj.release(); h->d_xt.release(); h->d_xq.release(); h->d_xq2.release(); h->d_keys.release(); h->d_keys2.release();
-  h->d_xinner.release(); h->d_exp2.release(); h->d_cubtmp.release(); h->d_flags.release(); h->d_scr_stats.release(); h->d_ipc_stage.release();
+  h->d_xinner.release(); h->d_exp2.release(); h->d_qnext.release(); h->d_cubtmp.release(); h->d_flags.release(); h->d_scr_stats.release(); h->d_ipc_stage.release();
   h->d_sendx.release(); h->d_recvx.release(); h->d_sendmeta.release(); h->d_recvmeta.release();
   if (h->h_pin) cudaFreeHost(h->h_pin);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->pev0); cudaEventDestroy(h->pev1);
   cudaEventDestroy(h->ev_flags);
   cudaEventDestroy(h->ev_force);
+  if (h->ev_xstage) cudaEventDestroy(h->ev_xstage);
+  for (auto ev : h->ev_fchunk) if (ev) cudaEventDestroy(ev);
+  if (h->h_fpin) cudaFreeHost(h->h_fpin);
+  h->d_xstage.release();
   cudaStreamDestroy(h->stream2);
   cudaFreeHost(h->h_flags);
   cudaStreamDestroy(h->stream);
@@ -303,6 +405,12 @@ int cph_set_extra_partition(cph_handle *h, double dHA, double dHB) {
   return CPH_OK;
 }
 
+int cph_set_excluded_policy(cph_handle *h, int drop) {
+  h->drop_excluded = drop != 0;
+  h->rowcap = 0;
+  return CPH_OK;
+}
+
 int cph_set_coordinate(cph_handle *h, int coordinate) {
   if (coordinate != CPH_COORD_LAMBDA && coordinate != CPH_COORD_THETA) return cph_fail(h, CPH_ERR_ARG, "bad coordinate");
   h->coord_theta = coordinate == CPH_COORD_THETA;
@@ -350,6 +458,12 @@ int cph_set_sites(cph_handle *h, int nsites, const double *pK, int ntitr, const 
     h->titr_entry_of_sorted_h[k] = byt[k];
     if (k && h->titr_tag_sorted_h[k] == h->titr_tag_sorted_h[k - 1])
       return cph_fail(h, CPH_ERR_ARG, "atom tag %d appears twice in the titratable-atom table", tag[byt[k]]);
+  }
+  {
+    std::vector<int> start(h->S + 1, 0);
+    for (int k = 0; k < ntitr; k++) start[site[k] + 1]++;
+    for (int s2 = 0; s2 < h->S; s2++) start[s2 + 1] += start[s2];
+    CPH_TRY(upload(h, h->d_site_start, start.data(), start.size()));
   }
   CPH_TRY(upload(h, h->d_titr_site, site.data(), ntitr));
   CPH_TRY(upload(h, h->d_titr_qA, a.data(), ntitr));
@@ -465,9 +579,9 @@ int cph_set_x(cph_handle *h, int where, const double *x) {
   const size_t n3 = 3 * (size_t)h->nlocal;
   const double *xd = x;
   if (where == CPH_HOST) {
-    CPH_CUDA(h, h->d_stage.reserve(n3 + 1));
-    CPH_CUDA(h, cudaMemcpyAsync(h->d_stage.p, x, n3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    xd = h->d_stage.p;
+    CPH_CUDA(h, h->d_xstage.reserve(n3 + 1));
+    CPH_TRY(upload_host_array(h, h->d_xstage.p, x, n3));
+    xd = h->d_xstage.p;
   }
   return cph_launch_set_x(h, xd);
 }
@@ -521,11 +635,9 @@ int cph_integrate_lambda(cph_handle *h, double dt) {
 int cph_initial_integrate(cph_handle *h, double dt) {
   if (h->fix.integ_mode != CPH_INTEGRATE_VV) return CPH_OK;
   cudaSetDevice(h->device);
-  CPH_TRY(cph_launch_integrate(h, dt, 1));
-  if (h->fix.dudl_mode == CPH_DUDL_CHARGE && h->have_atoms) {
-    CPH_TRY(cph_launch_apply_charges(h));
-    CPH_TRY(cph_forward_ghosts(h));
-  }
+  const bool charge = h->fix.dudl_mode == CPH_DUDL_CHARGE && h->have_atoms;
+  CPH_TRY(cph_launch_integrate(h, dt, 1, charge));      // kick + drift, charges follow in the same launch
+  if (charge) CPH_TRY(cph_forward_ghosts(h));
   return CPH_OK;
 }
 
@@ -548,7 +660,11 @@ int cph_set_force(cph_handle *h) {
   return cph_launch_set_force(h);
 }
 
-int cph_post_force(cph_handle *h, int64_t ntimestep, double dt, int where, const double *x, double *f) {
+// post_force() (cpp:67-79).  advance == false is setup(): everything is evaluated (forces, partition, site sums,
+// bias, F_lambda, H_lambda, force rescale) but lambda does not move -- the reference declares setup (h:35)
+// without a body and never integrates there.
+static int post_force_impl(cph_handle *h, int64_t ntimestep, double dt, int where, const double *x, double *f,
+                           bool advance) {
   CPH_TRY(need(h, h->have_atoms, "cph_set_atoms first"));
   cudaSetDevice(h->device);
   // new positions + neighbor->decide()
@@ -564,7 +680,7 @@ int cph_post_force(cph_handle *h, int64_t ntimestep, double dt, int where, const
   CPH_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_flags, 0));
   CPH_CUDA(h, cudaMemcpyAsync(h->h_flags, h->d_flags.p, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream2));
   CPH_TRY(cph_halo_finish(h));
-  const bool active = (ntimestep % h->fix.nevery) == 0;                 // cpp:69
+  const bool active = !advance || (ntimestep % h->fix.nevery) == 0;       // cpp:69
   // Most steps need neither a re-neighbouring nor a prune.  Enqueue the pair pass on that assumption,
   // gated on the device copy of the flags, so the GPU has work while the host waits for its copy;
   // when the guess is wrong the gated grid retires at once and the pass is launched again below.
@@ -583,28 +699,55 @@ int cph_post_force(cph_handle *h, int64_t ntimestep, double dt, int where, const
   h->have_pass = true;
   // In charge mode nothing after this point touches the forces, so their way back to the host
   // (gather to caller order + D2H) runs on the side stream under the site reduce / lambda update.
+  const size_t n3 = 3 * (size_t)h->nlocal;
   const bool early_f = f && where == CPH_HOST && h->fix.dudl_mode == CPH_DUDL_CHARGE && h->nlocal > 0 && !h->profiling;
   if (early_f) {
-    const size_t n3 = 3 * (size_t)h->nlocal;
     CPH_CUDA(h, h->d_stage.reserve(n3));
     CPH_CUDA(h, cudaEventRecord(h->ev_force, h->stream));
     CPH_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_force, 0));
     CPH_TRY(cph_launch_gather_out(h, 0, h->d_stage.p, h->stream2));
-    CPH_CUDA(h, cudaMemcpyAsync(f, h->d_stage.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream2));
   }
   if (active) {
     CPH_TRY(cph_site_reduce(h));                                        // cpp:70
-    const int phase = h->fix.integ_mode == CPH_INTEGRATE_REFERENCE ? 0 : 2;
-    CPH_TRY(cph_launch_integrate(h, dt * h->fix.nevery, phase));        // cpp:71-73; t_lambda = nevery*dt (cpp:113)
-    if (h->fix.dudl_mode == CPH_DUDL_CHARGE && phase == 0) CPH_TRY(cph_launch_apply_charges(h));
+    const int phase = (h->fix.integ_mode == CPH_INTEGRATE_REFERENCE && advance) ? 0 : 2;
+    // cpp:71-73; t_lambda = nevery*dt (cpp:113); the charges follow lambda in the same launch
+    CPH_TRY(cph_launch_integrate(h, dt * h->fix.nevery, phase, h->fix.dudl_mode == CPH_DUDL_CHARGE && phase == 0));
   }
   if (h->fix.dudl_mode == CPH_DUDL_REFERENCE) CPH_TRY(cph_launch_set_force(h));   // cpp:78, every step
   if (early_f) {
-    CPH_CUDA(h, cudaStreamSynchronize(h->stream2));
+    CPH_TRY(deliver_forces(h, f, n3, h->stream2));
     CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  } else if (f && where == CPH_HOST && h->nlocal > 0) {
+    CPH_CUDA(h, h->d_stage.reserve(n3));
+    CPH_TRY(cph_launch_gather_out(h, 0, h->d_stage.p));
+    CPH_TRY(deliver_forces(h, f, n3, h->stream));
   } else if (f) {
     CPH_TRY(fetch_atoms(h, 0, 3, where, f));
   }
+  return CPH_OK;
+}
+
+int cph_post_force(cph_handle *h, int64_t ntimestep, double dt, int where, const double *x, double *f) {
+  return post_force_impl(h, ntimestep, dt, where, x, f, true);
+}
+
+int cph_setup(cph_handle *h, int64_t ntimestep, int where, const double *x, double *f) {
+  return post_force_impl(h, ntimestep, 0.0, where, x, f, false);
+}
+
+int cph_set_force_mode(cph_handle *h, int accumulate) {
+  h->force_add = accumulate != 0;
+  return CPH_OK;
+}
+
+int cph_alloc_host(size_t bytes, void **p) {
+  if (!p) return CPH_ERR_ARG;
+  *p = nullptr;
+  return cudaMallocHost(p, bytes ? bytes : 1) == cudaSuccess ? CPH_OK : CPH_ERR_CUDA;
+}
+
+int cph_free_host(void *p) {
+  if (p) cudaFreeHost(p);
   return CPH_OK;
 }
 

@@ -85,7 +85,8 @@ struct EvalConst {
 
 struct EvalArgs {
   EvalConst c;
-  int nlocal, nt1, rowcap, rowcap2, eapw;
+  int nlocal, nt1, rowcap, rowcap2, nqueues;
+  int *qnext;                          // per-SM queue heads (pair.cu)
   const double4 *xq;
   const int *type, *neigh, *numspec, *neigh2, *numneigh2, *type_has_lj;
   const double4 *coef;
@@ -126,6 +127,12 @@ struct cph_handle {
   cudaStream_t stream2 = nullptr;    // side stream: decision flags to the host while the halo runs
   cudaEvent_t ev_flags = nullptr;
   cudaEvent_t ev_force = nullptr;    // forces final: their copy to the host overlaps the lambda tail of the step
+  cudaEvent_t ev_xstage = nullptr;   // the staged upload of x has left the page-locked staging buffer
+  cudaEvent_t ev_fchunk[4]{};        // pieces of the force read-back
+  bool force_add = false;            // host forces are ADDED to the caller's array (cph_set_force_mode)
+  double *h_fpin = nullptr;          // page-locked staging of the force read-back
+  size_t h_fpin_bytes = 0;
+  DevBuf<double> d_xstage;           // device-side landing buffer of x (caller order)
   unsigned int *h_flags = nullptr;   // pinned
   std::string err;
   // configuration
@@ -166,6 +173,7 @@ struct cph_handle {
   bool uniform_cut = true, kc_dirty = true;
   DevBuf<int> d_titr_tag_sorted, d_titr_entry_of_sorted;  // [ntitr]
   DevBuf<int> d_titr_site, d_titr_local;                   // [ntitr] site-major; local = owned index or -1
+  DevBuf<int> d_site_start;                                // [S+1] range of every site in the site-major table
   DevBuf<double> d_titr_qA, d_titr_dq;                     // [ntitr]
   DevBuf<double> d_scal;                                   // 16 doubles of scalar results
   DevBuf<double> d_part;                                   // block partials for deterministic sums
@@ -232,6 +240,7 @@ struct cph_handle {
   int rowcap2 = 0;                   // pitch of the inner rows
   EvalConst eval_const{};
   DevBuf<double> d_exp2;             // 2^(j/256), staged into shared memory by the evaluation kernel
+  DevBuf<int> d_qnext;               // per-SM queue heads of the evaluation kernel
   int num_sms = 148;
   bool speculate = true;        // enqueue the pair pass before the host has read the list flags (CPH_SPECULATE=0: off)
   int64_t nprunes = 0;
@@ -245,6 +254,7 @@ struct cph_handle {
   // f2: bonded terms of flexible molecules (bond_style harmonic, angle_style harmonic) + fix-nve atom dynamics
   int nbondtypes = 0, nangletypes = 0, maxbond = 0, maxangle = 0;
   bool have_bonded_coef = false, have_topology = false, md_on = false;
+  bool drop_excluded = false;        // cph_set_excluded_policy: dsf drops fully excluded specials like the cut styles
   int last_dropmask = 0;             // special classes the last list build left out of the rows
   DevBuf<double2> d_bond_coef, d_angle_coef;          // {K, r0} / {K, theta0} by type
   DevBuf<int> d_num_bond, d_bond_type, d_bond_atom;   // caller order, as uploaded (partner ids are tags)
@@ -282,7 +292,7 @@ int cph_inner_counts(cph_handle *h, int64_t *out2);
 int cph_launch_xt(cph_handle *h);
 // sites.cu
 int cph_launch_partition(cph_handle *h);        // HA, HB, E_vdwl, E_coul + per-site sums
-int cph_launch_integrate(cph_handle *h, double dt, int phase);
+int cph_launch_integrate(cph_handle *h, double dt, int phase, bool apply = false);
 int cph_launch_apply_charges(cph_handle *h);
 int cph_launch_water_phi(cph_handle *h);      // red[4+2S] = sum of dE/dq over owned buffer atoms
 int cph_launch_water_dudl(cph_handle *h);     // dU/dlambda_s -= dQ_s / n_W * red[4+2S] (after the allreduce)

@@ -98,4 +98,4 @@ extern "C" int cph_bench_seed_error(int device, double *out4) {
   return CPH_OK;
 }
 
-extern "C" int cph_refine_order(void) { return CPH_REFINE; }
+extern "C" int cph_refine_order(void) { return 10 * CPH_REFINE_RSQRT + CPH_REFINE_RCP; }

@@ -924,12 +924,11 @@ int cph_rebuild(cph_handle *h) {
   CPH_CUDA(h, h->d_numspec.reserve(n + 1));
   DevBuf<unsigned long long> &stats = h->d_scr_stats;
   CPH_CUDA(h, stats.reserve(2));
-  const PairParams &pp = h->pp;
   // build-time fp32 records {x, y, z, molecule id} of all atoms (owned + ghost + dummy)
   xb_kernel<<<nblk(h->nall + 1), TPB, 0, st>>>(h->nall, h->d_xq.p, h->have_mol ? h->d_mol.p : nullptr,
                                               make_double3(g.lo[0], g.lo[1], g.lo[2]), h->d_xb.p);
   int dropmask = 0;   // special class c is not stored when both weights are zero, except under coul/dsf
-  if (h->pp.style != CPH_PAIR_LJ_CUT_COUL_DSF && !h->have_topology)   // bonded partners are looked up among the specials
+  if ((h->pp.style != CPH_PAIR_LJ_CUT_COUL_DSF || h->drop_excluded) && !h->have_topology)   // bonded partners are looked up among the specials
     for (int c = 1; c <= 3; c++)
       if (h->pp.special_lj[c] == 0.0 && h->pp.special_coul[c] == 0.0) dropmask |= 1 << c;
   h->last_dropmask = dropmask;

@@ -19,9 +19,9 @@
 // K2b is bound by the fp64 pipe (a warp DFMA issues every second cycle on sm_100a), so the
 // loop is written to spend as few fp64 AND as few other issue slots per pair as possible
 // (round-2 instruction diet, profiles/r2_*):
-//   * 1/sqrt and 1/x: hardware seed (MUFU.RSQ64H / MUFU.RCP64H, relative error < 2^-20 measured
-//     by cph_bench_seed_error) + one second-order step: relative error < 1e-12 against the
-//     1e-10 parity tolerance (CPH_REFINE=3 selects the third-order step instead);
+//   * 1/sqrt and 1/x: hardware seed (MUFU.RSQ64H / MUFU.RCP64H, relative error 2^-20 measured by
+//     cph_bench_seed_error) + one Newton step (third order for 1/r, second order for the erfc
+//     argument: fastmath.cuh);
 //   * exp(-alpha^2 r^2): 256-entry table of 2^(j/256) in shared memory times a degree-4
 //     polynomial whose coefficients absorb -alpha^2, so the argument is r^2 itself;
 //   * qqrd2e and q_i are applied once per atom after the warp reduction, not per pair;
@@ -156,15 +156,14 @@ __device__ __forceinline__ void eval_one(const EvalConst &c, const double4 &pi, 
     fp = u * (fc * y);
   }
   if (LJ) {
-    const unsigned int ca = coef_i + (((unsigned int)e >> CPH_TYPESHIFT) << 5);
-    const double2 c12 = lds_v2f64(ca);                   // {12 lj3, 6 lj4}
+    // one 16-byte shared-memory load per pair: {lj3, lj4}; the force needs 12 lj3 and 6 lj4, which cost
+    // two fp64 multiplies -- the fp64 pipe has the slack, the L1 data pipe does not (profiles/r2a_eval_ncu.txt)
+    const double2 c34 = lds_v2f64(coef_i + (((unsigned int)e >> CPH_TYPESHIFT) << 4));
     const double r2 = y * y;
     const double r6 = keep_if(in_lj, r2 * r2 * r2);
-    fp = fma(qiq, fp, r6 * fma(c12.x, r6, -c12.y) * r2);
-    if (EFLAG) {
-      const double2 c34 = lds_v2f64(ca + 16);            // {lj3, lj4}
-      a.ev = fma(r6, fma(c34.x, r6, -c34.y), a.ev);
-    }
+    const double t3 = c34.x * r6;                        // lj3 r^-6
+    fp = fma(qiq, fp, r6 * fma(12.0, t3, -6.0 * c34.y) * r2);
+    if (EFLAG) a.ev = fma(r6, t3 - c34.y, a.ev);
   }
   a.fx = fma(dx, fp, a.fx);
   a.fy = fma(dy, fp, a.fy);
@@ -342,13 +341,13 @@ pair_eval_kernel(const __grid_constant__ EvalArgs A) {
   // if a re-neighbouring or a prune turns out to be due, the whole grid retires and the host
   // launches the pass again behind the rebuilt rows
   if (A.gate != nullptr && (A.gate[4] | A.gate[5]) != 0u) return;
-  __shared__ __align__(16) double4 s_coef[CPH_MAXNT1 * CPH_MAXNT1];
+  __shared__ __align__(16) double2 s_coef[CPH_MAXNT1 * CPH_MAXNT1];   // {lj3, lj4}
   __shared__ __align__(16) double2 s_cut[UNI ? 1 : CPH_MAXNT1 * CPH_MAXNT1];
   __shared__ __align__(16) double s_exp2[256];
   const EvalConst &c = A.c;
   const int nt1 = A.nt1;
   for (int k = threadIdx.x; k < nt1 * nt1; k += ETPB) {
-    s_coef[k] = A.coef[k];
+    s_coef[k] = make_double2(A.coef[k].z, A.coef[k].w);
     if (!UNI) s_cut[k] = A.cuts[k];   // per-pair cutoffs are only read when they differ from the global one
   }
   if (STYLE == CPH_PAIR_LJ_CUT_COUL_DSF)
@@ -356,21 +355,39 @@ pair_eval_kernel(const __grid_constant__ EvalArgs A) {
   __syncthreads();
   const unsigned int exp_tab = smem_u32(s_exp2), coef0 = smem_u32(s_coef), cut0 = smem_u32(s_cut);
   const int lane = threadIdx.x & 31;
-  const int w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform, and the compiler can tell
-  const int per_blk = EWARPS * A.eapw;
-  const int nblk = (A.nlocal + per_blk - 1) / per_blk;
-  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-    const int base = blk * per_blk + w;
-    for (int n = 0; n < A.eapw; n++) {
-      const int i = base + n * EWARPS;
-      if (i >= A.nlocal) break;
+  // Work distribution: the atoms (cell-sorted, so neighbours in index are neighbours in space) are split into
+  // one contiguous range per SM, and every warp of an SM takes the NEXT atom of its SM's range from an atomic
+  // counter.  The 32 warps resident on an SM therefore work on ~32 consecutive atoms at any moment, whose
+  // neighbour records overlap almost completely: the gathers hit in L1 instead of travelling to L2.  A warp
+  // whose own range is exhausted steals from the other ranges (same counters), so every atom is evaluated
+  // exactly once whatever the block placement, and the tail balances itself.  Results do not depend on who
+  // evaluates an atom.
+  unsigned int smid;
+  asm("mov.u32 %0, %%smid;" : "=r"(smid));
+  const int nq = A.nqueues;
+  const int per_q = (A.nlocal + nq - 1) / nq;
+  int q = __shfl_sync(0xffffffffu, (int)(smid % (unsigned int)nq), 0), scanned = 0;
+  auto next_atom = [&]() -> int {
+    while (scanned < nq) {
+      int t = 0;
+      if (lane == 0) t = atomicAdd(A.qnext + q, 1);
+      t = __shfl_sync(0xffffffffu, t, 0);                 // warp-uniform, and the compiler can tell
+      const int cand = q * per_q + t;
+      if (t < per_q && cand < A.nlocal) return cand;
+      scanned++;                                          // this range is done: on to the next one
+      q = q + 1 == nq ? 0 : q + 1;
+    }
+    return -1;
+  };
+  for (int i = next_atom(); i >= 0; i = next_atom()) {
+    {
       const double4 pi = A.xq[i];
       const int ti = A.type[i];
       const bool has_lj = A.type_has_lj[ti] != 0;       // warp-uniform: water H (2/3 of the atoms) skips all LJ work
       const int n2pad = (A.numneigh2[i] + 31) & ~31;
       const int *row2 = A.neigh2 + (size_t)i * A.rowcap2;
       const double qiq = pi.w * c.qqrd2e;
-      const unsigned int coef_i = coef0 + (unsigned int)(ti * nt1) * 32u, cut_i = cut0 + (unsigned int)(ti * nt1) * 16u;
+      const unsigned int coef_i = coef0 + (unsigned int)(ti * nt1) * 16u, cut_i = cut0 + (unsigned int)(ti * nt1) * 16u;
       Acc a;
       if (n2pad) {
         if (has_lj) {
@@ -537,21 +554,22 @@ int cph_launch_pair(cph_handle *h, int eflag, const unsigned int *gate) {
   if (h->kc_dirty) CPH_TRY(cph_pair_fill_constants(h));
   if (!h->inner_valid) CPH_TRY(cph_launch_prune(h));
   ProfScope ps(h, 0);
-  // atoms per warp: fewer on small boxes so that every CTA of the persistent grid still gets work
-  // (measured on B200, profiles/r1_scaling_and_bench.md: 2 and 4 tie at 125k atoms, 4 wins by 1 % at 250k)
-  static const int eapw_env = getenv("CPH_EAPW") ? atoi(getenv("CPH_EAPW")) : 0;
   static const int ctas_env = getenv("CPH_EVAL_CTAS_PER_SM") ? atoi(getenv("CPH_EVAL_CTAS_PER_SM")) : 0;
-  const int eapw = (eapw_env >= 1 && eapw_env <= 16) ? eapw_env : n < 200000 ? 2 : n < 300000 ? 4 : 8;
   EvalArgs A;
   A.c = h->eval_const;
-  A.nlocal = n; A.nt1 = h->pp.ntypes + 1; A.rowcap = h->rowcap; A.rowcap2 = h->rowcap2; A.eapw = eapw;
+  A.nlocal = n; A.nt1 = h->pp.ntypes + 1; A.rowcap = h->rowcap; A.rowcap2 = h->rowcap2;
   A.xq = h->d_xq.p; A.type = h->d_type.p; A.neigh = h->d_neigh.p; A.numspec = h->d_numspec.p;
   A.neigh2 = h->d_neigh2.p; A.numneigh2 = h->d_numneigh2.p; A.coef = h->d_coef4.p; A.cuts = h->d_cut2.p;
   A.type_has_lj = h->d_type_has_lj.p; A.exp2 = h->d_exp2.p;
   A.f = h->d_f.p; A.evdwl = h->d_evdwl.p; A.phi = h->d_phi.p; A.eatom = h->d_eatom.p; A.gate = gate;
-  const int nblk = (n + EWARPS * eapw - 1) / (EWARPS * eapw);
-  const int resident = h->num_sms * (ctas_env > 0 ? ctas_env : 16);     // 16 CTAs of 64 threads per SM at <= 64 registers
-  const int blocks = std::min(nblk, resident);
+  // persistent grid: as many 64-thread CTAs as are resident at once (16 per SM at <= 64 registers), but no more
+  // warps than atoms; the per-SM queue heads are cleared in front of every launch
+  const int per_sm = ctas_env > 0 ? ctas_env : 16;
+  const int blocks = std::max(1, std::min(h->num_sms * per_sm, (n + EWARPS - 1) / EWARPS));
+  A.nqueues = h->num_sms;
+  CPH_CUDA(h, h->d_qnext.reserve(h->num_sms));
+  A.qnext = h->d_qnext.p;
+  CPH_CUDA(h, cudaMemsetAsync(h->d_qnext.p, 0, h->num_sms * sizeof(int), h->stream));
   h->nlaunch++;
 #define LAUNCH(S, E, U) pair_eval_kernel<S, E, U><<<blocks, ETPB, 0, h->stream>>>(A)
 #define LAUNCH_E(S, U) do { if (eflag) LAUNCH(S, 1, U); else LAUNCH(S, 0, U); } while (0)

@@ -47,72 +47,77 @@ __global__ void final_sum_kernel(int nb, const double *__restrict__ partials, do
   if (lane == 0) out[c] = s;
 }
 
-// compute_Hs tail (cpp:259-267) over the owned atoms + energy totals
+// K3, one launch: compute_Hs tail (cpp:259-267: HA, HB over the owned atoms, plus E_vdwl, E_coul) in the first
+// nbP blocks, the per-site sums (cpp:264-267 per site + north_star's dU/dlambda_s = sum dq_i dE/dq_i) in the
+// rest: one warp per site over its contiguous range of the site-major titratable-atom table, lanes striding,
+// shuffle tree -- a fixed order whatever the site size, no atomics.  The last block to finish (ticket counter)
+// adds the block partials in a fixed order and writes red[0..3].
 __global__ void __launch_bounds__(TPB)
-partition_kernel(int n, const double *__restrict__ eatom, const double *__restrict__ evdwl,
-                 const int *__restrict__ mask, int Hbit, double *partials) {
-  double v[4] = {0, 0, 0, 0};   // HA, HB, E_vdwl, E_coul
-  for (int k = blockIdx.x * TPB + threadIdx.x; k < n; k += gridDim.x * TPB) {
-    double e = eatom[k], ev = evdwl[k];
-    v[0] += e;                                  // cpp:265
-    if (!(mask[k] & Hbit)) v[1] += e;           // cpp:266
-    v[2] += ev;
-    v[3] += e - ev;
+site_partition_kernel(int n, const double *__restrict__ eatom, const double *__restrict__ evdwl,
+                      const int *__restrict__ mask, int Hbit, int nbP, double *partials, int S,
+                      const int *__restrict__ site_start, const int *__restrict__ titr_local,
+                      const double *__restrict__ titr_dq, const double *__restrict__ phi, int implicit_site,
+                      double extra_HA, double extra_HB, const double *__restrict__ bonded_e, double *red,
+                      unsigned int *ticket) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if ((int)blockIdx.x < nbP) {
+    double v[4] = {0, 0, 0, 0};   // HA, HB, E_vdwl, E_coul
+    for (int k = blockIdx.x * TPB + threadIdx.x; k < n; k += nbP * TPB) {
+      double e = eatom[k], ev = evdwl[k];
+      v[0] += e;                                  // cpp:265
+      if (!(mask[k] & Hbit)) v[1] += e;           // cpp:266
+      v[2] += ev;
+      v[3] += e - ev;
+    }
+    block_reduce_store<4>(v, partials);
+  } else {
+    const int site = ((int)blockIdx.x - nbP) * (TPB / 32) + w;
+    if (site < S) {
+      double d = 0, hd = 0;
+      for (int t = site_start[site] + lane; t < site_start[site + 1]; t += 32) {
+        const int k = titr_local[t];
+        if (k >= 0) {                                         // owned by this rank (cpp:264: i < nlocal)
+          d += titr_dq[t] * phi[k];                           // Appendix B
+          if (mask[k] & Hbit) hd -= eatom[k];                 // HB_s - HA_s
+        }
+      }
+      for (int o = 16; o; o >>= 1) {
+        d += __shfl_xor_sync(0xffffffffu, d, o);
+        hd += __shfl_xor_sync(0xffffffffu, hd, o);
+      }
+      if (lane == 0) {
+        red[4 + site] = d;
+        if (!implicit_site) red[4 + S + site] = hd;
+      }
+    }
   }
-  block_reduce_store<4>(v, partials);
-}
-
-__global__ void partition_final_kernel(int nb, const double *__restrict__ partials, double *red, int implicit_site,
-                                       int S, double extra_HA, double extra_HB, const double *__restrict__ bonded_e) {
-  const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
   __shared__ double out[4];
-  if (c < 4) {
-    double s = 0;
-    for (int b = lane; b < nb; b += 32) s += partials[(size_t)b * 4 + c];
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (w < 4) {
+    double a = 0;
+    for (int b = lane; b < nbP; b += 32) a += partials[(size_t)b * 4 + w];
+    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     // extra_HA/HB: this rank's share of the per-atom energies LAMMPS tallied on the host (bonded styles,
     // KSpace: cpp:221-244), already partitioned by the fix exactly as cpp:264-267 does
     if (lane == 0) {
-      if (c == 0) s += extra_HA;
-      if (c == 1) s += extra_HB;
+      if (w == 0) a += extra_HA;
+      if (w == 1) a += extra_HB;
       // E_coul is summed as eatom - evdwl; with bonded terms on the device (f2) eatom also holds their shares
-      if (c == 3 && bonded_e) s -= bonded_e[0] + bonded_e[1];
-      out[c] = s;
-      red[c] = s;
+      if (w == 3 && bonded_e) a -= bonded_e[0] + bonded_e[1];
+      out[w] = a;
+      red[w] = a;
     }
   }
   __syncthreads();
-  // reference single site: HB - HA of the whole hydrogen group (cpp:111)
-  if (implicit_site && threadIdx.x == 0) red[4 + S] = out[1] - out[0];
-}
-
-// warp-shuffle segmented reduction over the site-major titratable-atom table
-__global__ void __launch_bounds__(TPB)
-site_sum_kernel(int ntitr, const int *__restrict__ titr_site, const int *__restrict__ titr_local,
-                const double *__restrict__ titr_dq, const double *__restrict__ phi, const double *__restrict__ eatom,
-                const int *__restrict__ mask, int Hbit, int S, int implicit_site, double *red) {
-  const int t = blockIdx.x * TPB + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  int site = -1;
-  double d = 0, hd = 0;
-  if (t < ntitr) {
-    site = titr_site[t];
-    int k = titr_local[t];
-    if (k >= 0) {                                         // owned by this rank (cpp:264: i < nlocal)
-      d = titr_dq[t] * phi[k];                            // Appendix B
-      if (mask[k] & Hbit) hd = -eatom[k];                 // HB_s - HA_s
-    }
-  }
-  for (int o = 1; o < 32; o <<= 1) {
-    double ud = __shfl_up_sync(0xffffffffu, d, o), uh = __shfl_up_sync(0xffffffffu, hd, o);
-    int us = __shfl_up_sync(0xffffffffu, site, o);
-    if (lane >= o && us == site) { d += ud; hd += uh; }
-  }
-  int next = __shfl_down_sync(0xffffffffu, site, 1);
-  bool tail = (lane == 31) || (next != site);
-  if (site >= 0 && tail) {
-    atomicAdd(red + 4 + site, d);
-    if (!implicit_site) atomicAdd(red + 4 + S + site, hd);
+  if (threadIdx.x == 0) {
+    if (implicit_site) red[4 + S] = out[1] - out[0];   // reference single site: HB - HA of the hydrogen group (cpp:111)
+    *ticket = 0u;
   }
 }
 
@@ -152,55 +157,130 @@ __device__ __forceinline__ BiasOut bias_terms(const BiasParams &bp, double lambd
   return o;
 }
 
-// phase 0: reference kinematic step (cpp:109-117)   phase 1: VV kick+drift
-// phase 2: VV force evaluation (a <- F/m)           phase 3: VV second kick + H_lambda
+struct LambdaArgs {
+  int S, phase, thermo, apply, thermo_post, nw;
+  double dt, SkT, Q, inv_nw;         // inv_nw = 1 / n_W when the water buffer is on, else 0
+  BiasParams bp;
+  FixParams fx;
+  const double *pK, *dQ, *wq, *titr_qA, *titr_dq;
+  const int *site_start, *titr_local, *wlocal;
+  double *red, *lam, *theta, *vlam, *alam, *flam, *fs, *dfs, *Us, *dUs, *partials, *scal;
+  double4 *xq;
+  unsigned int *ticket;
+};
+
+// K4 + K5, one launch.  Per site (one thread): calculate_df, calculate_dU, integrate_lambda (cpp:109-145) in
+// the requested phase, then q_i = (1-lambda_s) qA_i + lambda_s qB_i on the site's own atoms (north_star).
+//   phase 0: reference kinematic step (cpp:109-117)   phase 1: VV kick+drift
+//   phase 2: VV force evaluation (a <- F/m)           phase 3: VV second kick + H_lambda
+// The last block to finish (ticket counter) adds the block partials of H_lambda in a fixed order, takes the
+// second Nose-Hoover half step and, with the water buffer on, moves -(1/n_W) sum_s lambda_s dQ_s onto the
+// buffer atoms (modify_water, h:58).
 __global__ void __launch_bounds__(TPB)
-integrate_kernel(int S, double dt, int phase, BiasParams bp, FixParams fx, const double *__restrict__ pK,
-                 const double *__restrict__ red, double *lam, double *theta, double *vlam, double *alam, double *flam,
-                 double *fs, double *dfs, double *Us, double *dUs, double *partials, const double *__restrict__ scal,
-                 int thermo) {
+lambda_update_kernel(const __grid_constant__ LambdaArgs A) {
+  const int S = A.S, phase = A.phase;
+  const BiasParams &bp = A.bp;
+  const FixParams &fx = A.fx;
   // thermo: Nose-Hoover on the site velocities (velocity-Verlet form only); scal[9] = exp(-xi dt/2)
-  const double nh = thermo ? scal[9] : 1.0;
+  const double nh = A.thermo ? A.scal[9] : 1.0;
+  const double dt = A.dt;
   // theta != NULL: the dynamical coordinate is theta with lambda = sin^2(theta) (north_star's lambda/theta
   // variables; absent from the reference, which integrates lambda itself and confines it with U4/U5);
   // velocity, acceleration and mass then refer to theta and F_theta = F_lambda * sin(2 theta).
+  double *theta = A.theta;
   double v[3] = {0, 0, 0};   // sum of site terms of H_lambda, sum lambda*(HB_s-HA_s), kinetic
   for (int s = blockIdx.x * TPB + threadIdx.x; s < S; s += gridDim.x * TPB) {
-    double cq = theta ? theta[s] : lam[s];
-    double vel = vlam[s], acc = alam[s];
+    double cq = theta ? theta[s] : A.lam[s];
+    double vel = A.vlam[s], acc = A.alam[s];
+    double lambda;
     if (phase == 1) {
       vel = vel * nh + 0.5 * acc * dt;
       cq += vel * dt;
-      if (theta) { theta[s] = cq; const double sn = sin(cq); lam[s] = sn * sn; }
-      else lam[s] = cq;
-      vlam[s] = vel;
-      continue;
+      lambda = cq;
+      if (theta) { theta[s] = cq; const double sn = sin(cq); lambda = sn * sn; }
+      A.lam[s] = lambda;
+      A.vlam[s] = vel;
+    } else {
+      double chain = 1.0;
+      lambda = cq;
+      if (theta) { const double sn = sin(cq); lambda = sn * sn; chain = sin(2.0 * cq); }
+      if (phase == 3) vel = (vel + 0.5 * acc * dt) * nh;
+      BiasOut b = bias_terms(bp, lambda);
+      const double pk = fx.implicit_site ? fx.pK : A.pK[s];
+      const double hd = A.red[4 + S + s];
+      const double dE = (fx.dudl_mode == CPH_DUDL_REFERENCE) ? hd : A.red[4 + s];
+      const double ph = fx.boltz * fx.T * log(10.0) * (pk - fx.pH);
+      const double f_lambda = -(dE + b.df * ph + b.dU);                 // cpp:111
+      const double a_lambda = f_lambda * chain / bp.m_lambda * fx.ftm2v;   // cpp:112 (+ SURVEY D9)
+      const double kin = 0.5 * bp.m_lambda * vel * vel / fx.ftm2v;
+      v[0] += b.f * ph + b.U + kin;                                     // cpp:114 site terms
+      v[1] += lambda * hd;                                              // cpp:114 lambda*(HB-HA)
+      v[2] += kin;
+      A.fs[s] = b.f; A.dfs[s] = b.df; A.Us[s] = b.U; A.dUs[s] = b.dU; A.flam[s] = f_lambda;
+      if (phase == 0) {
+        cq = 0.5 * a_lambda * dt * dt + vel * dt + cq;                  // cpp:115
+        vel = a_lambda * dt + vel;                                      // cpp:116
+      }
+      lambda = cq;
+      if (theta) { theta[s] = cq; const double sn = sin(cq); lambda = sn * sn; }
+      A.lam[s] = lambda;
+      A.vlam[s] = vel;
+      A.alam[s] = a_lambda;
     }
-    double lambda = cq, chain = 1.0;
-    if (theta) { const double sn = sin(cq); lambda = sn * sn; chain = sin(2.0 * cq); }
-    if (phase == 3) vel = (vel + 0.5 * acc * dt) * nh;
-    BiasOut b = bias_terms(bp, lambda);
-    const double pk = fx.implicit_site ? fx.pK : pK[s];
-    const double hd = red[4 + S + s];
-    const double dE = (fx.dudl_mode == CPH_DUDL_REFERENCE) ? hd : red[4 + s];
-    const double ph = fx.boltz * fx.T * log(10.0) * (pk - fx.pH);
-    const double f_lambda = -(dE + b.df * ph + b.dU);                 // cpp:111
-    const double a_lambda = f_lambda * chain / bp.m_lambda * fx.ftm2v;   // cpp:112 (+ SURVEY D9)
-    const double kin = 0.5 * bp.m_lambda * vel * vel / fx.ftm2v;
-    v[0] += b.f * ph + b.U + kin;                                     // cpp:114 site terms
-    v[1] += lambda * hd;                                              // cpp:114 lambda*(HB-HA)
-    v[2] += kin;
-    fs[s] = b.f; dfs[s] = b.df; Us[s] = b.U; dUs[s] = b.dU; flam[s] = f_lambda;
-    if (phase == 0) {
-      cq = 0.5 * a_lambda * dt * dt + vel * dt + cq;                  // cpp:115
-      vel = a_lambda * dt + vel;                                      // cpp:116
-    }
-    if (theta) { theta[s] = cq; const double sn = sin(cq); lam[s] = sn * sn; }
-    else lam[s] = cq;
-    vlam[s] = vel;
-    alam[s] = a_lambda;
+    if (A.apply)    // the site's own atoms follow its lambda at once (owned atoms only)
+      for (int t = A.site_start[s]; t < A.site_start[s + 1]; t++) {
+        const int k = A.titr_local[t];
+        if (k >= 0) A.xq[k].w = A.titr_qA[t] + lambda * A.titr_dq[t];
+      }
   }
-  if (phase != 1) block_reduce_store<3>(v, partials);
+  const bool sums = phase != 1;
+  const bool water = A.apply && A.nw > 0;
+  if (!sums && !water) return;
+  if (sums) block_reduce_store<3>(v, A.partials);
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(A.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
+  if (sums) {
+    __shared__ double out[3];
+    if (c < 3) {
+      double a = 0;
+      for (int b = lane; b < (int)gridDim.x; b += 32) a += A.partials[(size_t)b * 3 + c];
+      for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) out[c] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      // cpp:114: (1-lambda)HA + lambda HB = HA + lambda (HB-HA); charge mode: E_ff at the current charges
+      const double eff = (fx.dudl_mode == CPH_DUDL_REFERENCE) ? A.red[0] + out[1] : A.red[2] + A.red[3];
+      A.scal[4] = eff + out[0];
+      A.scal[5] = out[2];
+      if (A.thermo_post) {   // second Nose-Hoover half step, with the kinetic energy after the scaled final kick
+        A.scal[10] += 0.5 * dt * A.scal[8];
+        A.scal[8] += 0.5 * dt * (2.0 * out[2] - A.SkT) / A.Q;
+        A.scal[11] = 0.5 * A.Q * A.scal[8] * A.scal[8] + A.SkT * A.scal[10];    // thermostat energy (conserved with H_lambda)
+      }
+    }
+  }
+  if (water) {   // tot = sum_s lambda_s dQ_s in a fixed order; the owned buffer atoms get q_base - tot / n_W
+    __shared__ double sm[TPB];
+    double a = 0;
+    for (int s = threadIdx.x; s < S; s += TPB) a += A.lam[s] * A.dQ[s];
+    sm[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = TPB / 2; o; o >>= 1) {
+      if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+      __syncthreads();
+    }
+    if ((int)threadIdx.x < A.nw && A.wlocal[threadIdx.x] >= 0)
+      A.xq[A.wlocal[threadIdx.x]].w = A.wq[threadIdx.x] - sm[0] * A.inv_nw;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *A.ticket = 0u;
 }
 
 // Nose-Hoover half step before the first kick: xi += dt/2 (2K - S kT)/Q, eta += xi dt/2,
@@ -211,30 +291,6 @@ __global__ void nh_pre_kernel(double *scal, double dt, double SkT, double Q) {
   scal[8] = xi;
   scal[10] += 0.5 * dt * xi;
   scal[9] = exp(-0.5 * dt * xi);
-}
-
-__global__ void integrate_final_kernel(int nb, const double *__restrict__ partials, const double *__restrict__ red,
-                                       int dudl_mode, double *scal, int thermo_post, double dt, double SkT, double Q) {
-  const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
-  __shared__ double out[3];
-  if (c < 3) {
-    double s = 0;
-    for (int b = lane; b < nb; b += 32) s += partials[(size_t)b * 3 + c];
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) out[c] = s;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    // cpp:114: (1-lambda)HA + lambda HB = HA + lambda (HB-HA); charge mode: E_ff at the current charges
-    double eff = (dudl_mode == CPH_DUDL_REFERENCE) ? red[0] + out[1] : red[2] + red[3];
-    scal[4] = eff + out[0];
-    scal[5] = out[2];
-    if (thermo_post) {   // second Nose-Hoover half step, with the kinetic energy after the scaled final kick
-      scal[10] += 0.5 * dt * scal[8];
-      scal[8] += 0.5 * dt * (2.0 * out[2] - SkT) / Q;
-      scal[11] = 0.5 * Q * scal[8] * scal[8] + SkT * scal[10];    // thermostat energy (conserved with H_lambda)
-    }
-  }
 }
 
 // q_i = (1-lambda_s) qA_i + lambda_s qB_i  (north_star; the reference never touches atom->q)
@@ -369,41 +425,48 @@ int cph_launch_partition(cph_handle *h) {
   const int n = h->nlocal, S = h->S;
   cudaStream_t st = h->stream;
   CPH_CUDA(h, h->d_part.reserve((size_t)MAXPART * 4));
-  CPH_CUDA(h, cudaMemsetAsync(h->d_red.p, 0, (4 + 2 * (size_t)S + 1) * sizeof(double), st));
-  int nb = std::max(1, std::min(MAXPART, nblk(n)));
-  partition_kernel<<<nb, TPB, 0, st>>>(n, h->d_eatom.p, h->d_evdwl.p, h->d_mask.p, h->fix.Hbit, h->d_part.p);
-  partition_final_kernel<<<1, 128, 0, st>>>(nb, h->d_part.p, h->d_red.p, h->fix.implicit_site, S, h->extra_HA,
-                                            h->extra_HB, h->have_topology ? h->d_bonded_e.p : nullptr);
+  const int nbP = std::max(1, std::min(MAXPART, nblk(n)));
+  const int nbS = (S + TPB / 32 - 1) / (TPB / 32);
+  site_partition_kernel<<<nbP + nbS, TPB, 0, st>>>(n, h->d_eatom.p, h->d_evdwl.p, h->d_mask.p, h->fix.Hbit, nbP,
+                                                  h->d_part.p, S, h->d_site_start.p, h->d_titr_local.p,
+                                                  h->d_titr_dq.p, h->d_phi.p, h->fix.implicit_site, h->extra_HA,
+                                                  h->extra_HB, h->have_topology ? h->d_bonded_e.p : nullptr,
+                                                  h->d_red.p, h->d_flags.p + 80);
   h->extra_HA = h->extra_HB = 0.0;   // consumed
-  if (h->ntitr)
-    site_sum_kernel<<<nblk(h->ntitr), TPB, 0, st>>>(h->ntitr, h->d_titr_site.p, h->d_titr_local.p, h->d_titr_dq.p,
-                                                    h->d_phi.p, h->d_eatom.p, h->d_mask.p, h->fix.Hbit, S,
-                                                    h->fix.implicit_site, h->d_red.p);
-  h->nlaunch += h->ntitr ? 3 : 2;
+  h->nlaunch += 1;
   CPH_CUDA(h, cudaGetLastError());
   return 0;
 }
 
-int cph_launch_integrate(cph_handle *h, double dt, int phase) {
+// phase as in lambda_update_kernel; apply: also move the charges of the titratable atoms (and of the water
+// buffer) to the new lambda in the same launch
+int cph_launch_integrate(cph_handle *h, double dt, int phase, bool apply) {
   ProfScope ps(h, 3);
   const int S = h->S;
   cudaStream_t st = h->stream;
   CPH_CUDA(h, h->d_part.reserve((size_t)MAXPART * 4));
-  int nb = std::max(1, std::min(MAXPART, nblk(S)));
+  const int nb = std::max(1, std::min(MAXPART, nblk(S)));
   const int thermo = (h->nh_tau > 0 && h->fix.integ_mode == CPH_INTEGRATE_VV && (phase == 1 || phase == 3)) ? 1 : 0;
   const double SkT = S * h->fix.boltz * h->fix.T, Q = SkT * h->nh_tau * h->nh_tau;
   if (thermo && phase == 1) {
     h->nlaunch++;
     nh_pre_kernel<<<1, 32, 0, st>>>(h->d_scal.p, dt, SkT, Q);
   }
-  integrate_kernel<<<nb, TPB, 0, st>>>(S, dt, phase, h->bias, h->fix, h->d_pK.p, h->d_red.p, h->d_lam.p,
-                                       h->coord_theta ? h->d_theta.p : nullptr, h->d_vlam.p,
-                                       h->d_alam.p, h->d_flam.p, h->d_fs.p, h->d_dfs.p, h->d_Us.p, h->d_dUs.p,
-                                       h->d_part.p, h->d_scal.p, thermo);
-  if (phase != 1)
-    integrate_final_kernel<<<1, 96, 0, st>>>(nb, h->d_part.p, h->d_red.p, h->fix.dudl_mode, h->d_scal.p,
-                                             thermo && phase == 3 && dt > 0, dt, SkT, Q);
-  h->nlaunch += phase != 1 ? 2 : 1;
+  LambdaArgs A;
+  A.S = S; A.phase = phase; A.thermo = thermo;
+  A.apply = (apply && h->ntitr > 0 && h->have_atoms) ? 1 : 0;
+  A.thermo_post = (thermo && phase == 3 && dt > 0) ? 1 : 0;
+  const bool water = h->water_n > 0 && h->fix.dudl_mode == CPH_DUDL_CHARGE;
+  A.nw = (water && h->have_atoms) ? h->nw_local : 0;
+  A.dt = dt; A.SkT = SkT; A.Q = Q; A.inv_nw = water ? 1.0 / h->water_n : 0.0;
+  A.bp = h->bias; A.fx = h->fix;
+  A.pK = h->d_pK.p; A.dQ = h->d_dQ.p; A.wq = h->d_wq.p; A.titr_qA = h->d_titr_qA.p; A.titr_dq = h->d_titr_dq.p;
+  A.site_start = h->d_site_start.p; A.titr_local = h->d_titr_local.p; A.wlocal = h->d_wlocal.p;
+  A.red = h->d_red.p; A.lam = h->d_lam.p; A.theta = h->coord_theta ? h->d_theta.p : nullptr; A.vlam = h->d_vlam.p;
+  A.alam = h->d_alam.p; A.flam = h->d_flam.p; A.fs = h->d_fs.p; A.dfs = h->d_dfs.p; A.Us = h->d_Us.p; A.dUs = h->d_dUs.p;
+  A.partials = h->d_part.p; A.scal = h->d_scal.p; A.xq = h->d_xq.p; A.ticket = h->d_flags.p + 81;
+  lambda_update_kernel<<<nb, TPB, 0, st>>>(A);
+  h->nlaunch += 1;
   CPH_CUDA(h, cudaGetLastError());
   return 0;
 }

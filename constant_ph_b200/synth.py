@@ -443,6 +443,15 @@ def jiggle_positions(box, params, t, x0=None):
     return x0 + A[m] * (np.sin(w[m] * t + p[m]) - np.sin(p[m]))
 
 
+def harness_jiggle(x0, amp, t):
+    """The atom motion of src/harness.cpp's `jiggle AMP` option, replayed for the oracle:
+    x_i(t) = x0_i + AMP sin(2 pi t / T_i + phi_i + d), T_i = 60 + i % 80, phi_i = 0.37 i, d = 0, 1, 2."""
+    i = np.arange(x0.shape[0], dtype=np.float64)
+    w = 2.0 * np.pi / (60.0 + (np.arange(x0.shape[0]) % 80))
+    ph = 0.37 * i
+    return x0 + amp * np.sin((w * t + ph)[:, None] + np.arange(3.0)[None, :])
+
+
 def write_harness_input(box, path_bin, path_sites=None):
     """Binary box + text site table for src/cph_harness (the drop-in fix driven through the
     LAMMPS shim).  Layout documented in src/harness.cpp."""

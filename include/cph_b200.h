@@ -17,7 +17,8 @@
  *   - per-atom arrays are in the CALLER's order (LAMMPS local index 0..nlocal-1);
  *     the library keeps its own cell-sorted order internally.
  *   - one handle per rank/GPU; a handle is not thread-safe, distinct handles are
- *     independent.  All device work is issued on one library-owned stream;
+ *     independent (all kernel constants travel as launch parameters; nothing lives in
+ *     device-global state).  All device work is issued on one library-owned stream;
  *     functions that return data to the host synchronise that stream themselves.
  *   - types follow the default LAMMPS build (-DLAMMPS_SMALLBIG): tagint = int32,
  *     bigint = int64.
@@ -29,6 +30,7 @@
 #ifndef CPH_B200_H
 #define CPH_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -107,6 +109,12 @@ int cph_set_mode(cph_handle *h, int dudl_mode, int integrator_mode, int fscale_m
  * the thermostat state (xi, eta, K), and out8[7] of cph_get_scalars is the thermostat energy Q xi^2/2 + S k T eta,
  * which together with H_lambda is conserved for frozen atoms. */
 int cph_set_thermostat(cph_handle *h, double tau);
+/* Special-bond pairs whose lj AND coul weights are both zero under lj/cut/coul/dsf.  drop == 0 (default, SURVEY.md
+ * Appendix A): they stay in the list and contribute -(1-factor_coul)*qqrd2e*qi*qj/r, the undamped term the damped
+ * sum over periodic images must not contain -- what the pair style's own factor_coul branch computes.  drop != 0:
+ * they are left out of the list and contribute nothing, as under the plain cut styles (what a LAMMPS build does
+ * whose Neighbor::init does not match "lj/cut/coul/dsf" against its anchored "^coul/dsf" pattern). */
+int cph_set_excluded_policy(cph_handle *h, int drop);
 #define CPH_COORD_LAMBDA 0
 #define CPH_COORD_THETA  1
 int cph_set_coordinate(cph_handle *h, int coordinate);
@@ -170,6 +178,20 @@ int cph_set_force(cph_handle *h);
  * x may be NULL (positions already set); f may be NULL (forces stay on the device),
  * otherwise the owned atoms' forces are written to it (caller order). */
 int cph_post_force(cph_handle *h, int64_t ntimestep, double dt, int where, const double *x, double *f);
+/* setup(int) (h:35: declared, never defined in the reference).  Everything cph_post_force evaluates on an active
+ * step -- forces, energy partition, site sums, f/df/U/dU, F_lambda, H_lambda, the force rescale of cpp:149-171 --
+ * without the lambda step: LAMMPS calls setup() at the start of every run, and the reference never integrates
+ * there. */
+int cph_setup(cph_handle *h, int64_t ntimestep, int where, const double *x, double *f);
+/* How cph_post_force / cph_setup hand forces to a HOST array: accumulate == 0 stores them, != 0 ADDS them to what
+ * the array already holds (the fix under `pair_modify compute no`: atom->f keeps what bonded styles, KSpace and
+ * other fixes put there, cpp:149-171 runs on the sum).  Pageable arrays (LAMMPS' atom->x, atom->f) are staged
+ * through page-locked memory by the library in pieces that overlap the DMA; page-locked arrays go straight
+ * through the copy engine. */
+int cph_set_force_mode(cph_handle *h, int accumulate);
+/* page-locked host memory for callers that want the direct path (cudaMallocHost / cudaFreeHost) */
+int cph_alloc_host(size_t bytes, void **p);
+int cph_free_host(void *p);
 
 /* ---- results ---------------------------------------------------------------------- */
 int cph_get_forces(cph_handle *h, int where, double *f);     /* nlocal*3 */
@@ -266,7 +288,7 @@ int cph_bench_fp64_peak(int device, double *dfma_warp_instr_per_s, double *tflop
 /* worst relative error over the argument ranges of the pair kernel: out[0] 1/sqrt seed, out[1] 1/x seed,
  * out[2] refined 1/sqrt, out[3] refined 1/x */
 int cph_bench_seed_error(int device, double *out4);
-/* order of the Newton step behind the seeds this library was built with (2 or 3) */
+/* orders of the Newton steps behind the seeds this library was built with: 10 * order(1/sqrt) + order(1/x) */
 int cph_refine_order(void);
 
 #ifdef __cplusplus

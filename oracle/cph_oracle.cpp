@@ -63,6 +63,8 @@ struct Oracle {
   double special_lj[4] = {1, 0, 0, 0}, special_coul[4] = {1, 0, 0, 0};
   double e_shift = 0, f_shift = 0;
   bool have_pair = false;
+  bool drop_excluded = false;   // orc_set_excluded_policy
+  bool force_add = false;   // orc_set_force_mode: post_force ADDS to the caller's force array
   // domain
   double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}, skin = 2.0;
   int periodic[3] = {1, 1, 1};
@@ -188,7 +190,8 @@ void build_list(Oracle *o) {
   for (int k = 0; k < 3; k++) {
     sx[k] = (int)std::ceil(rlist / bw[k]);
   }
-  const bool keep_all_special = (o->style == 1);  // coul/dsf keeps excluded pairs (Appendix A)
+  // coul/dsf keeps fully excluded pairs for the damped-term correction (Appendix A) unless told to drop them
+  const bool keep_all_special = (o->style == 1) && !o->drop_excluded;
   o->first.assign(n + 1, 0);
   std::vector<int> cnt(n, 0);
   // for each i visit distinct bins within the stencil (periodic wrap may alias bins when nb is small)
@@ -846,23 +849,35 @@ int orc_apply_charges(void *h) { apply_charges(ORC); return 0; }
 int orc_set_force(void *h) { set_force(ORC); return 0; }
 
 // post_force (cpp:67-79) in one call; same sequence as cph_post_force.
-int orc_post_force(void *h, int64_t ntimestep, double dt, int, const double *x, double *f) {
-  Oracle *o = ORC;
+// advance == false is setup() (h:35, declared without a body): everything is evaluated, lambda does not move
+static int post_force_impl(Oracle *o, int64_t ntimestep, double dt, const double *x, double *f, bool advance) {
   if (!o->have_atoms) return fail(o, -2, "set_atoms first");
   if (x) o->x.assign(x, x + 3 * (size_t)o->n);
   if (max_disp2(o) > 0.25 * o->skin * o->skin) build_list(o);
-  bool active = (ntimestep % o->nevery) == 0;   // cpp:69
+  bool active = !advance || (ntimestep % o->nevery) == 0;   // cpp:69
   pair_pass(o, active ? 1 : 0);
   bonded_pass(o, active ? 1 : 0);               // cpp:221-229: bonded eatom joins the partition
   if (active) {
     site_reduce(o);                             // cpp:70
-    integrate(o, dt * o->nevery, o->integ_mode == 0 ? 0 : 2);   // cpp:71-73, t_lambda = nevery*dt (cpp:113)
-    if (o->dudl_mode == 1 && o->integ_mode == 0) apply_charges(o);
+    const int phase = (o->integ_mode == 0 && advance) ? 0 : 2;
+    integrate(o, dt * o->nevery, phase);        // cpp:71-73, t_lambda = nevery*dt (cpp:113)
+    if (o->dudl_mode == 1 && phase == 0) apply_charges(o);
   }
   if (o->dudl_mode == 0) set_force(o);          // cpp:78, every step
-  if (f) std::memcpy(f, o->f.data(), sizeof(double) * 3 * (size_t)o->n);
+  if (f) {
+    if (o->force_add) for (size_t k = 0; k < 3 * (size_t)o->n; k++) f[k] += o->f[k];
+    else std::memcpy(f, o->f.data(), sizeof(double) * 3 * (size_t)o->n);
+  }
   return 0;
 }
+int orc_post_force(void *h, int64_t ntimestep, double dt, int, const double *x, double *f) {
+  return post_force_impl(ORC, ntimestep, dt, x, f, true);
+}
+int orc_setup(void *h, int64_t ntimestep, int, const double *x, double *f) {
+  return post_force_impl(ORC, ntimestep, 0.0, x, f, false);
+}
+int orc_set_excluded_policy(void *h, int drop) { ORC->drop_excluded = drop != 0; return 0; }
+int orc_set_force_mode(void *h, int accumulate) { ORC->force_add = accumulate != 0; return 0; }
 
 int orc_get_forces(void *h, int, double *f) { std::memcpy(f, ORC->f.data(), sizeof(double) * 3 * (size_t)ORC->n); return 0; }
 int orc_get_eatom(void *h, int, double *e) { std::memcpy(e, ORC->eatom.data(), sizeof(double) * ORC->n); return 0; }

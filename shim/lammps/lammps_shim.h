@@ -14,11 +14,60 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
 #define FLERR __FILE__, __LINE__
+
+// ---- the three MPI names the fix uses (upstream: <mpi.h> through lmptype.h).  The shim's "world" is a set of
+// harness processes that share a scratch directory: MPI_Bcast is a file the root writes and the others wait for.
+typedef int MPI_Comm;
+typedef int MPI_Datatype;
+#define MPI_BYTE 1
+#define MPI_INT 4
+struct ShimWorld {
+  int rank = 0, size = 1, seq = 0;
+  std::string dir;
+  static ShimWorld &get() {
+    static ShimWorld w;
+    static bool init = false;
+    if (!init) {
+      init = true;
+      if (const char *e = getenv("CPH_SHIM_RANK")) w.rank = atoi(e);
+      if (const char *e = getenv("CPH_SHIM_NRANKS")) w.size = atoi(e);
+      if (const char *e = getenv("CPH_SHIM_DIR")) w.dir = e;
+    }
+    return w;
+  }
+};
+inline int MPI_Bcast(void *buf, int count, MPI_Datatype type, int root, MPI_Comm) {
+  ShimWorld &w = ShimWorld::get();
+  if (w.size <= 1) return 0;
+  const size_t bytes = (size_t)count * (size_t)type;
+  const std::string path = w.dir + "/bcast_" + std::to_string(w.seq++);
+  if (w.rank == root) {
+    const std::string tmp = path + ".tmp";
+    FILE *fp = fopen(tmp.c_str(), "wb");
+    if (!fp || fwrite(buf, 1, bytes, fp) != bytes) { fprintf(stderr, "shim MPI_Bcast: cannot write %s\n", tmp.c_str()); exit(4); }
+    fclose(fp);
+    rename(tmp.c_str(), path.c_str());
+  } else {
+    for (int tries = 0;; tries++) {
+      FILE *fp = fopen(path.c_str(), "rb");
+      if (fp) {
+        const size_t got = fread(buf, 1, bytes, fp);
+        fclose(fp);
+        if (got == bytes) break;
+      }
+      if (tries > 60000) { fprintf(stderr, "shim MPI_Bcast: timed out on %s\n", path.c_str()); exit(4); }
+      struct timespec ts = {0, 1000000};
+      nanosleep(&ts, nullptr);
+    }
+  }
+  return 0;
+}
 
 namespace LAMMPS_NS {
 
@@ -89,7 +138,9 @@ class Group {
     return -1;
   }
   int *bitmask = nullptr;          // upstream: int *bitmask (indexed by group id)
+  bigint count_override = 0;       // harness, several ranks: upstream's count() is a sum over all ranks
   bigint count(int igroup) {
+    if (count_override > 0 && igroup > 0) return count_override;
     bigint n = 0;
     for (int i = 0; i < atom->nlocal; i++) if (atom->mask[i] & bitmask[igroup]) n++;
     return n;
@@ -171,7 +222,7 @@ class Comm {
  public:
   int me = 0, nprocs = 1;
   int procgrid[3] = {1, 1, 1}, myloc[3] = {0, 0, 0};
-  void reverse_comm(class Fix *) {}   // single rank: nothing to fold
+  void reverse_comm(class Fix *) {}   // the harness gives every rank only owned atoms: nothing to fold
   void forward_comm(class Fix *) {}
 };
 

@@ -14,6 +14,8 @@
        buffer yes|no         modify_water() (h:58): keep the box charge constant through groupW
        coordinate lambda|theta   integrate lambda itself (reference) or theta with lambda = sin^2(theta)
        tlambda TAU           Nose-Hoover thermostat (period TAU) on the site velocities at T; needs integrator vv
+       excluded keep|drop    lj/cut/coul/dsf only: keep fully excluded special pairs in the list and subtract their
+                             undamped Coulomb term (default), or drop them as plain cut styles do
        bias_w|bias_s|bias_h|bias_k|bias_a|bias_b|bias_r|bias_m|bias_d VALUE
                              override one constant of the bias potential (init() loads Donnini's table, cpp:86-94)
 
@@ -65,6 +67,7 @@ const Choice kChoices[] = {
     {"bias", "exact", "aswritten", CPH_BIAS_EXACT, CPH_BIAS_AS_WRITTEN},
     {"buffer", "no", "yes", 0, 1},
     {"coordinate", "lambda", "theta", CPH_COORD_LAMBDA, CPH_COORD_THETA},
+    {"excluded", "keep", "drop", 0, 1},
 };
 const int kNumChoices = sizeof(kChoices) / sizeof(kChoices[0]);
 const char kBiasNames[] = "wshkabrmd";      // bias_<letter> keywords, in the order of cpp:86-94
@@ -90,12 +93,16 @@ FixConstantPH::FixConstantPH(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg,
   host_energy_cap = 0;
   force_out = nullptr;
   force_cap = 0;
+  charge_buf = nullptr;
+  charge_cap = 0;
   pending_restart = nullptr;
   pending_n = 0;
   resend_atoms = true;
+  sites_on_device = false;
+  rank_group_ready = false;
   part[0] = part[1] = 0.0;
   tab = Sites{0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  opt = Options{CPH_DUDL_REFERENCE, CPH_INTEGRATE_REFERENCE, CPH_FSCALE_LAMBDA, CPH_BIAS_EXACT, 0, CPH_COORD_LAMBDA,
+  opt = Options{CPH_DUDL_REFERENCE, CPH_INTEGRATE_REFERENCE, CPH_FSCALE_LAMBDA, CPH_BIAS_EXACT, 0, CPH_COORD_LAMBDA, 0,
                 0.0, 0.5, nullptr, {}};
   for (double &u : opt.bias_user) u = NAN;
   bias = Bias{0, 0, 0, 0, 0, 0, 0, 0, 0, 20.0};         // mass: cpp:96; the rest is loaded in init()
@@ -125,7 +132,8 @@ FixConstantPH::FixConstantPH(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg,
   in.pH = utils::numeric(FLERR, arg[7], false, lmp);
   in.temperature = utils::numeric(FLERR, arg[8], false, lmp);
 
-  int *const choice_target[kNumChoices] = {&opt.dudl, &opt.integrator, &opt.fscale, &opt.bias_form, &opt.buffer, &opt.theta};
+  int *const choice_target[kNumChoices] = {&opt.dudl, &opt.integrator, &opt.fscale, &opt.bias_form, &opt.buffer, &opt.theta,
+                                              &opt.excluded_drop};
   for (int iarg = npositional; iarg < narg; iarg += 2) {
     if (iarg + 1 >= narg) utils::missing_cmd_args(FLERR, "fix constant_pH", error);
     const char *key = arg[iarg], *val = arg[iarg + 1];
@@ -171,7 +179,7 @@ FixConstantPH::~FixConstantPH()
 {
   if (cph) cph_destroy(cph);
   memory->destroy(host_energy);
-  void *owned[] = {opt.site_file, tab.pK, tab.lambda0, tab.qA, tab.qB, tab.tag, tab.site, pending_restart, force_out};
+  void *owned[] = {opt.site_file, tab.pK, tab.lambda0, tab.qA, tab.qB, tab.tag, tab.site, pending_restart, force_out, charge_buf};
   for (void *p : owned) free(p);
 }
 
@@ -240,6 +248,22 @@ void FixConstantPH::init()
     cph = fresh;
   }
 
+  // One rank per GPU: the library's rank group stands in for MPI_Allreduce(..., world) (cpp:274) and for the ghost
+  // exchange behind comm->reverse_comm(this) (cpp:253).  Its id travels over LAMMPS' own communicator once; the
+  // rank inside the group is this rank's place in the processor grid, x fastest, whatever `processors map` did.
+  if (comm->nprocs > 1 && !rank_group_ready) {
+    char id[128];
+    memset(id, 0, sizeof(id));
+    int rc = CPH_OK;
+    if (comm->me == 0) rc = cph_comm_unique_id(id);
+    MPI_Bcast(&rc, 1, MPI_INT, 0, world);
+    if (rc != CPH_OK) error->all(FLERR, "fix constant_pH: cannot create the NCCL rank group id");
+    MPI_Bcast(id, 128, MPI_BYTE, 0, world);
+    const int brick = (comm->myloc[2] * comm->procgrid[1] + comm->myloc[1]) * comm->procgrid[0] + comm->myloc[0];
+    require(cph_comm_init_nccl(cph, comm->nprocs, brick, id), "cph_comm_init_nccl");
+    rank_group_ready = true;
+  }
+
   require(cph_set_units(cph, force->qqrd2e, force->boltz, force->ftm2v), "cph_set_units");
 
   // the pair style whose eatom the reference reads (cpp:216-219); its arithmetic runs in the library
@@ -275,15 +299,20 @@ void FixConstantPH::init()
   require(cph_set_mode(cph, opt.dudl, opt.integrator, opt.fscale), "cph_set_mode");
   require(cph_set_thermostat(cph, opt.thermostat_period), "cph_set_thermostat");
   require(cph_set_coordinate(cph, opt.theta), "cph_set_coordinate");
+  require(cph_set_excluded_policy(cph, opt.excluded_drop), "cph_set_excluded_policy");
   require(cph_set_water_buffer(cph, opt.buffer ? (int) group->count(in.wat_group) : 0), "cph_set_water_buffer");
-  require(cph_set_sites(cph, tab.nsites, tab.pK, tab.natoms, tab.tag, tab.site, tab.qA, tab.qB), "cph_set_sites");
-
+  // LAMMPS calls init() at the start of EVERY run: the site table and the dynamical state (lambda, v_lambda,
+  // a_lambda, thermostat) are sent once; later runs continue from where the previous one stopped.
+  if (!sites_on_device) {
+    require(cph_set_sites(cph, tab.nsites, tab.pK, tab.natoms, tab.tag, tab.site, tab.qA, tab.qB), "cph_set_sites");
+    if (!pending_restart)
+      require(cph_set_lambda(cph, tab.nsites ? tab.lambda0 : &opt.lambda_start, nullptr), "cph_set_lambda");
+    sites_on_device = true;
+  }
   if (pending_restart) {
     require(cph_unpack_restart(cph, pending_restart, pending_n), "cph_unpack_restart");
     free(pending_restart);
     pending_restart = nullptr;
-  } else {
-    require(cph_set_lambda(cph, tab.nsites ? tab.lambda0 : &opt.lambda_start, nullptr), "cph_set_lambda");
   }
   size_vector = 4 * std::max(tab.nsites, 1);
   resend_atoms = true;
@@ -306,11 +335,6 @@ void FixConstantPH::upload_atoms()
   require(cph_set_atoms(cph, CPH_HOST, n, n ? atom->x[0] : nullptr, atom->q, atom->type, atom->tag, atom->mask,
                         atom->molecule_flag ? atom->molecule : nullptr, specials ? atom->nspecial[0] : nullptr,
                         specials ? atom->special[0] : nullptr, specials ? atom->maxspecial : 0), "cph_set_atoms");
-  if (n > force_cap) {
-    force_cap = n + n / 8 + 16;
-    free(force_out);
-    force_out = (double *) malloc(sizeof(double) * 3 * force_cap);
-  }
   resend_atoms = false;
 }
 
@@ -319,21 +343,30 @@ void FixConstantPH::post_neighbor()
   resend_atoms = true;     // LAMMPS migrated and re-sorted atoms: local indices changed
 }
 
-void FixConstantPH::setup(int vflag)
+void FixConstantPH::setup(int /*vflag*/)
 {
+  // The reference declares setup (h:35) without a body and never integrates there: evaluate everything
+  // (forces, partition, F_lambda, H_lambda, force rescale) at the current lambda, leave lambda where it is.
   upload_atoms();
-  post_force(vflag);       // as most fixes do; the reference declares setup (h:35) without a body
+  compute_Hs();
+  run_device_step(true);
 }
 
-/* ---------------------------------------------------------------------- */
+/* ----------------------------------------------------------------------
+   velocity-Verlet halves of the lambda dynamics.  LAMMPS calls these hooks on every step; lambda lives on the
+   nevery grid of post_force (cpp:69), so both act only on the steps whose post_force is active, with
+   t_lambda = nevery*dt (cpp:113): kick+drift at the start of such a step, the closing kick after its forces.
+------------------------------------------------------------------------- */
 
 void FixConstantPH::initial_integrate(int /*vflag*/)
 {
+  if (update->ntimestep % nevery) return;
   require(cph_initial_integrate(cph, update->dt * nevery), "cph_initial_integrate");
 }
 
 void FixConstantPH::final_integrate()
 {
+  if (update->ntimestep % nevery) return;
   require(cph_final_integrate(cph, update->dt * nevery), "cph_final_integrate");
 }
 
@@ -345,32 +378,40 @@ void FixConstantPH::final_integrate()
 void FixConstantPH::post_force(int /*vflag*/)
 {
   if (resend_atoms) upload_atoms();
-  const int n = atom->nlocal;
   if (update->ntimestep % nevery == 0) compute_Hs();       // host-tallied energy sources (cpp:221-253)
+  run_device_step(false);
+}
 
-  require(cph_post_force(cph, update->ntimestep, update->dt, CPH_HOST, n ? atom->x[0] : nullptr, force_out),
-          "cph_post_force");
+/* ----------------------------------------------------------------------
+   one device step: positions in, pair forces out.  Under `pair_modify compute no` the GPU pair pass IS the pair
+   computation: the library ADDS its forces to atom->f (cph_set_force_mode) while it copies them back, so no
+   host loop over 3N doubles runs here.  setup_only: cph_setup instead of cph_post_force (no lambda step).
+------------------------------------------------------------------------- */
 
-  double scalars[8];
-  require(cph_get_scalars(cph, scalars), "cph_get_scalars");
-  std::copy(scalars, scalars + 2, part);                    // HA, HB (cpp:276-277)
-
+void FixConstantPH::run_device_step(bool setup_only)
+{
+  const int n = atom->nlocal;
   const bool lammps_owns_pair_forces = force->pair && force->pair->compute_flag;
-  if (opt.dudl == CPH_DUDL_REFERENCE) {
+  const bool single_site_rescale = opt.dudl == CPH_DUDL_REFERENCE && tab.nsites == 0;
+  double *x = n ? atom->x[0] : nullptr;
+  double *f = (n && !lammps_owns_pair_forces) ? atom->f[0] : nullptr;
+
+  // The reference scales the TOTAL force on the hydrogen group (cpp:162-170).  The library scales the pair part
+  // it owns; whatever else LAMMPS put into atom->f (bonded terms, other fixes) gets the factor of the lambda the
+  // step starts from here, before the pair part is added -- except when lambda is about to move (reference
+  // integrator on an active step): then the new lambda is read back first and the scaling follows the add.
+  require(cph_set_force_mode(cph, 1), "cph_set_force_mode");
+  if (setup_only) require(cph_setup(cph, update->ntimestep, CPH_HOST, x, f), "cph_setup");
+  else require(cph_post_force(cph, update->ntimestep, update->dt, CPH_HOST, x, f), "cph_post_force");
+
+  if (single_site_rescale) {
     require(cph_get_sites(cph, &lambda_cached, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr),
             "cph_get_sites");
-    // The reference scales the TOTAL force on the hydrogen group (cpp:162-170).  The library has already
-    // scaled the pair part it owns; whatever else LAMMPS put into atom->f (bonded terms, other fixes)
-    // gets the same factor here, before the pair part is added.
-    if (tab.nsites == 0 && !lammps_owns_pair_forces) set_force();
+    if (lammps_owns_pair_forces) set_force();           // LAMMPS computed the pair forces itself: the factor applies to everything
+    else if (host_forces_present()) scale_host_part();  // bonded / kspace / other fixes: same factor as the pair part got
   }
-  if (!lammps_owns_pair_forces) {
-    // `pair_modify compute no`: the GPU pair pass IS the pair computation
-    double *f = n ? atom->f[0] : nullptr;
-    for (int k = 0; k < 3 * n; k++) f[k] += force_out[k];
-  } else if (opt.dudl == CPH_DUDL_REFERENCE) {
-    set_force();           // LAMMPS computed the pair forces itself: the factor applies to everything
-  }
+  // q(lambda) back into atom->q where the host consumes charges (its own pair compute, KSpace)
+  if (opt.dudl == CPH_DUDL_CHARGE && (lammps_owns_pair_forces || force->kspace)) pull_charges();
 }
 
 /* ----------------------------------------------------------------------
@@ -391,6 +432,47 @@ void FixConstantPH::scale_hydrogen_forces(double factor)
 void FixConstantPH::set_force()
 {
   scale_hydrogen_forces(opt.fscale == CPH_FSCALE_LAMBDA ? lambda_cached : 1.0 - lambda_cached);
+}
+
+bool FixConstantPH::host_forces_present() const
+{
+  return force->bond || force->angle || force->dihedral || force->improper || (force->kspace && force->kspace->compute_flag);
+}
+
+// atom->f = (host part) + (pair part, already scaled on the device by s): make the host part follow,
+// f <- s*f_host + f_pair = s*(f - f_pair) + f_pair, for the hydrogen group only.  The pair part of those few
+// atoms is fetched from the device.
+void FixConstantPH::scale_host_part()
+{
+  const int n = atom->nlocal;
+  const double s = opt.fscale == CPH_FSCALE_LAMBDA ? lambda_cached : 1.0 - lambda_cached;
+  if (n > force_cap) {
+    force_cap = n + n / 8 + 16;
+    free(force_out);
+    force_out = (double *) malloc(sizeof(double) * 3 * force_cap);
+  }
+  require(cph_get_forces(cph, CPH_HOST, force_out), "cph_get_forces");
+  const int *mask = atom->mask;
+  for (int i = 0; i < n; i++) {
+    if (!(mask[i] & in.hyd_bit)) continue;
+    for (int c = 0; c < 3; c++) {
+      const double fp = force_out[3 * i + c];
+      atom->f[i][c] = s * (atom->f[i][c] - fp) + fp;
+    }
+  }
+}
+
+// q_i(lambda) of the titratable atoms (and of the water buffer) from the device into atom->q
+void FixConstantPH::pull_charges()
+{
+  const int n = atom->nlocal;
+  if (n > charge_cap) {
+    charge_cap = n + n / 8 + 16;
+    free(charge_buf);
+    charge_buf = (double *) malloc(sizeof(double) * charge_cap);
+  }
+  require(cph_get_q(cph, CPH_HOST, charge_buf), "cph_get_q");
+  memcpy(atom->q, charge_buf, sizeof(double) * n);
 }
 
 /* ----------------------------------------------------------------------
@@ -441,22 +523,6 @@ void FixConstantPH::compute_Hs()
     if ((mask[i] & in.hyd_bit) == 0) without_hydrogens += host_energy[i];
   }
   require(cph_set_extra_partition(cph, everyone, without_hydrogens), "cph_set_extra_partition");
-}
-
-void FixConstantPH::calculate_df() {}                       // cpp:120-124: fused into the integrator kernel
-void FixConstantPH::calculate_dU() {}                       // cpp:128-145: fused into the integrator kernel
-
-void FixConstantPH::integrate_lambda()
-{
-  require(cph_integrate_lambda(cph, nevery * update->dt), "cph_integrate_lambda");       // cpp:109-117
-}
-
-void FixConstantPH::modify_water()
-{
-  // h:58: declared, never defined nor called in the reference (TODO at cpp:268).  With `buffer yes`
-  // the library moves -(1/3) sum_s lambda_s dQ_s onto each atom of the water group whenever it
-  // applies q(lambda) (cph_apply_charges inside cph_post_force), so the box charge stays constant.
-  require(cph_apply_charges(cph), "cph_apply_charges");
 }
 
 /* ---------------------------------------------------------------------- */

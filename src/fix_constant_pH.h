@@ -65,7 +65,7 @@ class FixConstantPH : public Fix {
 
   // keyword-selected behaviour (the reference's keyword loop, cpp:51-54, is empty)
   struct Options {
-    int dudl, integrator, fscale, bias_form, buffer, theta;
+    int dudl, integrator, fscale, bias_form, buffer, theta, excluded_drop;
     double thermostat_period;
     double lambda_start;
     char *site_file;
@@ -84,21 +84,26 @@ class FixConstantPH : public Fix {
   double lambda_cached;            // lambda of the reference's single site, for the host-side rescale
   double *host_energy;             // the reference's H_atom (h:51): host-tallied energy sources
   int host_energy_cap;             // its length (the reference's nmax)
-  double *force_out;               // pair forces coming back from the device, caller order
+  double *force_out;               // pair forces of the last pass (only fetched for the host-part rescale)
   int force_cap;
+  double *charge_buf;              // q(lambda) on its way into atom->q
+  int charge_cap;
+  bool sites_on_device;            // site table + initial lambda sent (once, not at every run)
+  bool rank_group_ready;           // NCCL rank group built over `world`
   double *pending_restart;         // restart record received before init()
   int pending_n;
   bool resend_atoms;
 
-  // the reference's private helpers (h:53-58), kept by name; their arithmetic runs in the library
+  // the reference's private helpers (h:53-58) that still have host-side work; calculate_df, calculate_dU,
+  // integrate_lambda and modify_water (h:54-58) are kernels of the library (sites.cu)
   void compute_Hs();               // cpp:177-280: host-tallied sources only, the pair part is on the device
-  void calculate_df();             // cpp:120-124: fused into the integrator kernel
-  void calculate_dU();             // cpp:128-145: fused into the integrator kernel
-  void integrate_lambda();         // cpp:109-117
   void set_force();                // cpp:149-171
-  void modify_water();             // h:58: never defined nor called in the reference
 
   void require(int rc, const char *what);
+  void run_device_step(bool setup_only);
+  bool host_forces_present() const;
+  void scale_host_part();
+  void pull_charges();
   void load_site_table(const char *path);
   void upload_atoms();
   void scale_hydrogen_forces(double factor);

@@ -72,14 +72,65 @@ def parse(out):
     return np.array(rows), extra
 
 
+def oracle_trajectory(box, mode, kw, nsteps, jiggle=0.0):
+    """The harness' Verlet loop replayed on the oracle: setup() = everything but the lambda step, then per step
+    initial_integrate / post_force / final_integrate with the velocity-Verlet halves on the nevery grid."""
+    orc = capi.configure(capi.Engine("orc"), box, **kw)
+    lam, H = [], []
+    f = np.zeros((box.n, 3))
+    nev = kw.get("nevery", 1)
+    vv = kw.get("integrator", capi.INTEGRATE_REFERENCE) == capi.INTEGRATE_VV
+
+    def extras(step):
+        if mode != "bonded" or step % nev:
+            return
+        e = 0.01 * (1 + np.arange(box.n) % 7)
+        Hm = (box.mask & synth.GROUP_H_BIT) != 0
+        orc.set_extra_partition(float(e.sum()), float(e[~Hm].sum()))
+
+    def pos(step):
+        return box.x if jiggle == 0.0 else synth.harness_jiggle(box.x, jiggle, step * box.dt)
+
+    extras(0)
+    orc.setup(0, box.x, f)                                     # setup()
+    lam.append(orc.get_sites()["lambda"].copy()); H.append(orc.compute_scalar())
+    for step in range(1, nsteps + 1):
+        if vv and step % nev == 0:
+            orc.initial_integrate(box.dt * nev)
+        extras(step)
+        orc.post_force(step, box.dt, pos(step), f)
+        if vv and step % nev == 0:
+            orc.final_integrate(box.dt * nev)
+        lam.append(orc.get_sites()["lambda"].copy()); H.append(orc.compute_scalar())
+    return np.array(lam), np.array(H), f
+
+
+MODES = ["charge", "reference", "vv", "vv_nevery2", "buffer", "theta", "bonded", "thermostat", "biasconst",
+         "two_runs", "moving", "excluded_drop"]
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["charge", "reference", "vv", "buffer", "theta", "bonded", "thermostat", "biasconst"])
+@pytest.mark.parametrize("mode", MODES)
 def test_fix_trajectory_matches_oracle(box_files, mode):
     box, b, s = box_files
     nsteps = 120
+    pre, jiggle = [], 0.0
     if mode == "charge":
         args = ["sites", s, "mlambda", 2000]
         kw = dict(bias=dict(m_lambda=2000.0))
+    elif mode == "two_runs":
+        # `run 60` twice: init() and setup() run again and must neither reset nor advance lambda
+        pre = ["runs", 2]
+        args = ["sites", s, "mlambda", 2000]
+        kw = dict(bias=dict(m_lambda=2000.0))
+    elif mode == "moving":
+        pre = ["jiggle", 0.6]
+        jiggle = 0.6
+        args = ["sites", s, "mlambda", 2000]
+        kw = dict(bias=dict(m_lambda=2000.0))
+    elif mode == "excluded_drop":
+        args = ["sites", s, "mlambda", 2000, "excluded", "drop"]
+        kw = dict(bias=dict(m_lambda=2000.0), drop_excluded=True)
     elif mode == "biasconst":
         # settable bias constants (the reference hard-codes Donnini's table in init(), cpp:86-94)
         args = ["sites", s, "mlambda", 2000, "bias_h", 2.5, "bias_w", 150, "bias_d", 1.5]
@@ -89,7 +140,8 @@ def test_fix_trajectory_matches_oracle(box_files, mode):
         kw = dict(bias=dict(m_lambda=2000.0), integrator=capi.INTEGRATE_VV, theta=True, thermostat=40.0)
     elif mode == "bonded":
         # reference mode + a host-side bonded energy source folded into HA/HB (cpp:221-253)
-        args = ["nevery", 2, "bonded", 0.01, "mlambda", 2000, "lambda0", 0.5]
+        pre = ["nevery", 2, "bonded", 0.01]
+        args = ["mlambda", 2000, "lambda0", 0.5]
         kw = dict(bias=dict(m_lambda=2000.0), dudl=capi.DUDL_REFERENCE, implicit_site=True, nevery=2)
     elif mode == "theta":
         args = ["sites", s, "mlambda", 2000, "coordinate", "theta"]
@@ -100,41 +152,96 @@ def test_fix_trajectory_matches_oracle(box_files, mode):
     elif mode == "vv":
         args = ["sites", s, "mlambda", 2000, "integrator", "vv"]
         kw = dict(bias=dict(m_lambda=2000.0), integrator=capi.INTEGRATE_VV)
+    elif mode == "vv_nevery2":
+        # LAMMPS calls initial/final_integrate on every step; lambda must only move on the nevery grid
+        pre = ["nevery", 2]
+        args = ["sites", s, "mlambda", 2000, "integrator", "vv"]
+        kw = dict(bias=dict(m_lambda=2000.0), integrator=capi.INTEGRATE_VV, nevery=2)
     else:
-        args = ["nevery", 3, "mlambda", 2000, "fscale", "oneminus", "lambda0", 0.5]
+        pre = ["nevery", 3]
+        args = ["mlambda", 2000, "fscale", "oneminus", "lambda0", 0.5]
         kw = dict(bias=dict(m_lambda=2000.0), dudl=capi.DUDL_REFERENCE, implicit_site=True, nevery=3,
                   fscale=capi.FSCALE_ONE_MINUS)
-    r = run([b, nsteps] + args)
+    if box.style != synth.STYLE_COUL_DSF and mode == "excluded_drop":
+        pytest.skip("the policy only matters under lj/cut/coul/dsf")
+    r = run([b, nsteps] + pre + args)
     assert r.returncode == 0, r.stderr
     rows, extra = parse(r.stdout)
     assert rows.shape[0] == nsteps + 1
 
-    orc = capi.configure(capi.Engine("orc"), box, **kw)
-    lam, H = [], []
-    f = np.zeros((box.n, 3))
-    nev = kw.get("nevery", 1)
-
-    def extras(step):
-        if mode != "bonded" or step % nev:
-            return
-        e = 0.01 * (1 + np.arange(box.n) % 7)
-        Hm = (box.mask & synth.GROUP_H_BIT) != 0
-        orc.set_extra_partition(float(e.sum()), float(e[~Hm].sum()))
-
-    extras(0)
-    orc.post_force(0, box.dt, box.x, f)                       # setup()
-    lam.append(orc.get_sites()["lambda"].copy()); H.append(orc.compute_scalar())
-    for step in range(1, nsteps + 1):
-        if mode in ("vv", "thermostat"):
-            orc.initial_integrate(box.dt * nev)
-        extras(step)
-        orc.post_force(step, box.dt, box.x, f)
-        if mode in ("vv", "thermostat"):
-            orc.final_integrate(box.dt * nev)
-        lam.append(orc.get_sites()["lambda"].copy()); H.append(orc.compute_scalar())
-    lam, H = np.array(lam), np.array(H)
+    lam, H, f = oracle_trajectory(box, mode, kw, nsteps, jiggle)
     assert np.abs(rows[:, 2:] - lam).max() <= 1e-8
     assert np.abs(rows[:, 1] - H).max() <= 1e-8 * np.abs(H).max()
+    assert np.abs(lam[-1] - lam[0]).max() > 1e-4              # lambda moved
     assert abs(extra["FORCES_ABS_SUM"] - np.abs(f).sum()) <= 1e-9 * np.abs(f).sum()
     assert extra["RESTART_BYTES"] == 8 * (2 + 3 * max(1, lam.shape[1]) + (3 if mode == "thermostat" else 0))
     assert extra["MEMORY_USAGE"] > 1e6
+
+
+@pytest.fixture(scope="module")
+def dsf_box_files(built, tmp_path_factory):
+    d = tmp_path_factory.mktemp("harness_dsf")
+    box = synth.config(2, scale=0.25)
+    b, s = str(d / "box.bin"), str(d / "sites.txt")
+    synth.write_harness_input(box, b, s)
+    return box, b, s, str(d)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("policy", ["keep", "drop"])
+def test_fix_dsf_excluded_pair_policy(dsf_box_files, policy):
+    """lj/cut/coul/dsf with special_bonds 0 0 0: fully excluded pairs kept with the undamped correction (default)
+    or dropped (keyword `excluded drop`); both against the oracle, and the two must differ."""
+    box, b, s, _ = dsf_box_files
+    kw = dict(bias=dict(m_lambda=2000.0), drop_excluded=(policy == "drop"))
+    r = run([b, 40, "sites", s, "mlambda", 2000, "excluded", policy])
+    assert r.returncode == 0, r.stderr
+    rows, extra = parse(r.stdout)
+    lam, H, f = oracle_trajectory(box, "charge", kw, 40)
+    assert np.abs(rows[:, 2:] - lam).max() <= 1e-8
+    assert np.abs(rows[:, 1] - H).max() <= 1e-8 * np.abs(H).max()
+    other = capi.configure(capi.Engine("orc"), box, bias=dict(m_lambda=2000.0), drop_excluded=(policy != "drop"))
+    other.setup(0, box.x, None)
+    assert abs(other.compute_scalar() - H[0]) > 1e-3 * abs(H[0])
+
+
+def gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nranks", [2])
+def test_fix_two_ranks_matches_one_rank(dsf_box_files, nranks):
+    """The fix builds its own NCCL rank group in init() (id broadcast over `world`, here the shim's file-based
+    MPI_Bcast): NRANKS harness processes, one GPU each, bricks along x, against the single-rank run and the oracle."""
+    if gpu_count() < nranks:
+        pytest.skip("needs %d GPUs" % nranks)
+    box, b, s, d = dsf_box_files
+    nsteps = 40
+    args = [b, nsteps, "jiggle", 0.5, "sites", s, "mlambda", 2000]
+    one = run(args)
+    assert one.returncode == 0, one.stderr
+    rows1, extra1 = parse(one.stdout)
+    import tempfile
+    with tempfile.TemporaryDirectory(dir=d) as scratch:
+        procs = []
+        for rank in range(nranks):
+            env = dict(os.environ, CPH_SHIM_RANK=str(rank), CPH_SHIM_NRANKS=str(nranks), CPH_SHIM_DIR=scratch,
+                       LOCAL_RANK=str(rank))
+            procs.append(subprocess.Popen([HARNESS] + [str(a) for a in args], stdout=subprocess.PIPE,
+                                          stderr=subprocess.PIPE, text=True, env=env))
+        outs = [p.communicate(timeout=600) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, e
+    rows, extra = parse(outs[0][0])
+    assert rows.shape == rows1.shape
+    assert np.abs(rows[:, 2:] - rows1[:, 2:]).max() <= 1e-9
+    assert np.abs(rows[:, 1] - rows1[:, 1]).max() <= 1e-9 * np.abs(rows1[:, 1]).max()
+    fsum = sum(parse(o)[1]["FORCES_ABS_SUM"] for o, _ in outs)
+    assert abs(fsum - extra1["FORCES_ABS_SUM"]) <= 1e-9 * extra1["FORCES_ABS_SUM"]
+    lam, H, f = oracle_trajectory(box, "charge", dict(bias=dict(m_lambda=2000.0)), nsteps, jiggle=0.5)
+    assert np.abs(rows[:, 2:] - lam).max() <= 1e-8
