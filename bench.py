@@ -34,7 +34,7 @@ from constant_ph_b200 import capi, synth  # noqa: E402
 import oracle.binding  # noqa: E402,F401  -- the CPU checker, for the cpu_baseline / --impl reference legs only
 
 # fp64 instructions (DADD/DMUL/DFMA/DSETP) per 32-pair trip of pair_eval_kernel's row loop, from cuobjdump -sass
-FP64_PER_TRIP = {"dsf": 42, "dsf_lj": 53}
+FP64_PER_TRIP = {"dsf": 45, "dsf_lj": 56}
 METRIC = "timesteps_per_s_1M_atoms"
 UNIT = "timesteps/s"
 M_LAMBDA = 2000.0     # see tests/test_gpu_parity.py: Donnini's 20 u nm^2 in Angstrom^2

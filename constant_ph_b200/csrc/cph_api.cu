@@ -222,6 +222,11 @@ int cph_create(int device, cph_handle **out) {
   if (const char *e = getenv("CPH_SPECULATE")) h->speculate = atoi(e) != 0;
   if (const char *e = getenv("CPH_HALO")) h->peer_halo_wanted = strcmp(e, "nccl") != 0;   // "nccl" forces ncclSend/Recv
   int rc = size_sites(h);
+  if (rc == 0) {   // no site table yet: the reference's single site with an empty titratable-atom range
+    const int zero2[2] = {0, 0};
+    rc = upload(h, h->d_site_start, zero2, 2);
+    if (rc == 0 && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = CPH_ERR_CUDA;
+  }
   if (rc) { g_create_error = h->err; delete h; return rc; }
   *out = h;
   return CPH_OK;

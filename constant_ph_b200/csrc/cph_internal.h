@@ -74,8 +74,8 @@ struct PairParams {
 // constants of the evaluation loop (pair.cu); passed to the kernel by value with every launch
 struct EvalConst {
   double cutsq, cut_coulsq;            // global cutoff^2 (max over type pairs), Coulomb cutoff^2
-  double exp_scale, exp_magic, exp_c1s;   // -alpha^2 256/ln2, 2^52+2^51, ln2/(256 alpha^2)
-  double b1, b2, b3, b4;               // (-alpha^2)^k / k!
+  double exp_scale, exp_magic, exp_c1s;   // -alpha^2 16/ln2, 2^52+2^51, ln2/(16 alpha^2)
+  double b1, b2, b3, b4, b5, b6, b7;   // (-alpha^2)^k / k!
   double pa, a1, a2, a3, a4, a5;       // EWALD_P alpha and LAMMPS' erfc polynomial
   double cD, e_shift, f_shift;         // 2 alpha/sqrt(pi), dsf shifts
   double qqrd2e, c_self;
@@ -85,7 +85,8 @@ struct EvalConst {
 
 struct EvalArgs {
   EvalConst c;
-  int nlocal, nt1, rowcap, rowcap2, nqueues;
+  int nlocal, nt1, rowcap, rowcap2, nqueues, pf_atoms;
+  unsigned int pf_bytes;               // L2 prefetch of the inner rows: how far ahead, how many bytes
   int *qnext;                          // per-SM queue heads (pair.cu)
   const double4 *xq;
   const int *type, *neigh, *numspec, *neigh2, *numneigh2, *type_has_lj;
@@ -239,7 +240,7 @@ struct cph_handle {
   bool inner_valid = false;
   int rowcap2 = 0;                   // pitch of the inner rows
   EvalConst eval_const{};
-  DevBuf<double> d_exp2;             // 2^(j/256), staged into shared memory by the evaluation kernel
+  DevBuf<double> d_exp2;             // 2^(j/16), staged into shared memory by the evaluation kernel
   DevBuf<int> d_qnext;               // per-SM queue heads of the evaluation kernel
   int num_sms = 148;
   bool speculate = true;        // enqueue the pair pass before the host has read the list flags (CPH_SPECULATE=0: off)

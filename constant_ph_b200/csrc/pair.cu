@@ -22,8 +22,8 @@
 //   * 1/sqrt and 1/x: hardware seed (MUFU.RSQ64H / MUFU.RCP64H, relative error 2^-20 measured by
 //     cph_bench_seed_error) + one Newton step (third order for 1/r, second order for the erfc
 //     argument: fastmath.cuh);
-//   * exp(-alpha^2 r^2): 256-entry table of 2^(j/256) in shared memory times a degree-4
-//     polynomial whose coefficients absorb -alpha^2, so the argument is r^2 itself;
+//   * exp(-alpha^2 r^2): conflict-free 16-entry table of 2^(j/16) in shared memory times a
+//     degree-7 polynomial whose coefficients absorb -alpha^2, so the argument is r^2 itself;
 //   * qqrd2e and q_i are applied once per atom after the warp reduction, not per pair;
 //   * out-of-range lanes are neutralised by ONE select on the high word of q_j/r (the value
 //     becomes a denormal that cannot change any sum), not by 64-bit selects on every output;
@@ -131,18 +131,24 @@ __device__ __forceinline__ void eval_one(const EvalConst &c, const double4 &pi, 
     fp = u * (y * y);
   } else {
     const double r = s * y;
-    // erfcd = exp(-alpha^2 s) = 2^(n/256) * P4(rho),  n = round(-alpha^2 s 256/ln2),  rho = s + n ln2/(256 alpha^2)
+    // erfcd = exp(-alpha^2 s) = 2^(n/16) * P7(rho),  n = round(-alpha^2 s 16/ln2),  rho = s + n ln2/(16 alpha^2).
+    // 16 table entries fill one 128-byte row of shared memory, one bank pair each: the look-up is conflict-free
+    // whatever the lanes ask for (a 256-entry table with a degree-4 polynomial cost 7 wavefronts per look-up
+    // on the L1 data pipe, which is this kernel's busiest unit: profiles/r2b_eval_ncu.txt)
     const double tm = fma(s, c.exp_scale, c.exp_magic);
     int ni = __double2loint(tm);
     ni = in_c ? ni : 0;                                  // out-of-range lanes (the far-away dummy) stay finite
     const double nd = tm - c.exp_magic;
     const double rho = fma(nd, c.exp_c1s, s);
-    double p = fma(rho, c.b4, c.b3);
+    double p = fma(rho, c.b7, c.b6);
+    p = fma(rho, p, c.b5);
+    p = fma(rho, p, c.b4);
+    p = fma(rho, p, c.b3);
     p = fma(rho, p, c.b2);
     p = fma(rho, p, c.b1);
     p = fma(rho, p, 1.0);
-    const double v = lds_f64(exp_tab + ((ni & 255) << 3)) * p;
-    const double D = __hiloint2double(__double2hiint(v) + (int)((unsigned int)(ni & ~255) << 12), __double2loint(v));
+    const double v = lds_f64(exp_tab + ((ni & 15) << 3)) * p;
+    const double D = __hiloint2double(__double2hiint(v) + (int)((unsigned int)(ni & ~15) << 16), __double2loint(v));
     // LAMMPS' polynomial erfc: t = 1/(1 + p alpha r), erfcc = t (a1 + t (a2 + ...)) erfcd
     const double t = fast_rcp(fma(c.pa, r, 1.0));
     double q = fma(t, c.a5, c.a4);
@@ -343,7 +349,7 @@ pair_eval_kernel(const __grid_constant__ EvalArgs A) {
   if (A.gate != nullptr && (A.gate[4] | A.gate[5]) != 0u) return;
   __shared__ __align__(16) double2 s_coef[CPH_MAXNT1 * CPH_MAXNT1];   // {lj3, lj4}
   __shared__ __align__(16) double2 s_cut[UNI ? 1 : CPH_MAXNT1 * CPH_MAXNT1];
-  __shared__ __align__(16) double s_exp2[256];
+  __shared__ __align__(128) double s_exp2[16];
   const EvalConst &c = A.c;
   const int nt1 = A.nt1;
   for (int k = threadIdx.x; k < nt1 * nt1; k += ETPB) {
@@ -351,7 +357,7 @@ pair_eval_kernel(const __grid_constant__ EvalArgs A) {
     if (!UNI) s_cut[k] = A.cuts[k];   // per-pair cutoffs are only read when they differ from the global one
   }
   if (STYLE == CPH_PAIR_LJ_CUT_COUL_DSF)
-    for (int k = threadIdx.x; k < 256; k += ETPB) s_exp2[k] = A.exp2[k];
+    if (threadIdx.x < 16) s_exp2[threadIdx.x] = A.exp2[threadIdx.x];
   __syncthreads();
   const unsigned int exp_tab = smem_u32(s_exp2), coef0 = smem_u32(s_coef), cut0 = smem_u32(s_cut);
   const int lane = threadIdx.x & 31;
@@ -381,6 +387,11 @@ pair_eval_kernel(const __grid_constant__ EvalArgs A) {
   };
   for (int i = next_atom(); i >= 0; i = next_atom()) {
     {
+      // The inner rows stream from HBM exactly once; a row is asked for PF atoms before a warp of this SM gets to
+      // it (the SM's warps take consecutive atoms), so its index loads find it in L2 instead of waiting ~1 us.
+      if (lane == 0 && i + A.pf_atoms < A.nlocal)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.neigh2 + (size_t)(i + A.pf_atoms) * A.rowcap2),
+                     "r"(A.pf_bytes) : "memory");
       const double4 pi = A.xq[i];
       const int ti = A.type[i];
       const bool has_lj = A.type_has_lj[ti] != 0;       // warp-uniform: water H (2/3 of the atoms) skips all LJ work
@@ -489,9 +500,11 @@ int cph_pair_fill_constants(cph_handle *h) {
   c.exp_magic = 6755399441055744.0;   // 2^52 + 2^51
   if (pp.style == CPH_PAIR_LJ_CUT_COUL_DSF) {
     const double A = pp.alpha * pp.alpha;
-    c.exp_scale = -A * 256.0 / ln2;
-    c.exp_c1s = ln2 / (256.0 * A);
-    c.b1 = -A; c.b2 = A * A / 2.0; c.b3 = -A * A * A / 6.0; c.b4 = A * A * A * A / 24.0;
+    c.exp_scale = -A * 16.0 / ln2;
+    c.exp_c1s = ln2 / (16.0 * A);
+    double bk = 1.0;
+    double *b[7] = {&c.b1, &c.b2, &c.b3, &c.b4, &c.b5, &c.b6, &c.b7};
+    for (int k = 1; k <= 7; k++) { bk *= -A / k; *b[k - 1] = bk; }      // (-alpha^2)^k / k!
   }
   for (int k = 0; k < 4; k++) {
     c.flj[k] = pp.special_lj[k];
@@ -500,9 +513,9 @@ int cph_pair_fill_constants(cph_handle *h) {
   }
   h->eval_const = c;
   if (!h->d_exp2.p) {
-    double e2[256];
-    for (int j = 0; j < 256; j++) e2[j] = (double)exp2l((long double)j / 256.0L);
-    CPH_CUDA(h, h->d_exp2.reserve(256));
+    double e2[16];
+    for (int j = 0; j < 16; j++) e2[j] = (double)exp2l((long double)j / 16.0L);
+    CPH_CUDA(h, h->d_exp2.reserve(16));
     CPH_CUDA(h, cudaMemcpyAsync(h->d_exp2.p, e2, sizeof(e2), cudaMemcpyHostToDevice, h->stream));
     CPH_CUDA(h, cudaStreamSynchronize(h->stream));
   }
@@ -567,6 +580,16 @@ int cph_launch_pair(cph_handle *h, int eflag, const unsigned int *gate) {
   const int per_sm = ctas_env > 0 ? ctas_env : 16;
   const int blocks = std::max(1, std::min(h->num_sms * per_sm, (n + EWARPS - 1) / EWARPS));
   A.nqueues = h->num_sms;
+  {
+    // bytes of a typical inner row (from the mean Verlet row and the two radii), a little generously, whole 128-byte lines
+    static const int pf_env = getenv("CPH_EVAL_PREFETCH") ? atoi(getenv("CPH_EVAL_PREFETCH")) : -1;
+    const double rc = std::sqrt(h->pp.cutsq_max), ratio = (rc + h->inner_skin) / (rc + h->skin);
+    const double mean_inner = (double)h->stored_neigh / std::max(1, n) * ratio * ratio * ratio;
+    const int entries = std::min(h->rowcap2, (int)(mean_inner * 1.1) + 64);
+    A.pf_bytes = (unsigned int)((entries * 4 + 127) / 128 * 128);
+    A.pf_atoms = pf_env >= 0 ? pf_env : 2 * EWARPS * per_sm;     // two rounds of the SM's warps ahead
+    if (A.pf_atoms == 0) A.pf_atoms = 1 << 30;                   // CPH_EVAL_PREFETCH=0: off
+  }
   CPH_CUDA(h, h->d_qnext.reserve(h->num_sms));
   A.qnext = h->d_qnext.p;
   CPH_CUDA(h, cudaMemsetAsync(h->d_qnext.p, 0, h->num_sms * sizeof(int), h->stream));

@@ -19,7 +19,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--atoms", type=int, default=1_000_000)
     ap.add_argument("--steps", type=int, default=60)
-    ap.add_argument("--jiggle", type=float, default=0.45)
+    ap.add_argument("--jiggle", type=float, default=0.26,
+                    help="per-dimension amplitude; 0.26 A per dimension = 0.45 A in total, the bench workload's amplitude")
     args = ap.parse_args()
     box = synth.config(3, scale=args.atoms / 1_000_000.0)
     with tempfile.TemporaryDirectory() as d:
