@@ -365,7 +365,7 @@ class Engine:
     def get_halo_mode(self):
         m = C.c_int(0)
         self._call("get_halo_mode", C.byref(m))
-        return ("none", "nccl", "peer")[m.value]
+        return ("none", "nccl", "peer", "peer+mailbox")[m.value]
 
     def get_inner_counts(self):
         """(entries of the pruned inner rows, the same padded to 32 per row)."""

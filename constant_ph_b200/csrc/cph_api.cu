@@ -221,6 +221,7 @@ int cph_create(int device, cph_handle **out) {
   if (const char *e = getenv("CPH_INNER_SKIN")) h->inner_skin = std::max(0.0, atof(e));   // tuning knobs
   if (const char *e = getenv("CPH_SPECULATE")) h->speculate = atoi(e) != 0;
   if (const char *e = getenv("CPH_HALO")) h->peer_halo_wanted = strcmp(e, "nccl") != 0;   // "nccl" forces ncclSend/Recv
+  if (const char *e = getenv("CPH_MAIL")) h->mail_wanted = atoi(e) != 0;                   // 0: NCCL for the small all-reduces
   int rc = size_sites(h);
   if (rc == 0) {   // no site table yet: the reference's single site with an empty titratable-atom range
     const int zero2[2] = {0, 0};
@@ -237,6 +238,7 @@ int cph_destroy(cph_handle *h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   cph_halo_close(h);
+  cph_mail_close(h);
   cph_comm_destroy(h);
   cph_bonded_release(h);
   DevBuf<double> *db[] = {&h->d_pK, &h->d_lam, &h->d_vlam, &h->d_alam, &h->d_flam, &h->d_fs, &h->d_dfs, &h->d_Us,
@@ -251,7 +253,7 @@ int cph_destroy(cph_handle *h) {
   for (auto *b : ib) b->release();
   h->d_xb.release(); h->d_molecule.release(); h->d_coef.release(); h->d_coef4.release(); h->d_cut2.release(); h->d_type_has_lj.release(); h->d_xt.release(); h->d_xq.release(); h->d_xq2.release(); h->d_keys.release(); h->d_keys2.release();
   h->d_xinner.release(); h->d_exp2.release(); h->d_qnext.release(); h->d_cubtmp.release(); h->d_flags.release(); h->d_scr_stats.release(); h->d_ipc_stage.release();
-  h->d_sendx.release(); h->d_recvx.release(); h->d_sendmeta.release(); h->d_recvmeta.release();
+  h->d_mail.release(); h->d_sendx.release(); h->d_recvx.release(); h->d_sendmeta.release(); h->d_recvmeta.release();
   if (h->h_pin) cudaFreeHost(h->h_pin);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->pev0); cudaEventDestroy(h->pev1);
   cudaEventDestroy(h->ev_flags);
@@ -622,15 +624,30 @@ int cph_pair_pass(cph_handle *h, int eflag) {
   return CPH_OK;
 }
 
-int cph_site_reduce(cph_handle *h) {
+// compute_Hs() tail: partition + per-site sums + the all-reduce that replaces MPI_Allreduce (cpp:274).
+// fused: the caller launches the lambda update next, which completes the mailbox all-reduce itself.
+static int site_reduce_impl(cph_handle *h, bool fused) {
   CPH_TRY(need(h, h->have_pass, "cph_pair_pass (with eflag) first"));
   cudaSetDevice(h->device);
+  if (h->red_pending) CPH_TRY(cph_launch_red_gather(h));        // an earlier reduction nobody consumed
+  if (cph_mail_red_usable(h)) {
+    // one-shot all-reduce over NVLink: every rank stores its block into every rank's mailbox
+    CPH_TRY(cph_launch_water_phi(h));                             // its slot travels with the block
+    CPH_TRY(cph_launch_partition(h, true));
+    if (!fused) {
+      CPH_TRY(cph_launch_red_gather(h));
+      if (h->fix.dudl_mode == CPH_DUDL_CHARGE) CPH_TRY(cph_launch_water_dudl(h));
+    }
+    return CPH_OK;
+  }
   CPH_TRY(cph_launch_partition(h));
   CPH_TRY(cph_launch_water_phi(h));
   CPH_TRY(cph_comm_allreduce(h, h->d_red.p, 4 + 2 * h->S + 1));   // cpp:274
   if (h->fix.dudl_mode == CPH_DUDL_CHARGE) CPH_TRY(cph_launch_water_dudl(h));
   return CPH_OK;
 }
+
+int cph_site_reduce(cph_handle *h) { return site_reduce_impl(h, false); }
 
 int cph_integrate_lambda(cph_handle *h, double dt) {
   cudaSetDevice(h->device);
@@ -679,7 +696,7 @@ static int post_force_impl(cph_handle *h, int64_t ntimestep, double dt, int wher
   // pack kernel has stored this rank's copies into the neighbours' buffers; the all-reduce of the
   // decision flags that follows is also the barrier after which every rank may read its own buffer.
   CPH_TRY(cph_halo_send(h));
-  CPH_TRY(cph_comm_allreduce_max_u32_dev(h, h->d_flags.p, 6));   // global decision, one host sync
+  CPH_TRY(cph_flags_allreduce(h, h->d_flags.p));                  // global decision, one host sync
   // the flags travel to the host on a side stream while the main stream builds the ghost atoms
   CPH_CUDA(h, cudaEventRecord(h->ev_flags, h->stream));
   CPH_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_flags, 0));
@@ -713,7 +730,7 @@ static int post_force_impl(cph_handle *h, int64_t ntimestep, double dt, int wher
     CPH_TRY(cph_launch_gather_out(h, 0, h->d_stage.p, h->stream2));
   }
   if (active) {
-    CPH_TRY(cph_site_reduce(h));                                        // cpp:70
+    CPH_TRY(site_reduce_impl(h, true));                                 // cpp:70
     const int phase = (h->fix.integ_mode == CPH_INTEGRATE_REFERENCE && advance) ? 0 : 2;
     // cpp:71-73; t_lambda = nevery*dt (cpp:113); the charges follow lambda in the same launch
     CPH_TRY(cph_launch_integrate(h, dt * h->fix.nevery, phase, h->fix.dudl_mode == CPH_DUDL_CHARGE && phase == 0));
@@ -914,7 +931,7 @@ int cph_get_counts(cph_handle *h, int64_t *out8) {
 }
 
 int cph_get_halo_mode(cph_handle *h, int *mode) {
-  *mode = h->nranks == 1 ? 0 : (h->peer_halo ? 2 : 1);
+  *mode = h->nranks == 1 ? 0 : (h->peer_halo ? (h->mail_ok ? 3 : 2) : 1);
   return CPH_OK;
 }
 

@@ -13,6 +13,8 @@
 #define CPH_SBSHIFT 30             // LAMMPS SBBITS: top 2 bits = special-bond class (outer rows)
 #define CPH_TYPESHIFT 28           // inner rows: type of j in the top 4 bits, index in the low 28
 #define CPH_JMASK 0x0FFFFFFF
+#define CPH_MAIL_MAXP 8             // peer mailboxes serve up to 8 ranks (one NVSwitch domain); beyond that NCCL
+#define CPH_MAIL_FSLOT 16           // 32-bit words per flag slot: [0..5] flags, [8..9] sequence number
 #define CPH_MAXNT1 12              // ntypes+1 <= 12: the (ntypes+1)^2 * 32 B coefficient table lives in shared memory
 
 // device buffer that only ever grows
@@ -115,6 +117,23 @@ struct Grid {         // cell grid over the extended sub-box
   int ncell;
 };
 
+// byte offsets inside a mailbox
+inline size_t mail_flag_off(int P, int parity, int src) { return ((size_t)parity * P + src) * CPH_MAIL_FSLOT * 4; }
+inline size_t mail_red_base(int P) { return ((size_t)2 * P * CPH_MAIL_FSLOT * 4 + 255) / 256 * 256; }
+inline size_t mail_red_off(int P, size_t cap, int parity, int src) {
+  return mail_red_base(P) + ((size_t)parity * P + src) * (cap + 2) * sizeof(double);
+}
+inline size_t mail_bytes(int P, size_t cap) { return mail_red_off(P, cap, 2, 0); }
+
+// where this rank's site-sum block goes (one slot per destination rank), and where the blocks of all ranks arrive
+struct MailRed {
+  int P = 0;                         // 0: mailboxes off (single rank or NCCL fallback)
+  int seq_index = 0;                 // the sequence number sits at doubles[seq_index] of a slot
+  unsigned long long seq = 0;
+  double *dst[CPH_MAIL_MAXP];        // push side: my slot in rank p's mailbox
+  const double *src[CPH_MAIL_MAXP];  // gather side: rank p's slot in MY mailbox
+};
+
 struct ProfSlot {
   double ms = 0;
   int64_t launches = 0;
@@ -211,6 +230,20 @@ struct cph_handle {
   std::vector<unsigned char> peer_handle_cache;  // [nranks * 64] handle each mapping was opened from
   std::vector<int> peer_table;                   // [nranks * 28] recv_off[27] + recv_half of every rank
   DevBuf<unsigned char> d_ipc_stage;
+  // Peer mailboxes: a one-shot all-reduce over NVLink for the two small per-step reductions (decision flags at the
+  // start of a step, site sums before the lambda update).  Every rank stores its block straight into a slot of
+  // every other rank's mailbox (mapped through CUDA IPC like the halo buffers) and publishes a sequence number;
+  // the consuming kernel waits for all sequence numbers and combines the blocks in rank order, so every rank gets
+  // bit-identical totals without NCCL and without a host round trip.  Two parities: a writer can be at most one
+  // reduction ahead of the slowest reader.
+  DevBuf<unsigned char> d_mail;
+  size_t mail_red_cap = 0;                       // doubles per site-sum slot (the sequence number sits behind them)
+  bool mail_ok = false;                          // every rank's mailbox is mapped on every rank
+  bool mail_wanted = true;                       // CPH_MAIL=0: keep the two NCCL all-reduces (A/B)
+  std::vector<void *> mail_base;                 // [nranks] mapped base of every rank's mailbox (own entry: d_mail.p)
+  std::vector<unsigned char> mail_handle_cache;  // [nranks * 64]
+  unsigned long long seq_flags = 0, seq_red = 0; // reductions published so far
+  bool red_pending = false;                      // site sums pushed; the totals are gathered by the next consumer
   DevBuf<int4> d_sendmeta, d_recvmeta;
   DevBuf<double> d_f, d_evdwl, d_phi, d_eatom;  // [3*nlocal], [nlocal]...
   DevBuf<int> d_hlist;      // owned atoms in the hydrogen group
@@ -281,9 +314,11 @@ struct cph_handle {
 // neigh.cu
 int cph_rebuild(cph_handle *h);                 // sort, ghosts, cells, list, site map
 int cph_forward_ghosts(cph_handle *h);          // refresh ghost x and q (send + barrier if needed + finish)
+int cph_flags_allreduce(cph_handle *h, unsigned int *dst);   // max over ranks of this step's decision flags -> dst[0..5] (mailboxes or NCCL)
 int cph_halo_send(cph_handle *h);               // pack + ship the copies (peer stores over NVLink, or NCCL p2p)
 int cph_halo_finish(cph_handle *h);             // ghost atoms from self images + received copies
 void cph_halo_close(cph_handle *h);
+void cph_mail_close(cph_handle *h);
 int cph_neighbors_to_host(cph_handle *h, int *numneigh, int64_t *keys, int64_t cap);
 // pair.cu
 int cph_launch_pair(cph_handle *h, int eflag, const unsigned int *gate = nullptr);
@@ -292,7 +327,9 @@ int cph_pair_fill_constants(cph_handle *h);
 int cph_inner_counts(cph_handle *h, int64_t *out2);
 int cph_launch_xt(cph_handle *h);
 // sites.cu
-int cph_launch_partition(cph_handle *h);        // HA, HB, E_vdwl, E_coul + per-site sums
+int cph_launch_partition(cph_handle *h, bool push = false);   // HA, HB, E_vdwl, E_coul + per-site sums (+ push to the mailboxes)
+bool cph_mail_red_usable(const cph_handle *h);
+int cph_launch_red_gather(cph_handle *h);
 int cph_launch_integrate(cph_handle *h, double dt, int phase, bool apply = false);
 int cph_launch_apply_charges(cph_handle *h);
 int cph_launch_water_phi(cph_handle *h);      // red[4+2S] = sum of dE/dq over owned buffer atoms

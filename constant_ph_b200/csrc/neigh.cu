@@ -170,10 +170,21 @@ struct PeerTab {
   double4 *dst[27];      // dst[d][r - start[d]]: where record r of direction d lands in the neighbour's buffer
 };
 
+struct MailFlags {
+  int P;                                   // 0: no mailboxes
+  unsigned long long seq;
+  unsigned int *dst[CPH_MAIL_MAXP];        // my flag slot in every rank's mailbox (my own included)
+};
+
 // K6 fused pack + NVLink store: every copy that belongs to another rank is shifted across the
 // periodic boundary and stored straight into that rank's receive buffer (mapped peer memory).
+// With mailboxes the same kernel also publishes this rank's decision flags: the last block to
+// finish (ticket counter; every block has fenced its stores system-wide by then) writes the six
+// flag words and then the sequence number into its slot on every rank -- the consumer that sees
+// the sequence number therefore also sees the positions.
 __global__ void halo_pack_peer_kernel(int nrec, const int *__restrict__ rsrc, const int *__restrict__ rdir,
-                                      DirTable tab, GhostDirs gd, const double4 *__restrict__ xq, PeerTab pt) {
+                                      DirTable tab, GhostDirs gd, const double4 *__restrict__ xq, PeerTab pt,
+                                      MailFlags mf, const unsigned int *__restrict__ flags, unsigned int *ticket) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < nrec) {
     const int d = rdir[r];
@@ -186,6 +197,44 @@ __global__ void halo_pack_peer_kernel(int nrec, const int *__restrict__ rsrc, co
     }
   }
   __threadfence_system();   // the stores must have landed before this rank joins the next collective
+  if (mf.P == 0) return;
+  __shared__ unsigned int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  if ((int)threadIdx.x < mf.P) {
+    unsigned int *dst = mf.dst[threadIdx.x];
+    for (int k = 0; k < 6; k++) dst[k] = flags[k];
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long *>(dst + 8) = mf.seq;
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// The other half of the one-shot all-reduce: wait until every rank's flags of this step have arrived
+// (lane p watches rank p's slot in MY mailbox), take the maximum, leave it where the ncclAllReduce left it.
+__global__ void flags_gather_kernel(const unsigned int *mail, int P, unsigned long long seq, unsigned int *out,
+                                    unsigned int *status) {
+  const int lane = threadIdx.x;
+  unsigned int v[6] = {0, 0, 0, 0, 0, 0};
+  if (lane < P) {
+    const unsigned int *slot = mail + (size_t)lane * CPH_MAIL_FSLOT;
+    const volatile unsigned long long *sq = reinterpret_cast<const volatile unsigned long long *>(slot + 8);
+    const long long t0 = clock64();
+    while (*sq != seq) {
+      if (clock64() - t0 > 400000000000LL) { atomicOr(status, 1u); break; }   // minutes: a rank is gone
+      __nanosleep(200);
+    }
+    __threadfence_system();
+    for (int k = 0; k < 6; k++) v[k] = reinterpret_cast<const volatile unsigned int *>(slot)[k];
+  }
+  for (int k = 0; k < 6; k++) {
+    unsigned int m = v[k];
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) out[k] = m;
+  }
 }
 
 // unsorted ghost candidates: local self images first (direction order), then received copies
@@ -553,7 +602,16 @@ int cph_halo_send(cph_handle *h) {
   cudaStream_t st = h->stream;
   h->halo_parity ^= 1;     // every rank toggles in lockstep: writers never touch the half being read
   if (h->peer_halo) {
-    if (h->nsend) {
+    MailFlags mf;
+    mf.P = 0;
+    if (h->mail_ok) {      // this step's decision flags travel with the positions
+      mf.P = h->nranks;
+      mf.seq = ++h->seq_flags;
+      const int par = (int)(mf.seq & 1);
+      for (int p = 0; p < h->nranks; p++)
+        mf.dst[p] = (unsigned int *)((unsigned char *)h->mail_base[p] + mail_flag_off(h->nranks, par, h->rank));
+    }
+    if (h->nsend || mf.P) {
       PeerTab pt;
       for (int d = 0; d < 27; d++) {
         pt.dst[d] = nullptr;
@@ -563,8 +621,9 @@ int cph_halo_send(cph_handle *h) {
         pt.dst[d] = (double4 *)h->peer_base[p] + (size_t)h->halo_parity * (size_t)row[27] + row[d];
       }
       h->nlaunch++;
-      halo_pack_peer_kernel<<<nblk(h->nrec), TPB, 0, st>>>(h->nrec, h->d_rec_src.p, h->d_rec_dir.p, send_table(h), gd,
-                                                          h->d_xq.p, pt);
+      halo_pack_peer_kernel<<<std::max(1, nblk(h->nrec)), TPB, 0, st>>>(h->nrec, h->d_rec_src.p, h->d_rec_dir.p,
+                                                                       send_table(h), gd, h->d_xq.p, pt, mf, h->d_flags.p,
+                                                                       h->d_flags.p + 82);
     }
   } else {
     if (h->nsend) {
@@ -593,12 +652,30 @@ int cph_halo_finish(cph_handle *h) {
   return 0;
 }
 
+// max over ranks of the six decision words of this step -> dst[0..5].  With mailboxes: the flags were published by
+// cph_halo_send's pack kernel; one warp waits for all of them and reduces (no NCCL, no host).  Otherwise ncclAllReduce
+// in place on d_flags (dst is then d_flags itself).  Either way it is also the barrier behind which a rank may read
+// the copies its neighbours stored into its receive buffer.
+int cph_flags_allreduce(cph_handle *h, unsigned int *dst) {
+  if (h->nranks == 1) return 0;
+  if (h->peer_halo && h->mail_ok) {
+    ProfScope ps(h, 5);
+    const int par = (int)(h->seq_flags & 1);
+    h->nlaunch++;
+    flags_gather_kernel<<<1, 32, 0, h->stream>>>(
+        (const unsigned int *)((unsigned char *)h->d_mail.p + mail_flag_off(h->nranks, par, 0)), h->nranks, h->seq_flags, dst,
+        h->d_flags.p + 83);
+    CPH_CUDA(h, cudaGetLastError());
+    return 0;
+  }
+  if (dst != h->d_flags.p) CPH_CUDA(h, cudaMemcpyAsync(dst, h->d_flags.p, 6 * sizeof(unsigned int), cudaMemcpyDeviceToDevice, h->stream));
+  return cph_comm_allreduce_max_u32_dev(h, dst, 6);
+}
+
 int cph_forward_ghosts(cph_handle *h) {
   CPH_TRY(cph_halo_send(h));
-  if (h->nranks > 1 && h->peer_halo) {
-    // stand-alone call: a (tiny) collective orders the peer stores before the reads
-    CPH_TRY(cph_comm_allreduce_max_u32_dev(h, h->d_flags.p + 8, 1));
-  }
+  // stand-alone call: a (tiny) collective orders the peer stores before the reads; its result is not used
+  if (h->nranks > 1 && h->peer_halo) CPH_TRY(cph_flags_allreduce(h, h->d_flags.p + 84));
   return cph_halo_finish(h);
 }
 
@@ -610,13 +687,30 @@ void cph_halo_close(cph_handle *h) {
   h->peer_halo = false;
 }
 
+void cph_mail_close(cph_handle *h) {
+  for (size_t p = 0; p < h->mail_base.size(); p++)
+    if (h->mail_base[p] && (int)p != h->rank) cudaIpcCloseMemHandle(h->mail_base[p]);
+  h->mail_base.clear();
+  h->mail_handle_cache.clear();
+  h->mail_ok = false;
+}
+
 // Map the neighbours' receive buffers (CUDA IPC).  Called at every list build: handles and
 // layouts are all-gathered, mappings are reopened only when a neighbour's buffer moved.
 static int halo_map_peers(cph_handle *h, const GhostDirs &gd) {
   const int P = h->nranks;
   h->peer_halo = false;
+  h->mail_ok = false;
   if (P == 1 || !h->peer_halo_wanted) return 0;
-  const size_t rec = 64 + 28 * sizeof(int);   // IPC handle + recv_off[27] + recv_half
+  // this rank's mailbox, allocated once (its address is exported): room for twice the current site table
+  if (!h->d_mail.p && P <= CPH_MAIL_MAXP && h->mail_wanted) {
+    h->mail_red_cap = std::max((size_t)32768, (size_t)2 * (4 + 2 * (size_t)h->S + 1));
+    const size_t bytes = mail_bytes(P, h->mail_red_cap);
+    if (h->d_mail.reserve_exact(bytes) == cudaSuccess) cudaMemsetAsync(h->d_mail.p, 0, bytes, h->stream);
+    else { cudaGetLastError(); h->mail_red_cap = 0; }
+  }
+  // record: IPC handle of the receive buffer + recv_off[27] + recv_half + IPC handle of the mailbox + its slot size
+  const size_t rec = 64 + 28 * sizeof(int) + 64 + sizeof(unsigned long long);
   CPH_CUDA(h, h->d_ipc_stage.reserve(rec * (P + 1)));
   std::vector<unsigned char> mine(rec, 0), all(rec * P, 0);
   cudaIpcMemHandle_t hd;
@@ -627,6 +721,15 @@ static int halo_map_peers(cph_handle *h, const GhostDirs &gd) {
   for (int d = 0; d < 27; d++) tab[d] = h->recv_off[d];
   tab[27] = (int)h->recv_half;
   memcpy(mine.data() + 64, tab, sizeof(tab));
+  unsigned int mok = 0;
+  if (h->d_mail.p) {
+    cudaIpcMemHandle_t mh;
+    mok = cudaIpcGetMemHandle(&mh, h->d_mail.p) == cudaSuccess ? 1u : 0u;
+    if (!mok) cudaGetLastError();
+    memcpy(mine.data() + 64 + sizeof(tab), &mh, 64);
+    const unsigned long long cap = h->mail_red_cap;
+    memcpy(mine.data() + 64 + sizeof(tab) + 64, &cap, sizeof(cap));
+  }
   CPH_CUDA(h, cudaMemcpyAsync(h->d_ipc_stage.p, mine.data(), rec, cudaMemcpyHostToDevice, h->stream));
   CPH_TRY(cph_comm_allgather(h, h->d_ipc_stage.p, h->d_ipc_stage.p + rec, rec));
   CPH_CUDA(h, cudaMemcpyAsync(all.data(), h->d_ipc_stage.p + rec, rec * P, cudaMemcpyDeviceToHost, h->stream));
@@ -649,10 +752,34 @@ static int halo_map_peers(cph_handle *h, const GhostDirs &gd) {
     h->peer_base[p] = ptr;
     memcpy(h->peer_handle_cache.data() + (size_t)p * 64, hp, 64);
   }
+  // mailboxes: EVERY rank maps EVERY other rank's (the reductions are all-to-all), same slot size everywhere
+  h->mail_base.resize(P, nullptr);
+  h->mail_handle_cache.resize((size_t)P * 64, 0);
+  for (int p = 0; p < P && mok; p++) {
+    const unsigned char *hp = all.data() + rec * p + 64 + sizeof(tab);
+    unsigned long long cap = 0;
+    memcpy(&cap, hp + 64, sizeof(cap));
+    if (cap != h->mail_red_cap) { mok = 0; break; }
+    if (p == h->rank) { h->mail_base[p] = h->d_mail.p; continue; }
+    if (h->mail_base[p] && memcmp(hp, h->mail_handle_cache.data() + (size_t)p * 64, 64) == 0) continue;
+    if (h->mail_base[p]) { cudaIpcCloseMemHandle(h->mail_base[p]); h->mail_base[p] = nullptr; }
+    cudaIpcMemHandle_t ph;
+    memcpy(&ph, hp, 64);
+    void *ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, ph, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); mok = 0; break; }
+    h->mail_base[p] = ptr;
+    memcpy(h->mail_handle_cache.data() + (size_t)p * 64, hp, 64);
+  }
   // every rank must agree: one failure anywhere falls back to NCCL everywhere
-  unsigned int bad = ok ? 0u : 1u;
-  CPH_TRY(cph_comm_allreduce_max_u32(h, &bad, 1));
-  h->peer_halo = bad == 0;
+  unsigned int bad[2] = {ok ? 0u : 1u, (ok && mok) ? 0u : 1u};
+  CPH_TRY(cph_comm_allreduce_max_u32(h, bad, 2));
+  h->peer_halo = bad[0] == 0;
+  h->mail_ok = bad[1] == 0;
+  // a waiting kernel gave up on a rank earlier: say so now (the host is synchronised here anyway)
+  unsigned int status = 0;
+  CPH_CUDA(h, cudaMemcpyAsync(&status, h->d_flags.p + 83, sizeof(status), cudaMemcpyDeviceToHost, h->stream));
+  CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (status) return cph_fail(h, CPH_ERR_COMM, "a rank did not publish its block of a mailbox reduction in time");
   return 0;
 }
 

@@ -186,19 +186,21 @@ __device__ __forceinline__ void row_loop(const EvalConst &c, const double4 *__re
                                          const unsigned int coef_i, const unsigned int cut_i, const unsigned int exp_tab,
                                          Acc &a) {
   const int last = n2pad - 32 + lane;
+  // indices run TWO trips ahead of their use (they stream from HBM / L2), records one chunk ahead (mostly L1 hits)
   int eA = row[lane];
   int eB = row[min(lane + 32, last)];
+  int eC = row[min(lane + 64, last)];
+  int eD = row[min(lane + 96, last)];
   double4 pA = ld256(rec_addr(xq, (unsigned int)eA & CPH_JMASK));
   for (int k = 0; k < n2pad; k += 64) {
     const double4 pB = ld256(rec_addr(xq, (unsigned int)eB & CPH_JMASK));
-    const int eC = row[min(k + 64 + lane, last)];
+    const int eE = row[min(k + 128 + lane, last)];
+    const int eF = row[min(k + 160 + lane, last)];
     eval_one<STYLE, EFLAG, LJ, UNI>(c, pi, pA, eA, qiq, coef_i, cut_i, exp_tab, a);
     if (k + 32 >= n2pad) break;                          // warp-uniform
     pA = ld256(rec_addr(xq, (unsigned int)eC & CPH_JMASK));
-    const int eD = row[min(k + 96 + lane, last)];
     eval_one<STYLE, EFLAG, LJ, UNI>(c, pi, pB, eB, qiq, coef_i, cut_i, exp_tab, a);
-    eA = eC;
-    eB = eD;
+    eA = eC; eB = eD; eC = eE; eD = eF;
   }
 }
 
@@ -337,6 +339,10 @@ prune_kernel(int nlocal, const float4 *__restrict__ xt, const int *__restrict__ 
 #define CPH_EVAL_MAXNREG 64
 #endif
 constexpr int EWARPS = CPH_EVAL_WARPS;
+#ifndef CPH_EVAL_CLAIM
+#define CPH_EVAL_CLAIM 4
+#endif
+constexpr int CLAIM = CPH_EVAL_CLAIM;   // atoms per queue claim
 constexpr int ETPB = EWARPS * 32;
 
 // K2b: one warp per atom over the pruned inner row.
@@ -373,10 +379,11 @@ pair_eval_kernel(const __grid_constant__ EvalArgs A) {
   const int nq = A.nqueues;
   const int per_q = (A.nlocal + nq - 1) / nq;
   int q = __shfl_sync(0xffffffffu, (int)(smid % (unsigned int)nq), 0), scanned = 0;
-  auto next_atom = [&]() -> int {
+  // a claim is CLAIM consecutive atoms (one atomic round trip to L2 per CLAIM atoms)
+  auto next_claim = [&]() -> int {
     while (scanned < nq) {
       int t = 0;
-      if (lane == 0) t = atomicAdd(A.qnext + q, 1);
+      if (lane == 0) t = atomicAdd(A.qnext + q, CLAIM);
       t = __shfl_sync(0xffffffffu, t, 0);                 // warp-uniform, and the compiler can tell
       const int cand = q * per_q + t;
       if (t < per_q && cand < A.nlocal) return cand;
@@ -385,8 +392,19 @@ pair_eval_kernel(const __grid_constant__ EvalArgs A) {
     }
     return -1;
   };
-  for (int i = next_atom(); i >= 0; i = next_atom()) {
-    {
+  for (int i0 = next_claim(); i0 >= 0; i0 = next_claim()) {
+    const int iend = min(min(i0 + CLAIM, (i0 / per_q + 1) * per_q), A.nlocal);   // claims do not cross a range end
+    for (int i = i0; i < iend; i++) {
+      // the next atom's scalars and the head of its row: into L1 now, so that its prologue does not wait on L2
+      if (i + 1 < iend && lane < 6) {
+        const int inext = i + 1;
+        const void *pf = lane == 0 ? (const void *)(A.xq + inext)
+                       : lane == 1 ? (const void *)(A.type + inext)
+                       : lane == 2 ? (const void *)(A.numneigh2 + inext)
+                       : lane == 3 ? (const void *)(A.numspec + inext)
+                                   : (const void *)(A.neigh2 + (size_t)inext * A.rowcap2 + (lane - 4) * 32);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+      }
       // The inner rows stream from HBM exactly once; a row is asked for PF atoms before a warp of this SM gets to
       // it (the SM's warps take consecutive atoms), so its index loads find it in L2 instead of waiting ~1 us.
       if (lane == 0 && i + A.pf_atoms < A.nlocal)

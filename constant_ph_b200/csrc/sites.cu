@@ -58,7 +58,7 @@ site_partition_kernel(int n, const double *__restrict__ eatom, const double *__r
                       const int *__restrict__ site_start, const int *__restrict__ titr_local,
                       const double *__restrict__ titr_dq, const double *__restrict__ phi, int implicit_site,
                       double extra_HA, double extra_HB, const double *__restrict__ bonded_e, double *red,
-                      unsigned int *ticket) {
+                      unsigned int *ticket, const __grid_constant__ MailRed mr) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if ((int)blockIdx.x < nbP) {
     double v[4] = {0, 0, 0, 0};   // HA, HB, E_vdwl, E_coul
@@ -89,10 +89,16 @@ site_partition_kernel(int n, const double *__restrict__ eatom, const double *__r
         red[4 + site] = d;
         if (!implicit_site) red[4 + S + site] = hd;
       }
+      // one-shot all-reduce over NVLink, push side: this rank's sums of the site go straight into its slot of
+      // every rank's mailbox (lane p stores to rank p; its own mailbox included)
+      if (lane < mr.P) {
+        mr.dst[lane][4 + site] = d;
+        if (!implicit_site) mr.dst[lane][4 + S + site] = hd;
+      }
     }
   }
   __shared__ unsigned int s_last;
-  __threadfence();
+  if (mr.P) __threadfence_system(); else __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
   __syncthreads();
@@ -119,6 +125,46 @@ site_partition_kernel(int n, const double *__restrict__ eatom, const double *__r
     if (implicit_site) red[4 + S] = out[1] - out[0];   // reference single site: HB - HA of the hydrogen group (cpp:111)
     *ticket = 0u;
   }
+  // every block has fenced its stores system-wide before taking its ticket: the scalars go out, then the
+  // sequence number that tells the gathering kernels on all ranks that this rank's block is complete
+  if ((int)threadIdx.x < mr.P) {
+    double *dst = mr.dst[threadIdx.x];
+    for (int c = 0; c < 4; c++) dst[c] = out[c];
+    if (implicit_site) dst[4 + S] = out[1] - out[0];
+    dst[4 + 2 * S] = red[4 + 2 * S];                   // modify_water slot (filled before this launch)
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long *>(dst + mr.seq_index) = mr.seq;
+  }
+}
+
+// One-shot all-reduce, gather side: wait until every rank's block of this reduction has arrived in MY mailbox.
+// Called by all threads of a block; the first P threads watch one rank each.
+__device__ __forceinline__ void mail_wait(const MailRed &mr, unsigned int *status) {
+  if ((int)threadIdx.x < mr.P) {
+    const volatile unsigned long long *sq =
+        reinterpret_cast<const volatile unsigned long long *>(mr.src[threadIdx.x] + mr.seq_index);
+    const long long t0 = clock64();
+    while (*sq != mr.seq) {
+      if (clock64() - t0 > 400000000000LL) { atomicOr(status, 1u); break; }   // minutes: a rank is gone
+      __nanosleep(200);
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+}
+// total of entry k over the ranks, in rank order: every rank computes bit-identical sums
+__device__ __forceinline__ double mail_total(const MailRed &mr, int k) {
+  double t = 0.0;
+  for (int p = 0; p < mr.P; p++) t += reinterpret_cast<const volatile double *>(mr.src[p])[k];
+  return t;
+}
+
+// stand-alone gather (cph_site_reduce called on its own): totals of all entries into red[]
+__global__ void __launch_bounds__(TPB)
+red_gather_kernel(int nred, const __grid_constant__ MailRed mr, double *red, unsigned int *status) {
+  mail_wait(mr, status);
+  const int k = blockIdx.x * TPB + threadIdx.x;
+  if (k < nred) red[k] = mail_total(mr, k);
 }
 
 struct BiasOut { double f, df, U, dU; };
@@ -167,6 +213,8 @@ struct LambdaArgs {
   double *red, *lam, *theta, *vlam, *alam, *flam, *fs, *dfs, *Us, *dUs, *partials, *scal;
   double4 *xq;
   unsigned int *ticket;
+  MailRed mr;                        // mr.P != 0: the site sums of all ranks wait in my mailbox (gather them first)
+  unsigned int *status;
 };
 
 // K4 + K5, one launch.  Per site (one thread): calculate_df, calculate_dU, integrate_lambda (cpp:109-145) in
@@ -188,6 +236,12 @@ lambda_update_kernel(const __grid_constant__ LambdaArgs A) {
   // variables; absent from the reference, which integrates lambda itself and confines it with U4/U5);
   // velocity, acceleration and mass then refer to theta and F_theta = F_lambda * sin(2 theta).
   double *theta = A.theta;
+  const bool gather = A.mr.P != 0;
+  double wphi = 0.0;         // modify_water: -(dQ_s/n_W) sum_W dE/dq still to be applied to the gathered dU/dlambda_s
+  if (gather) {
+    mail_wait(A.mr, A.status);
+    if (A.inv_nw != 0.0 && fx.dudl_mode == CPH_DUDL_CHARGE) wphi = A.inv_nw * mail_total(A.mr, 4 + 2 * S);
+  }
   double v[3] = {0, 0, 0};   // sum of site terms of H_lambda, sum lambda*(HB_s-HA_s), kinetic
   for (int s = blockIdx.x * TPB + threadIdx.x; s < S; s += gridDim.x * TPB) {
     double cq = theta ? theta[s] : A.lam[s];
@@ -207,8 +261,18 @@ lambda_update_kernel(const __grid_constant__ LambdaArgs A) {
       if (phase == 3) vel = (vel + 0.5 * acc * dt) * nh;
       BiasOut b = bias_terms(bp, lambda);
       const double pk = fx.implicit_site ? fx.pK : A.pK[s];
-      const double hd = A.red[4 + S + s];
-      const double dE = (fx.dudl_mode == CPH_DUDL_REFERENCE) ? hd : A.red[4 + s];
+      double hd, dq_e;
+      if (gather) {          // fused all-reduce: totals over the ranks, written back for the getters
+        hd = mail_total(A.mr, 4 + S + s);
+        dq_e = mail_total(A.mr, 4 + s);
+        if (wphi != 0.0) dq_e -= A.dQ[s] * wphi;
+        A.red[4 + S + s] = hd;
+        A.red[4 + s] = dq_e;
+      } else {
+        hd = A.red[4 + S + s];
+        dq_e = A.red[4 + s];
+      }
+      const double dE = (fx.dudl_mode == CPH_DUDL_REFERENCE) ? hd : dq_e;
       const double ph = fx.boltz * fx.T * log(10.0) * (pk - fx.pH);
       const double f_lambda = -(dE + b.df * ph + b.dU);                 // cpp:111
       const double a_lambda = f_lambda * chain / bp.m_lambda * fx.ftm2v;   // cpp:112 (+ SURVEY D9)
@@ -255,6 +319,10 @@ lambda_update_kernel(const __grid_constant__ LambdaArgs A) {
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+      if (gather) {
+        for (int c2 = 0; c2 < 4; c2++) A.red[c2] = mail_total(A.mr, c2);
+        A.red[4 + 2 * S] = mail_total(A.mr, 4 + 2 * S);
+      }
       // cpp:114: (1-lambda)HA + lambda HB = HA + lambda (HB-HA); charge mode: E_ff at the current charges
       const double eff = (fx.dudl_mode == CPH_DUDL_REFERENCE) ? A.red[0] + out[1] : A.red[2] + A.red[3];
       A.scal[4] = eff + out[0];
@@ -420,10 +488,46 @@ __global__ void gather_out_kernel(int n, int width, const int *__restrict__ inv,
 
 }  // namespace
 
-int cph_launch_partition(cph_handle *h) {
+// slots of reduction number `seq` on the push side (my slot everywhere) and on the gather side (everyone's slot here)
+static MailRed mail_red_args(const cph_handle *h, unsigned long long seq) {
+  MailRed mr;
+  mr.P = h->nranks;
+  mr.seq = seq;
+  mr.seq_index = (int)h->mail_red_cap;
+  const int par = (int)(seq & 1);
+  for (int p = 0; p < h->nranks; p++) {
+    mr.dst[p] = (double *)((unsigned char *)h->mail_base[p] + mail_red_off(h->nranks, h->mail_red_cap, par, h->rank));
+    mr.src[p] = (const double *)((const unsigned char *)h->d_mail.p + mail_red_off(h->nranks, h->mail_red_cap, par, p));
+  }
+  return mr;
+}
+
+bool cph_mail_red_usable(const cph_handle *h) {
+  return h->nranks > 1 && h->peer_halo && h->mail_ok && (size_t)(4 + 2 * h->S + 1) <= h->mail_red_cap;
+}
+
+// The totals of the reduction pushed last, gathered into d_red by a kernel of its own (cph_site_reduce called alone).
+int cph_launch_red_gather(cph_handle *h) {
+  if (!h->red_pending) return 0;
+  ProfScope ps(h, 5);
+  const int nred = 4 + 2 * h->S + 1;
+  h->nlaunch++;
+  red_gather_kernel<<<nblk(nred), TPB, 0, h->stream>>>(nred, mail_red_args(h, h->seq_red), h->d_red.p, h->d_flags.p + 83);
+  h->red_pending = false;
+  CPH_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+// push: also store this rank's block into every rank's mailbox (the caller checked cph_mail_red_usable)
+int cph_launch_partition(cph_handle *h, bool push) {
   ProfScope ps(h, 2);
   const int n = h->nlocal, S = h->S;
   cudaStream_t st = h->stream;
+  MailRed mr;
+  if (push) {
+    mr = mail_red_args(h, ++h->seq_red);
+    h->red_pending = true;
+  }
   CPH_CUDA(h, h->d_part.reserve((size_t)MAXPART * 4));
   const int nbP = std::max(1, std::min(MAXPART, nblk(n)));
   const int nbS = (S + TPB / 32 - 1) / (TPB / 32);
@@ -431,7 +535,7 @@ int cph_launch_partition(cph_handle *h) {
                                                   h->d_part.p, S, h->d_site_start.p, h->d_titr_local.p,
                                                   h->d_titr_dq.p, h->d_phi.p, h->fix.implicit_site, h->extra_HA,
                                                   h->extra_HB, h->have_topology ? h->d_bonded_e.p : nullptr,
-                                                  h->d_red.p, h->d_flags.p + 80);
+                                                  h->d_red.p, h->d_flags.p + 80, mr);
   h->extra_HA = h->extra_HB = 0.0;   // consumed
   h->nlaunch += 1;
   CPH_CUDA(h, cudaGetLastError());
@@ -465,6 +569,11 @@ int cph_launch_integrate(cph_handle *h, double dt, int phase, bool apply) {
   A.red = h->d_red.p; A.lam = h->d_lam.p; A.theta = h->coord_theta ? h->d_theta.p : nullptr; A.vlam = h->d_vlam.p;
   A.alam = h->d_alam.p; A.flam = h->d_flam.p; A.fs = h->d_fs.p; A.dfs = h->d_dfs.p; A.Us = h->d_Us.p; A.dUs = h->d_dUs.p;
   A.partials = h->d_part.p; A.scal = h->d_scal.p; A.xq = h->d_xq.p; A.ticket = h->d_flags.p + 81;
+  A.status = h->d_flags.p + 83;
+  if (h->red_pending && phase != 1) {          // the all-reduce of the site sums completes inside this launch
+    A.mr = mail_red_args(h, h->seq_red);
+    h->red_pending = false;
+  }
   lambda_update_kernel<<<nb, TPB, 0, st>>>(A);
   h->nlaunch += 1;
   CPH_CUDA(h, cudaGetLastError());

@@ -214,7 +214,8 @@ int cph_memory_usage(cph_handle *h, double *bytes);
  * out[5]=list builds so far out[6]=titratable atoms owned out[7]=nsites */
 int cph_get_counts(cph_handle *h, int64_t *out8);
 /* how the per-step ghost refresh travels: 0 = single rank (periodic self images only), 1 = ncclSend/ncclRecv,
- * 2 = stores into the neighbours' receive buffers over NVLink (CUDA IPC peer memory) */
+ * 2 = stores into the neighbours' receive buffers over NVLink (CUDA IPC peer memory), 3 = the same plus the two
+ * small per-step all-reduces (decision flags, site sums) as one-shot stores into peer mailboxes instead of NCCL */
 int cph_get_halo_mode(cph_handle *h, int *mode);
 /* bookkeeping checks (bit-exact parity): site index of every owned atom (-1 = none), caller order */
 int cph_get_site_map(cph_handle *h, int *site_of_atom);

@@ -71,7 +71,7 @@ def main():
         c_r = ref.get_counts()
         out = dict(worst=worst, nlocal=int(tot[0]), neighbors=int(tot[1]), titr=int(tot[2]), builds=counts["builds"],
                    ref_nlocal=c_r["nlocal"], ref_neighbors=c_r["neighbors"], ref_titr=c_r["titr_owned"],
-                   ref_builds=c_r["builds"], world=world, nghost=counts["nghost"])
+                   ref_builds=c_r["builds"], world=world, nghost=counts["nghost"], halo=eng.get_halo_mode())
         print("MGPU_RESULT " + json.dumps(out))
     dist.barrier()
     dist.destroy_process_group()
