@@ -35,7 +35,6 @@ import oracle.binding  # noqa: E402,F401  -- the CPU checker, for the cpu_baseli
 
 # fp64 instructions (DADD/DMUL/DFMA/DSETP) per 32-pair trip of pair_eval_kernel's row loop, from cuobjdump -sass
 FP64_PER_TRIP = {"dsf": 45, "dsf_lj": 56}
-METRIC = "timesteps_per_s_1M_atoms"
 UNIT = "timesteps/s"
 M_LAMBDA = 2000.0     # see tests/test_gpu_parity.py: Donnini's 20 u nm^2 in Angstrom^2
 
@@ -143,11 +142,40 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def workload(args):
-    scale = args.atoms / 1_000_000.0
-    box = synth.config(3, scale=scale)
+def workload(args, nranks=1):
+    """The box and the prescribed-motion parameters of the selected BASELINE config.
+    3 (default, the metric's configuration): 1M atoms, strong scaling.  4: 500k atoms PER RANK (weak scaling of the
+    4M-atom / 50k-site box: 2 ranks = 1M atoms ... 8 ranks = 4M).  5: 512k atoms, 10 % titratable, one site each.
+    2: 32k atoms, 20 sites (the pH sweep runs through run_ph_sweep)."""
+    c = args.config
+    if c == 3:
+        box = synth.config(3, scale=args.atoms / 1_000_000.0)
+    elif c == 4:
+        box = synth.config(4, scale=0.125 * nranks * args.atoms / 1_000_000.0)
+    elif c == 5:
+        box = synth.config(5, scale=args.atoms / 1_000_000.0)
+    else:
+        box = synth.config(2, scale=args.atoms / 1_000_000.0, pH=args.pH)
     params = synth.jiggle_params(box, amp=0.45, period_lo=60.0, period_hi=140.0)
     return box, params
+
+
+CONFIG_TEXT = {
+    3: ("timesteps_per_s_1M_atoms", "strong",
+        "BASELINE configs[2]: synthetic replicated SPC/E water box, %d atoms, 2000 titration sites (1000 carboxyl + 1000 "
+        "amine solutes), lj/cut/coul/dsf rc=10 A alpha=0.2, skin 2 A, nevery=1, charge-derivative dU/dlambda, prescribed "
+        "+-0.45 A molecular jiggle"),
+    4: ("timesteps_per_s_cfg4_500k_atoms_per_gpu", "weak",
+        "BASELINE configs[3] stand-in: 4M-atom / 50k-site box weak-scaled at 500k atoms per GPU (%d atoms per GPU at "
+        "--atoms scale); the titratable monomers are 8-atom solutes in SPC/E water, not a bonded PAA chain; "
+        "lj/cut/coul/dsf, same motion and cadence as config 3"),
+    5: ("timesteps_per_s_cfg5_512k_dense_sites", "strong",
+        "BASELINE configs[4]: dense titration stress test, 512k-atom box (%d at --atoms scale), 10 %% of the atoms "
+        "titratable, one site each (51 200 sites), lj/cut/coul/dsf"),
+    2: ("timesteps_per_s_cfg2_32k_atoms", "strong",
+        "BASELINE configs[1]: 20 titratable carboxyl/amine sites in a 32k-atom water box (%d at --atoms scale), "
+        "lj/cut/coul/dsf, pH sweep 2-10"),
+}
 
 
 def decompose(box, nranks):
@@ -205,7 +233,13 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--atoms", type=int, default=1_000_000, help="atoms in the box (config 3 = 1M)")
+    ap.add_argument("--atoms", type=int, default=1_000_000,
+                    help="size knob: 1000000 = the config as BASELINE states it (other values scale it)")
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3, 4, 5],
+                    help="BASELINE config (1-based as in SURVEY 8d): 3 = the metric's 1M-atom box (default); 4, 5, 2 = "
+                         "the other stated configurations, reported under their own metric names")
+    ap.add_argument("--pH", type=float, default=7.0)
+    ap.add_argument("--sweep", action="store_true", help="config 2: run pH 2..10 and report every point")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the parity check against the committed golden values")
@@ -218,17 +252,19 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
-    config = {"workload": "BASELINE configs[2]: synthetic replicated SPC/E water box, %d atoms, 2000 titration "
-                          "sites (1000 carboxyl + 1000 amine solutes), lj/cut/coul/dsf rc=10 A alpha=0.2, skin 2 A, "
-                          "nevery=1, charge-derivative dU/dlambda, prescribed +-0.45 A molecular jiggle" % args.atoms,
-              "atoms": args.atoms, "sites": 2000, "pair_style": "lj/cut/coul/dsf",
-              "l2_policy": "inputs larger than L2 (neighbour list alone is ~2.9 GB per step vs 126 MB L2)"}
+    METRIC, scaling, text = CONFIG_TEXT[args.config]
+    natoms_cfg = {3: args.atoms, 4: int(0.5 * args.atoms), 5: int(0.512 * args.atoms), 2: int(0.032 * args.atoms)}[args.config]
+    nsites_cfg = {3: max(2, int(2000 * args.atoms / 1e6)), 4: None, 5: None, 2: None}[args.config]
+    config = {"workload": text % natoms_cfg, "atoms": natoms_cfg, "sites": nsites_cfg, "pair_style": "lj/cut/coul/dsf",
+              "l2_policy": "inputs larger than L2 (the neighbour rows alone are GBs per step vs 126 MB L2)"}
+    if args.config == 3:
+        config["atoms"], config["sites"] = args.atoms, 2000
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return 0
-        box, params = workload(args)
+        box, params = workload(args, max(1, args.gpus))
         steps, warm = args.steps, args.warmup          # the same trajectory window as the CUDA arm, rebuilds included
         r = run_cpu(args, box, params, steps=steps, warmup=warm)
         aff, nproc = host_cores()
@@ -237,7 +273,7 @@ def main():
                   % (box.n, steps, warm, r["cores"], aff, nproc, r["builds_timed"], r["setup_s"]))
         line = {"impl": "reference", "metric": METRIC, "value": r["steps_per_s"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": r["steps_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                                  "sample": sample, "nproc": nproc, "affinity_cores": aff},
                 "e2e": {"value": r["steps_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -245,6 +281,37 @@ def main():
                 "note": "restated CPU reference (oracle/cph_oracle.cpp, g++ -O3 -march=native -fopenmp); the upstream "
                         "fix does not compile and LAMMPS is not available, so this is a port, not an upstream binary"}
         print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ config 2: pH sweep on one GPU
+    if args.config == 2 and args.sweep:
+        import torch
+        torch.cuda.set_device(local_rank)
+        per_pH = {}
+        for pH in (2.0, 3.0, 4.0, 5.0, 6.0, 7.0, 8.0, 9.0, 10.0):
+            args.pH = pH
+            box, params = workload(args, 1)
+            eng = capi.configure(capi.Engine("cph", device=local_rank), box, bias=dict(m_lambda=M_LAMBDA))
+            W, K = args.warmup, args.steps
+            fr = torch.stack([torch.from_numpy(synth.jiggle_positions(box, params, s * box.dt)) for s in range(W + K)]).cuda()
+            for s in range(W):
+                eng.post_force(s, box.dt, fr[s].data_ptr(), None, where=capi.DEVICE)
+            eng.sync()
+            eng.timer_start()
+            for s in range(W, W + K):
+                eng.post_force(s, box.dt, fr[s].data_ptr(), None, where=capi.DEVICE)
+            ms = eng.timer_stop()
+            t = eng.get_sites()
+            per_pH[str(pH)] = {"steps_per_s": K / (ms * 1e-3), "ms_per_step": ms / K,
+                               "mean_lambda": float(t["lambda"].mean()), "mean_F_lambda": float(t["f_lambda"].mean())}
+            eng.close()
+        vals = [v["steps_per_s"] for v in per_pH.values()]
+        print(json.dumps({"metric": METRIC, "value": float(np.mean(vals)), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": float(np.mean([v["ms_per_step"] for v in per_pH.values()])),
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic", "config": config, "per_pH": per_pH,
+                          "note": "value = mean over pH 2..10; a 32k-atom box is launch-bound on a B200 (the step is a "
+                                  "dozen kernels of a few microseconds each), so throughput does not depend on pH"}))
         return 0
 
     # ------------------------------------------------------------------ CUDA arm
@@ -258,7 +325,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     nranks = world
 
-    box, params = workload(args)
+    box, params = workload(args, nranks)
+    config["sites"] = int(box.nsites) if args.config != 3 else config["sites"]
     grid = decompose(box, nranks)
     loc, sublo, subhi = rank_domain(box, grid, rank)
     if nranks > 1:
@@ -291,7 +359,7 @@ def main():
 
     # ---- parity of THIS engine on THIS workload against the committed oracle values, at every rank count ------
     check = {"skipped": "golden values exist for the full-size workload only (--atoms 1000000)"}
-    if os.path.exists(GOLDEN_CFG3) and args.atoms == 1_000_000 and not args.no_check:
+    if os.path.exists(GOLDEN_CFG3) and args.config == 3 and args.atoms == 1_000_000 and not args.no_check:
         golden = json.load(open(GOLDEN_CFG3))
         if golden["atoms"] == box.n:
             check = parity_check(eng, box, frame, golden, allsum)
@@ -375,7 +443,7 @@ def main():
     achieved = abytes / (pair_avg_ms * 1e-3) / 1e9
     traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "r2_pair_traffic.json")
-    if os.path.exists(tp) and nranks == 1 and args.atoms == 1_000_000:
+    if os.path.exists(tp) and nranks == 1 and args.config == 3 and args.atoms == 1_000_000:
         tj = json.load(open(tp))
         traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]     # per launch
         traffic_src = "profiles/r2_pair_traffic.json: dram__bytes_read+write of one `ncu --set full` capture of this kernel " \
@@ -410,6 +478,22 @@ def main():
                              "fp64 instruction counts per 32-pair loop trip are counted from the SASS of the committed "
                              "kernel (profiles/r2_eval_sass_counts.md) and cross-checked against ncu's "
                              "smsp__inst_executed_pipe_fp64 in profiles/"}
+    # K3 (partition + site sums) and K4/K5 (lambda update + charges): the streaming kernels SURVEY 8(d) expects to be
+    # HBM-bound; their own fraction of the measured copy peak (what matters in config 5: 51 200 sites)
+    A_t, S_sites = counts["titr_owned"], max(1, counts["nsites"])
+    k3_bytes = nloc * 20.0 + A_t * 28.0 + S_sites * 16.0
+    k45_bytes = S_sites * 88.0 + A_t * 28.0
+    k3_ms = prof["site_reduce"][0] / max(prof["site_reduce"][1], 1)
+    k45_ms = prof["integrate"][0] / max(prof["integrate"][1], 1)
+    site_roofline = {"bound": "hbm", "unit": "GB/s", "peak": peak,
+                     "site_partition_kernel": {"algorithmic_bytes": k3_bytes, "ms": k3_ms,
+                                               "achieved": k3_bytes / max(k3_ms, 1e-9) / 1e6,
+                                               "frac": k3_bytes / max(k3_ms, 1e-9) / 1e6 / peak},
+                     "lambda_update_kernel": {"algorithmic_bytes": k45_bytes, "ms": k45_ms,
+                                              "achieved": k45_bytes / max(k45_ms, 1e-9) / 1e6,
+                                              "frac": k45_bytes / max(k45_ms, 1e-9) / 1e6 / peak},
+                     "note": "one launch each per step; at these sizes (tens of MB at most) both sit on the ~2-3 us floor "
+                             "of a kernel launch, far below the HBM roofline"}
     launches = launches_timed       # counted by the library's launchers during the timed `value` loop
 
     cpu = None
@@ -427,7 +511,7 @@ def main():
     # The jittered-lattice start is far from equilibrium, so the box heats up and re-neighbours more
     # often than the prescribed-motion workload above; this line is informative, not the headline.
     md = None
-    if args.md_steps > 0 and nranks == 1:
+    if args.md_steps > 0 and nranks == 1 and args.config == 3:
         try:
             # its own box: same lattice and composition, but a start an integrator can run from (solutes kept
             # apart, the water slots beside them emptied, lattice jitter 0.1 A): in the headline box
@@ -461,12 +545,12 @@ def main():
     if rank == 0:
         value = K / (ms_dev * 1e-3)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": nranks, "steps": K, "warmup": W,
-                "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config,
                 "parallelism": "spatial %dx%dx%d" % grid, "rebuilds_in_timed_region": rebuilds,
                 "prunes_in_timed_region": prunes, "check": check,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-                "roofline_fp64": roofline_fp64, "cpu_baseline": cpu,
+                "roofline_fp64": roofline_fp64, "site_kernels_roofline": site_roofline, "cpu_baseline": cpu,
                 "kernels_ms_per_step": {k: v[0] / K for k, v in prof.items()}, "wall_ms_per_step": wall_dev / K,
                 "seed_error": capi.bench_seed_error(local_rank),
                 "step_ms_profiled": step_ms_prof, "md": md}

@@ -469,7 +469,10 @@ int cph_set_sites(cph_handle *h, int nsites, const double *pK, int ntitr, const 
   {
     std::vector<int> start(h->S + 1, 0);
     for (int k = 0; k < ntitr; k++) start[site[k] + 1]++;
-    for (int s2 = 0; s2 < h->S; s2++) start[s2 + 1] += start[s2];
+    int biggest = 1;
+    for (int s2 = 0; s2 < h->S; s2++) { biggest = std::max(biggest, start[s2 + 1]); start[s2 + 1] += start[s2]; }
+    h->site_lps = 1;
+    while (h->site_lps < 32 && h->site_lps < biggest) h->site_lps *= 2;
     CPH_TRY(upload(h, h->d_site_start, start.data(), start.size()));
   }
   CPH_TRY(upload(h, h->d_titr_site, site.data(), ntitr));
@@ -715,7 +718,11 @@ static int post_force_impl(cph_handle *h, int64_t ntimestep, double dt, int wher
   float md;
   memcpy(&md, &fl[0], 4);
   h->scal_h[6] = md;
-  if (any) CPH_TRY(cph_rebuild(h));
+  if (any) {
+    memcpy(&h->drift_value, &fl[2], 4);   // all-reduced with the other decision words: no second round trip
+    h->drift_known = true;
+    CPH_TRY(cph_rebuild(h));
+  }
   if (!guessed || any || fl[5]) CPH_TRY(cph_launch_pair(h, active ? 1 : 0));
   CPH_TRY(cph_launch_bonded(h, active ? 1 : 0));                        // cpp:221-229: bonded eatom joins the partition
   h->have_pass = true;

@@ -87,7 +87,7 @@ struct EvalConst {
 
 struct EvalArgs {
   EvalConst c;
-  int nlocal, nt1, rowcap, rowcap2, nqueues, pf_atoms;
+  int nlocal, nt1, rowcap, rowcap2, nqueues, pf_atoms, dummy;
   unsigned int pf_bytes;               // L2 prefetch of the inner rows: how far ahead, how many bytes
   int *qnext;                          // per-SM queue heads (pair.cu)
   const double4 *xq;
@@ -193,6 +193,7 @@ struct cph_handle {
   bool uniform_cut = true, kc_dirty = true;
   DevBuf<int> d_titr_tag_sorted, d_titr_entry_of_sorted;  // [ntitr]
   DevBuf<int> d_titr_site, d_titr_local;                   // [ntitr] site-major; local = owned index or -1
+  int site_lps = 32;                                       // lanes per site in the site-sum kernel (power of two)
   DevBuf<int> d_site_start;                                // [S+1] range of every site in the site-major table
   DevBuf<double> d_titr_qA, d_titr_dq;                     // [ntitr]
   DevBuf<double> d_scal;                                   // 16 doubles of scalar results
@@ -278,6 +279,8 @@ struct cph_handle {
   int num_sms = 148;
   bool speculate = true;        // enqueue the pair pass before the host has read the list flags (CPH_SPECULATE=0: off)
   int64_t nprunes = 0;
+  bool drift_known = false;          // the step's all-reduced flags already carry the drift beyond the sub-box
+  float drift_value = 0.f;
   int rowcap = 0;
   int64_t nbuilds = 0, stored_neigh = 0, special_pairs = 0;
   int64_t nlaunch = 0;               // kernels of this library launched so far

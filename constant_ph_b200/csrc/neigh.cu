@@ -423,6 +423,7 @@ list_build_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__re
     numneigh[i] = fits ? cnt : 0;
     numspec[i] = fits ? nsp : 0;
     if (!fits) atomicMax(flags + 1, (unsigned int)(padded + nsp));
+    if (nsp > 32) atomicMax(flags + 7, (unsigned int)nsp);   // the evaluation kernel takes one special partner per lane
     atomicAdd(stats, (unsigned long long)(cnt + nsp));
     if (nsp) atomicAdd(stats + 1, (unsigned long long)nsp);
     atomicMax(flags + 3, (unsigned int)(cnt + nsp));
@@ -732,8 +733,11 @@ static int halo_map_peers(cph_handle *h, const GhostDirs &gd) {
   }
   CPH_CUDA(h, cudaMemcpyAsync(h->d_ipc_stage.p, mine.data(), rec, cudaMemcpyHostToDevice, h->stream));
   CPH_TRY(cph_comm_allgather(h, h->d_ipc_stage.p, h->d_ipc_stage.p + rec, rec));
+  unsigned int status = 0;   // a waiting kernel gave up on a rank earlier: say so now (the host synchronises here anyway)
   CPH_CUDA(h, cudaMemcpyAsync(all.data(), h->d_ipc_stage.p + rec, rec * P, cudaMemcpyDeviceToHost, h->stream));
+  CPH_CUDA(h, cudaMemcpyAsync(&status, h->d_flags.p + 83, sizeof(status), cudaMemcpyDeviceToHost, h->stream));
   CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (status) return cph_fail(h, CPH_ERR_COMM, "a rank did not publish its block of a mailbox reduction in time");
   h->peer_base.resize(P, nullptr);
   h->peer_handle_cache.resize((size_t)P * 64, 0);
   h->peer_table.assign((size_t)P * 28, 0);
@@ -775,11 +779,6 @@ static int halo_map_peers(cph_handle *h, const GhostDirs &gd) {
   CPH_TRY(cph_comm_allreduce_max_u32(h, bad, 2));
   h->peer_halo = bad[0] == 0;
   h->mail_ok = bad[1] == 0;
-  // a waiting kernel gave up on a rank earlier: say so now (the host is synchronised here anyway)
-  unsigned int status = 0;
-  CPH_CUDA(h, cudaMemcpyAsync(&status, h->d_flags.p + 83, sizeof(status), cudaMemcpyDeviceToHost, h->stream));
-  CPH_CUDA(h, cudaStreamSynchronize(h->stream));
-  if (status) return cph_fail(h, CPH_ERR_COMM, "a rank did not publish its block of a mailbox reduction in time");
   return 0;
 }
 
@@ -858,12 +857,18 @@ int cph_rebuild(cph_handle *h) {
   double3 slo = make_double3(h->sublo[0], h->sublo[1], h->sublo[2]);
   double3 shi = make_double3(h->subhi[0], h->subhi[1], h->subhi[2]);
   unsigned int flags_h[8];
-  if (n) drift_kernel<<<nblk(n), TPB, 0, st>>>(n, h->d_xq.p, slo, shi, h->d_flags.p);
-  CPH_CUDA(h, cudaMemcpyAsync(flags_h, h->d_flags.p, sizeof(flags_h), cudaMemcpyDeviceToHost, st));
-  CPH_CUDA(h, cudaStreamSynchronize(st));
-  CPH_TRY(cph_comm_allreduce_max_u32(h, flags_h + 2, 1));
   float drift;
-  memcpy(&drift, &flags_h[2], 4);
+  if (h->drift_known && !h->md_on) {
+    // measured by this step's set_x / check kernel and all-reduced with the decision flags
+    drift = h->drift_value;
+  } else {
+    if (n) drift_kernel<<<nblk(n), TPB, 0, st>>>(n, h->d_xq.p, slo, shi, h->d_flags.p);
+    CPH_CUDA(h, cudaMemcpyAsync(flags_h, h->d_flags.p, sizeof(flags_h), cudaMemcpyDeviceToHost, st));
+    CPH_CUDA(h, cudaStreamSynchronize(st));
+    CPH_TRY(cph_comm_allreduce_max_u32(h, flags_h + 2, 1));
+    memcpy(&drift, &flags_h[2], 4);
+  }
+  h->drift_known = false;
   if (drift > h->skin)
     return cph_fail(h, CPH_ERR_DOMAIN, "owned atoms drifted %.3f beyond the sub-box (> skin %.3f): "
                     "the host must migrate atoms and call cph_set_atoms", drift, h->skin);
@@ -1095,6 +1100,9 @@ int cph_rebuild(cph_handle *h) {
       if (attempt == 3) return cph_fail(h, CPH_ERR_OVERFLOW, "neighbour rows overflowed after regrow");
       continue;
     }
+    if (flags_h[7] > 32u)
+      return cph_fail(h, CPH_ERR_OVERFLOW, "an atom has %u special-bond partners inside the list cutoff; at most 32 are supported",
+                      flags_h[7]);
     h->stored_neigh = (int64_t)stats_h[0];
     h->special_pairs = (int64_t)stats_h[1];
     h->maxneigh = (int)flags_h[3];

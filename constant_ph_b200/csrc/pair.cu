@@ -52,6 +52,13 @@ constexpr int CH = 128;           // candidates per tile (4 per lane)
 constexpr int NBUF = 4;           // tiles in flight per warp
 constexpr int MAXTILES = 64;      // per-warp tile schedule entries (rows of up to 2048 neighbours)
 
+#ifndef CPH_EVAL_ILP
+#define CPH_EVAL_ILP 1                // pairs per lane evaluated side by side (1 or 2)
+#endif
+#ifndef CPH_EVAL_DEPTH
+#define CPH_EVAL_DEPTH 1              // chunks of neighbour records in flight ahead of the evaluation (1 or 2)
+#endif
+
 // ---- small PTX helpers ------------------------------------------------------------------------
 __device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ double lds_f64(unsigned int a) {
@@ -67,7 +74,18 @@ __device__ __forceinline__ double2 lds_v2f64(unsigned int a) {
 // the fp64 record {x,y,z,q} of one atom: one 32-byte request per lane (LDG.E.ENL2.256 on sm_100a)
 __device__ __forceinline__ double4 ld256(const void *p) {
   double4 v;
+#ifdef CPH_EXP_NOGATHER   // limiter experiment: the arithmetic alone, records synthesised from the address
+  const unsigned long long a = (unsigned long long)p;
+  const double t = (double)(unsigned int)(a >> 5 & 1023u);
+  return make_double4(3.0 + 0.001 * t, 4.0 + 0.002 * t, 5.0 - 0.001 * t, 0.4);
+#endif
   asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+// inner-row entries are read exactly once: do not let them displace the neighbour records in L1
+__device__ __forceinline__ int ld_stream(const int *p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
 // xq + 32 * j as one IMAD.WIDE.U32
@@ -115,6 +133,10 @@ __device__ __forceinline__ void eval_one(const EvalConst &c, const double4 &pi, 
                                          const unsigned int exp_tab, Acc &a) {
   const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
   const double s = fma(dz, dz, fma(dy, dy, dx * dx));
+#ifdef CPH_EXP_NOMATH     // limiter experiment: the memory side alone (gathers, index stream), no pair arithmetic
+  a.fx = fma(s, pj.w, a.fx);
+  return;
+#endif
   bool in_c, in_lj;
   if (UNI) {
     in_c = in_lj = s < c.cutsq;                          // the exact (fp64) cutoff decision
@@ -184,24 +206,65 @@ template <int STYLE, int EFLAG, bool LJ, bool UNI>
 __device__ __forceinline__ void row_loop(const EvalConst &c, const double4 *__restrict__ xq, const int *__restrict__ row,
                                          const int n2pad, const int lane, const double4 &pi, const double qiq,
                                          const unsigned int coef_i, const unsigned int cut_i, const unsigned int exp_tab,
-                                         Acc &a) {
+                                         const int dummy, Acc &a) {
   const int last = n2pad - 32 + lane;
+#if CPH_EVAL_ILP == 2
+  Acc a2;
+#endif
   // indices run TWO trips ahead of their use (they stream from HBM / L2), records one chunk ahead (mostly L1 hits)
-  int eA = row[lane];
-  int eB = row[min(lane + 32, last)];
-  int eC = row[min(lane + 64, last)];
-  int eD = row[min(lane + 96, last)];
+  int eA = ld_stream(row + lane);
+  int eB = ld_stream(row + min(lane + 32, last));
+  int eC = ld_stream(row + min(lane + 64, last));
+  int eD = ld_stream(row + min(lane + 96, last));
+#if CPH_EVAL_ILP == 2
+  // TWO pairs per lane per trip, evaluated side by side: the arithmetic of one pair is a chain of ~30 dependent
+  // fp64 operations (1/sqrt -> r -> 1/(1+p alpha r) -> erfc polynomial -> force), and eight such chains per
+  // scheduler do not fill the fp64 pipe (measured with the gathers switched off: profiles/r2f_limiter.md).  Two
+  // independent chains per warp do.  A second chunk past the row end is pointed at the far-away dummy atom.
+  double4 pA = ld256(rec_addr(xq, (unsigned int)eA & CPH_JMASK));
+  if (32 >= n2pad) eB = dummy;
+  double4 pB = ld256(rec_addr(xq, (unsigned int)eB & CPH_JMASK));
+  for (int k = 0; k < n2pad; k += 64) {
+    if (k + 96 >= n2pad) eD = dummy;                      // warp-uniform: chunk k+96 does not exist
+    const double4 pC = ld256(rec_addr(xq, (unsigned int)eC & CPH_JMASK));
+    const double4 pD = ld256(rec_addr(xq, (unsigned int)eD & CPH_JMASK));
+    const int eE = ld_stream(row + min(k + 128 + lane, last));
+    const int eF = ld_stream(row + min(k + 160 + lane, last));
+    eval_one<STYLE, EFLAG, LJ, UNI>(c, pi, pA, eA, qiq, coef_i, cut_i, exp_tab, a);
+    eval_one<STYLE, EFLAG, LJ, UNI>(c, pi, pB, eB, qiq, coef_i, cut_i, exp_tab, a2);
+    pA = pC; pB = pD;
+    eA = eC; eB = eD; eC = eE; eD = eF;
+  }
+  a.fx += a2.fx; a.fy += a2.fy; a.fz += a2.fz; a.ev += a2.ev; a.phi += a2.phi;
+#elif CPH_EVAL_DEPTH == 2
+  // records TWO chunks ahead: nearly every 32-lane gather has at least one lane that misses L1, so a gather
+  // completes at L2 latency; two evaluations of distance cover it where one does not
+  double4 pA = ld256(rec_addr(xq, (unsigned int)eA & CPH_JMASK));
+  double4 pB = ld256(rec_addr(xq, (unsigned int)eB & CPH_JMASK));
+  for (int k = 0; k < n2pad; k += 64) {
+    const double4 pC = ld256(rec_addr(xq, (unsigned int)eC & CPH_JMASK));
+    const int eE = ld_stream(row + min(k + 128 + lane, last));
+    const int eF = ld_stream(row + min(k + 160 + lane, last));
+    eval_one<STYLE, EFLAG, LJ, UNI>(c, pi, pA, eA, qiq, coef_i, cut_i, exp_tab, a);
+    if (k + 32 >= n2pad) break;                          // warp-uniform
+    pA = ld256(rec_addr(xq, (unsigned int)eD & CPH_JMASK));
+    eval_one<STYLE, EFLAG, LJ, UNI>(c, pi, pB, eB, qiq, coef_i, cut_i, exp_tab, a);
+    pB = pA; pA = pC;                                    // (chunk k+64 -> A, chunk k+96 -> B)
+    eA = eC; eB = eD; eC = eE; eD = eF;
+  }
+#else
   double4 pA = ld256(rec_addr(xq, (unsigned int)eA & CPH_JMASK));
   for (int k = 0; k < n2pad; k += 64) {
     const double4 pB = ld256(rec_addr(xq, (unsigned int)eB & CPH_JMASK));
-    const int eE = row[min(k + 128 + lane, last)];
-    const int eF = row[min(k + 160 + lane, last)];
+    const int eE = ld_stream(row + min(k + 128 + lane, last));
+    const int eF = ld_stream(row + min(k + 160 + lane, last));
     eval_one<STYLE, EFLAG, LJ, UNI>(c, pi, pA, eA, qiq, coef_i, cut_i, exp_tab, a);
     if (k + 32 >= n2pad) break;                          // warp-uniform
     pA = ld256(rec_addr(xq, (unsigned int)eC & CPH_JMASK));
     eval_one<STYLE, EFLAG, LJ, UNI>(c, pi, pB, eB, qiq, coef_i, cut_i, exp_tab, a);
     eA = eC; eB = eD; eC = eE; eD = eF;
   }
+#endif
 }
 
 // Slow path for special-bond pairs (factor_lj / factor_coul and, under
@@ -340,7 +403,7 @@ prune_kernel(int nlocal, const float4 *__restrict__ xt, const int *__restrict__ 
 #endif
 constexpr int EWARPS = CPH_EVAL_WARPS;
 #ifndef CPH_EVAL_CLAIM
-#define CPH_EVAL_CLAIM 4
+#define CPH_EVAL_CLAIM 2
 #endif
 constexpr int CLAIM = CPH_EVAL_CLAIM;   // atoms per queue claim
 constexpr int ETPB = EWARPS * 32;
@@ -420,9 +483,9 @@ pair_eval_kernel(const __grid_constant__ EvalArgs A) {
       Acc a;
       if (n2pad) {
         if (has_lj) {
-          row_loop<STYLE, EFLAG, true, UNI>(c, A.xq, row2, n2pad, lane, pi, qiq, coef_i, cut_i, exp_tab, a);
+          row_loop<STYLE, EFLAG, true, UNI>(c, A.xq, row2, n2pad, lane, pi, qiq, coef_i, cut_i, exp_tab, A.dummy, a);
         } else {
-          row_loop<STYLE, EFLAG, false, UNI>(c, A.xq, row2, n2pad, lane, pi, qiq, coef_i, cut_i, exp_tab, a);
+          row_loop<STYLE, EFLAG, false, UNI>(c, A.xq, row2, n2pad, lane, pi, qiq, coef_i, cut_i, exp_tab, A.dummy, a);
           a.fx *= qiq; a.fy *= qiq; a.fz *= qiq;
         }
         if (EFLAG) a.phi *= c.qqrd2e;
@@ -588,7 +651,7 @@ int cph_launch_pair(cph_handle *h, int eflag, const unsigned int *gate) {
   static const int ctas_env = getenv("CPH_EVAL_CTAS_PER_SM") ? atoi(getenv("CPH_EVAL_CTAS_PER_SM")) : 0;
   EvalArgs A;
   A.c = h->eval_const;
-  A.nlocal = n; A.nt1 = h->pp.ntypes + 1; A.rowcap = h->rowcap; A.rowcap2 = h->rowcap2;
+  A.nlocal = n; A.nt1 = h->pp.ntypes + 1; A.rowcap = h->rowcap; A.rowcap2 = h->rowcap2; A.dummy = h->nall | (1 << CPH_TYPESHIFT);
   A.xq = h->d_xq.p; A.type = h->d_type.p; A.neigh = h->d_neigh.p; A.numspec = h->d_numspec.p;
   A.neigh2 = h->d_neigh2.p; A.numneigh2 = h->d_numneigh2.p; A.coef = h->d_coef4.p; A.cuts = h->d_cut2.p;
   A.type_has_lj = h->d_type_has_lj.p; A.exp2 = h->d_exp2.p;
@@ -612,7 +675,13 @@ int cph_launch_pair(cph_handle *h, int eflag, const unsigned int *gate) {
   A.qnext = h->d_qnext.p;
   CPH_CUDA(h, cudaMemsetAsync(h->d_qnext.p, 0, h->num_sms * sizeof(int), h->stream));
   h->nlaunch++;
-#define LAUNCH(S, E, U) pair_eval_kernel<S, E, U><<<blocks, ETPB, 0, h->stream>>>(A)
+  static const int carve_env = getenv("CPH_EVAL_CARVEOUT") ? atoi(getenv("CPH_EVAL_CARVEOUT")) : -1;
+#define LAUNCH(S, E, U)                                                                                               \
+  do {                                                                                                                \
+    if (carve_env >= 0)                                                                                               \
+      cudaFuncSetAttribute(pair_eval_kernel<S, E, U>, cudaFuncAttributePreferredSharedMemoryCarveout, carve_env);     \
+    pair_eval_kernel<S, E, U><<<blocks, ETPB, 0, h->stream>>>(A);                                                     \
+  } while (0)
 #define LAUNCH_E(S, U) do { if (eflag) LAUNCH(S, 1, U); else LAUNCH(S, 0, U); } while (0)
   if (h->pp.style == CPH_PAIR_LJ_CUT_COUL_CUT) {
     if (h->uniform_cut) LAUNCH_E(CPH_PAIR_LJ_CUT_COUL_CUT, true); else LAUNCH_E(CPH_PAIR_LJ_CUT_COUL_CUT, false);

@@ -49,12 +49,12 @@ __global__ void final_sum_kernel(int nb, const double *__restrict__ partials, do
 
 // K3, one launch: compute_Hs tail (cpp:259-267: HA, HB over the owned atoms, plus E_vdwl, E_coul) in the first
 // nbP blocks, the per-site sums (cpp:264-267 per site + north_star's dU/dlambda_s = sum dq_i dE/dq_i) in the
-// rest: one warp per site over its contiguous range of the site-major titratable-atom table, lanes striding,
-// shuffle tree -- a fixed order whatever the site size, no atomics.  The last block to finish (ticket counter)
+// rest: a group of lanes per site over its contiguous range of the site-major titratable-atom table, lanes striding,
+// shuffle butterfly -- a fixed order whatever the site size, no atomics.  The last block to finish (ticket counter)
 // adds the block partials in a fixed order and writes red[0..3].
 __global__ void __launch_bounds__(TPB)
 site_partition_kernel(int n, const double *__restrict__ eatom, const double *__restrict__ evdwl,
-                      const int *__restrict__ mask, int Hbit, int nbP, double *partials, int S,
+                      const int *__restrict__ mask, int Hbit, int nbP, double *partials, int S, int lps,
                       const int *__restrict__ site_start, const int *__restrict__ titr_local,
                       const double *__restrict__ titr_dq, const double *__restrict__ phi, int implicit_site,
                       double extra_HA, double extra_HB, const double *__restrict__ bonded_e, double *red,
@@ -71,29 +71,34 @@ site_partition_kernel(int n, const double *__restrict__ eatom, const double *__r
     }
     block_reduce_store<4>(v, partials);
   } else {
-    const int site = ((int)blockIdx.x - nbP) * (TPB / 32) + w;
+    // lps lanes per site (a power of two chosen from the largest site: 1 for one-atom sites, 8 for carboxyl /
+    // amine groups, 32 beyond), lanes striding over the site's range, butterfly inside the group
+    const int site = ((int)blockIdx.x - nbP) * (TPB / lps) + (int)threadIdx.x / lps;
+    const int sub = (int)threadIdx.x & (lps - 1);
+    double d = 0, hd = 0;
     if (site < S) {
-      double d = 0, hd = 0;
-      for (int t = site_start[site] + lane; t < site_start[site + 1]; t += 32) {
+      for (int t = site_start[site] + sub; t < site_start[site + 1]; t += lps) {
         const int k = titr_local[t];
         if (k >= 0) {                                         // owned by this rank (cpp:264: i < nlocal)
           d += titr_dq[t] * phi[k];                           // Appendix B
           if (mask[k] & Hbit) hd -= eatom[k];                 // HB_s - HA_s
         }
       }
-      for (int o = 16; o; o >>= 1) {
-        d += __shfl_xor_sync(0xffffffffu, d, o);
-        hd += __shfl_xor_sync(0xffffffffu, hd, o);
-      }
-      if (lane == 0) {
+    }
+    for (int o = lps >> 1; o; o >>= 1) {
+      d += __shfl_xor_sync(0xffffffffu, d, o);
+      hd += __shfl_xor_sync(0xffffffffu, hd, o);
+    }
+    if (site < S) {
+      if (sub == 0) {
         red[4 + site] = d;
         if (!implicit_site) red[4 + S + site] = hd;
       }
       // one-shot all-reduce over NVLink, push side: this rank's sums of the site go straight into its slot of
-      // every rank's mailbox (lane p stores to rank p; its own mailbox included)
-      if (lane < mr.P) {
-        mr.dst[lane][4 + site] = d;
-        if (!implicit_site) mr.dst[lane][4 + S + site] = hd;
+      // every rank's mailbox (the group's lanes share the ranks; its own mailbox included)
+      for (int p = sub; p < mr.P; p += lps) {
+        mr.dst[p][4 + site] = d;
+        if (!implicit_site) mr.dst[p][4 + S + site] = hd;
       }
     }
   }
@@ -418,14 +423,17 @@ __global__ void set_force_kernel(int nh, const int *__restrict__ hlist, const in
 // new positions from the caller (caller order) + the neighbor->decide() displacement test
 __global__ void set_x_kernel(int n, const double *__restrict__ xc, const int *__restrict__ perm,
                              const double *__restrict__ xbuild, double thresh2, const double *__restrict__ xinner,
-                             double thresh2_inner, double4 *xq, unsigned int *flags) {
+                             double thresh2_inner, double3 lo, double3 hi, double4 *xq, unsigned int *flags) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
-  float d2f = 0.f;
+  float d2f = 0.f, drift = 0.f;
   bool over = false, over_in = false;
   if (k < n) {
     size_t c = (size_t)perm[k] * 3;
     double x = xc[c], y = xc[c + 1], z = xc[c + 2];
     xq[k].x = x; xq[k].y = y; xq[k].z = z;
+    // how far outside its sub-box the atom sits (the next list build sizes the ghost shell with it)
+    const double e = fmax(fmax(lo.x - x, x - hi.x), fmax(fmax(lo.y - y, y - hi.y), fmax(lo.z - z, z - hi.z)));
+    drift = e > 0 ? __double2float_ru(e) : 0.f;
     double dx = x - xbuild[3 * (size_t)k], dy = y - xbuild[3 * (size_t)k + 1], dz = z - xbuild[3 * (size_t)k + 2];
     double d2 = dx * dx + dy * dy + dz * dz;
     over = d2 > thresh2;
@@ -435,23 +443,30 @@ __global__ void set_x_kernel(int n, const double *__restrict__ xc, const int *__
       over_in = dx * dx + dy * dy + dz * dz > thresh2_inner;
     }
   }
-  for (int o = 16; o; o >>= 1) d2f = fmaxf(d2f, __shfl_xor_sync(0xffffffffu, d2f, o));
+  for (int o = 16; o; o >>= 1) {
+    d2f = fmaxf(d2f, __shfl_xor_sync(0xffffffffu, d2f, o));
+    drift = fmaxf(drift, __shfl_xor_sync(0xffffffffu, drift, o));
+  }
   unsigned int any = __ballot_sync(0xffffffffu, over);
   unsigned int any_in = __ballot_sync(0xffffffffu, over_in);
   if ((threadIdx.x & 31) == 0) {
     if (d2f > 0.f) atomicMax(flags + 0, __float_as_uint(d2f));
+    if (drift > 0.f) atomicMax(flags + 2, __float_as_uint(drift));
     if (any) atomicOr(flags + 4, 1u);
     if (any_in) atomicOr(flags + 5, 1u);
   }
 }
 
 __global__ void check_kernel(int n, const double *__restrict__ xbuild, double thresh2, const double *__restrict__ xinner,
-                             double thresh2_inner, const double4 *__restrict__ xq, unsigned int *flags) {
+                             double thresh2_inner, double3 lo, double3 hi, const double4 *__restrict__ xq,
+                             unsigned int *flags) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
-  float d2f = 0.f;
+  float d2f = 0.f, drift = 0.f;
   bool over = false, over_in = false;
   if (k < n) {
     double4 p = xq[k];
+    const double e = fmax(fmax(lo.x - p.x, p.x - hi.x), fmax(fmax(lo.y - p.y, p.y - hi.y), fmax(lo.z - p.z, p.z - hi.z)));
+    drift = e > 0 ? __double2float_ru(e) : 0.f;
     double dx = p.x - xbuild[3 * (size_t)k], dy = p.y - xbuild[3 * (size_t)k + 1], dz = p.z - xbuild[3 * (size_t)k + 2];
     double d2 = dx * dx + dy * dy + dz * dz;
     over = d2 > thresh2;
@@ -461,11 +476,15 @@ __global__ void check_kernel(int n, const double *__restrict__ xbuild, double th
       over_in = dx * dx + dy * dy + dz * dz > thresh2_inner;
     }
   }
-  for (int o = 16; o; o >>= 1) d2f = fmaxf(d2f, __shfl_xor_sync(0xffffffffu, d2f, o));
+  for (int o = 16; o; o >>= 1) {
+    d2f = fmaxf(d2f, __shfl_xor_sync(0xffffffffu, d2f, o));
+    drift = fmaxf(drift, __shfl_xor_sync(0xffffffffu, drift, o));
+  }
   unsigned int any = __ballot_sync(0xffffffffu, over);
   unsigned int any_in = __ballot_sync(0xffffffffu, over_in);
   if ((threadIdx.x & 31) == 0) {
     if (d2f > 0.f) atomicMax(flags + 0, __float_as_uint(d2f));
+    if (drift > 0.f) atomicMax(flags + 2, __float_as_uint(drift));
     if (any) atomicOr(flags + 4, 1u);
     if (any_in) atomicOr(flags + 5, 1u);
   }
@@ -530,9 +549,10 @@ int cph_launch_partition(cph_handle *h, bool push) {
   }
   CPH_CUDA(h, h->d_part.reserve((size_t)MAXPART * 4));
   const int nbP = std::max(1, std::min(MAXPART, nblk(n)));
-  const int nbS = (S + TPB / 32 - 1) / (TPB / 32);
+  const int lps = h->site_lps;
+  const int nbS = (S + TPB / lps - 1) / (TPB / lps);
   site_partition_kernel<<<nbP + nbS, TPB, 0, st>>>(n, h->d_eatom.p, h->d_evdwl.p, h->d_mask.p, h->fix.Hbit, nbP,
-                                                  h->d_part.p, S, h->d_site_start.p, h->d_titr_local.p,
+                                                  h->d_part.p, S, lps, h->d_site_start.p, h->d_titr_local.p,
                                                   h->d_titr_dq.p, h->d_phi.p, h->fix.implicit_site, h->extra_HA,
                                                   h->extra_HB, h->have_topology ? h->d_bonded_e.p : nullptr,
                                                   h->d_red.p, h->d_flags.p + 80, mr);
@@ -633,9 +653,12 @@ int cph_launch_set_x(cph_handle *h, const double *xc) {
   const double *xin = h->inner_valid ? h->d_xinner.p : nullptr;
   if (n) {
     h->nlaunch++;
-    if (xc) set_x_kernel<<<nblk(n), TPB, 0, st>>>(n, xc, h->d_perm.p, h->d_xbuild.p, thresh2, xin, thresh2_in, h->d_xq.p,
-                                                 h->d_flags.p);
-    else check_kernel<<<nblk(n), TPB, 0, st>>>(n, h->d_xbuild.p, thresh2, xin, thresh2_in, h->d_xq.p, h->d_flags.p);
+    const double3 slo = make_double3(h->sublo[0], h->sublo[1], h->sublo[2]);
+    const double3 shi = make_double3(h->subhi[0], h->subhi[1], h->subhi[2]);
+    if (xc) set_x_kernel<<<nblk(n), TPB, 0, st>>>(n, xc, h->d_perm.p, h->d_xbuild.p, thresh2, xin, thresh2_in, slo, shi,
+                                                 h->d_xq.p, h->d_flags.p);
+    else check_kernel<<<nblk(n), TPB, 0, st>>>(n, h->d_xbuild.p, thresh2, xin, thresh2_in, slo, shi, h->d_xq.p,
+                                               h->d_flags.p);
   }
   CPH_CUDA(h, cudaGetLastError());
   return 0;
