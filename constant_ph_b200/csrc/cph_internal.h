@@ -11,8 +11,9 @@
 
 #define CPH_NEIGHMASK 0x1FFFFFFF   // LAMMPS NEIGHMASK: low 29 bits = atom index
 #define CPH_SBSHIFT 30             // LAMMPS SBBITS: top 2 bits = special-bond class (outer rows)
-#define CPH_TYPESHIFT 28           // inner rows: type of j in the top 4 bits, index in the low 28
-#define CPH_JMASK 0x0FFFFFFF
+#define CPH_TYPESHIFT 28           // inner rows: type of j in the top 4 bits, special-bond class in bits 26-27, index in the low 26
+#define CPH_SB2SHIFT 26
+#define CPH_JMASK 0x03FFFFFF
 #define CPH_MAIL_MAXP 8             // peer mailboxes serve up to 8 ranks (one NVSwitch domain); beyond that NCCL
 #define CPH_MAIL_FSLOT 16           // 32-bit words per flag slot: [0..5] flags, [8..9] sequence number
 #define CPH_MAXNT1 12              // ntypes+1 <= 12: the (ntypes+1)^2 * 32 B coefficient table lives in shared memory
@@ -87,11 +88,11 @@ struct EvalConst {
 
 struct EvalArgs {
   EvalConst c;
-  int nlocal, nt1, rowcap, rowcap2, nqueues, pf_atoms, dummy;
+  int nlocal, nt1, rowcap2, nqueues, pf_atoms;
   unsigned int pf_bytes;               // L2 prefetch of the inner rows: how far ahead, how many bytes
   int *qnext;                          // per-SM queue heads (pair.cu)
   const double4 *xq;
-  const int *type, *neigh, *numspec, *neigh2, *numneigh2, *type_has_lj;
+  const int *neigh2, *numneigh2;
   const double4 *coef;
   const double2 *cuts;
   const double *exp2;

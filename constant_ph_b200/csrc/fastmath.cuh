@@ -39,13 +39,10 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
   return fma(y, p, y);                                  // y (1 + e/2 + 3/8 e^2)
 #endif
 }
+template <int ORDER = CPH_REFINE_RCP>
 __device__ __forceinline__ double fast_rcp(double x) {
   const double y = rcp_seed(x);
   const double e = fma(-x, y, 1.0);
-#if CPH_REFINE_RCP == 2
-  return fma(y, e, y);                                  // y (1 + e): error e^2
-#else
-  return fma(y, fma(e, e, e), y);
-#endif
+  if (ORDER == 2) return fma(y, e, y);                  // y (1 + e): error e^2
+  return fma(y, fma(e, e, e), y);                       // y (1 + e + e^2): error e^3
 }
-

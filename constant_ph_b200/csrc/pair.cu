@@ -127,7 +127,10 @@ struct Acc {
 //   a.phi += q_j * K(r) / qqrd2e
 // UNI: every type pair has cut_lj == cut_coul == the one global cutoff (one exact fp64 decision);
 // otherwise the three decisions of SURVEY Appendix A are taken from the per-type-pair table.
-template <int STYLE, int EFLAG, bool LJ, bool UNI>
+// SPECIAL: the chunk may hold special-bond partners (class in bits 26-27 of the entry; only the LAST chunk of a row
+// does): their LJ and Coulomb terms are weighted with special_lj / special_coul, and under dsf the undamped term
+// (1 - factor_coul) q_i q_j qqrd2e / r is taken out of energy and force, branch-free.
+template <int STYLE, int EFLAG, bool LJ, bool UNI, bool SPECIAL = false>
 __device__ __forceinline__ void eval_one(const EvalConst &c, const double4 &pi, const double4 &pj, const int e,
                                          const double qiq, const unsigned int coef_i, const unsigned int cut_i,
                                          const unsigned int exp_tab, Acc &a) {
@@ -146,10 +149,17 @@ __device__ __forceinline__ void eval_one(const EvalConst &c, const double4 &pi, 
     in_lj = s < cc.x && s < cc.y;
   }
   const double y = fast_rsqrt(s);                        // 1/r
-  const double u = keep_if(in_c, pj.w * y);              // q_j / r, neutralised when out of range
+  double u = keep_if(in_c, pj.w * y);                    // q_j / r, neutralised when out of range
+  double f_lj = 1.0, omf = 0.0;                          // factor_lj, 1 - factor_coul
+  if (SPECIAL) {
+    const int sb = (e >> CPH_SB2SHIFT) & 3;
+    f_lj = c.flj[sb];
+    omf = c.one_m_fc[sb];
+    if (STYLE == CPH_PAIR_LJ_CUT_COUL_CUT) u *= c.fcoul[sb];
+  }
   double fp;
   if (STYLE == CPH_PAIR_LJ_CUT_COUL_CUT) {
-    if (EFLAG) a.phi += u;                               // E_ij = qqrd2e q_i q_j / r
+    if (EFLAG) a.phi += u;                               // E_ij = factor_coul qqrd2e q_i q_j / r
     fp = u * (y * y);
   } else {
     const double r = s * y;
@@ -172,15 +182,22 @@ __device__ __forceinline__ void eval_one(const EvalConst &c, const double4 &pi, 
     const double v = lds_f64(exp_tab + ((ni & 15) << 3)) * p;
     const double D = __hiloint2double(__double2hiint(v) + (int)((unsigned int)(ni & ~15) << 16), __double2loint(v));
     // LAMMPS' polynomial erfc: t = 1/(1 + p alpha r), erfcc = t (a1 + t (a2 + ...)) erfcd
-    const double t = fast_rcp(fma(c.pa, r, 1.0));
+    // special partners are all bonded pairs of like sign pattern (O-H, H-H): their terms add up coherently, and so
+    // would the always-negative 1e-12 error of the second-order step; the one chunk that holds them takes the third
+    const double t = fast_rcp<SPECIAL ? 3 : CPH_REFINE_RCP>(fma(c.pa, r, 1.0));
     double q = fma(t, c.a5, c.a4);
     q = fma(t, q, c.a3);
     q = fma(t, q, c.a2);
     q = fma(t, q, c.a1);
     const double E = (t * q) * D;
-    if (EFLAG) a.phi = fma(u, fma(-s, c.f_shift, fma(-r, c.e_shift, E)), a.phi);
+    double kk = fma(-s, c.f_shift, fma(-r, c.e_shift, E));
     // forcecoul / r^2 = q_i q_j qqrd2e / r * (erfcc/r + 2 alpha/sqrt(pi) erfcd + r f_shift) / r
-    const double fc = fma(E, y, fma(c.cD, D, r * c.f_shift));
+    double fc = fma(E, y, fma(c.cD, D, r * c.f_shift));
+    if (SPECIAL) {
+      kk -= omf;
+      fc = fma(-omf, y, fc);
+    }
+    if (EFLAG) a.phi = fma(u, kk, a.phi);
     fp = u * (fc * y);
   }
   if (LJ) {
@@ -188,10 +205,12 @@ __device__ __forceinline__ void eval_one(const EvalConst &c, const double4 &pi, 
     // two fp64 multiplies -- the fp64 pipe has the slack, the L1 data pipe does not (profiles/r2a_eval_ncu.txt)
     const double2 c34 = lds_v2f64(coef_i + (((unsigned int)e >> CPH_TYPESHIFT) << 4));
     const double r2 = y * y;
-    const double r6 = keep_if(in_lj, r2 * r2 * r2);
+    double r6 = keep_if(in_lj, r2 * r2 * r2);
+    double lj_scale = r2;
+    if (SPECIAL) lj_scale *= f_lj;
     const double t3 = c34.x * r6;                        // lj3 r^-6
-    fp = fma(qiq, fp, r6 * fma(12.0, t3, -6.0 * c34.y) * r2);
-    if (EFLAG) a.ev = fma(r6, t3 - c34.y, a.ev);
+    fp = fma(qiq, fp, r6 * fma(12.0, t3, -6.0 * c34.y) * lj_scale);
+    if (EFLAG) a.ev = fma(SPECIAL ? r6 * f_lj : r6, t3 - c34.y, a.ev);
   }
   a.fx = fma(dx, fp, a.fx);
   a.fy = fma(dy, fp, a.fy);
@@ -206,106 +225,30 @@ template <int STYLE, int EFLAG, bool LJ, bool UNI>
 __device__ __forceinline__ void row_loop(const EvalConst &c, const double4 *__restrict__ xq, const int *__restrict__ row,
                                          const int n2pad, const int lane, const double4 &pi, const double qiq,
                                          const unsigned int coef_i, const unsigned int cut_i, const unsigned int exp_tab,
-                                         const int dummy, Acc &a) {
+                                         Acc &a) {
   const int last = n2pad - 32 + lane;
-#if CPH_EVAL_ILP == 2
-  Acc a2;
-#endif
+  const int nmain = n2pad - 32;                          // the last chunk (special partners, padding) is evaluated apart
   // indices run TWO trips ahead of their use (they stream from HBM / L2), records one chunk ahead (mostly L1 hits)
   int eA = ld_stream(row + lane);
   int eB = ld_stream(row + min(lane + 32, last));
   int eC = ld_stream(row + min(lane + 64, last));
   int eD = ld_stream(row + min(lane + 96, last));
-#if CPH_EVAL_ILP == 2
-  // TWO pairs per lane per trip, evaluated side by side: the arithmetic of one pair is a chain of ~30 dependent
-  // fp64 operations (1/sqrt -> r -> 1/(1+p alpha r) -> erfc polynomial -> force), and eight such chains per
-  // scheduler do not fill the fp64 pipe (measured with the gathers switched off: profiles/r2f_limiter.md).  Two
-  // independent chains per warp do.  A second chunk past the row end is pointed at the far-away dummy atom.
   double4 pA = ld256(rec_addr(xq, (unsigned int)eA & CPH_JMASK));
-  if (32 >= n2pad) eB = dummy;
-  double4 pB = ld256(rec_addr(xq, (unsigned int)eB & CPH_JMASK));
-  for (int k = 0; k < n2pad; k += 64) {
-    if (k + 96 >= n2pad) eD = dummy;                      // warp-uniform: chunk k+96 does not exist
-    const double4 pC = ld256(rec_addr(xq, (unsigned int)eC & CPH_JMASK));
-    const double4 pD = ld256(rec_addr(xq, (unsigned int)eD & CPH_JMASK));
-    const int eE = ld_stream(row + min(k + 128 + lane, last));
-    const int eF = ld_stream(row + min(k + 160 + lane, last));
-    eval_one<STYLE, EFLAG, LJ, UNI>(c, pi, pA, eA, qiq, coef_i, cut_i, exp_tab, a);
-    eval_one<STYLE, EFLAG, LJ, UNI>(c, pi, pB, eB, qiq, coef_i, cut_i, exp_tab, a2);
-    pA = pC; pB = pD;
-    eA = eC; eB = eD; eC = eE; eD = eF;
-  }
-  a.fx += a2.fx; a.fy += a2.fy; a.fz += a2.fz; a.ev += a2.ev; a.phi += a2.phi;
-#elif CPH_EVAL_DEPTH == 2
-  // records TWO chunks ahead: nearly every 32-lane gather has at least one lane that misses L1, so a gather
-  // completes at L2 latency; two evaluations of distance cover it where one does not
-  double4 pA = ld256(rec_addr(xq, (unsigned int)eA & CPH_JMASK));
-  double4 pB = ld256(rec_addr(xq, (unsigned int)eB & CPH_JMASK));
-  for (int k = 0; k < n2pad; k += 64) {
-    const double4 pC = ld256(rec_addr(xq, (unsigned int)eC & CPH_JMASK));
-    const int eE = ld_stream(row + min(k + 128 + lane, last));
-    const int eF = ld_stream(row + min(k + 160 + lane, last));
-    eval_one<STYLE, EFLAG, LJ, UNI>(c, pi, pA, eA, qiq, coef_i, cut_i, exp_tab, a);
-    if (k + 32 >= n2pad) break;                          // warp-uniform
-    pA = ld256(rec_addr(xq, (unsigned int)eD & CPH_JMASK));
-    eval_one<STYLE, EFLAG, LJ, UNI>(c, pi, pB, eB, qiq, coef_i, cut_i, exp_tab, a);
-    pB = pA; pA = pC;                                    // (chunk k+64 -> A, chunk k+96 -> B)
-    eA = eC; eB = eD; eC = eE; eD = eF;
-  }
-#else
-  double4 pA = ld256(rec_addr(xq, (unsigned int)eA & CPH_JMASK));
-  for (int k = 0; k < n2pad; k += 64) {
+  for (int k = 0; k < nmain; k += 64) {
     const double4 pB = ld256(rec_addr(xq, (unsigned int)eB & CPH_JMASK));
     const int eE = ld_stream(row + min(k + 128 + lane, last));
     const int eF = ld_stream(row + min(k + 160 + lane, last));
     eval_one<STYLE, EFLAG, LJ, UNI>(c, pi, pA, eA, qiq, coef_i, cut_i, exp_tab, a);
-    if (k + 32 >= n2pad) break;                          // warp-uniform
+    if (k + 32 >= nmain) {                               // warp-uniform: chunk B is the last chunk of the row
+      pA = pB;
+      eA = eB;
+      break;
+    }
     pA = ld256(rec_addr(xq, (unsigned int)eC & CPH_JMASK));
     eval_one<STYLE, EFLAG, LJ, UNI>(c, pi, pB, eB, qiq, coef_i, cut_i, exp_tab, a);
     eA = eC; eB = eD; eC = eE; eD = eF;
   }
-#endif
-}
-
-// Slow path for special-bond pairs (factor_lj / factor_coul and, under
-// dsf, the -(1-factor_coul)*prefactor correction).  A handful of lanes per atom; libm arithmetic.
-template <int STYLE, int EFLAG>
-__device__ __noinline__ void eval_special(const EvalConst &c, const double4 *__restrict__ coef,
-                                          const double2 *__restrict__ cuts, int tt, double delx, double dely,
-                                          double delz, double rsq, double qi, double qj, int sb, double *out5) {
-  const double2 cc = cuts[tt];
-  out5[0] = out5[1] = out5[2] = out5[3] = out5[4] = 0.0;
-  if (rsq >= cc.y) return;
-  const double factor_lj = c.flj[sb], factor_coul = c.fcoul[sb];
-  const double rinv = 1.0 / sqrt(rsq);
-  const double r2inv = rinv * rinv;
-  double fpair = 0.0, ev = 0.0, ph = 0.0;
-  if (rsq < cc.x) {
-    const double4 k = coef[tt];
-    const double r6inv = r2inv * r2inv * r2inv;
-    fpair = factor_lj * r6inv * (k.x * r6inv - k.y) * r2inv;
-    ev = factor_lj * (r6inv * (k.z * r6inv - k.w));
-  }
-  if (rsq < c.cut_coulsq) {
-    if (STYLE == CPH_PAIR_LJ_CUT_COUL_CUT) {
-      const double k = c.qqrd2e * factor_coul * rinv;
-      fpair += qi * qj * k * r2inv;
-      ph = qj * k;
-    } else {
-      const double r = rsq * rinv;
-      const double erfcd = exp(c.neg_alpha2 * rsq);
-      const double t = 1.0 / (1.0 + c.pa * r);
-      const double erfcc = t * (c.a1 + t * (c.a2 + t * (c.a3 + t * (c.a4 + t * c.a5)))) * erfcd;
-      const double pre = c.qqrd2e * rinv;
-      double fc = erfcc * rinv + c.cD * erfcd + r * c.f_shift;
-      double kk = erfcc - r * c.e_shift - rsq * c.f_shift;
-      fc -= c.one_m_fc[sb] * rinv;
-      kk -= c.one_m_fc[sb];
-      fpair += qi * qj * pre * fc * rinv;
-      ph = qj * pre * kk;
-    }
-  }
-  out5[0] = delx * fpair; out5[1] = dely * fpair; out5[2] = delz * fpair; out5[3] = ev; out5[4] = ph;
+  eval_one<STYLE, EFLAG, LJ, UNI, true>(c, pi, pA, eA, qiq, coef_i, cut_i, exp_tab, a);
 }
 
 struct WarpSmem {
@@ -318,8 +261,9 @@ struct WarpSmem {
 // as (j | type_j << 28), padded to a multiple of 32 with the dummy atom.
 __global__ void __launch_bounds__(TPB, 4)
 prune_kernel(int nlocal, const float4 *__restrict__ xt, const int *__restrict__ neigh,
-             const int *__restrict__ numneigh, int rowcap, float cutf_inner, int dummy, int *__restrict__ neigh2,
-             int rowcap2, int *__restrict__ numneigh2) {
+             const int *__restrict__ numneigh, const int *__restrict__ numspec, int rowcap, float cutf_inner,
+             int dummy, const int *__restrict__ type_has_lj, int *__restrict__ neigh2, int rowcap2,
+             int *__restrict__ numneigh2) {
   __shared__ __align__(128) WarpSmem s_w[WARPS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const unsigned int ltmask = (1u << lane) - 1;
@@ -385,10 +329,31 @@ prune_kernel(int nlocal, const float4 *__restrict__ xt, const int *__restrict__ 
         cnt += __popc(m);
       }
     }
-    // an inner row never holds more than its outer row: cnt <= numneigh[i] <= rowcap2 - 32 (list build)
-    const int padded = (cnt + 31) & ~31;
+    // Special-bond partners (at the end of the outer row, class in bits 30-31) ride in the LAST chunk of the inner
+    // row, class in bits 26-27, where the evaluation kernel applies their factors; they use lanes that would
+    // otherwise hold padding.  If they do not fit behind the ordinary entries of the last chunk, that chunk is
+    // padded out and they get one of their own.  No distance test: an excluded pair is a bonded pair.
+    const int nsp = min(numspec[i], 32);
+    if (nsp > 0) {
+      if ((cnt & 31) + nsp > 32) {
+        const int padded0 = (cnt + 31) & ~31;
+        if (cnt + lane < padded0) row2[cnt + lane] = dummy | (1 << CPH_TYPESHIFT);
+        cnt = padded0;
+      }
+      if (lane < nsp) {
+        const int raw = neigh[(size_t)i * rowcap + (rowcap - 1 - lane)];
+        const int j = raw & CPH_NEIGHMASK, sb = (raw >> CPH_SBSHIFT) & 3;
+        row2[cnt + lane] = j | (sb << CPH_SB2SHIFT) | (__float_as_int(xt[j].w) << CPH_TYPESHIFT);
+      }
+      cnt += nsp;
+    }
+    // an inner row holds at most its outer row (ordinary + special entries) plus padding: <= rowcap2 (cph_launch_prune)
+    const int padded = max((cnt + 31) & ~31, 32);
     if (cnt + lane < padded) row2[cnt + lane] = dummy | (1 << CPH_TYPESHIFT);
-    if (lane == 0) numneigh2[i] = cnt;
+    if (lane == 0) {                                     // at least one (all-padding) chunk, so every row has a last chunk
+      const int ti = __float_as_int(pti.w);
+      numneigh2[i] = max(cnt, 1) | (ti << 24) | (type_has_lj[ti] ? 1 << 30 : 0);
+    }
   }
 }
 
@@ -456,17 +421,14 @@ pair_eval_kernel(const __grid_constant__ EvalArgs A) {
     return -1;
   };
   for (int i0 = next_claim(); i0 >= 0; i0 = next_claim()) {
-    const int iend = min(min(i0 + CLAIM, (i0 / per_q + 1) * per_q), A.nlocal);   // claims do not cross a range end
+    const int iend = min(min(i0 + CLAIM, (q + 1) * per_q), A.nlocal);   // claims do not cross a range end (q: the claim's range)
     for (int i = i0; i < iend; i++) {
-      // the next atom's scalars and the head of its row: into L1 now, so that its prologue does not wait on L2
-      if (i + 1 < iend && lane < 6) {
-        const int inext = i + 1;
-        const void *pf = lane == 0 ? (const void *)(A.xq + inext)
-                       : lane == 1 ? (const void *)(A.type + inext)
-                       : lane == 2 ? (const void *)(A.numneigh2 + inext)
-                       : lane == 3 ? (const void *)(A.numspec + inext)
-                                   : (const void *)(A.neigh2 + (size_t)inext * A.rowcap2 + (lane - 4) * 32);
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+      // the next atom's record, row length and the head of its row: into L1 now, so that its prologue does not wait on L2
+      if (i + 1 < iend && lane == 0) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(A.xq + i + 1));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(A.numneigh2 + i + 1));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(A.neigh2 + (size_t)(i + 1) * A.rowcap2));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(A.neigh2 + (size_t)(i + 1) * A.rowcap2 + 32));
       }
       // The inner rows stream from HBM exactly once; a row is asked for PF atoms before a warp of this SM gets to
       // it (the SM's warps take consecutive atoms), so its index loads find it in L2 instead of waiting ~1 us.
@@ -474,37 +436,22 @@ pair_eval_kernel(const __grid_constant__ EvalArgs A) {
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.neigh2 + (size_t)(i + A.pf_atoms) * A.rowcap2),
                      "r"(A.pf_bytes) : "memory");
       const double4 pi = A.xq[i];
-      const int ti = A.type[i];
-      const bool has_lj = A.type_has_lj[ti] != 0;       // warp-uniform: water H (2/3 of the atoms) skips all LJ work
-      const int n2pad = (A.numneigh2[i] + 31) & ~31;
+      const int packed = A.numneigh2[i];                // row length | type << 24 | "has an LJ partner" << 30 (prune kernel)
+      const int ti = (packed >> 24) & 15;
+      const bool has_lj = (packed >> 30) & 1;           // warp-uniform: water H (2/3 of the atoms) skips all LJ work
+      const int n2pad = ((packed & 0xffffff) + 31) & ~31;
       const int *row2 = A.neigh2 + (size_t)i * A.rowcap2;
       const double qiq = pi.w * c.qqrd2e;
       const unsigned int coef_i = coef0 + (unsigned int)(ti * nt1) * 16u, cut_i = cut0 + (unsigned int)(ti * nt1) * 16u;
       Acc a;
       if (n2pad) {
         if (has_lj) {
-          row_loop<STYLE, EFLAG, true, UNI>(c, A.xq, row2, n2pad, lane, pi, qiq, coef_i, cut_i, exp_tab, A.dummy, a);
+          row_loop<STYLE, EFLAG, true, UNI>(c, A.xq, row2, n2pad, lane, pi, qiq, coef_i, cut_i, exp_tab, a);
         } else {
-          row_loop<STYLE, EFLAG, false, UNI>(c, A.xq, row2, n2pad, lane, pi, qiq, coef_i, cut_i, exp_tab, A.dummy, a);
+          row_loop<STYLE, EFLAG, false, UNI>(c, A.xq, row2, n2pad, lane, pi, qiq, coef_i, cut_i, exp_tab, a);
           a.fx *= qiq; a.fy *= qiq; a.fz *= qiq;
         }
         if (EFLAG) a.phi *= c.qqrd2e;
-      }
-      const int nsp = A.numspec[i];
-      if (nsp > 0) {   // special-bond partners sit at the end of the OUTER row
-        if (lane < nsp) {
-          const int raw = A.neigh[(size_t)i * A.rowcap + (A.rowcap - 1 - lane)];
-          const int j = raw & CPH_NEIGHMASK, sb = (raw >> CPH_SBSHIFT) & 3;
-          const double4 pq = ld256(A.xq + j);
-          const int tt = ti * nt1 + A.type[j];
-          const double delx = pi.x - pq.x, dely = pi.y - pq.y, delz = pi.z - pq.z;
-          const double rsq = fma(delz, delz, fma(dely, dely, delx * delx));
-          double o5[5];
-          eval_special<STYLE, EFLAG>(c, A.coef, A.cuts, tt, delx, dely, delz, rsq, pi.w, pq.w, sb, o5);
-          a.fx += o5[0]; a.fy += o5[1]; a.fz += o5[2];
-          if (EFLAG) { a.ev += o5[3]; a.phi += o5[4]; }
-        }
-        __syncwarp();
       }
       for (int o = 16; o; o >>= 1) {
         a.fx += __shfl_xor_sync(0xffffffffu, a.fx, o);
@@ -551,8 +498,9 @@ __global__ void xt_kernel(int nall, const double4 *__restrict__ xq, const int *_
 __global__ void sum_int_kernel(int n, const int *__restrict__ v, unsigned long long *out2) {
   unsigned long long s = 0, sp = 0;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    s += (unsigned long long)v[k];
-    sp += (unsigned long long)((v[k] + 31) & ~31);
+    const int len = v[k] & 0xffffff;
+    s += (unsigned long long)len;
+    sp += (unsigned long long)((len + 31) & ~31);
   }
   for (int o = 16; o; o >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -625,15 +573,18 @@ int cph_launch_prune(cph_handle *h) {
   const double cut = std::sqrt(h->pp.cutsq_max) + h->inner_skin;
   const float cutf = (float)(cut * cut + 32.0 * cut * extent * 5.97e-8 + 1e-5 * cut * cut);
   // an inner row holds at most what its outer row holds (+ padding to 32)
-  h->rowcap2 = std::min(h->rowcap, ((h->maxneigh + 31) & ~31) + 32);
+  h->rowcap2 = ((h->maxneigh + 31) & ~31) + 64;   // ordinary + special entries, padding of the last ordinary chunk, one more chunk
+  if (h->nall + 1 > CPH_JMASK)
+    return cph_fail(h, CPH_ERR_OVERFLOW, "%d atoms and ghosts on this rank exceed the 26-bit indices of the inner rows", h->nall);
   CPH_CUDA(h, h->d_neigh2.reserve((size_t)n * h->rowcap2));
   CPH_CUDA(h, h->d_numneigh2.reserve(n + 1));
   CPH_CUDA(h, h->d_xinner.reserve(3 * (size_t)n + 3));
   if (h->rowcap / CH * APW > MAXTILES)
     return cph_fail(h, CPH_ERR_OVERFLOW, "neighbour rows of %d entries exceed the prune kernel's tile schedule", h->rowcap);
   h->nlaunch += 2;
-  prune_kernel<<<(n + APB - 1) / APB, TPB, 0, h->stream>>>(n, h->d_xt.p, h->d_neigh.p, h->d_numneigh.p, h->rowcap, cutf,
-                                                          h->nall, h->d_neigh2.p, h->rowcap2, h->d_numneigh2.p);
+  prune_kernel<<<(n + APB - 1) / APB, TPB, 0, h->stream>>>(n, h->d_xt.p, h->d_neigh.p, h->d_numneigh.p, h->d_numspec.p,
+                                                          h->rowcap, cutf, h->nall, h->d_type_has_lj.p, h->d_neigh2.p,
+                                                          h->rowcap2, h->d_numneigh2.p);
   snapshot_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(n, h->d_xq.p, h->d_xinner.p);
   CPH_CUDA(h, cudaGetLastError());
   h->inner_valid = true;
@@ -651,10 +602,10 @@ int cph_launch_pair(cph_handle *h, int eflag, const unsigned int *gate) {
   static const int ctas_env = getenv("CPH_EVAL_CTAS_PER_SM") ? atoi(getenv("CPH_EVAL_CTAS_PER_SM")) : 0;
   EvalArgs A;
   A.c = h->eval_const;
-  A.nlocal = n; A.nt1 = h->pp.ntypes + 1; A.rowcap = h->rowcap; A.rowcap2 = h->rowcap2; A.dummy = h->nall | (1 << CPH_TYPESHIFT);
-  A.xq = h->d_xq.p; A.type = h->d_type.p; A.neigh = h->d_neigh.p; A.numspec = h->d_numspec.p;
+  A.nlocal = n; A.nt1 = h->pp.ntypes + 1; A.rowcap2 = h->rowcap2;
+  A.xq = h->d_xq.p;
   A.neigh2 = h->d_neigh2.p; A.numneigh2 = h->d_numneigh2.p; A.coef = h->d_coef4.p; A.cuts = h->d_cut2.p;
-  A.type_has_lj = h->d_type_has_lj.p; A.exp2 = h->d_exp2.p;
+  A.exp2 = h->d_exp2.p;
   A.f = h->d_f.p; A.evdwl = h->d_evdwl.p; A.phi = h->d_phi.p; A.eatom = h->d_eatom.p; A.gate = gate;
   // persistent grid: as many 64-thread CTAs as are resident at once (16 per SM at <= 64 registers), but no more
   // warps than atoms; the per-SM queue heads are cleared in front of every launch
