@@ -88,7 +88,7 @@ struct EvalConst {
 
 struct EvalArgs {
   EvalConst c;
-  int nlocal, nt1, rowcap2, nqueues, pf_atoms;
+  int nlocal, nt1, rowcap2, nqueues, pf_atoms, maxscan, sweep;
   unsigned int pf_bytes;               // L2 prefetch of the inner rows: how far ahead, how many bytes
   int *qnext;                          // per-SM queue heads (pair.cu)
   const double4 *xq;

@@ -406,10 +406,15 @@ pair_eval_kernel(const __grid_constant__ EvalArgs A) {
   asm("mov.u32 %0, %%smid;" : "=r"(smid));
   const int nq = A.nqueues;
   const int per_q = (A.nlocal + nq - 1) / nq;
-  int q = __shfl_sync(0xffffffffu, (int)(smid % (unsigned int)nq), 0), scanned = 0;
+  // main launch: a warp starts on its SM's range and, when that is dry, helps on the next maxscan - 1 ranges (load
+  // balance at the end without walking all the ranges: every hop is an atomic round trip to L2).  The sweep launch
+  // that follows binds one CTA to every range instead (no hops): whatever the main launch left -- a range whose SM
+  // hosted no CTA, say -- is evaluated there, so the cover is exact whatever the block placement was.
+  const int maxscan = A.sweep ? 1 : A.maxscan;
+  int q = __shfl_sync(0xffffffffu, (int)((A.sweep ? blockIdx.x : smid) % (unsigned int)nq), 0), scanned = 0;
   // a claim is CLAIM consecutive atoms (one atomic round trip to L2 per CLAIM atoms)
   auto next_claim = [&]() -> int {
-    while (scanned < nq) {
+    while (scanned < maxscan) {
       int t = 0;
       if (lane == 0) t = atomicAdd(A.qnext + q, CLAIM);
       t = __shfl_sync(0xffffffffu, t, 0);                 // warp-uniform, and the compiler can tell
@@ -627,11 +632,18 @@ int cph_launch_pair(cph_handle *h, int eflag, const unsigned int *gate) {
   CPH_CUDA(h, cudaMemsetAsync(h->d_qnext.p, 0, h->num_sms * sizeof(int), h->stream));
   h->nlaunch++;
   static const int carve_env = getenv("CPH_EVAL_CARVEOUT") ? atoi(getenv("CPH_EVAL_CARVEOUT")) : -1;
+  static const int scan_env = getenv("CPH_EVAL_MAXSCAN") ? atoi(getenv("CPH_EVAL_MAXSCAN")) : 0;
+  A.maxscan = std::min(A.nqueues, scan_env > 0 ? scan_env : 4);
+  EvalArgs B = A;                                   // the sweep: one CTA per range, bound to it
+  B.sweep = 1;
+  A.sweep = 0;
+  h->nlaunch++;
 #define LAUNCH(S, E, U)                                                                                               \
   do {                                                                                                                \
     if (carve_env >= 0)                                                                                               \
       cudaFuncSetAttribute(pair_eval_kernel<S, E, U>, cudaFuncAttributePreferredSharedMemoryCarveout, carve_env);     \
     pair_eval_kernel<S, E, U><<<blocks, ETPB, 0, h->stream>>>(A);                                                     \
+    pair_eval_kernel<S, E, U><<<A.nqueues, ETPB, 0, h->stream>>>(B);                                                  \
   } while (0)
 #define LAUNCH_E(S, U) do { if (eflag) LAUNCH(S, 1, U); else LAUNCH(S, 0, U); } while (0)
   if (h->pp.style == CPH_PAIR_LJ_CUT_COUL_CUT) {

@@ -65,10 +65,13 @@ def parse(out):
         t = line.split()
         if not t:
             continue
-        if t[0].isupper():
-            extra[t[0]] = float(t[1])
-        else:
-            rows.append([float(v) for v in t])
+        try:
+            if t[0].isupper():
+                extra[t[0]] = float(t[1])
+            else:
+                rows.append([float(v) for v in t])
+        except ValueError:
+            continue           # e.g. the "NCCL version ..." banner of a multi-rank run
     return np.array(rows), extra
 
 
