@@ -395,8 +395,12 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]), float(t[1])
 
-    step_dev = lambda s: eng.post_force(s, box.dt, frames_d[s].data_ptr(), None, where=capi.DEVICE)
-    step_e2e = lambda s: eng.post_force(s, box.dt, frames_h[s].numpy(), f_h.numpy(), where=capi.HOST)
+    # pointers / views made once, outside the clock: the per-step Python work is one ctypes call
+    dev_ptr = [frames_d[s].data_ptr() for s in range(nfr)]
+    host_x = [frames_h[s].numpy() for s in range(nfr)]
+    host_f = f_h.numpy()
+    step_dev = lambda s: eng.post_force(s, box.dt, dev_ptr[s], None, where=capi.DEVICE)
+    step_e2e = lambda s: eng.post_force(s, box.dt, host_x[s], host_f, where=capi.HOST)
 
     # ---- value: device-resident -----------------------------------------------------------
     for s in range(W):

@@ -124,7 +124,12 @@ inline size_t mail_red_base(int P) { return ((size_t)2 * P * CPH_MAIL_FSLOT * 4 
 inline size_t mail_red_off(int P, size_t cap, int parity, int src) {
   return mail_red_base(P) + ((size_t)parity * P + src) * (cap + 2) * sizeof(double);
 }
-inline size_t mail_bytes(int P, size_t cap) { return mail_red_off(P, cap, 2, 0); }
+// third region: 32-int blocks for the all-gather of the list rebuild (send counts per direction), sequence number behind
+#define CPH_MAIL_GSLOT 40            // ints per gather slot: [0..31] payload, [32..33] sequence number
+inline size_t mail_gather_off(int P, size_t cap, int parity, int src) {
+  return mail_red_off(P, cap, 2, 0) + ((size_t)parity * P + src) * CPH_MAIL_GSLOT * sizeof(int);
+}
+inline size_t mail_bytes(int P, size_t cap) { return mail_gather_off(P, cap, 2, 0); }
 
 // where this rank's site-sum block goes (one slot per destination rank), and where the blocks of all ranks arrive
 struct MailRed {
@@ -244,7 +249,7 @@ struct cph_handle {
   bool mail_wanted = true;                       // CPH_MAIL=0: keep the two NCCL all-reduces (A/B)
   std::vector<void *> mail_base;                 // [nranks] mapped base of every rank's mailbox (own entry: d_mail.p)
   std::vector<unsigned char> mail_handle_cache;  // [nranks * 64]
-  unsigned long long seq_flags = 0, seq_red = 0; // reductions published so far
+  unsigned long long seq_flags = 0, seq_red = 0, seq_gather = 0; // reductions / gathers published so far
   bool red_pending = false;                      // site sums pushed; the totals are gathered by the next consumer
   DevBuf<int4> d_sendmeta, d_recvmeta;
   DevBuf<double> d_f, d_evdwl, d_phi, d_eatom;  // [3*nlocal], [nlocal]...

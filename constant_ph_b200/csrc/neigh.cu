@@ -504,7 +504,9 @@ int exclusive_scan(cph_handle *h, int n, int *in, int *out) {
   return 0;
 }
 
-void make_ghost_dirs(const cph_handle *h, GhostDirs &gd) {
+// the 27 directions as seen from the rank at grid position `myloc` (any rank's, not only this one's: the steady-state
+// rebuild derives every rank's receive layout locally from one all-gather of the send counts)
+void make_ghost_dirs_at(const cph_handle *h, const int *myloc, GhostDirs &gd) {
   auto rank_of = [&](const int *loc) { return (loc[2] * h->procgrid[1] + loc[1]) * h->procgrid[0] + loc[0]; };
   for (int d = 0; d < 27; d++) {
     int dv[3] = {d % 3 - 1, (d / 3) % 3 - 1, d / 9 - 1};
@@ -512,18 +514,18 @@ void make_ghost_dirs(const cph_handle *h, GhostDirs &gd) {
     bool remote = false;
     for (int k = 0; k < 3; k++) {
       gd.shift[d][k] = 0.0;
-      to[k] = fr[k] = h->myloc[k];
+      to[k] = fr[k] = myloc[k];
       if (dv[k] == 0) continue;
       const int pg = h->procgrid[k];
-      int nb = h->myloc[k] + dv[k], nf = h->myloc[k] - dv[k];
+      int nb = myloc[k] + dv[k], nf = myloc[k] - dv[k];
       if (!h->periodic[k]) {
         // non-periodic: a copy only exists if there is a neighbour rank in that direction
         if (nb < 0 || nb >= pg) active = 0;
         // (the mirror test for `from` is done by the sender; counts of absent senders are zero)
       } else {
         // periodic wrap: the copy lands across the box
-        if (dv[k] > 0 && h->myloc[k] == pg - 1) { gd.shift[d][k] = -(h->boxhi[k] - h->boxlo[k]); img[k] = -1; }
-        if (dv[k] < 0 && h->myloc[k] == 0) { gd.shift[d][k] = (h->boxhi[k] - h->boxlo[k]); img[k] = 1; }
+        if (dv[k] > 0 && myloc[k] == pg - 1) { gd.shift[d][k] = -(h->boxhi[k] - h->boxlo[k]); img[k] = -1; }
+        if (dv[k] < 0 && myloc[k] == 0) { gd.shift[d][k] = (h->boxhi[k] - h->boxlo[k]); img[k] = 1; }
       }
       to[k] = ((nb % pg) + pg) % pg;
       fr[k] = ((nf % pg) + pg) % pg;
@@ -537,12 +539,14 @@ void make_ghost_dirs(const cph_handle *h, GhostDirs &gd) {
     bool from_ok = (d != 13);
     for (int k = 0; k < 3; k++)
       if (dv[k] != 0 && !h->periodic[k]) {
-        int nf = h->myloc[k] - dv[k];
+        int nf = myloc[k] - dv[k];
         if (nf < 0 || nf >= h->procgrid[k]) from_ok = false;
       }
     if (!from_ok || !remote) gd.from[d] = -1;
   }
 }
+
+void make_ghost_dirs(const cph_handle *h, GhostDirs &gd) { make_ghost_dirs_at(h, h->myloc, gd); }
 
 template <typename T>
 int permute_buf(cph_handle *h, int n, const int *idx, DevBuf<T> &buf, DevBuf<T> &tmp, size_t total) {
@@ -694,6 +698,73 @@ void cph_mail_close(cph_handle *h) {
   h->mail_base.clear();
   h->mail_handle_cache.clear();
   h->mail_ok = false;
+}
+
+namespace {
+// All-gather of one 32-int block per rank through the mailboxes: post mine into my slot on every rank, wait for
+// everybody's sequence number in MY mailbox, copy the P blocks out.  One block of 32 * P threads.
+__global__ void mail_gather_kernel(const int *mine, int P, int me, unsigned long long seq, int *const *dst_slots,
+                                   const int *my_slots, int *out, unsigned int *status) {
+  const int p = threadIdx.x >> 5, k = threadIdx.x & 31;
+  if (p < P) dst_slots[p][k] = mine[k];                       // my block into rank p's mailbox
+  __threadfence_system();
+  __syncthreads();
+  if (k == 0 && p < P) *reinterpret_cast<volatile unsigned long long *>(dst_slots[p] + 32) = seq;
+  if (p < P) {
+    const int *slot = my_slots + (size_t)p * CPH_MAIL_GSLOT;  // rank p's block in MY mailbox
+    if (k == 0) {
+      const volatile unsigned long long *sq = reinterpret_cast<const volatile unsigned long long *>(slot + 32);
+      const long long t0 = clock64();
+      while (*sq != seq) {
+        if (clock64() - t0 > 400000000000LL) { atomicOr(status, 1u); break; }
+        __nanosleep(200);
+      }
+      __threadfence_system();
+    }
+    __syncwarp();
+    out[p * 32 + k] = reinterpret_cast<const volatile int *>(slot)[k];
+  }
+}
+}  // namespace
+
+// host blocks in (32 ints) and out (32 ints per rank); one kernel, one synchronisation
+static int mail_gather32(cph_handle *h, const int *mine32, int *all) {
+  const int P = h->nranks;
+  const unsigned long long seq = ++h->seq_gather;
+  const int par = (int)(seq & 1);
+  CPH_CUDA(h, h->d_ipc_stage.reserve(4096));
+  int *d_mine = (int *)h->d_ipc_stage.p;                      // [32] mine, [64..64+8 ptrs] slots, [256..] out
+  int **d_dst = (int **)(h->d_ipc_stage.p + 256);
+  int *d_out = (int *)(h->d_ipc_stage.p + 512);
+  int *dst_h[CPH_MAIL_MAXP];
+  for (int p = 0; p < P; p++)
+    dst_h[p] = (int *)((unsigned char *)h->mail_base[p] + mail_gather_off(P, h->mail_red_cap, par, h->rank));
+  CPH_CUDA(h, cudaMemcpyAsync(d_mine, mine32, 32 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CPH_CUDA(h, cudaMemcpyAsync(d_dst, dst_h, P * sizeof(int *), cudaMemcpyHostToDevice, h->stream));
+  h->nlaunch++;
+  mail_gather_kernel<<<1, 32 * P, 0, h->stream>>>(d_mine, P, h->rank, seq, d_dst,
+      (const int *)((unsigned char *)h->d_mail.p + mail_gather_off(P, h->mail_red_cap, par, 0)), d_out, h->d_flags.p + 83);
+  CPH_CUDA(h, cudaGetLastError());
+  CPH_CUDA(h, cudaMemcpyAsync(all, d_out, (size_t)P * 32 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// receive layout of the rank at grid position loc, from the matrix of every rank's send counts per direction:
+// the same rule cph_rebuild applies to itself (blocks grouped by source rank, directions in order inside a block)
+static void recv_layout_of(const cph_handle *h, const int *loc, const int *matrix32, int *recv_count, int *recv_off,
+                           int *nrecv_out) {
+  GhostDirs gd;
+  make_ghost_dirs_at(h, loc, gd);
+  int nrecv = 0;
+  for (int d = 0; d < 27; d++) {
+    recv_count[d] = gd.from[d] >= 0 ? matrix32[gd.from[d] * 32 + d] : 0;
+    recv_off[d] = 0;
+  }
+  for (int p = 0; p < h->nranks; p++)
+    for (int d = 0; d < 27; d++)
+      if (gd.from[d] == p) { recv_off[d] = nrecv; nrecv += recv_count[d]; }
+  *nrecv_out = nrecv;
 }
 
 // Map the neighbours' receive buffers (CUDA IPC).  Called at every list build: handles and
@@ -960,8 +1031,26 @@ int cph_rebuild(cph_handle *h) {
   for (int d = 0; d < 27; d++) { h->recv_count[d] = 0; h->recv_off[d] = 0; }
   h->peer_rank.clear(); h->peer_soff.clear(); h->peer_scnt.clear(); h->peer_roff.clear(); h->peer_rcnt.clear();
   if (h->nranks > 1) {
-    // counts first (one int per direction), then the records
-    CPH_TRY(cph_comm_exchange_counts(h, gd.active, gd.peer, gd.from, h->send_count, h->recv_count));
+    // Counts first (one int per direction), then the records.  Steady state (mailboxes mapped by an earlier build):
+    // ONE all-gather of every rank's 27 send counts through the mailboxes; each rank then derives its own receive
+    // counts, everybody's receive layout and the "does anyone have to grow its receive buffer" decision locally,
+    // so the five small NCCL calls + host synchronisations of the first build are not repeated.
+    const int P = h->nranks;
+    const bool fast = h->mail_ok && h->peer_halo && (int)h->peer_table.size() == P * 28;
+    std::vector<int> matrix;
+    auto loc_of = [&](int r, int *loc) {
+      loc[0] = r % h->procgrid[0]; loc[1] = (r / h->procgrid[0]) % h->procgrid[1]; loc[2] = r / (h->procgrid[0] * h->procgrid[1]);
+    };
+    if (fast) {
+      int mine[32] = {0};
+      for (int d = 0; d < 27; d++) mine[d] = h->send_count[d];
+      matrix.resize((size_t)P * 32);
+      CPH_TRY(mail_gather32(h, mine, matrix.data()));
+      int off_unused[27], n_unused;
+      recv_layout_of(h, h->myloc, matrix.data(), h->recv_count, off_unused, &n_unused);
+    } else {
+      CPH_TRY(cph_comm_exchange_counts(h, gd.active, gd.peer, gd.from, h->send_count, h->recv_count));
+    }
     for (int p = 0; p < h->nranks; p++) {
       int so = nsend, sc = 0, ro = nrecv, rc = 0;
       for (int d = 0; d < 27; d++) {
@@ -983,7 +1072,16 @@ int cph_rebuild(cph_handle *h) {
       // close, synchronise, then grow (with head room, so this is rare).
       unsigned int grow = ((size_t)nrecv + 1 > h->recv_half) ? 1u : 0u;
       unsigned int any_grow = grow;
-      CPH_TRY(cph_comm_allreduce_max_u32(h, &any_grow, 1));
+      if (fast) {   // every rank's need, from the matrix and the buffer sizes exchanged at the last mapping
+        for (int r = 0; r < P; r++) {
+          int loc[3], cnt[27], off[27], nr;
+          loc_of(r, loc);
+          recv_layout_of(h, loc, matrix.data(), cnt, off, &nr);
+          if ((size_t)nr + 1 > (size_t)h->peer_table[(size_t)r * 28 + 27]) any_grow = 1;
+        }
+      } else {
+        CPH_TRY(cph_comm_allreduce_max_u32(h, &any_grow, 1));
+      }
       if (any_grow) {
         cph_halo_close(h);
         unsigned int closed = 1;
@@ -1002,7 +1100,18 @@ int cph_rebuild(cph_handle *h) {
                                                   h->d_type.p, h->d_tag.p, h->d_mask.p,
                                                   h->have_mol ? h->d_mol.p : nullptr, h->d_sendx.p, h->d_sendmeta.p);
     CPH_TRY(halo_exchange(h, gd, true));
-    CPH_TRY(halo_map_peers(h, gd));
+    if (fast && h->peer_halo) {
+      // nobody grew: buffers, mappings and sizes are those of the last mapping; the receive offsets of every rank
+      // follow from the matrix
+      for (int r = 0; r < P; r++) {
+        int loc[3], cnt[27], off[27], nr;
+        loc_of(r, loc);
+        recv_layout_of(h, loc, matrix.data(), cnt, off, &nr);
+        for (int d = 0; d < 27; d++) h->peer_table[(size_t)r * 28 + d] = off[d];
+      }
+    } else {
+      CPH_TRY(halo_map_peers(h, gd));
+    }
   }
   h->nrecv = nrecv;
   const int nghost = nloc + nrecv;

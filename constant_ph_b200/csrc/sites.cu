@@ -208,6 +208,52 @@ __device__ __forceinline__ BiasOut bias_terms(const BiasParams &bp, double lambd
   return o;
 }
 
+// The same terms with the eight transcendental evaluations of a site spread over the eight lanes of its group
+// (sub = lane within the group): one exp / erf call deep instead of eight.  Every lane returns all four values.
+__device__ __forceinline__ BiasOut bias_terms_lanes(const BiasParams &bp, double lambda, int sub, int lane_base) {
+  const double a = bp.a, b = bp.b, s = bp.s, k = bp.k, d = bp.d, w = bp.w, r = bp.r, m = bp.m;
+  const double SQRT_PI = 1.77245385090551602729;
+  const bool exact = bp.mode == CPH_BIAS_EXACT;
+  const double m4 = exact ? m : 0.5;                                              // cpp:140 as written uses (lambda + 0.5)
+  double arg;
+  switch (sub) {
+    case 0: arg = -50.0 * (lambda - 0.5); break;                                  // cpp:122
+    case 1: arg = -(lambda - 1 - b) * (lambda - 1 - b) / (2 * a * a); break;      // cpp:132
+    case 2: arg = -(lambda + b) * (lambda + b) / (2 * a * a); break;              // cpp:133
+    case 3: arg = -(lambda - 0.5) * (lambda - 0.5) / (2 * s * s); break;          // cpp:134
+    case 4: arg = r * (lambda + m); break;                                        // cpp:135
+    case 5: arg = r * (lambda - 1 - m); break;                                    // cpp:136
+    case 6: arg = -r * r * (lambda + m4) * (lambda + m4); break;                  // cpp:140
+    default: arg = -r * r * (lambda - 1 - m) * (lambda - 1 - m); break;           // cpp:141
+  }
+  double val;
+  if (sub == 4 || sub == 5) val = exact ? erf(arg) : (double)erff((float)arg);    // D16
+  else val = exp(arg);
+  double e[8];
+#pragma unroll
+  for (int q = 0; q < 8; q++) e[q] = __shfl_sync(0xffffffffu, val, lane_base + q);
+  BiasOut o;
+  o.f = 1.0 / (1.0 + e[0]);
+  const double U1 = -k * e[1], U2 = -k * e[2], U3 = d * e[3];
+  const double U4 = 0.5 * w * (1 - e[4]), U5 = 0.5 * w * (1 + e[5]);
+  double dU1, dU2;
+  if (exact) {
+    o.df = 50.0 * e[0] * o.f * o.f;
+    dU1 = -((lambda - 1 - b) / (a * a)) * U1;                                     // D14
+    dU2 = -((lambda + b) / (a * a)) * U2;
+  } else {
+    o.df = 50.0 * e[0] / (o.f * o.f);                                             // cpp:123 verbatim
+    dU1 = -((lambda - 1 - b) / (2 * a * a)) * U1;                                 // cpp:137
+    dU2 = -((lambda + b) / (2 * a * a)) * U2;                                     // cpp:138
+  }
+  const double dU3 = -((lambda - 0.5) / (s * s)) * U3;                            // cpp:139
+  const double dU4 = -0.5 * w * r * 2 * e[6] / SQRT_PI;
+  const double dU5 = 0.5 * w * r * 2 * e[7] / SQRT_PI;
+  o.U = U1 + U2 + U3 + U4 + U5;             // cpp:143
+  o.dU = dU1 + dU2 + dU3 + dU4 + dU5;       // cpp:144
+  return o;
+}
+
 struct LambdaArgs {
   int S, phase, thermo, apply, thermo_post, nw;
   double dt, SkT, Q, inv_nw;         // inv_nw = 1 / n_W when the water buffer is on, else 0
@@ -248,31 +294,43 @@ lambda_update_kernel(const __grid_constant__ LambdaArgs A) {
     if (A.inv_nw != 0.0 && fx.dudl_mode == CPH_DUDL_CHARGE) wphi = A.inv_nw * mail_total(A.mr, 4 + 2 * S);
   }
   double v[3] = {0, 0, 0};   // sum of site terms of H_lambda, sum lambda*(HB_s-HA_s), kinetic
-  for (int s = blockIdx.x * TPB + threadIdx.x; s < S; s += gridDim.x * TPB) {
+  // eight lanes per site: they share the site's eight exp / erf evaluations and its titratable atoms; lane 0 of
+  // the group does the bookkeeping.  The loop bound is warp-uniform (whole groups), inactive groups idle inside.
+  const int sub = threadIdx.x & 7, lane_base = threadIdx.x & 24;
+  const int ngroups = gridDim.x * (TPB / 8);
+  for (int s0 = blockIdx.x * (TPB / 8); s0 < S; s0 += ngroups) {
+    const int s = min(s0 + (int)(threadIdx.x >> 3), S - 1);
+    const bool live = s0 + (int)(threadIdx.x >> 3) < S, lead = live && sub == 0;
     double cq = theta ? theta[s] : A.lam[s];
     double vel = A.vlam[s], acc = A.alam[s];
+    __syncwarp();            // every lane of the group holds the site's state before its lead lane overwrites it
     double lambda;
     if (phase == 1) {
       vel = vel * nh + 0.5 * acc * dt;
       cq += vel * dt;
       lambda = cq;
-      if (theta) { theta[s] = cq; const double sn = sin(cq); lambda = sn * sn; }
-      A.lam[s] = lambda;
-      A.vlam[s] = vel;
+      if (theta) { const double sn = sin(cq); lambda = sn * sn; }
+      if (lead) {
+        if (theta) theta[s] = cq;
+        A.lam[s] = lambda;
+        A.vlam[s] = vel;
+      }
     } else {
       double chain = 1.0;
       lambda = cq;
       if (theta) { const double sn = sin(cq); lambda = sn * sn; chain = sin(2.0 * cq); }
       if (phase == 3) vel = (vel + 0.5 * acc * dt) * nh;
-      BiasOut b = bias_terms(bp, lambda);
+      BiasOut b = bias_terms_lanes(bp, lambda, sub, lane_base);
       const double pk = fx.implicit_site ? fx.pK : A.pK[s];
       double hd, dq_e;
       if (gather) {          // fused all-reduce: totals over the ranks, written back for the getters
         hd = mail_total(A.mr, 4 + S + s);
         dq_e = mail_total(A.mr, 4 + s);
         if (wphi != 0.0) dq_e -= A.dQ[s] * wphi;
-        A.red[4 + S + s] = hd;
-        A.red[4 + s] = dq_e;
+        if (lead) {
+          A.red[4 + S + s] = hd;
+          A.red[4 + s] = dq_e;
+        }
       } else {
         hd = A.red[4 + S + s];
         dq_e = A.red[4 + s];
@@ -282,22 +340,27 @@ lambda_update_kernel(const __grid_constant__ LambdaArgs A) {
       const double f_lambda = -(dE + b.df * ph + b.dU);                 // cpp:111
       const double a_lambda = f_lambda * chain / bp.m_lambda * fx.ftm2v;   // cpp:112 (+ SURVEY D9)
       const double kin = 0.5 * bp.m_lambda * vel * vel / fx.ftm2v;
-      v[0] += b.f * ph + b.U + kin;                                     // cpp:114 site terms
-      v[1] += lambda * hd;                                              // cpp:114 lambda*(HB-HA)
-      v[2] += kin;
-      A.fs[s] = b.f; A.dfs[s] = b.df; A.Us[s] = b.U; A.dUs[s] = b.dU; A.flam[s] = f_lambda;
+      if (lead) {
+        v[0] += b.f * ph + b.U + kin;                                   // cpp:114 site terms
+        v[1] += lambda * hd;                                            // cpp:114 lambda*(HB-HA)
+        v[2] += kin;
+        A.fs[s] = b.f; A.dfs[s] = b.df; A.Us[s] = b.U; A.dUs[s] = b.dU; A.flam[s] = f_lambda;
+      }
       if (phase == 0) {
         cq = 0.5 * a_lambda * dt * dt + vel * dt + cq;                  // cpp:115
         vel = a_lambda * dt + vel;                                      // cpp:116
       }
       lambda = cq;
-      if (theta) { theta[s] = cq; const double sn = sin(cq); lambda = sn * sn; }
-      A.lam[s] = lambda;
-      A.vlam[s] = vel;
-      A.alam[s] = a_lambda;
+      if (theta) { const double sn = sin(cq); lambda = sn * sn; }
+      if (lead) {
+        if (theta) theta[s] = cq;
+        A.lam[s] = lambda;
+        A.vlam[s] = vel;
+        A.alam[s] = a_lambda;
+      }
     }
-    if (A.apply)    // the site's own atoms follow its lambda at once (owned atoms only)
-      for (int t = A.site_start[s]; t < A.site_start[s + 1]; t++) {
+    if (A.apply && live)    // the site's own atoms follow its lambda at once (owned atoms only), one lane each
+      for (int t = A.site_start[s] + sub; t < A.site_start[s + 1]; t += 8) {
         const int k = A.titr_local[t];
         if (k >= 0) A.xq[k].w = A.titr_qA[t] + lambda * A.titr_dq[t];
       }
@@ -569,7 +632,7 @@ int cph_launch_integrate(cph_handle *h, double dt, int phase, bool apply) {
   const int S = h->S;
   cudaStream_t st = h->stream;
   CPH_CUDA(h, h->d_part.reserve((size_t)MAXPART * 4));
-  const int nb = std::max(1, std::min(MAXPART, nblk(S)));
+  const int nb = std::max(1, std::min(MAXPART, (S + TPB / 8 - 1) / (TPB / 8)));   // eight lanes per site
   const int thermo = (h->nh_tau > 0 && h->fix.integ_mode == CPH_INTEGRATE_VV && (phase == 1 || phase == 3)) ? 1 : 0;
   const double SkT = S * h->fix.boltz * h->fix.T, Q = SkT * h->nh_tau * h->nh_tau;
   if (thermo && phase == 1) {
