@@ -255,7 +255,7 @@ __device__ __forceinline__ BiasOut bias_terms_lanes(const BiasParams &bp, double
 }
 
 struct LambdaArgs {
-  int S, phase, thermo, apply, thermo_post, nw;
+  int S, phase, thermo, apply, thermo_post, nw, lanes;
   double dt, SkT, Q, inv_nw;         // inv_nw = 1 / n_W when the water buffer is on, else 0
   BiasParams bp;
   FixParams fx;
@@ -296,11 +296,13 @@ lambda_update_kernel(const __grid_constant__ LambdaArgs A) {
   double v[3] = {0, 0, 0};   // sum of site terms of H_lambda, sum lambda*(HB_s-HA_s), kinetic
   // eight lanes per site: they share the site's eight exp / erf evaluations and its titratable atoms; lane 0 of
   // the group does the bookkeeping.  The loop bound is warp-uniform (whole groups), inactive groups idle inside.
-  const int sub = threadIdx.x & 7, lane_base = threadIdx.x & 24;
-  const int ngroups = gridDim.x * (TPB / 8);
-  for (int s0 = blockIdx.x * (TPB / 8); s0 < S; s0 += ngroups) {
-    const int s = min(s0 + (int)(threadIdx.x >> 3), S - 1);
-    const bool live = s0 + (int)(threadIdx.x >> 3) < S, lead = live && sub == 0;
+  // (A.lanes == 1, chosen for very many sites where throughput matters more than latency: one thread per site.)
+  const int gshift = A.lanes == 8 ? 3 : 0, glanes = 1 << gshift;
+  const int sub = threadIdx.x & (glanes - 1), lane_base = threadIdx.x & 24;
+  const int ngroups = gridDim.x * (TPB >> gshift);
+  for (int s0 = blockIdx.x * (TPB >> gshift); s0 < S; s0 += ngroups) {
+    const int s = min(s0 + (int)(threadIdx.x >> gshift), S - 1);
+    const bool live = s0 + (int)(threadIdx.x >> gshift) < S, lead = live && sub == 0;
     double cq = theta ? theta[s] : A.lam[s];
     double vel = A.vlam[s], acc = A.alam[s];
     __syncwarp();            // every lane of the group holds the site's state before its lead lane overwrites it
@@ -320,7 +322,7 @@ lambda_update_kernel(const __grid_constant__ LambdaArgs A) {
       lambda = cq;
       if (theta) { const double sn = sin(cq); lambda = sn * sn; chain = sin(2.0 * cq); }
       if (phase == 3) vel = (vel + 0.5 * acc * dt) * nh;
-      BiasOut b = bias_terms_lanes(bp, lambda, sub, lane_base);
+      BiasOut b = glanes == 8 ? bias_terms_lanes(bp, lambda, sub, lane_base) : bias_terms(bp, lambda);
       const double pk = fx.implicit_site ? fx.pK : A.pK[s];
       double hd, dq_e;
       if (gather) {          // fused all-reduce: totals over the ranks, written back for the getters
@@ -360,7 +362,7 @@ lambda_update_kernel(const __grid_constant__ LambdaArgs A) {
       }
     }
     if (A.apply && live)    // the site's own atoms follow its lambda at once (owned atoms only), one lane each
-      for (int t = A.site_start[s] + sub; t < A.site_start[s + 1]; t += 8) {
+      for (int t = A.site_start[s] + sub; t < A.site_start[s + 1]; t += glanes) {
         const int k = A.titr_local[t];
         if (k >= 0) A.xq[k].w = A.titr_qA[t] + lambda * A.titr_dq[t];
       }
@@ -632,7 +634,8 @@ int cph_launch_integrate(cph_handle *h, double dt, int phase, bool apply) {
   const int S = h->S;
   cudaStream_t st = h->stream;
   CPH_CUDA(h, h->d_part.reserve((size_t)MAXPART * 4));
-  const int nb = std::max(1, std::min(MAXPART, (S + TPB / 8 - 1) / (TPB / 8)));   // eight lanes per site
+  const int lanes = S <= 8192 ? 8 : 1;     // eight lanes per site (latency) up to a few thousand sites, one beyond (throughput)
+  const int nb = std::max(1, std::min(MAXPART, (S * lanes + TPB - 1) / TPB));
   const int thermo = (h->nh_tau > 0 && h->fix.integ_mode == CPH_INTEGRATE_VV && (phase == 1 || phase == 3)) ? 1 : 0;
   const double SkT = S * h->fix.boltz * h->fix.T, Q = SkT * h->nh_tau * h->nh_tau;
   if (thermo && phase == 1) {
@@ -640,7 +643,7 @@ int cph_launch_integrate(cph_handle *h, double dt, int phase, bool apply) {
     nh_pre_kernel<<<1, 32, 0, st>>>(h->d_scal.p, dt, SkT, Q);
   }
   LambdaArgs A;
-  A.S = S; A.phase = phase; A.thermo = thermo;
+  A.S = S; A.phase = phase; A.thermo = thermo; A.lanes = lanes;
   A.apply = (apply && h->ntitr > 0 && h->have_atoms) ? 1 : 0;
   A.thermo_post = (thermo && phase == 3 && dt > 0) ? 1 : 0;
   const bool water = h->water_n > 0 && h->fix.dudl_mode == CPH_DUDL_CHARGE;
