@@ -166,9 +166,10 @@ CONFIG_TEXT = {
         "amine solutes), lj/cut/coul/dsf rc=10 A alpha=0.2, skin 2 A, nevery=1, charge-derivative dU/dlambda, prescribed "
         "+-0.45 A molecular jiggle"),
     4: ("timesteps_per_s_cfg4_500k_atoms_per_gpu", "weak",
-        "BASELINE configs[3] stand-in: 4M-atom / 50k-site box weak-scaled at 500k atoms per GPU (%d atoms per GPU at "
-        "--atoms scale); the titratable monomers are 8-atom solutes in SPC/E water, not a bonded PAA chain; "
-        "lj/cut/coul/dsf, same motion and cadence as config 3"),
+        "BASELINE configs[3]: 4M-atom box with 50 000 titratable poly(acrylic acid) repeat units (9 atoms, one site "
+        "each) bonded into 25-unit chains in SPC/E water, weak-scaled at 500k atoms and 6250 sites per GPU (%d atoms "
+        "per GPU at --atoms scale); special-bond lists run along the backbone (up to 20 partners per atom); "
+        "lj/cut/coul/dsf, same motion and cadence as config 3 (a chain moves as one molecule)"),
     5: ("timesteps_per_s_cfg5_512k_dense_sites", "strong",
         "BASELINE configs[4]: dense titration stress test, 512k-atom box (%d at --atoms scale), 10 %% of the atoms "
         "titratable, one site each (51 200 sites), lj/cut/coul/dsf"),

@@ -89,6 +89,40 @@ _AMINE_QB = np.array([0.10, -0.96, 0.00, 0.34, 0.34, 0.06, 0.06, 0.06])    # dep
 _AMINE_BONDS = [(0, 1), (1, 2), (1, 3), (1, 4), (0, 5), (0, 6), (0, 7)]
 _AMINE_HGROUP = [2]
 
+# poly(acrylic acid) repeat unit -CH2-CH(COOH)-, 9 atoms, backbone along x at one lattice spacing per
+# monomer (a slightly stretched all-trans chain), the carboxyl group in the y-z plane; consecutive
+# monomers are bonded CH(3) - CH2'(0), so the special-bond lists run across monomers (BASELINE configs[3])
+_PAA_LOCAL = np.array([
+    [-0.776, -0.30, 0.00],   # 0 CT backbone CH2
+    [-0.776, -0.93, 0.89],   # 1 HC
+    [-0.776, -0.93, -0.89],  # 2 HC
+    [0.776, 0.30, 0.00],     # 3 CT backbone CH
+    [0.776, -0.25, 0.95],    # 4 HC
+    [0.776, 1.82, 0.00],     # 5 CC carboxyl carbon
+    [0.776, 2.44, 1.05],     # 6 OC carbonyl oxygen
+    [0.776, 2.50, -1.12],    # 7 OH hydroxyl oxygen
+    [0.776, 3.46, -1.02],    # 8 HO titratable proton
+])
+_PAA_TYPE = np.array([3, 8, 8, 3, 8, 4, 5, 6, 7], dtype=np.int32)
+_PAA_QA = np.array([-0.18, 0.09, 0.09, -0.12, 0.09, 0.75, -0.55, -0.61, 0.44])   # protonated, sum 0
+_PAA_QB = np.array([-0.18, 0.09, 0.09, -0.19, 0.09, 0.62, -0.76, -0.76, 0.00])   # deprotonated, sum -1
+_PAA_BONDS = [(0, 1), (0, 2), (0, 3), (3, 4), (3, 5), (5, 6), (5, 7), (7, 8)]
+_PAA_LINK = (3, 0)           # CH of monomer m - CH2 of monomer m+1
+_PAA_HGROUP = [8]
+_PAA_Y_MID = 1.265           # middle of the monomer's y extent: it sits across two emptied lattice rows
+
+
+def _paa_chain(nmono, pitch):
+    """Local coordinates, types and bond list of one chain of `nmono` repeat units."""
+    xs = [_PAA_LOCAL + np.array([m * pitch, 0.0, 0.0]) for m in range(nmono)]
+    bonds = []
+    for m in range(nmono):
+        bonds += [(9 * m + a, 9 * m + b) for a, b in _PAA_BONDS]
+        if m + 1 < nmono:
+            bonds.append((9 * m + _PAA_LINK[0], 9 * (m + 1) + _PAA_LINK[1]))
+    return np.concatenate(xs), np.tile(_PAA_TYPE, nmono), bonds
+
+
 PK_CARBOXYL = 4.76
 PK_AMINE = 10.6
 
@@ -216,13 +250,14 @@ def _lattice_dims(n_atoms_target):
 
 def make_box(name="custom", n_atoms=3000, n_acid=1, n_amine=0, style=STYLE_COUL_CUT,
              seed=1, cut=10.0, skin=2.0, alpha=0.2, pH=4.8, T=300.0, dense_titr_frac=0.0,
-             jitter=0.3, shuffle=False, special_14=0.5, md_safe=False):
+             jitter=0.3, shuffle=False, special_14=0.5, md_safe=False, n_paa=0, chain_len=25):
     """Build a water + solute box.
 
     n_acid / n_amine solutes each take three lattice slots along x (the solute
     sits in the middle one) so that no water overlaps them.  dense_titr_frac > 0
     additionally turns that fraction of *water* atoms into single-atom sites
-    (BASELINE config 5).
+    (BASELINE config 5).  n_paa > 0 adds that many poly(acrylic acid) repeat units, one site each, bonded
+    into chains of `chain_len` units that run along x across two emptied lattice rows (BASELINE config 4).
 
     md_safe: a start that real dynamics can run from.  The default placement lets
     solutes sit in adjacent lattice rows, where their 8-atom bodies interpenetrate -- harmless for
@@ -255,6 +290,22 @@ def make_box(name="custom", n_atoms=3000, n_acid=1, n_amine=0, style=STYLE_COUL_
                 for dj, dk in ((1, 0), (-1, 0), (0, 1), (0, -1)):
                     occupied[i, (j + dj) % ny, (k + dk) % nz] = 2
             centres.append((i, j, k))
+    # chains: `chain_len` slots along x in rows j and j+1, one free slot between chains of a row, every other
+    # z layer (the carboxyl groups of chains in adjacent layers would interpenetrate)
+    chains = []
+    if n_paa:
+        if n_paa % chain_len or chain_len + 1 > nx:
+            raise ValueError("n_paa must be a multiple of chain_len and a chain must fit the box")
+        ccand = [(i, j, k) for i in range(0, nx - chain_len + 1, chain_len + 1) for j in range(0, ny - 1, 2)
+                 for k in range(0, nz, 2) if not occupied[i:i + chain_len, j:j + 2, k].any()]
+        if len(ccand) < n_paa // chain_len:
+            raise ValueError("box too small for %d chains" % (n_paa // chain_len))
+        pick = rng.choice(len(ccand), size=n_paa // chain_len, replace=False)
+        pick.sort()
+        for p in pick:
+            i, j, k = ccand[p]
+            occupied[i:i + chain_len, j:j + 2, k] = 2
+            chains.append((i, j, k))
     wi, wj, wk = np.nonzero(occupied == 0)
     nwat = wi.size
 
@@ -270,8 +321,12 @@ def make_box(name="custom", n_atoms=3000, n_acid=1, n_amine=0, style=STYLE_COUL_
     mol = [np.repeat(np.arange(1, nwat + 1, dtype=np.int32), 3)]
     maxspecial = 7 if nsol else 2
     wt = _special_template(3, _WATER_BONDS)
+    if n_paa:
+        cx, ctype, cbonds = _paa_chain(chain_len, spacing)
+        ct = _special_template(9 * chain_len, cbonds)
+        maxspecial = max(maxspecial, max(len(a) + len(b) + len(c) for a, b, c in ct))
 
-    n = n_w_atoms + 8 * nsol
+    n = n_w_atoms + 8 * nsol + 9 * n_paa
     nspecial = np.zeros((n, 3), dtype=np.int32)
     special = np.zeros((n, maxspecial), dtype=np.int32)
     base = np.arange(nwat, dtype=np.int32) * 3 + 1                       # tag of atom 0 of each water
@@ -324,6 +379,31 @@ def make_box(name="custom", n_atoms=3000, n_acid=1, n_amine=0, style=STYLE_COUL_
                 qB.append(b_q[a])
         pK.append(PK_CARBOXYL if kind == 0 else PK_AMINE)
         off += 8
+    # --- poly(acrylic acid) chains: one molecule per chain, one site per repeat unit ---------------
+    nchain_atoms = 9 * chain_len
+    for c, (i, j, k) in enumerate(chains):
+        c0 = np.array([(i + 0.5) * spacing, (j + 1.0) * spacing - _PAA_Y_MID, (k + 0.5) * spacing])
+        x.append(c0 + cx)
+        q.append(np.tile(_PAA_QA, chain_len))
+        typ.append(ctype)
+        mol.append(np.full(nchain_atoms, nwat + 1 + nsol + c, dtype=np.int32))
+        for a in range(nchain_atoms):
+            l12, l13, l14 = ct[a]
+            nspecial[off + a] = (len(l12), len(l12) + len(l13), len(l12) + len(l13) + len(l14))
+            for cc, b in enumerate(l12 + l13 + l14):
+                special[off + a, cc] = off + b + 1
+        for m in range(chain_len):
+            site = nsol + c * chain_len + m
+            for a in _PAA_HGROUP:
+                mask[off + 9 * m + a] |= GROUP_H_BIT
+            for a in range(9):
+                if _PAA_QA[a] != _PAA_QB[a]:
+                    titr_tag.append(off + 9 * m + a + 1)
+                    titr_site.append(site)
+                    qA.append(_PAA_QA[a])
+                    qB.append(_PAA_QB[a])
+            pK.append(PK_CARBOXYL)
+        off += nchain_atoms
 
     x = np.concatenate(x).astype(np.float64)
     q = np.concatenate(q).astype(np.float64)
@@ -331,7 +411,7 @@ def make_box(name="custom", n_atoms=3000, n_acid=1, n_amine=0, style=STYLE_COUL_
     mol = np.concatenate(mol).astype(np.int32)
     tag = np.arange(1, n + 1, dtype=np.int32)
 
-    nsites = nsol
+    nsites = nsol + n_paa
     # --- dense single-atom sites on water atoms (config 5) --------------------
     if dense_titr_frac > 0.0:
         nd = int(round(dense_titr_frac * n))
@@ -393,7 +473,8 @@ def make_box(name="custom", n_atoms=3000, n_acid=1, n_amine=0, style=STYLE_COUL_
         skin=skin, nsites=nsites, pK=pK, titr_tag=titr_tag, titr_site=titr_site, qA=qA, qB=qB,
         lambda0=lam0, v0=np.zeros(nsites), pH=pH, T=T, dt=1.0,
         meta={"seed": seed, "lattice": (nx, ny, nz), "n_water": int(nwat), "n_acid": n_acid,
-              "n_amine": n_amine, "tag_to_index": tag_to_index},
+              "n_amine": n_amine, "n_paa": n_paa, "chain_len": chain_len if n_paa else 0,
+              "tag_to_index": tag_to_index},
     )
 
 
@@ -412,9 +493,11 @@ def config(k, scale=1.0, **kw):
         return make_box("cfg3", n_atoms=int(1_000_000 * scale), n_acid=ns // 2, n_amine=ns - ns // 2,
                         style=STYLE_COUL_DSF, seed=3, pH=kw.pop("pH", 7.0), **kw)
     if k == 4:
-        # stand-in for the 4M-atom PAA melt: same atom / site counts, solutes as monomers
-        ns = max(2, int(50_000 * scale))
-        return make_box("cfg4", n_atoms=int(4_000_000 * scale), n_acid=ns, n_amine=0,
+        # 4M atoms, 50 000 titratable repeat units of poly(acrylic acid) in bonded 25-unit chains, in water
+        clen = kw.pop("chain_len", 25)
+        ns = max(clen, int(50_000 * scale) // clen * clen)
+        # a repeat unit (9 atoms) takes the place of two waters (6 atoms): aim the lattice at the stated total
+        return make_box("cfg4", n_atoms=int(4_000_000 * scale) - 3 * ns, n_acid=0, n_amine=0, n_paa=ns, chain_len=clen,
                         style=STYLE_COUL_DSF, seed=4, pH=kw.pop("pH", 4.8), **kw)
     if k == 5:
         return make_box("cfg5", n_atoms=int(512_000 * scale), n_acid=0, n_amine=0,
@@ -520,8 +603,9 @@ class Topology:
 def _type_tables():
     """Bond types keyed on the unordered atom-type pair, angle types on (end, centre, end)."""
     bonds, angles = {}, {}
+    spacing = (1.0 / 0.0334) ** (1.0 / 3.0)
     for local, types, blist in ((_WATER_LOCAL, _WATER_TYPE, _WATER_BONDS), (_ACID_LOCAL, _ACID_TYPE, _ACID_BONDS),
-                                (_AMINE_LOCAL, _AMINE_TYPE, _AMINE_BONDS)):
+                                (_AMINE_LOCAL, _AMINE_TYPE, _AMINE_BONDS), _paa_chain(3, spacing)):
         water = local is _WATER_LOCAL
         adj = [[] for _ in range(len(types))]
         for a, b in blist:

@@ -33,6 +33,36 @@ def test_topology_generator_is_consistent():
     assert topo.bond_k[1] == pytest.approx(529.581) and topo.bond_r0[1] == pytest.approx(1.012)
 
 
+def test_chain_box_topology_runs_along_the_backbone():
+    """BASELINE config 4: poly(acrylic acid) repeat units bonded into chains.  8 bonds inside a unit plus one link
+    to the next unit; special lists are symmetric and cross unit boundaries; every unit is one site of net charge
+    0 (protonated) / -1 (deprotonated)."""
+    box = synth.config(4, scale=0.008, chain_len=10)
+    nm, cl = box.meta["n_paa"], box.meta["chain_len"]
+    assert (nm, cl, box.nsites) == (400, 10, 400)
+    topo = synth.topology(box)
+    assert topo.num_bond.sum() // 2 == 2 * box.meta["n_water"] + 8 * nm + (nm // cl) * (cl - 1)
+    t2i = box.meta["tag_to_index"]
+    # special partners are mutual, class by class
+    edges = [set(), set(), set()]
+    for i in range(3 * box.meta["n_water"], box.n):
+        lo = 0
+        for c in range(3):
+            for k in range(lo, box.nspecial[i, c]):
+                edges[c].add((int(box.tag[i]), int(box.special[i, k])))
+            lo = box.nspecial[i, c]
+    for c in range(3):
+        assert all((b, a) in edges[c] for a, b in edges[c])
+    first = 3 * box.meta["n_water"]
+    ch_tag, next_ch2 = int(box.tag[first + 3]), int(box.tag[first + 9])
+    assert (ch_tag, next_ch2) in edges[0]                                     # the link bond
+    assert box.maxspecial == 20 and box.nspecial[:, 2].max() == 20
+    q0 = box.charges_at(np.zeros(box.nsites))[first:].reshape(nm, 9).sum(axis=1)
+    q1 = box.charges_at(np.ones(box.nsites))[first:].reshape(nm, 9).sum(axis=1)
+    assert np.allclose(q0, 0.0, atol=1e-12) and np.allclose(q1, -1.0, atol=1e-12)
+    assert len(np.unique(box.molecule[first:])) == nm // cl                   # a chain is one molecule
+
+
 def test_md_safe_start_has_no_interpenetrating_molecules():
     """The headline boxes let neighbouring solutes overlap (harmless for prescribed motion, an LJ-core explosion
     for an integrator: profiles/r1_scaling_and_bench.md).  md_safe keeps every pair of LJ-carrying atoms of

@@ -336,10 +336,10 @@ def test_full_size_config5_dense_sites_against_oracle(built):
 
 
 def test_config4_scaled_many_solutes(built):
-    """BASELINE config 4 (polyelectrolyte stand-in: many titratable solutes) at 1/40 size:
-    100k atoms, 1250 eight-atom sites, against the oracle."""
+    """BASELINE config 4 (bonded poly(acrylic acid) chains, one site per repeat unit) at 1/40 size:
+    100k atoms, 50 chains of 25 units, special-bond lists of up to 20 partners, against the oracle."""
     box = synth.config(4, scale=0.025)
-    assert box.nsites == 1250
+    assert box.nsites == 1250 and box.maxspecial == 20
     gpu, orc = engines(box, bias=HEAVY)
     check_pass(gpu, orc)
     ng, kg = gpu.get_neighbors()

@@ -93,9 +93,9 @@ def test_nevery_gate_and_argument_errors():
 
 
 # ---- internal consistency of the restated pair arithmetic ----------------------------------------------
-@pytest.mark.parametrize("cfg,scale", [(1, 1.0), (2, 0.2)])
+@pytest.mark.parametrize("cfg,scale", [(1, 1.0), (2, 0.2), (4, 0.008)])
 def test_energy_partition_and_newton(cfg, scale):
-    box = synth.config(cfg, scale=scale)
+    box = synth.config(cfg, scale=scale, **({"chain_len": 10} if cfg == 4 else {}))
     o = capi.configure(capi.Engine("orc"), box)
     o.pair_pass(1); o.site_reduce()
     s = o.get_scalars()
@@ -111,11 +111,12 @@ def test_energy_partition_and_newton(cfg, scale):
     assert abs(0.5 * (q * phi).sum() - s["ecoul"]) < 1e-10 * abs(s["ecoul"])
 
 
-@pytest.mark.parametrize("cfg,scale", [(1, 1.0), (2, 0.2)])
+@pytest.mark.parametrize("cfg,scale", [(1, 1.0), (2, 0.2), (4, 0.008)])
 def test_analytic_dudl_equals_perturbed_charge_reevaluation(cfg, scale):
     """north_star: dU/dlambda from re-evaluating the pair energy at lambda +- dlambda.  E is
-    quadratic in each lambda_s, so the central difference equals the analytic value."""
-    box = synth.config(cfg, scale=scale)
+    quadratic in each lambda_s, so the central difference equals the analytic value.  Config 4: bonded chains,
+    neighbouring sites are 1-3 / 1-4 partners of each other."""
+    box = synth.config(cfg, scale=scale, **({"chain_len": 10} if cfg == 4 else {}))
     o = capi.configure(capi.Engine("orc"), box)
     o.pair_pass(1); o.site_reduce()
     dudl = o.get_sites()["dudl"].copy()
