@@ -52,13 +52,6 @@ constexpr int CH = 128;           // candidates per tile (4 per lane)
 constexpr int NBUF = 4;           // tiles in flight per warp
 constexpr int MAXTILES = 64;      // per-warp tile schedule entries (rows of up to 2048 neighbours)
 
-#ifndef CPH_EVAL_ILP
-#define CPH_EVAL_ILP 1                // pairs per lane evaluated side by side (1 or 2)
-#endif
-#ifndef CPH_EVAL_DEPTH
-#define CPH_EVAL_DEPTH 1              // chunks of neighbour records in flight ahead of the evaluation (1 or 2)
-#endif
-
 // ---- small PTX helpers ------------------------------------------------------------------------
 __device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ double lds_f64(unsigned int a) {
@@ -74,11 +67,6 @@ __device__ __forceinline__ double2 lds_v2f64(unsigned int a) {
 // the fp64 record {x,y,z,q} of one atom: one 32-byte request per lane (LDG.E.ENL2.256 on sm_100a)
 __device__ __forceinline__ double4 ld256(const void *p) {
   double4 v;
-#ifdef CPH_EXP_NOGATHER   // limiter experiment: the arithmetic alone, records synthesised from the address
-  const unsigned long long a = (unsigned long long)p;
-  const double t = (double)(unsigned int)(a >> 5 & 1023u);
-  return make_double4(3.0 + 0.001 * t, 4.0 + 0.002 * t, 5.0 - 0.001 * t, 0.4);
-#endif
   asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
   return v;
 }
@@ -136,10 +124,6 @@ __device__ __forceinline__ void eval_one(const EvalConst &c, const double4 &pi, 
                                          const unsigned int exp_tab, Acc &a) {
   const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
   const double s = fma(dz, dz, fma(dy, dy, dx * dx));
-#ifdef CPH_EXP_NOMATH     // limiter experiment: the memory side alone (gathers, index stream), no pair arithmetic
-  a.fx = fma(s, pj.w, a.fx);
-  return;
-#endif
   bool in_c, in_lj;
   if (UNI) {
     in_c = in_lj = s < c.cutsq;                          // the exact (fp64) cutoff decision
