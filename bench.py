@@ -74,8 +74,14 @@ def parity_check(eng, box, frame, golden, allsum):
         tot = allsum([float(np.abs(eng.get_forces()).sum()), float(c["neighbors"]), float(c["special_pairs"]),
                       float(c["nlocal"])])
         gd = np.array(g["dudl"])
-        worst["dudl_max_rel"] = max(worst["dudl_max_rel"], float(np.abs(t["dudl"] - gd).max() / np.abs(gd).max()))
-        worst["lambda_max_abs"] = max(worst["lambda_max_abs"], float(np.abs(t["lambda"] - np.array(g["lambda"])).max()))
+        idx = np.array(golden["site_index"]) if "site_index" in golden else np.arange(gd.size)   # sampled sites
+        worst["dudl_max_rel"] = max(worst["dudl_max_rel"], float(np.abs(t["dudl"][idx] - gd).max() / np.abs(gd).max()))
+        if "dudl_sum" in g:       # all sites, through their first two moments
+            sq = float((t["dudl"] * t["dudl"]).sum())
+            worst["dudl_max_rel"] = max(worst["dudl_max_rel"], abs(sq - g["dudl_sq_sum"]) / g["dudl_sq_sum"],
+                                        abs(float(t["dudl"].sum()) - g["dudl_sum"]) / np.sqrt(g["dudl_sq_sum"]))
+        worst["lambda_max_abs"] = max(worst["lambda_max_abs"],
+                                      float(np.abs(t["lambda"][idx] - np.array(g["lambda"])).max()))
         for k in ("HA", "HB", "evdwl", "ecoul", "H_lambda"):
             worst["energy_rel"] = max(worst["energy_rel"], abs(s[k] - g["scalars"][k]) / abs(g["scalars"][k]))
         worst["force_abs_sum_rel"] = max(worst["force_abs_sum_rel"], abs(tot[0] - g["f_abs_sum"]) / g["f_abs_sum"])
@@ -84,7 +90,7 @@ def parity_check(eng, box, frame, golden, allsum):
     ok = (worst["dudl_max_rel"] <= 1e-10 and worst["energy_rel"] <= 1e-10 and worst["lambda_max_abs"] <= 1e-8
           and worst["force_abs_sum_rel"] <= 1e-10 and neighbors_equal)
     return dict(worst, neighbors_equal=bool(neighbors_equal), ok=bool(ok), halo=eng.get_halo_mode(),
-                against="tests/golden/cfg3_full_golden.json (oracle, steps 0 and 3 of this trajectory)")
+                against="%s (oracle, steps 0 and 3 of this trajectory)" % golden.get("path", "tests/golden"))
 
 
 class ClockSampler:
@@ -359,9 +365,12 @@ def main():
         return [float(v) for v in t.cpu()]
 
     # ---- parity of THIS engine on THIS workload against the committed oracle values, at every rank count ------
-    check = {"skipped": "golden values exist for the full-size workload only (--atoms 1000000)"}
-    if os.path.exists(GOLDEN_CFG3) and args.config == 3 and args.atoms == 1_000_000 and not args.no_check:
-        golden = json.load(open(GOLDEN_CFG3))
+    check = {"skipped": "golden values exist for the full-size workloads only (--atoms 1000000; config 4: 1/2/4/8 ranks)"}
+    gpath = GOLDEN_CFG3 if args.config == 3 else os.path.join(
+        os.path.dirname(GOLDEN_CFG3), "bench_cfg%d_n%d_golden.json" % (args.config, nranks if args.config == 4 else 1))
+    if os.path.exists(gpath) and args.atoms == 1_000_000 and not args.no_check and not (args.config == 2 and args.sweep):
+        golden = json.load(open(gpath))
+        golden["path"] = os.path.relpath(gpath, os.path.dirname(os.path.abspath(__file__)))
         if golden["atoms"] == box.n:
             check = parity_check(eng, box, frame, golden, allsum)
             # back to the start of the trajectory for the measurement

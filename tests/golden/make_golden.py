@@ -71,8 +71,43 @@ def make_cfg3_full(path, scale=1.0):
     print("wrote", path)
 
 
+# The other bench workloads (bench.py --config 4 / 5): the same record for the box each rank count runs (config 4 is
+# weak-scaled: one box per rank count).  Site values are SAMPLED (every k-th site, at most ~2048) to keep the files
+# small; the sums over all sites are stored beside them.
+def make_bench_golden(path, config, nranks):
+    import argparse
+    sys.path.insert(0, ROOT)
+    import bench
+    args = argparse.Namespace(config=config, atoms=1_000_000, pH=7.0)
+    box, params = bench.workload(args, nranks)
+    o = capi.Engine("orc")
+    o.lib.orc_set_threads(os.cpu_count() or 1)
+    capi.configure(o, box, **CFG3_KW)
+    stride = max(1, -(-box.nsites // 2048))
+    idx = list(range(0, box.nsites, stride))
+    rec = {"generated_by": "tests/golden/make_golden.py --bench %d %d (oracle output)" % (config, nranks),
+           "config": config, "nranks": nranks, "atoms": int(box.n), "sites": int(box.nsites), "kw": CFG3_KW,
+           "site_index": idx, "steps": {}}
+    for step in range(max(CFG3_STEPS) + 1):
+        o.post_force(step, box.dt, synth.jiggle_positions(box, params, step * box.dt), None)
+        if step in CFG3_STEPS:
+            snap = snapshot(o)
+            d, lam = np.array(snap["dudl"]), np.array(snap["lambda"])
+            snap["dudl_sum"], snap["dudl_sq_sum"] = float(d.sum()), float((d * d).sum())
+            snap["dudl"], snap["lambda"] = [float(v) for v in d[idx]], [float(v) for v in lam[idx]]
+            rec["steps"][str(step)] = snap
+    with open(path, "w") as fh:
+        json.dump(rec, fh)
+    print("wrote", path, box.n, box.nsites)
+
+
 def main():
     here = os.path.dirname(os.path.abspath(__file__))
+    if "--bench" in sys.argv:
+        k = sys.argv.index("--bench")
+        config, nranks = int(sys.argv[k + 1]), int(sys.argv[k + 2])
+        make_bench_golden(os.path.join(here, "bench_cfg%d_n%d_golden.json" % (config, nranks)), config, nranks)
+        return
     if "--cfg3" in sys.argv or "--all" in sys.argv:
         make_cfg3_full(os.path.join(here, "cfg3_full_golden.json"))
         if "--cfg3" in sys.argv:
