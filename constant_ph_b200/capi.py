@@ -182,6 +182,11 @@ class Engine:
         self._call("set_sites", C.c_int(nsites), _d(pK), C.c_int(ntitr), _i(tt), _i(ts), _d(qA), _d(qB))
         self.nsites = max(1, int(nsites))
 
+    def set_lj_states(self, typeB):
+        """B-state atom type of every titratable atom of set_sites (0 = one LJ identity); before set_atoms."""
+        tb = _i32(typeB)
+        self._call("set_lj_states", C.c_int(int(tb.size)), _i(tb))
+
     def set_lambda(self, lam, v=None):
         l, vv = _f64(lam), _f64(v)
         self._call("set_lambda", _d(l), _d(vv))
@@ -456,14 +461,15 @@ def configure(eng, box, nevery=1, dudl=DUDL_CHARGE, integrator=INTEGRATE_REFEREN
               fscale=FSCALE_LAMBDA, bias_mode=BIAS_EXACT, implicit_site=False, ftm2v=None,
               sublo=None, subhi=None, procgrid=(1, 1, 1), myloc=(0, 0, 0), owned=None, bias=None,
               water_buffer=False, theta=False, cut_lj=None, cut_coul=None, thermostat=0.0,
-              topology=None, velocities=None, drop_excluded=False):
+              topology=None, velocities=None, drop_excluded=False, lj_typeB=None):
     """Push a synth.Box into an engine: the calls FixConstantPH's constructor/init/setup make.
 
     implicit_site=True reproduces the reference's single global lambda over the hydrogen
     group (nsites = 0, pK from the fix arguments, fix_constant_pH.cpp:47).
     owned: index array of the atoms this rank owns (None = all).
     bias: overrides of the init() constants (fix_constant_pH.cpp:86-96), e.g. m_lambda.
-    topology: a synth.Topology -> bonded terms on; velocities: (n,3) -> fix-nve dynamics on."""
+    topology: a synth.Topology -> bonded terms on; velocities: (n,3) -> fix-nve dynamics on.
+    lj_typeB: B-state atom type per titratable atom (LJ end states, docs/SPEC.md), aligned with box.titr_tag."""
     from . import synth
     eng.set_units(synth.QQRD2E, synth.BOLTZ, synth.FTM2V if ftm2v is None else ftm2v)
     # cut_lj: optional (ntypes+1)^2 table of per-type-pair LJ cutoffs (pair_coeff ... cut_lj); cut_coul: override
@@ -487,6 +493,8 @@ def configure(eng, box, nevery=1, dudl=DUDL_CHARGE, integrator=INTEGRATE_REFEREN
         eng.set_lambda(box.lambda0[:1], box.v0[:1])
     else:
         eng.set_sites(box.nsites, box.pK, box.titr_tag, box.titr_site, box.qA, box.qB)
+        if lj_typeB is not None:
+            eng.set_lj_states(lj_typeB)
         eng.set_lambda(box.lambda0, box.v0)
     sel = slice(None) if owned is None else owned
     eng.set_atoms(box.x[sel], box.q[sel], box.type[sel], box.tag[sel], box.mask[sel], box.molecule[sel],

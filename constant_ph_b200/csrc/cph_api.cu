@@ -448,6 +448,8 @@ int cph_set_sites(cph_handle *h, int nsites, const double *pK, int ntitr, const 
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
     return titr_site[a] != titr_site[b] ? titr_site[a] < titr_site[b] : titr_tag[a] < titr_tag[b];
   });
+  h->titr_order_h = order;
+  h->lj_states = false;                      // cph_set_lj_states follows a new table
   std::vector<int> site(ntitr), tag(ntitr);
   std::vector<double> a(ntitr), dq(ntitr);
   for (int k = 0; k < ntitr; k++) {
@@ -490,6 +492,11 @@ int cph_set_sites(cph_handle *h, int nsites, const double *pK, int ntitr, const 
   CPH_TRY(size_sites(h));
   h->have_sites = true;
   return CPH_OK;
+}
+
+int cph_set_lj_states(cph_handle *h, int ntitr, const int *typeB) {
+  cudaSetDevice(h->device);
+  return cph_ljstates_set(h, ntitr, typeB);
 }
 
 int cph_set_lambda(cph_handle *h, const double *lambda, const double *v_lambda) {
@@ -623,6 +630,7 @@ int cph_pair_pass(cph_handle *h, int eflag) {
   cudaSetDevice(h->device);
   CPH_TRY(cph_launch_pair(h, eflag ? 1 : 0));
   CPH_TRY(cph_launch_bonded(h, eflag ? 1 : 0));
+  CPH_TRY(cph_launch_ljstates(h, eflag ? 1 : 0));
   h->have_pass = true;
   return CPH_OK;
 }
@@ -725,6 +733,7 @@ static int post_force_impl(cph_handle *h, int64_t ntimestep, double dt, int wher
   }
   if (!guessed || any || fl[5]) CPH_TRY(cph_launch_pair(h, active ? 1 : 0));
   CPH_TRY(cph_launch_bonded(h, active ? 1 : 0));                        // cpp:221-229: bonded eatom joins the partition
+  CPH_TRY(cph_launch_ljstates(h, active ? 1 : 0));                      // LJ end states, when the caller declared any
   h->have_pass = true;
   // In charge mode nothing after this point touches the forces, so their way back to the host
   // (gather to caller order + D2H) runs on the side stream under the site reduce / lambda update.

@@ -176,6 +176,14 @@ struct cph_handle {
   int S = 1, ntitr = 0;
   std::vector<int> titr_tag_sorted_h;  // titr tags sorted ascending (for the device binary search)
   std::vector<int> titr_entry_of_sorted_h;
+  std::vector<int> titr_order_h;       // site-major entry k = caller's entry titr_order_h[k] of cph_set_sites
+  // LJ end states (ljstates.cu): B-state type per titration entry; per-atom views; CSR list of the inner-row
+  // entries that touch an atom with end states; g = dE/dlambda carried by each owned atom's own end states
+  bool lj_states = false;
+  DevBuf<int> d_titr_typeB, d_es_tB, d_es_site, d_es_cnt, d_es_off, d_es_ent;
+  DevBuf<unsigned int> d_es_tmask;     // bit t set: some owned or ghost atom of (A-state) type t has end states
+  DevBuf<double> d_es_g;
+  int es_entries = 0;
   // device: sites
   DevBuf<double> d_pK, d_lam, d_vlam, d_alam, d_flam, d_fs, d_dfs, d_Us, d_dUs;
   DevBuf<double> d_theta;            // dynamical coordinate when coord_theta (lambda = sin^2 theta)
@@ -335,6 +343,11 @@ int cph_launch_prune(cph_handle *h);
 int cph_pair_fill_constants(cph_handle *h);
 int cph_inner_counts(cph_handle *h, int64_t *out2);
 int cph_launch_xt(cph_handle *h);
+// ljstates.cu
+int cph_ljstates_set(cph_handle *h, int ntitr, const int *typeB);
+int cph_ljstates_map(cph_handle *h);            // after a list build
+int cph_ljstates_collect(cph_handle *h);        // after a prune
+int cph_launch_ljstates(cph_handle *h, int eflag);   // after the pair pass: adds the end-state difference
 // sites.cu
 int cph_launch_partition(cph_handle *h, bool push = false);   // HA, HB, E_vdwl, E_coul + per-site sums (+ push to the mailboxes)
 bool cph_mail_red_usable(const cph_handle *h);

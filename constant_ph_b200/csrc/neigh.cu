@@ -1245,6 +1245,7 @@ int cph_rebuild(cph_handle *h) {
     CPH_CUDA(h, h->d_hlist.reserve(nh + 1));
     if (nh) hlist_kernel<<<nblk(n), TPB, 0, st>>>(n, h->d_vals.p, h->d_vals2.p, h->d_hlist.p);
   }
+  CPH_TRY(cph_ljstates_map(h));     // LJ end states: B type / site of every owned and ghost atom
   // result arrays
   CPH_CUDA(h, h->d_f.reserve(3 * (size_t)n + 3));
   CPH_CUDA(h, h->d_evdwl.reserve(n + 1));

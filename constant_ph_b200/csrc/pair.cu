@@ -578,6 +578,7 @@ int cph_launch_prune(cph_handle *h) {
   CPH_CUDA(h, cudaGetLastError());
   h->inner_valid = true;
   h->nprunes++;
+  CPH_TRY(cph_ljstates_collect(h));         // the pairs that touch an atom with LJ end states, from the new rows
   return 0;
 }
 

@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(TPB)
 site_partition_kernel(int n, const double *__restrict__ eatom, const double *__restrict__ evdwl,
                       const int *__restrict__ mask, int Hbit, int nbP, double *partials, int S, int lps,
                       const int *__restrict__ site_start, const int *__restrict__ titr_local,
-                      const double *__restrict__ titr_dq, const double *__restrict__ phi, int implicit_site,
+                      const double *__restrict__ titr_dq, const double *__restrict__ phi,
+                      const double *__restrict__ lj_g, int implicit_site,
                       double extra_HA, double extra_HB, const double *__restrict__ bonded_e, double *red,
                       unsigned int *ticket, const __grid_constant__ MailRed mr) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -81,6 +82,7 @@ site_partition_kernel(int n, const double *__restrict__ eatom, const double *__r
         const int k = titr_local[t];
         if (k >= 0) {                                         // owned by this rank (cpp:264: i < nlocal)
           d += titr_dq[t] * phi[k];                           // Appendix B
+          if (lj_g) d += lj_g[k];                             // LJ end states of atom k (ljstates.cu)
           if (mask[k] & Hbit) hd -= eatom[k];                 // HB_s - HA_s
         }
       }
@@ -618,7 +620,8 @@ int cph_launch_partition(cph_handle *h, bool push) {
   const int nbS = (S + TPB / lps - 1) / (TPB / lps);
   site_partition_kernel<<<nbP + nbS, TPB, 0, st>>>(n, h->d_eatom.p, h->d_evdwl.p, h->d_mask.p, h->fix.Hbit, nbP,
                                                   h->d_part.p, S, lps, h->d_site_start.p, h->d_titr_local.p,
-                                                  h->d_titr_dq.p, h->d_phi.p, h->fix.implicit_site, h->extra_HA,
+                                                  h->d_titr_dq.p, h->d_phi.p,
+                                                  h->lj_states ? h->d_es_g.p : nullptr, h->fix.implicit_site, h->extra_HA,
                                                   h->extra_HB, h->have_topology ? h->d_bonded_e.p : nullptr,
                                                   h->d_red.p, h->d_flags.p + 80, mr);
   h->extra_HA = h->extra_HB = 0.0;   // consumed

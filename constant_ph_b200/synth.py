@@ -506,6 +506,16 @@ def config(k, scale=1.0, **kw):
     raise ValueError("unknown config %r" % (k,))
 
 
+def lj_end_state_types(box):
+    """B-state atom types for the LJ-end-state tests (docs/SPEC.md): a titratable proton loses its LJ site in the
+    deprotonated state (HO / HN -> HW, epsilon 0), the hydroxyl oxygen becomes a carbonyl oxygen, a water oxygen
+    (config 5's one-atom sites) a hydroxyl oxygen, a water hydrogen gains the small HO site; everything else keeps one
+    identity (0).  Aligned with box.titr_tag."""
+    swap = {7: 2, 10: 2, 6: 5, 1: 6, 2: 7}
+    t = box.type[box.meta["tag_to_index"][box.titr_tag]]
+    return np.array([swap.get(int(v), 0) for v in t], dtype=np.int32)
+
+
 def jiggle_params(box, amp=0.45, period_lo=60.0, period_hi=140.0, seed=12345):
     """Prescribed rigid-molecule motion x_i(t) = x_i(0) + A_m sin(w_m t + p_m) used by the
     tests and the bench as the stand-in for the host MD integrator (which is LAMMPS's
@@ -535,7 +545,7 @@ def harness_jiggle(x0, amp, t):
     return x0 + amp * np.sin((w * t + ph)[:, None] + np.arange(3.0)[None, :])
 
 
-def write_harness_input(box, path_bin, path_sites=None):
+def write_harness_input(box, path_bin, path_sites=None, lj_typeB=None):
     """Binary box + text site table for src/cph_harness (the drop-in fix driven through the
     LAMMPS shim).  Layout documented in src/harness.cpp."""
     pK0 = float(box.pK[0]) if box.nsites else 0.0
@@ -556,7 +566,8 @@ def write_harness_input(box, path_bin, path_sites=None):
             for s in range(box.nsites):
                 fh.write("%.17g %.17g\n" % (box.pK[s], box.lambda0[s]))
             for t in range(box.titr_tag.size):
-                fh.write("%d %d %.17g %.17g\n" % (box.titr_tag[t], box.titr_site[t], box.qA[t], box.qB[t]))
+                fh.write("%d %d %.17g %.17g%s\n" % (box.titr_tag[t], box.titr_site[t], box.qA[t], box.qB[t],
+                                                    "" if lj_typeB is None else " %d" % lj_typeB[t]))
 
 
 # ---- flexible molecules: bonded topology and masses -----------------------

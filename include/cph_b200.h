@@ -128,6 +128,15 @@ int cph_set_water_buffer(cph_handle *h, int enable);
  * reference's single global lambda (one site = the whole hydrogen group, pK from cph_set_fix) is used. */
 int cph_set_sites(cph_handle *h, int nsites, const double *pK, int ntitr, const int *titr_tag,
                   const int *titr_site, const double *qA, const double *qB);
+/* LJ end states (north_star "end states"; absent from the reference, which only rescales forces, cpp:149-171).
+ * typeB[t] is the atom type titratable atom t of cph_set_sites has in state B (0: it keeps one LJ identity);
+ * its own atom->type is the state-A type.  Such an atom interacts as the lambda-weighted superposition of its two
+ * types: E_LJ(i,j) = sum_ab w_i^a w_j^b E_LJ(type_i^a, type_j^b; r), w^A = 1 - lambda_site, w^B = lambda_site
+ * (1 and 0 for ordinary atoms), forces likewise, and dU/dlambda_s gains sum_{i in s} sum_j sum_b w_j^b
+ * (E_LJ(type_i^B, type_j^b) - E_LJ(type_i^A, type_j^b)), special-bond weights applied.  ntitr must equal the count
+ * given to cph_set_sites; call after cph_set_sites / cph_set_pair_style and before cph_set_atoms.  Evaluated by a
+ * separate kernel over the few pairs that touch such an atom; the main pair kernel is unchanged. */
+int cph_set_lj_states(cph_handle *h, int ntitr, const int *typeB);
 /* lambda / v_lambda initial values (never initialised in the reference). */
 int cph_set_lambda(cph_handle *h, const double *lambda, const double *v_lambda);
 

@@ -89,6 +89,11 @@ struct Oracle {
   std::vector<int> titr_tag, titr_site;
   std::vector<double> qA, qB;
   std::vector<double> lam, vlam, alam;
+  // LJ end states (docs/SPEC.md "LJ end states"): B-state atom type per titration entry (0 = one LJ identity),
+  // per atom after set_atoms; g[i] = dE_vdwl/dlambda carried by atom i's own end states
+  std::vector<int> titr_typeB, typeB_of;
+  std::vector<double> lj_g;
+  bool lj_states = false;
   // per-site outputs
   std::vector<double> dudl, hdiff, flam, fs, dfs, Us, dUs;
   double HA = 0, HB = 0, evdwl = 0, ecoul = 0, Hlambda = 0, ke_sites = 0, maxdisp2 = 0;
@@ -287,6 +292,8 @@ void pair_pass(Oracle *o, int eflag) {
   std::vector<std::vector<double>> acc(nthreads);
   std::vector<int> wlo(nthreads, 0), whi(nthreads, 0), c0(nthreads, 0), c1(nthreads, 0);
   std::vector<long double> tv(nthreads, 0.0L), tc(nthreads, 0.0L);
+  std::vector<std::vector<std::pair<int, double>>> glist(nthreads);
+  const bool lj_states = o->lj_states && !o->typeB_of.empty();
   const double qqrd2e = o->qqrd2e, alpha = o->alpha, e_shift = o->e_shift, f_shift = o->f_shift;
   const int style = o->style;
   {
@@ -318,6 +325,8 @@ void pair_pass(Oracle *o, int eflag) {
     abuf.assign((size_t)std::max(0, hi - lo) * 5, 0.0);
     double *a = abuf.data() - (size_t)lo * 5;   // indexable by global atom index
     long double ev_t = 0.0L, ec_t = 0.0L;
+    std::vector<std::pair<int, double>> &gl = glist[tid];
+    gl.clear();
     for (int i = c0[tid]; i < c1[tid]; i++) {
       const double xi = o->x[3 * i], yi = o->x[3 * i + 1], zi = o->x[3 * i + 2];
       const double qi = o->q[i];
@@ -340,13 +349,38 @@ void pair_pass(Oracle *o, int eflag) {
         const int tj = o->type[j];
         const int tt = ti * nt1 + tj;
         const double cutljsq = o->cut_ljsq[tt];
-        const double cutsq = std::max(cutljsq, cut_coulsq);
+        double cutsq = std::max(cutljsq, cut_coulsq);
+        if (lj_states && (o->typeB_of[i] | o->typeB_of[j])) cutsq = std::max(cutsq, o->cut_lj_max * o->cut_lj_max);
         if (rsq >= cutsq) continue;
         const double factor_lj = o->special_lj[sb], factor_coul = o->special_coul[sb];
         const double qj = o->q[j];
         double r2inv = 1.0 / rsq;
         double forcecoul = 0.0, forcelj = 0.0, ecoul = 0.0, evdwl = 0.0, kij = 0.0;
-        if (rsq < cutljsq) {
+        const int tBi = lj_states ? o->typeB_of[i] : 0, tBj = lj_states ? o->typeB_of[j] : 0;
+        if (tBi | tBj) {
+          // an atom with LJ end states is the lambda-weighted superposition of its two types:
+          // E = sum_ab w_i^a w_j^b E_LJ(t_i^a, t_j^b),  w^A = 1 - lambda, w^B = lambda  (1, 0 for ordinary atoms)
+          const double li = tBi ? o->lam[o->site_of[i]] : 0.0, lj = tBj ? o->lam[o->site_of[j]] : 0.0;
+          const double wi[2] = {1.0 - li, li}, wj[2] = {1.0 - lj, lj};
+          const int tis[2] = {ti, tBi}, tjs[2] = {tj, tBj};
+          const double r6inv = r2inv * r2inv * r2inv;
+          double dEi = 0.0, dEj = 0.0;
+          for (int a = 0; a <= (tBi ? 1 : 0); a++)
+            for (int b = 0; b <= (tBj ? 1 : 0); b++) {
+              const int t2 = tis[a] * nt1 + tjs[b];
+              if (rsq >= o->cut_ljsq[t2]) continue;
+              const double e_ab = r6inv * (o->lj3[t2] * r6inv - o->lj4[t2]);
+              forcelj += wi[a] * wj[b] * (r6inv * (o->lj1[t2] * r6inv - o->lj2[t2]));
+              evdwl += wi[a] * wj[b] * e_ab;
+              if (tBi) dEi += (a ? wj[b] : -wj[b]) * e_ab;
+              if (tBj) dEj += (b ? wi[a] : -wi[a]) * e_ab;
+            }
+          evdwl *= factor_lj;
+          if (eflag) {
+            if (tBi) gl.push_back({i, factor_lj * dEi});
+            if (tBj) gl.push_back({j, factor_lj * dEj});
+          }
+        } else if (rsq < cutljsq) {
           double r6inv = r2inv * r2inv * r2inv;
           forcelj = r6inv * (o->lj1[tt] * r6inv - o->lj2[tt]);
           evdwl = factor_lj * (r6inv * (o->lj3[tt] * r6inv - o->lj4[tt]));
@@ -409,6 +443,10 @@ void pair_pass(Oracle *o, int eflag) {
     if (eflag) { o->eatom[i] = s[3]; o->phi[i] = s[4] + 2.0 * o->q[i] * cself(o); }
   }
   if (eflag) {
+    o->lj_g.assign(lj_states ? n : 0, 0.0);
+    if (lj_states)
+      for (int t = 0; t < nthreads; t++)
+        for (const auto &c : glist[t]) o->lj_g[c.first] += c.second;
     long double ev = 0, ec = 0;
     for (int t = 0; t < nthreads; t++) { ev += tv[t]; ec += tc[t]; }
     o->evdwl = (double)ev;
@@ -514,6 +552,7 @@ void site_reduce(Oracle *o) {
     if (o->mask[i] & o->Hbit) hd[s] -= o->eatom[i];      // HB_s - HA_s = -sum_{i in H of s} eatom_i
     int t = o->titr_of[i];
     if (t >= 0) d[s] += (long double)(o->qB[t] - o->qA[t]) * o->phi[i];  // Appendix B (phi holds dE/dq_i)
+    if (!o->lj_g.empty()) d[s] += o->lj_g[i];                            // LJ end states of atom i
   }
   if (o->water_buffer && o->dudl_mode == 1) {
     // modify_water (h:58; TODO at cpp:268): the buffer atoms carry -(1/nW) sum_s lambda_s dQ_s each,
@@ -761,7 +800,23 @@ int orc_set_sites(void *h, int nsites, const double *pK, int ntitr, const int *t
   o->qA.assign(qA, qA + ntitr); o->qB.assign(qB, qB + ntitr);
   for (int t = 0; t < ntitr; t++) if (tsite[t] < 0 || tsite[t] >= o->S) return fail(o, -1, "site index out of range");
   o->lam.clear(); o->vlam.clear(); o->alam.clear(); o->theta.clear();
+  o->titr_typeB.clear(); o->lj_states = false;
   size_sites(o);
+  return 0;
+}
+
+// LJ end states: typeB[t] = atom type of titration entry t in state B (0: the atom has one LJ identity); the
+// atom's own type is its state-A type.  Before set_atoms.
+int orc_set_lj_states(void *h, int ntitr, const int *typeB) {
+  Oracle *o = ORC;
+  if (ntitr != (int)o->titr_tag.size()) return fail(o, -1, "set_lj_states: one entry per titratable atom of set_sites");
+  if (o->have_atoms) return fail(o, -2, "set_lj_states before set_atoms");
+  o->lj_states = false;
+  for (int t = 0; t < ntitr; t++) {
+    if (typeB[t] < 0 || typeB[t] > o->ntypes) return fail(o, -1, "set_lj_states: type out of range");
+    if (typeB[t]) o->lj_states = true;
+  }
+  o->titr_typeB.assign(typeB, typeB + ntitr);
   return 0;
 }
 
@@ -806,6 +861,10 @@ int orc_set_atoms(void *h, int, int n, const double *x, const double *q, const i
     if (t >= 0) { o->titr_of[i] = t; o->site_of[i] = o->titr_site[t]; }
     else if (o->implicit_site && (mask[i] & o->Hbit)) o->site_of[i] = 0;
   }
+  o->typeB_of.assign(o->lj_states ? n : 0, 0);
+  if (o->lj_states)
+    for (int i = 0; i < n; i++)
+      if (o->titr_of[i] >= 0) o->typeB_of[i] = o->titr_typeB[o->titr_of[i]];
   o->f.assign(3 * (size_t)n, 0); o->eatom.assign(n, 0); o->phi.assign(n, 0);
   o->have_topology = false;   // per-atom lists follow the atom order: resend after every set_atoms
   o->md = false;

@@ -101,7 +101,7 @@ FixConstantPH::FixConstantPH(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg,
   sites_on_device = false;
   rank_group_ready = false;
   part[0] = part[1] = 0.0;
-  tab = Sites{0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  tab = Sites{0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
   opt = Options{CPH_DUDL_REFERENCE, CPH_INTEGRATE_REFERENCE, CPH_FSCALE_LAMBDA, CPH_BIAS_EXACT, 0, CPH_COORD_LAMBDA, 0,
                 0.0, 0.5, nullptr, {}};
   for (double &u : opt.bias_user) u = NAN;
@@ -179,7 +179,8 @@ FixConstantPH::~FixConstantPH()
 {
   if (cph) cph_destroy(cph);
   memory->destroy(host_energy);
-  void *owned[] = {opt.site_file, tab.pK, tab.lambda0, tab.qA, tab.qB, tab.tag, tab.site, pending_restart, force_out, charge_buf};
+  void *owned[] = {opt.site_file, tab.pK, tab.lambda0, tab.qA, tab.qB, tab.tag, tab.site, tab.typeB, pending_restart, force_out,
+                   charge_buf};
   for (void *p : owned) free(p);
 }
 
@@ -200,7 +201,8 @@ void FixConstantPH::require(int rc, const char *what)
 }
 
 /* ----------------------------------------------------------------------
-   site table:  line 1 "nsites ntitr"; nsites lines "pK lambda0"; ntitr lines "tag site qA qB"
+   site table:  line 1 "nsites ntitr"; nsites lines "pK lambda0"; ntitr lines "tag site qA qB [typeB]"
+   typeB (optional): the atom type the atom has in state B -- LJ end states, cph_set_lj_states
 ------------------------------------------------------------------------- */
 
 void FixConstantPH::load_site_table(const char *path)
@@ -215,12 +217,22 @@ void FixConstantPH::load_site_table(const char *path)
   tab.site = (int *) calloc(tab.natoms + 1, sizeof(int));
   tab.qA = (double *) calloc(tab.natoms + 1, sizeof(double));
   tab.qB = (double *) calloc(tab.natoms + 1, sizeof(double));
+  tab.typeB = (int *) calloc(tab.natoms + 1, sizeof(int));
+  tab.lj_states = 0;
   for (int s = 0; s < tab.nsites; s++)
     if (fscanf(fp, "%lf %lf", &tab.pK[s], &tab.lambda0[s]) != 2)
       error->all(FLERR, "Bad site line {} in fix constant_pH site file", s);
-  for (int t = 0; t < tab.natoms; t++)
-    if (fscanf(fp, "%d %d %lf %lf", &tab.tag[t], &tab.site[t], &tab.qA[t], &tab.qB[t]) != 4)
-      error->all(FLERR, "Bad atom line {} in fix constant_pH site file", t);
+  char line[256];
+  if (!fgets(line, sizeof(line), fp)) line[0] = 0;      // rest of the last site line
+  for (int t = 0; t < tab.natoms; t++) {
+    do {
+      if (!fgets(line, sizeof(line), fp)) error->all(FLERR, "Bad atom line {} in fix constant_pH site file", t);
+    } while (line[strspn(line, " \t\r\n")] == 0);     // blank lines
+    const int got = sscanf(line, "%d %d %lf %lf %d", &tab.tag[t], &tab.site[t], &tab.qA[t], &tab.qB[t], &tab.typeB[t]);
+    if (got < 4) error->all(FLERR, "Bad atom line {} in fix constant_pH site file", t);
+    if (got < 5) tab.typeB[t] = 0;
+    if (tab.typeB[t]) tab.lj_states = 1;
+  }
   fclose(fp);
 }
 
@@ -305,6 +317,7 @@ void FixConstantPH::init()
   // a_lambda, thermostat) are sent once; later runs continue from where the previous one stopped.
   if (!sites_on_device) {
     require(cph_set_sites(cph, tab.nsites, tab.pK, tab.natoms, tab.tag, tab.site, tab.qA, tab.qB), "cph_set_sites");
+    if (tab.lj_states) require(cph_set_lj_states(cph, tab.natoms, tab.typeB), "cph_set_lj_states");
     if (!pending_restart)
       require(cph_set_lambda(cph, tab.nsites ? tab.lambda0 : &opt.lambda_start, nullptr), "cph_set_lambda");
     sites_on_device = true;

@@ -77,6 +77,8 @@ class FixConstantPH : public Fix {
     int nsites, natoms;
     double *pK, *lambda0, *qA, *qB;
     int *tag, *site;
+    int *typeB;                    // optional fifth column: atom type in state B (LJ end states), 0 = none
+    int lj_states;
   } tab;
 
   cph_handle *cph;                 // the device side

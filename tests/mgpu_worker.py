@@ -22,6 +22,7 @@ def main():
     scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
     nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 40
     bonded = len(sys.argv) > 3 and sys.argv[3] == "bonded"
+    ljstates = len(sys.argv) > 3 and sys.argv[3] == "ljstates"
     box = synth.config(2, scale=scale, shuffle=True)
     params = synth.jiggle_params(box, amp=0.9, period_lo=40.0, period_hi=90.0)
     grid = bench.decompose(box, world)
@@ -36,6 +37,8 @@ def main():
     kw = dict(bias=dict(m_lambda=2000.0))
     if bonded:   # bond / angle partners of atoms near a sub-box face are ghosts
         kw["topology"] = synth.topology(box)
+    if ljstates:  # atoms with LJ end states act on the owned atoms of neighbouring ranks as ghosts
+        kw["lj_typeB"] = synth.lj_end_state_types(box)
     capi.configure(eng, box, sublo=sublo, subhi=subhi, procgrid=grid, myloc=loc, owned=owned, **kw)
     ref = capi.configure(capi.Engine("cph", device=lrank), box, **kw) if rank == 0 else None
 

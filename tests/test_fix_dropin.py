@@ -109,7 +109,7 @@ def oracle_trajectory(box, mode, kw, nsteps, jiggle=0.0):
 
 
 MODES = ["charge", "reference", "vv", "vv_nevery2", "buffer", "theta", "bonded", "thermostat", "biasconst",
-         "two_runs", "moving", "excluded_drop"]
+         "two_runs", "moving", "excluded_drop", "ljstates"]
 
 
 @pytest.mark.gpu
@@ -131,6 +131,15 @@ def test_fix_trajectory_matches_oracle(box_files, mode):
         jiggle = 0.6
         args = ["sites", s, "mlambda", 2000]
         kw = dict(bias=dict(m_lambda=2000.0))
+    elif mode == "ljstates":
+        # fifth column of the site file: the atom type in state B (LJ end states), atoms moving
+        typeB = synth.lj_end_state_types(box)
+        s5 = s + ".lj"
+        synth.write_harness_input(box, b + ".lj", s5, lj_typeB=typeB)
+        pre = ["jiggle", 0.6]
+        jiggle = 0.6
+        args = ["sites", s5, "mlambda", 2000]
+        kw = dict(bias=dict(m_lambda=2000.0), lj_typeB=typeB)
     elif mode == "excluded_drop":
         args = ["sites", s, "mlambda", 2000, "excluded", "drop"]
         kw = dict(bias=dict(m_lambda=2000.0), drop_excluded=True)

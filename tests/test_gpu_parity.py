@@ -347,6 +347,53 @@ def test_config4_scaled_many_solutes(built):
     assert np.array_equal(ng, no) and np.array_equal(kg, ko)
 
 
+@pytest.mark.parametrize("cfg,scale", [(2, 0.25), (5, 0.05), (4, 0.008)])
+def test_lj_end_states_match_oracle(built, cfg, scale):
+    """LJ end states (docs/SPEC.md; cph_set_lj_states): the correction kernel against the oracle's mixed pair loop.
+    Config 2: a few eight-atom sites (proton + hydroxyl oxygen change type).  Config 5: 10 % of the atoms are
+    one-atom sites, so most corrected pairs have end states on BOTH sides and many are special pairs.  Config 4:
+    bonded chains, corrected 1-4 pairs."""
+    box = synth.config(cfg, scale=scale, **({"chain_len": 10} if cfg == 4 else {}))
+    typeB = synth.lj_end_state_types(box)
+    assert (typeB > 0).any()
+    gpu, orc = engines(box, bias=HEAVY, lj_typeB=typeB)
+    check_pass(gpu, orc)
+    plain = capi.configure(capi.Engine("cph", device=0), box, bias=HEAVY)
+    plain.pair_pass(1); plain.site_reduce()
+    assert np.abs(plain.get_sites()["dudl"] - gpu.get_sites()["dudl"]).max() > 1e-6      # the term is there
+    assert np.abs(plain.get_forces() - gpu.get_forces()).max() > 1e-6
+    # a moving trajectory: lists are rebuilt and pruned, lambda moves, the weights follow
+    params = synth.jiggle_params(box, amp=0.9, period_lo=40.0, period_hi=90.0)
+    fg, fo = np.zeros_like(box.x), np.zeros_like(box.x)
+    for step in range(40):
+        x = synth.jiggle_positions(box, params, step * box.dt)
+        gpu.post_force(step, box.dt, x, fg)
+        orc.post_force(step, box.dt, x, fo)
+        if step % 13 == 0:
+            close(fg, fo)
+    close(fg, fo)
+    tg, to = gpu.get_sites(), orc.get_sites()
+    close(tg["dudl"], to["dudl"])
+    assert np.abs(tg["lambda"] - to["lambda"]).max() <= 1e-8
+    sg, so = gpu.get_scalars(), orc.get_scalars()
+    for k in ("HA", "HB", "evdwl", "ecoul", "H_lambda"):
+        assert abs(sg[k] - so[k]) <= RTOL * abs(so[k]), (k, sg[k], so[k])
+    assert gpu.get_counts()["builds"] == orc.get_counts()["builds"] > 1
+
+
+def test_lj_end_states_argument_errors(built):
+    box = synth.config(1)
+    eng = capi.Engine("cph", device=0)
+    with pytest.raises(capi.CphError):
+        eng.set_lj_states(np.zeros(3, dtype=np.int32))            # no site table yet
+    capi.configure(eng, box)
+    with pytest.raises(capi.CphError):
+        eng.set_lj_states(np.zeros(box.titr_tag.size, dtype=np.int32))   # after set_atoms
+    eng2 = capi.Engine("cph", device=0)
+    with pytest.raises(capi.CphError):
+        capi.configure(eng2, box, lj_typeB=np.full(box.titr_tag.size, 99, dtype=np.int32))   # no such type
+
+
 def test_water_buffer_modify_water(built):
     """charge buffer on the 3-atom water group, CUDA path against the oracle."""
     box = synth.config(2, scale=0.25)

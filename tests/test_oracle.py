@@ -130,6 +130,63 @@ def test_analytic_dudl_equals_perturbed_charge_reevaluation(cfg, scale):
         assert abs(fd - dudl[site]) < 1e-8 * max(1.0, abs(dudl[site]))
 
 
+def test_lj_end_states_limits_and_derivatives():
+    """docs/SPEC.md, LJ end states.  lambda = 0: the plain run; lambda = 1: the run with the B types written into
+    atom->type; in between: dU/dlambda equals the central difference of the total energy (E is a polynomial of
+    degree <= 2 in every lambda_s) and the force on an end-state atom equals -dE/dx."""
+    box = synth.config(2, scale=0.2)
+    typeB = synth.lj_end_state_types(box)
+    assert (typeB > 0).sum() >= 2 * box.nsites - 2
+    pos = box.meta["tag_to_index"][box.titr_tag]
+
+    def energy(o):
+        o.pair_pass(1); o.site_reduce()
+        sc = o.get_scalars()
+        return sc["evdwl"] + sc["ecoul"], sc
+
+    # end points
+    for lam_all, swapped in ((0.0, False), (1.0, True)):
+        lam = np.full(box.nsites, lam_all)
+        plain_box = synth.config(2, scale=0.2)
+        if swapped:
+            plain_box.type[pos[typeB > 0]] = typeB[typeB > 0]
+        plain = capi.configure(capi.Engine("orc"), plain_box)
+        plain.set_lambda(lam); plain.apply_charges()
+        mixed = capi.configure(capi.Engine("orc"), box, lj_typeB=typeB)
+        mixed.set_lambda(lam); mixed.apply_charges()
+        (ep, sp), (em, sm) = energy(plain), energy(mixed)
+        assert abs(ep - em) <= 1e-12 * abs(ep)
+        assert np.abs(plain.get_forces() - mixed.get_forces()).max() <= 1e-11 * np.abs(plain.get_forces()).max()
+    # derivative in lambda
+    o = capi.configure(capi.Engine("orc"), box, lj_typeB=typeB)
+    e0, _ = energy(o)
+    dudl = o.get_sites()["dudl"].copy()
+    plain = capi.configure(capi.Engine("orc"), box)
+    _ = energy(plain)
+    assert np.abs(dudl - plain.get_sites()["dudl"]).max() > 1e-3          # the LJ term is there
+    for site in range(min(box.nsites, 4)):
+        es = []
+        for sign in (+1, -1):
+            lam = box.lambda0.copy(); lam[site] += sign * 0.05
+            o.set_lambda(lam); o.apply_charges()
+            es.append(energy(o)[0])
+        fd = (es[0] - es[1]) / 0.1
+        assert abs(fd - dudl[site]) < 1e-8 * max(1.0, abs(dudl[site]))
+    # force on an end-state atom
+    o.set_lambda(box.lambda0); o.apply_charges()
+    energy(o)
+    f = o.get_forces()
+    i = int(pos[np.nonzero(typeB > 0)[0][0]])
+    h = 1e-4
+    for k in range(3):
+        es = []
+        for sign in (+1, -1):
+            x = box.x.copy(); x[i, k] += sign * h
+            o.set_x(x)
+            es.append(energy(o)[0])
+        assert abs(-(es[0] - es[1]) / (2 * h) - f[i, k]) < 2e-5 * max(1.0, abs(f[i, k]))
+
+
 def test_neighbor_list_is_symmetric_and_complete():
     box = synth.config(1)
     o = capi.configure(capi.Engine("orc"), box)

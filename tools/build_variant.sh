@@ -8,6 +8,6 @@ DIR=$(cd "$(dirname "$0")/../constant_ph_b200/csrc" && pwd)
 mkdir -p "$DIR/variants"
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a $* -O3 -std=c++17 -lineinfo -ccbin /usr/bin/g++ \
   -Xcompiler -fPIC,-fopenmp --expt-relaxed-constexpr -shared -o "$DIR/variants/libcph_b200_$TAG.so" \
-  "$DIR"/cph_api.cu "$DIR"/neigh.cu "$DIR"/pair.cu "$DIR"/sites.cu "$DIR"/comm.cu "$DIR"/bonded.cu "$DIR"/microbench.cu \
+  "$DIR"/cph_api.cu "$DIR"/neigh.cu "$DIR"/pair.cu "$DIR"/sites.cu "$DIR"/comm.cu "$DIR"/bonded.cu "$DIR"/ljstates.cu "$DIR"/microbench.cu \
   -lcudart -ldl -lgomp
 echo "$DIR/variants/libcph_b200_$TAG.so"
