@@ -24,7 +24,9 @@ def main():
     bonded = len(sys.argv) > 3 and sys.argv[3] == "bonded"
     ljstates = len(sys.argv) > 3 and sys.argv[3] == "ljstates"
     box = synth.config(2, scale=scale, shuffle=True)
-    params = synth.jiggle_params(box, amp=0.9, period_lo=40.0, period_hi=90.0)
+    # an atom that gains an LJ site must not be driven into its neighbours: gentler motion in that mode
+    params = synth.jiggle_params(box, amp=0.35 if len(sys.argv) > 3 and sys.argv[3] == "ljstates" else 0.9,
+                                 period_lo=40.0, period_hi=90.0)
     grid = bench.decompose(box, world)
     loc, sublo, subhi = bench.rank_domain(box, grid, rank)
     owned = np.nonzero(np.all((box.x >= sublo) & (box.x < subhi), axis=1))[0]

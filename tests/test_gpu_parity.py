@@ -355,17 +355,23 @@ def test_lj_end_states_match_oracle(built, cfg, scale):
     bonded chains, corrected 1-4 pairs."""
     box = synth.config(cfg, scale=scale, **({"chain_len": 10} if cfg == 4 else {}))
     typeB = synth.lj_end_state_types(box)
+    if cfg == 5:
+        # the prescribed motion lets water hydrogens (no LJ site) come within 0.3 A of other molecules; giving
+        # them an LJ site there overflows both implementations alike: only the oxygens change type here
+        typeB[box.type[box.meta["tag_to_index"][box.titr_tag]] == 2] = 0
     assert (typeB > 0).any()
-    gpu, orc = engines(box, bias=HEAVY, lj_typeB=typeB)
+    bias = dict(m_lambda=2e5) if cfg == 4 else HEAVY      # the chain's 1-4 contacts make dU/dlambda ~ 1e3
+    gpu, orc = engines(box, bias=bias, lj_typeB=typeB)
     check_pass(gpu, orc)
-    plain = capi.configure(capi.Engine("cph", device=0), box, bias=HEAVY)
+    plain = capi.configure(capi.Engine("cph", device=0), box, bias=bias)
     plain.pair_pass(1); plain.site_reduce()
     assert np.abs(plain.get_sites()["dudl"] - gpu.get_sites()["dudl"]).max() > 1e-6      # the term is there
     assert np.abs(plain.get_forces() - gpu.get_forces()).max() > 1e-6
     # a moving trajectory: lists are rebuilt and pruned, lambda moves, the weights follow
-    params = synth.jiggle_params(box, amp=0.9, period_lo=40.0, period_hi=90.0)
+    # (a gentle one: an atom that GAINS an LJ site must not be driven into its neighbours)
+    params = synth.jiggle_params(box, amp=0.35, period_lo=40.0, period_hi=90.0)
     fg, fo = np.zeros_like(box.x), np.zeros_like(box.x)
-    for step in range(40):
+    for step in range(60):
         x = synth.jiggle_positions(box, params, step * box.dt)
         gpu.post_force(step, box.dt, x, fg)
         orc.post_force(step, box.dt, x, fo)
@@ -375,6 +381,7 @@ def test_lj_end_states_match_oracle(built, cfg, scale):
     tg, to = gpu.get_sites(), orc.get_sites()
     close(tg["dudl"], to["dudl"])
     assert np.abs(tg["lambda"] - to["lambda"]).max() <= 1e-8
+    assert np.abs(to["lambda"]).max() < 1.5
     sg, so = gpu.get_scalars(), orc.get_scalars()
     for k in ("HA", "HB", "evdwl", "ecoul", "H_lambda"):
         assert abs(sg[k] - so[k]) <= RTOL * abs(so[k]), (k, sg[k], so[k])
