@@ -250,6 +250,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the parity check against the committed golden values")
+    ap.add_argument("--lj-states", action="store_true",
+                    help="also give the titratable protons / hydroxyl oxygens LJ end states (cph_set_lj_states): the cost "
+                         "of the optional correction kernels; not the BASELINE workload, no golden check")
     ap.add_argument("--md-steps", type=int, default=100,
                     help="extra leg: flexible-water dynamics integrated on the device (0 = skip; 1 rank only)")
     args = ap.parse_args()
@@ -347,8 +350,9 @@ def main():
             idbuf.copy_(torch.frombuffer(bytearray(eng.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(idbuf, 0)
         eng.comm_init_nccl(nranks, rank, bytes(idbuf.cpu().numpy().tobytes()))
+    lj_kw = dict(lj_typeB=synth.lj_end_state_types(box)) if args.lj_states else {}
     capi.configure(eng, box, bias=dict(m_lambda=M_LAMBDA), sublo=sublo, subhi=subhi, procgrid=grid, myloc=loc,
-                   owned=owned)
+                   owned=owned, **lj_kw)
     nloc = eng.nlocal
     sel = slice(None) if owned is None else owned
 
@@ -368,7 +372,8 @@ def main():
     check = {"skipped": "golden values exist for the full-size workloads only (--atoms 1000000; config 4: 1/2/4/8 ranks)"}
     gpath = GOLDEN_CFG3 if args.config == 3 else os.path.join(
         os.path.dirname(GOLDEN_CFG3), "bench_cfg%d_n%d_golden.json" % (args.config, nranks if args.config == 4 else 1))
-    if os.path.exists(gpath) and args.atoms == 1_000_000 and not args.no_check and not (args.config == 2 and args.sweep):
+    if os.path.exists(gpath) and args.atoms == 1_000_000 and not args.no_check and not args.lj_states \
+            and not (args.config == 2 and args.sweep):
         golden = json.load(open(gpath))
         golden["path"] = os.path.relpath(gpath, os.path.dirname(os.path.abspath(__file__)))
         if golden["atoms"] == box.n:
@@ -562,7 +567,7 @@ def main():
                 "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config,
                 "parallelism": "spatial %dx%dx%d" % grid, "rebuilds_in_timed_region": rebuilds,
-                "prunes_in_timed_region": prunes, "check": check,
+                "prunes_in_timed_region": prunes, "check": check, "lj_states": bool(args.lj_states),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "roofline_fp64": roofline_fp64, "site_kernels_roofline": site_roofline, "cpu_baseline": cpu,
                 "kernels_ms_per_step": {k: v[0] / K for k, v in prof.items()}, "wall_ms_per_step": wall_dev / K,
