@@ -310,6 +310,20 @@ __global__ void mol_owned_kernel(int n, const int *__restrict__ perm, const int 
   if (k < n) mol[k] = molecule[perm[k]];
 }
 
+// build record of atom j / store of row entry `pos`: one IMAD.WIDE.U32 each for the address
+__device__ __forceinline__ float4 ld_xb(const float4 *xb, int j) {
+  unsigned long long a;
+  asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(a) : "r"(j), "l"(xb));
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a));
+  return v;
+}
+__device__ __forceinline__ void st_row(unsigned long long rowp, unsigned int pos, int j) {
+  unsigned long long a;
+  asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(a) : "r"(pos), "l"(rowp));
+  asm volatile("st.global.b32 [%0], %1;" ::"l"(a), "r"(j) : "memory");
+}
+
 // One warp per owned atom.  Lanes sweep, for each of the 5x5 (y,z) cell rows around the atom,
 // the x-run of cells that can hold a neighbour (contiguous in the sorted order; the run is
 // trimmed to the chord of the cutoff sphere at that row), test candidates on the packed fp32
@@ -324,7 +338,9 @@ list_build_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__re
                   int rowcap, int dummy, int *neigh, int *numneigh,
                   int *numspec, unsigned int *flags, unsigned long long *stats) {
   const int lane = threadIdx.x & 31;
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // the atom index is the same in every lane; taking it from lane 0 lets ptxas SEE that (warp-uniform control flow
+  // below: no divergence guards around the votes, loop bounds in uniform registers)
+  const int i = __shfl_sync(0xffffffffu, (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), 0);
   if (i >= nlocal) return;
   const double4 pi = xq[i];
   const float4 pti = xt[i];
@@ -342,6 +358,7 @@ list_build_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__re
   // xt.w here is the molecule id (0 = unknown): only same-molecule candidates can be special partners
   const int moli = __float_as_int(pti.w);
   int *row = neigh + (size_t)i * rowcap;
+  const unsigned long long rowp = (unsigned long long)row;
   int cnt = 0, nsp = 0;
   const float rl2 = (float)rlist2;
   const float lo2 = rl2 - margin, hi2 = rl2 + margin;
@@ -351,67 +368,78 @@ list_build_kernel(int nlocal, const double4 *__restrict__ xq, const float4 *__re
   // an atom whose +-2 stencil stays inside the interior never meets a ghost: skip that half of the loops
   const bool near_ghost = cx < gl.x + 2 || cx >= g.n[0] - gl.x - 2 || cy < gl.y + 2 || cy >= g.n[1] - gl.y - 2 ||
                           cz < gl.z + 2 || cz >= g.n[2] - gl.z - 2;
-  const int nsets = near_ghost ? 2 : 1;
-  for (int dz = -2; dz <= 2; dz++) {
-    const int z = cz + dz;
-    if (z < 0 || z >= g.n[2]) continue;
-    // distance from the atom to the z-slab of that cell row (xt is relative to the grid origin)
-    const float gz = dz == 0 ? 0.f : (dz > 0 ? z * wz - pti.z : pti.z - (z + 1) * wz);
-    for (int dy = -2; dy <= 2; dy++) {
-      const int y = cy + dy;
-      if (y < 0 || y >= g.n[1]) continue;
+  // The 25 rows' candidate runs are worked out by 25 lanes AT ONCE (one pass of arithmetic and one round of
+  // cell-start loads instead of 25 dependent ones), then handed out by shuffles in the fixed order
+  // dz, dy, owned-before-ghost -- the order the rows have always had.
+  int run_so = 0, run_eo = 0, run_sg = 0, run_eg = 0;
+  if (lane < 25) {
+    const int dz = lane / 5 - 2, dy = lane % 5 - 2;
+    const int z = cz + dz, y = cy + dy;
+    if (z >= 0 && z < g.n[2] && y >= 0 && y < g.n[1]) {
+      // distance from the atom to the z-slab / y-slab of that cell row (xt is relative to the grid origin)
+      const float gz = dz == 0 ? 0.f : (dz > 0 ? z * wz - pti.z : pti.z - (z + 1) * wz);
       const float gy = dy == 0 ? 0.f : (dy > 0 ? y * wy - pti.y : pti.y - (y + 1) * wy);
       const float rem = hi2 - fmaxf(gz, 0.f) * fmaxf(gz, 0.f) - fmaxf(gy, 0.f) * fmaxf(gy, 0.f);
-      if (rem < 0.f) continue;
-      const float xr = sqrtf(rem) * 1.0001f + 1e-3f;
-      const int x0 = max((int)floorf((pti.x - xr) * ivx), 0), x1 = min((int)floorf((pti.x + xr) * ivx), g.n[0] - 1);
-      if (x1 < x0) continue;
-      const int c0 = (z * g.n[1] + y) * g.n[0];
-      for (int set = 0; set < nsets; set++) {
-        const int *st = set ? start_g : start_o;
-        const int base = set ? nlocal : 0;
-        const int s = st[c0 + x0], e = st[c0 + x1 + 1];
-        for (int p0 = s; p0 < e; p0 += 32) {
-          const int p = p0 + lane;
-          bool ok = p < e;
-          const int j = base + p;
-          bool spc = false;    // candidate for a special-bond partner (same molecule): rare
-          if (ok) {
-            const float4 pj = xt[j];
-            const float fx = pti.x - pj.x, fy = pti.y - pj.y, fz = pti.z - pj.z;
-            const float r2 = fmaf(fx, fx, fmaf(fy, fy, fz * fz));
-            ok = r2 < hi2 && j != i;
-            if (ok && r2 > lo2) {   // borderline: decide in fp64, exactly as the reference rule
-              const double4 qj = xq[j];
-              const double dx = pi.x - qj.x, dy_ = pi.y - qj.y, dz_ = pi.z - qj.z;
-              ok = dx * dx + dy_ * dy_ + dz_ * dz_ < rlist2;
-            }
-            spc = ok && ns3 && __float_as_int(pj.w) == moli;
+      if (rem >= 0.f) {
+        const float xr = sqrtf(rem) * 1.0001f + 1e-3f;
+        const int x0 = max((int)floorf((pti.x - xr) * ivx), 0), x1 = min((int)floorf((pti.x + xr) * ivx), g.n[0] - 1);
+        if (x1 >= x0) {
+          const int c0 = (z * g.n[1] + y) * g.n[0];
+          run_so = start_o[c0 + x0];
+          run_eo = start_o[c0 + x1 + 1];
+          if (near_ghost) {
+            run_sg = start_g[c0 + x0];
+            run_eg = start_g[c0 + x1 + 1];
           }
-          if (__any_sync(0xffffffffu, spc)) {
-            // slow path (a few chunks per atom): look the tag up in special[i]; special-bond partners
-            // fill the row from the back, the rest of the chunk goes on to the fast path below
-            int sb = 0;
-            if (spc) {
-              const int tj = tag[j];
-              for (int k = 0; k < ns3; k++)
-                if (sp[k] == tj) { sb = k < ns1 ? 1 : (k < ns2 ? 2 : 3); break; }
-              if ((dropmask >> sb) & 1) { ok = false; sb = 0; }   // both weights zero (and not dsf): not stored
-            }
-            const unsigned int ms = __ballot_sync(0xffffffffu, ok && sb);
-            const int poss = nsp + __popc(ms & ((1u << lane) - 1));
-            if (ok && sb && poss < rowcap) row[rowcap - 1 - poss] = j | (sb << CPH_SBSHIFT);
-            nsp += __popc(ms);
-            if (sb) ok = false;
-          }
-          // ordinary neighbours fill the row from the front
-          const unsigned int m = __ballot_sync(0xffffffffu, ok);
-          const int pos = cnt + __popc(m & ((1u << lane) - 1));
-          if (ok && pos < rowcap) row[pos] = j;
-          cnt += __popc(m);
         }
       }
     }
+  }
+  const unsigned int ltmask = (1u << lane) - 1;
+  auto sweep = [&](const int s, const int e, const int base) {
+    for (int p0 = s; p0 < e; p0 += 32) {
+      const int p = p0 + lane;
+      // lanes past the end of the run re-read its last record (a valid address) and are masked out below: the
+      // test runs on predicates only, no divergent region around the load
+      const int j = base + min(p, e - 1);
+      const float4 pj = ld_xb(xt, j);
+      const float fx = pti.x - pj.x, fy = pti.y - pj.y, fz = pti.z - pj.z;
+      const float r2 = fmaf(fx, fx, fmaf(fy, fy, fz * fz));
+      bool ok = p < e && r2 < hi2 && j != i;
+      if (ok && r2 > lo2) {   // borderline (rare): decide in fp64, exactly as the reference rule
+        const double4 qj = xq[j];
+        const double dx = pi.x - qj.x, dy_ = pi.y - qj.y, dz_ = pi.z - qj.z;
+        ok = dx * dx + dy_ * dy_ + dz_ * dz_ < rlist2;
+      }
+      // candidate for a special-bond partner (same molecule): rare
+      const bool spc = ok && ns3 != 0 && __float_as_int(pj.w) == moli;
+      if (__any_sync(0xffffffffu, spc)) {
+        // slow path (a few chunks per atom): look the tag up in special[i]; special-bond partners
+        // fill the row from the back, the rest of the chunk goes on to the fast path below
+        int sb = 0;
+        if (spc) {
+          const int tj = tag[j];
+          for (int k = 0; k < ns3; k++)
+            if (sp[k] == tj) { sb = k < ns1 ? 1 : (k < ns2 ? 2 : 3); break; }
+          if ((dropmask >> sb) & 1) { ok = false; sb = 0; }   // both weights zero (and not dsf): not stored
+        }
+        const unsigned int ms = __ballot_sync(0xffffffffu, ok && sb);
+        const int poss = nsp + __popc(ms & ltmask);
+        if (ok && sb && poss < rowcap) row[rowcap - 1 - poss] = j | (sb << CPH_SBSHIFT);
+        nsp += __popc(ms);
+        if (sb) ok = false;
+      }
+      // ordinary neighbours fill the row from the front
+      const unsigned int m = __ballot_sync(0xffffffffu, ok);
+      const unsigned int pos = (unsigned int)(cnt + __popc(m & ltmask));
+      if (ok && pos < (unsigned int)rowcap) st_row(rowp, pos, j);
+      cnt += __popc(m);
+    }
+  };
+  auto uni = [](int v, int r) { return __shfl_sync(0xffffffffu, __shfl_sync(0xffffffffu, v, r), 0); };
+  for (int r = 0; r < 25; r++) {
+    sweep(uni(run_so, r), uni(run_eo, r), 0);
+    if (near_ghost) sweep(uni(run_sg, r), uni(run_eg, r), nlocal);
   }
   // pad the row to a whole 128-entry tile with the far-away dummy atom, so the pair kernel
   // streams full tiles and needs no tail logic

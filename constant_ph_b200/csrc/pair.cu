@@ -82,6 +82,19 @@ __device__ __forceinline__ const void *rec_addr(const double4 *xq, unsigned int 
   asm("mad.wide.u32 %0, %1, 32, %2;" : "=l"(a) : "r"(j), "l"(xq));
   return (const void *)a;
 }
+// prune kernel: fp32 record of atom j and the store of inner-row entry `pos`, one IMAD.WIDE.U32 per address
+__device__ __forceinline__ float4 ld_xt(const float4 *xt, int j) {
+  unsigned long long a;
+  asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(a) : "r"(j), "l"(xt));
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a));
+  return v;
+}
+__device__ __forceinline__ void st_entry(unsigned long long rowp, unsigned int pos, int v) {
+  unsigned long long a;
+  asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(a) : "r"(pos), "l"(rowp));
+  asm volatile("st.global.b32 [%0], %1;" ::"l"(a), "r"(v) : "memory");
+}
 // ---- TMA bulk copy + mbarrier (per-warp ring of the prune kernel) ------------------------------
 __device__ __forceinline__ void mbar_init(unsigned int bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -249,7 +262,10 @@ prune_kernel(int nlocal, const float4 *__restrict__ xt, const int *__restrict__ 
              int dummy, const int *__restrict__ type_has_lj, int *__restrict__ neigh2, int rowcap2,
              int *__restrict__ numneigh2) {
   __shared__ __align__(128) WarpSmem s_w[WARPS];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  // the warp index taken from lane 0: ptxas then KNOWS it is warp-uniform (ring addresses and the tile schedule
+  // live in uniform registers, the bulk-copy issue needs no per-lane waterfall)
+  const int w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const unsigned int ltmask = (1u << lane) - 1;
   WarpSmem &sm = s_w[w];
   const unsigned int bar0 = smem_u32(&sm.bar[0]);
@@ -292,6 +308,7 @@ prune_kernel(int nlocal, const float4 *__restrict__ xt, const int *__restrict__ 
     const int ntile = __shfl_sync(0xffffffffu, nt_mine, n);
     const float4 pti = xt[i];
     int *row2 = neigh2 + (size_t)i * rowcap2;
+    const unsigned long long row2p = (unsigned long long)row2;
     int cnt = 0;
     for (int t = 0; t < ntile; t++) {
       const unsigned int slot = cslot & (NBUF - 1);
@@ -301,7 +318,7 @@ prune_kernel(int nlocal, const float4 *__restrict__ xt, const int *__restrict__ 
       __syncwarp();
       cslot++;
       issue();
-      const float4 p0 = xt[r0], p1 = xt[r1], p2 = xt[r2], p3 = xt[r3];
+      const float4 p0 = ld_xt(xt, r0), p1 = ld_xt(xt, r1), p2 = ld_xt(xt, r2), p3 = ld_xt(xt, r3);
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         const int raw = u == 0 ? r0 : u == 1 ? r1 : u == 2 ? r2 : r3;
@@ -309,7 +326,7 @@ prune_kernel(int nlocal, const float4 *__restrict__ xt, const int *__restrict__ 
         const float dx = pti.x - pj.x, dy = pti.y - pj.y, dz = pti.z - pj.z;
         const bool in = fmaf(dx, dx, fmaf(dy, dy, dz * dz)) < cutf_inner;
         const unsigned int m = __ballot_sync(0xffffffffu, in);
-        if (in) row2[cnt + __popc(m & ltmask)] = raw | (__float_as_int(pj.w) << CPH_TYPESHIFT);
+        if (in) st_entry(row2p, (unsigned int)(cnt + __popc(m & ltmask)), raw | (__float_as_int(pj.w) << CPH_TYPESHIFT));
         cnt += __popc(m);
       }
     }
