@@ -180,10 +180,11 @@ struct cph_handle {
   // LJ end states (ljstates.cu): B-state type per titration entry; per-atom views; CSR list of the inner-row
   // entries that touch an atom with end states; g = dE/dlambda carried by each owned atom's own end states
   bool lj_states = false;
-  DevBuf<int> d_titr_typeB, d_es_tB, d_es_site, d_es_cnt, d_es_off, d_es_ent;
+  DevBuf<int> d_titr_typeB, d_es_tB, d_es_site, d_es_cnt, d_es_ent, d_es_own, d_es_word;
   DevBuf<unsigned int> d_es_tmask;     // bit t set: some owned or ghost atom of (A-state) type t has end states
   DevBuf<double> d_es_g;
-  int es_entries = 0;
+  int es_cap = 8;                      // slots per atom in the correction lists (grown to the largest list seen)
+  int es_nown = 0;                     // owned atoms that have end states themselves
   // device: sites
   DevBuf<double> d_pK, d_lam, d_vlam, d_alam, d_flam, d_fs, d_dfs, d_Us, d_dUs;
   DevBuf<double> d_theta;            // dynamical coordinate when coord_theta (lambda = sin^2 theta)
@@ -346,7 +347,9 @@ int cph_launch_xt(cph_handle *h);
 // ljstates.cu
 int cph_ljstates_set(cph_handle *h, int ntitr, const int *typeB);
 int cph_ljstates_map(cph_handle *h);            // after a list build
-int cph_ljstates_collect(cph_handle *h);        // after a prune
+// buffers the prune kernel fills when end states are declared (sized for the current atom count and capacity)
+int cph_ljstates_lists(cph_handle *h, const int **tB, const unsigned int **tmask, int **cnt, int **ent, int **over,
+                       int *cap);
 int cph_launch_ljstates(cph_handle *h, int eflag);   // after the pair pass: adds the end-state difference
 // sites.cu
 int cph_launch_partition(cph_handle *h, bool push = false);   // HA, HB, E_vdwl, E_coul + per-site sums (+ push to the mailboxes)

@@ -256,11 +256,20 @@ struct WarpSmem {
 
 // K2a: one warp per atom; TMA tile ring over the outer row; survivors written to the inner row
 // as (j | type_j << 28), padded to a multiple of 32 with the dummy atom.
+// ES (LJ end states declared, ljstates.cu): while an atom WITHOUT end states is pruned, the survivors that have
+// them are also written to the atom's short correction list (entry-major, es.cap slots per atom).
+struct PruneEs {
+  const int *tB;                 // [nall+1] B-state type of every owned / ghost atom, 0 = none
+  const unsigned int *tmask;     // bit t: some atom of A-state type t has end states (saves the tB gather)
+  int *cnt, *ent, *over;         // per-atom count, entries [k * nlocal + i], largest count seen
+  int cap;
+};
+template <bool ES>
 __global__ void __launch_bounds__(TPB, 4)
 prune_kernel(int nlocal, const float4 *__restrict__ xt, const int *__restrict__ neigh,
              const int *__restrict__ numneigh, const int *__restrict__ numspec, int rowcap, float cutf_inner,
              int dummy, const int *__restrict__ type_has_lj, int *__restrict__ neigh2, int rowcap2,
-             int *__restrict__ numneigh2) {
+             int *__restrict__ numneigh2, const __grid_constant__ PruneEs es) {
   __shared__ __align__(128) WarpSmem s_w[WARPS];
   const int lane = threadIdx.x & 31;
   // the warp index taken from lane 0: ptxas then KNOWS it is warp-uniform (ring addresses and the tile schedule
@@ -310,6 +319,20 @@ prune_kernel(int nlocal, const float4 *__restrict__ xt, const int *__restrict__ 
     int *row2 = neigh2 + (size_t)i * rowcap2;
     const unsigned long long row2p = (unsigned long long)row2;
     int cnt = 0;
+    // correction list of an atom without end states of its own (an atom WITH end states needs none: every entry
+    // of its row is corrected)
+    int ecnt = 0;
+    unsigned int tmask = 0;
+    if (ES) tmask = es.tB[i] ? 0u : *es.tmask;
+    auto collect = [&](const bool in, const int entry) {
+      const bool q = in && ((tmask >> ((unsigned int)entry >> CPH_TYPESHIFT)) & 1u) && es.tB[entry & CPH_JMASK] != 0;
+      const unsigned int mq = __ballot_sync(0xffffffffu, q);
+      if (mq) {
+        const int pos = ecnt + __popc(mq & ltmask);
+        if (q && pos < es.cap) es.ent[(size_t)pos * nlocal + i] = entry;
+        ecnt += __popc(mq);
+      }
+    };
     for (int t = 0; t < ntile; t++) {
       const unsigned int slot = cslot & (NBUF - 1);
       mbar_wait(bar0 + 8 * slot, (cslot / NBUF) & 1);
@@ -326,8 +349,10 @@ prune_kernel(int nlocal, const float4 *__restrict__ xt, const int *__restrict__ 
         const float dx = pti.x - pj.x, dy = pti.y - pj.y, dz = pti.z - pj.z;
         const bool in = fmaf(dx, dx, fmaf(dy, dy, dz * dz)) < cutf_inner;
         const unsigned int m = __ballot_sync(0xffffffffu, in);
-        if (in) st_entry(row2p, (unsigned int)(cnt + __popc(m & ltmask)), raw | (__float_as_int(pj.w) << CPH_TYPESHIFT));
+        const int entry = raw | (__float_as_int(pj.w) << CPH_TYPESHIFT);
+        if (in) st_entry(row2p, (unsigned int)(cnt + __popc(m & ltmask)), entry);
         cnt += __popc(m);
+        if (ES) collect(in, entry);
       }
     }
     // Special-bond partners (at the end of the outer row, class in bits 30-31) ride in the LAST chunk of the inner
@@ -341,11 +366,14 @@ prune_kernel(int nlocal, const float4 *__restrict__ xt, const int *__restrict__ 
         if (cnt + lane < padded0) row2[cnt + lane] = dummy | (1 << CPH_TYPESHIFT);
         cnt = padded0;
       }
+      int entry = 0;
       if (lane < nsp) {
         const int raw = neigh[(size_t)i * rowcap + (rowcap - 1 - lane)];
         const int j = raw & CPH_NEIGHMASK, sb = (raw >> CPH_SBSHIFT) & 3;
-        row2[cnt + lane] = j | (sb << CPH_SB2SHIFT) | (__float_as_int(xt[j].w) << CPH_TYPESHIFT);
+        entry = j | (sb << CPH_SB2SHIFT) | (__float_as_int(xt[j].w) << CPH_TYPESHIFT);
+        row2[cnt + lane] = entry;
       }
+      if (ES) collect(lane < nsp, entry);
       cnt += nsp;
     }
     // an inner row holds at most its outer row (ordinary + special entries) plus padding: <= rowcap2 (cph_launch_prune)
@@ -354,6 +382,10 @@ prune_kernel(int nlocal, const float4 *__restrict__ xt, const int *__restrict__ 
     if (lane == 0) {                                     // at least one (all-padding) chunk, so every row has a last chunk
       const int ti = __float_as_int(pti.w);
       numneigh2[i] = max(cnt, 1) | (ti << 24) | (type_has_lj[ti] ? 1 << 30 : 0);
+      if (ES) {
+        es.cnt[i] = min(ecnt, es.cap);
+        if (ecnt > es.cap) atomicMax(es.over, ecnt);
+      }
     }
   }
 }
@@ -588,14 +620,33 @@ int cph_launch_prune(cph_handle *h) {
   if (h->rowcap / CH * APW > MAXTILES)
     return cph_fail(h, CPH_ERR_OVERFLOW, "neighbour rows of %d entries exceed the prune kernel's tile schedule", h->rowcap);
   h->nlaunch += 2;
-  prune_kernel<<<(n + APB - 1) / APB, TPB, 0, h->stream>>>(n, h->d_xt.p, h->d_neigh.p, h->d_numneigh.p, h->d_numspec.p,
-                                                          h->rowcap, cutf, h->nall, h->d_type_has_lj.p, h->d_neigh2.p,
-                                                          h->rowcap2, h->d_numneigh2.p);
+  const int pblocks = (n + APB - 1) / APB;
+  if (!h->lj_states) {
+    prune_kernel<false><<<pblocks, TPB, 0, h->stream>>>(n, h->d_xt.p, h->d_neigh.p, h->d_numneigh.p, h->d_numspec.p,
+                                                        h->rowcap, cutf, h->nall, h->d_type_has_lj.p, h->d_neigh2.p,
+                                                        h->rowcap2, h->d_numneigh2.p, PruneEs{});
+  } else {
+    // LJ end states: the correction lists are written by the same pass; a list that outgrows its slots is the
+    // only reason to run it again (the capacity then fits the largest list seen)
+    for (int attempt = 0; attempt < 2; attempt++) {
+      PruneEs es;
+      CPH_TRY(cph_ljstates_lists(h, &es.tB, &es.tmask, &es.cnt, &es.ent, &es.over, &es.cap));
+      prune_kernel<true><<<pblocks, TPB, 0, h->stream>>>(n, h->d_xt.p, h->d_neigh.p, h->d_numneigh.p, h->d_numspec.p,
+                                                         h->rowcap, cutf, h->nall, h->d_type_has_lj.p, h->d_neigh2.p,
+                                                         h->rowcap2, h->d_numneigh2.p, es);
+      int over = 0;
+      CPH_CUDA(h, cudaMemcpyAsync(&over, es.over, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+      if (over <= h->es_cap) break;
+      if (attempt == 1) return cph_fail(h, CPH_ERR_OVERFLOW, "LJ end-state lists grew past %d entries twice", over);
+      h->es_cap = (over + 7) & ~7;
+      h->nlaunch++;
+    }
+  }
   snapshot_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(n, h->d_xq.p, h->d_xinner.p);
   CPH_CUDA(h, cudaGetLastError());
   h->inner_valid = true;
   h->nprunes++;
-  CPH_TRY(cph_ljstates_collect(h));         // the pairs that touch an atom with LJ end states, from the new rows
   return 0;
 }
 
