@@ -169,6 +169,10 @@ class Engine:
     def set_extra_partition(self, dHA, dHB):
         self._call("set_extra_partition", C.c_double(dHA), C.c_double(dHB))
 
+    def set_extra_dudl(self, dudl):
+        d = _f64(dudl)
+        self._call("set_extra_dudl", C.c_int(int(d.size)), _d(d))
+
     def set_coordinate(self, theta=True):
         self._call("set_coordinate", C.c_int(1 if theta else 0))
 

@@ -412,6 +412,17 @@ int cph_set_extra_partition(cph_handle *h, double dHA, double dHB) {
   return CPH_OK;
 }
 
+int cph_set_extra_dudl(cph_handle *h, int nsites, const double *dudl) {
+  CPH_TRY(need(h, h->have_sites, "cph_set_sites first"));
+  if (nsites != h->S || !dudl)
+    return cph_fail(h, CPH_ERR_ARG, "cph_set_extra_dudl: %d values for %d sites", dudl ? nsites : 0, h->S);
+  cudaSetDevice(h->device);
+  // a pageable source has been read completely when cudaMemcpyAsync returns: the caller may reuse its array
+  CPH_TRY(upload(h, h->d_extra_dudl, dudl, (size_t)nsites));
+  h->extra_dudl = true;
+  return CPH_OK;
+}
+
 int cph_set_excluded_policy(cph_handle *h, int drop) {
   h->drop_excluded = drop != 0;
   h->rowcap = 0;

@@ -172,6 +172,8 @@ struct cph_handle {
   FixParams fix{1, 0, 0, 0.0, 7.0, 300.0, 0.0019872067, 1.0, 1, 0, 0, 1};
   double qqrd2e = 332.06371;
   double extra_HA = 0.0, extra_HB = 0.0;   // host-tallied energy sources for the next site reduce (cpp:221-244)
+  DevBuf<double> d_extra_dudl;             // their per-site dE/dlambda (host KSpace, cpp:241-244), this rank's share
+  bool extra_dudl = false;                 // set for the next site reduce, then cleared
   // sites (host copies, site-major order)
   int S = 1, ntitr = 0;
   std::vector<int> titr_tag_sorted_h;  // titr tags sorted ascending (for the device binary search)

@@ -57,7 +57,7 @@ site_partition_kernel(int n, const double *__restrict__ eatom, const double *__r
                       const int *__restrict__ mask, int Hbit, int nbP, double *partials, int S, int lps,
                       const int *__restrict__ site_start, const int *__restrict__ titr_local,
                       const double *__restrict__ titr_dq, const double *__restrict__ phi,
-                      const double *__restrict__ lj_g, int implicit_site,
+                      const double *__restrict__ lj_g, const double *__restrict__ extra_dudl, int implicit_site,
                       double extra_HA, double extra_HB, const double *__restrict__ bonded_e, double *red,
                       unsigned int *ticket, const __grid_constant__ MailRed mr) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -92,6 +92,8 @@ site_partition_kernel(int n, const double *__restrict__ eatom, const double *__r
       hd += __shfl_xor_sync(0xffffffffu, hd, o);
     }
     if (site < S) {
+      // host-tallied dE/dlambda_s of this rank (KSpace stays with LAMMPS: cpp:241-244, cph_set_extra_dudl)
+      if (extra_dudl) d += extra_dudl[site];
       if (sub == 0) {
         red[4 + site] = d;
         if (!implicit_site) red[4 + S + site] = hd;
@@ -621,10 +623,12 @@ int cph_launch_partition(cph_handle *h, bool push) {
   site_partition_kernel<<<nbP + nbS, TPB, 0, st>>>(n, h->d_eatom.p, h->d_evdwl.p, h->d_mask.p, h->fix.Hbit, nbP,
                                                   h->d_part.p, S, lps, h->d_site_start.p, h->d_titr_local.p,
                                                   h->d_titr_dq.p, h->d_phi.p,
-                                                  h->lj_states ? h->d_es_g.p : nullptr, h->fix.implicit_site, h->extra_HA,
+                                                  h->lj_states ? h->d_es_g.p : nullptr,
+                                                  h->extra_dudl ? h->d_extra_dudl.p : nullptr, h->fix.implicit_site, h->extra_HA,
                                                   h->extra_HB, h->have_topology ? h->d_bonded_e.p : nullptr,
                                                   h->d_red.p, h->d_flags.p + 80, mr);
   h->extra_HA = h->extra_HB = 0.0;   // consumed
+  h->extra_dudl = false;
   h->nlaunch += 1;
   CPH_CUDA(h, cudaGetLastError());
   return 0;

@@ -173,6 +173,14 @@ int cph_site_reduce(cph_handle *h);
  * them as cpp:264-267 does and hands this rank's two sums over; they enter HA and HB (and HB-HA of the
  * reference's single site) at the next site reduce and are then cleared. */
 int cph_set_extra_partition(cph_handle *h, double dHA, double dHB);
+/* The same sources seen by north_star's charge derivative: dU/dlambda_s = sum_i dq_i dE/dq_i needs dE/dq_i of
+ * every term that depends on the charges.  KSpace (cpp:241-244) stays with LAMMPS; its per-atom energy is
+ * e_i = q_i phi_i / 2 with phi_i = dE_kspace/dq_i (E is a quadratic form of the charges), so the fix recovers
+ * phi_i = 2 eatom_i / q_i on the titratable atoms it owns and hands over this rank's sums
+ * dudl[s] = sum_{i in s, owned} (qB_i - qA_i) phi_i.  They are added to the rank's per-site sums before the
+ * all-reduce that replaces cpp:274, at the next site reduce, and are then cleared.  nsites must equal the
+ * site count of cph_set_sites. */
+int cph_set_extra_dudl(cph_handle *h, int nsites, const double *dudl);
 /* calculate_df + calculate_dU + integrate_lambda (cpp:109-145), dt = nevery*update->dt. */
 int cph_integrate_lambda(cph_handle *h, double dt);
 /* north_star hooks absent from the reference. */

@@ -80,6 +80,7 @@ struct Oracle {
   int coord_theta = 0;            // 1: the dynamical coordinate is theta, lambda = sin^2 theta
   std::vector<double> theta;
   double extra_HA = 0, extra_HB = 0;   // host-tallied sources of compute_Hs (cpp:221-249)
+  std::vector<double> extra_dudl;      // their per-site dE/dlambda (host KSpace), consumed by the next site_reduce
   int water_buffer = 0;           // modify_water(): keep the box charge constant through the 3-atom water group
   std::vector<double> qbase;      // charges as supplied by the host (the lambda = 0 state of the buffer atoms)
   // sites
@@ -568,6 +569,8 @@ void site_reduce(Oracle *o) {
   }
   if (o->implicit_site) hd[0] += (long double)o->extra_HB - (long double)o->extra_HA;
   o->extra_HA = o->extra_HB = 0;
+  for (size_t s = 0; s < o->extra_dudl.size() && s < (size_t)o->S; s++) d[s] += o->extra_dudl[s];
+  o->extra_dudl.clear();
   for (int s = 0; s < o->S; s++) { o->dudl[s] = (double)d[s]; o->hdiff[s] = (double)hd[s]; }
 }
 
@@ -782,6 +785,11 @@ int orc_set_bias(void *h, double w, double s, double hbar, double k, double a, d
 
 int orc_set_thermostat(void *h, double tau) { ORC->nh_tau = tau; return 0; }
 int orc_set_extra_partition(void *h, double a, double b) { ORC->extra_HA = a; ORC->extra_HB = b; return 0; }
+int orc_set_extra_dudl(void *h, int nsites, const double *d) {
+  if (nsites != ORC->S || !d) return -1;
+  ORC->extra_dudl.assign(d, d + nsites);
+  return 0;
+}
 int orc_set_coordinate(void *h, int c) { ORC->coord_theta = c == 1; return 0; }
 int orc_set_water_buffer(void *h, int enable) { ORC->water_buffer = enable ? 1 : 0; return 0; }
 

@@ -126,6 +126,10 @@ class Atom {
   tagint **special = nullptr;
   int maxspecial = 0;
   int q_flag = 1, molecule_flag = 1;
+  enum { MAP_NONE = 0, MAP_ARRAY = 1, MAP_HASH = 2, MAP_YES = 3 };
+  int map_style = MAP_ARRAY;
+  std::vector<int> map_array;      // harness: tag -> local index (owned copy), -1 when not on this rank
+  int map(tagint t) const { return (t >= 0 && (size_t)t < map_array.size()) ? map_array[t] : -1; }
 };
 
 class Group {
@@ -222,7 +226,13 @@ class Comm {
  public:
   int me = 0, nprocs = 1;
   int procgrid[3] = {1, 1, 1}, myloc[3] = {0, 0, 0};
-  void reverse_comm(class Fix *) {}   // the harness gives every rank only owned atoms: nothing to fold
+  // Ghosts of the harness are periodic images of the rank's own atoms (upstream: the swaps with sendproc == me).
+  // ghost g = atom nlocal+g is an image of owned atom ghost_owner[g]; reverse_comm folds what the fix tallied on
+  // the ghosts back onto their owners through the fix's own pack/unpack_reverse_comm, as Comm::reverse_comm(Fix *)
+  // does upstream (defined below, after class Fix).
+  std::vector<int> ghost_owner;
+  int first_ghost = 0;
+  inline void reverse_comm(class Fix *);
   void forward_comm(class Fix *) {}
 };
 
@@ -330,6 +340,14 @@ class Fix : protected Pointers {
   virtual double compute_vector(int) { return 0.0; }
   virtual double memory_usage() { return 0.0; }
 };
+
+inline void Comm::reverse_comm(Fix *fix) {
+  const int n = (int)ghost_owner.size();
+  if (n == 0) return;
+  std::vector<double> buf((size_t)n * (fix->comm_reverse > 0 ? fix->comm_reverse : 1));
+  fix->pack_reverse_comm(n, first_ghost, buf.data());
+  fix->unpack_reverse_comm(n, ghost_owner.data(), buf.data());
+}
 
 namespace utils {
 inline void missing_cmd_args(const std::string &file, int line, const std::string &cmd, Error *error) {

@@ -536,6 +536,37 @@ void FixConstantPH::compute_Hs()
     if ((mask[i] & in.hyd_bit) == 0) without_hydrogens += host_energy[i];
   }
   require(cph_set_extra_partition(cph, everyone, without_hydrogens), "cph_set_extra_partition");
+
+  // north_star's charge derivative needs the k-space share of dE/dq_i as well
+  if (opt.dudl == CPH_DUDL_CHARGE && tab.nsites > 0 && force->kspace && force->kspace->compute_flag &&
+      force->kspace->eatom)
+    kspace_site_derivative(force->kspace->eatom);
+}
+
+/* ----------------------------------------------------------------------
+   KSpace (cpp:241-244) stays with LAMMPS.  Its energy is a quadratic form of the charges, so the per-atom
+   energy it tallies is e_i = q_i phi_i / 2 with phi_i = dE_kspace/dq_i (self and neutralising terms included).
+   dU/dlambda_s gains sum_{i in s} (qB_i - qA_i) phi_i over the titratable atoms this rank owns; the library
+   adds the sums to its own before the all-reduce.  An atom whose charge is exactly zero at this lambda gives
+   no handle on phi_i and contributes nothing.
+------------------------------------------------------------------------- */
+
+void FixConstantPH::kspace_site_derivative(const double *ekspace)
+{
+  if (force->kspace->tip4pflag)
+    error->all(FLERR, "fix constant_pH dudl charge cannot take the k-space potential from a TIP4P KSpace style");
+  if (atom->map_style == Atom::MAP_NONE)
+    error->all(FLERR, "fix constant_pH with a KSpace style requires an atom map, see atom_modify");
+  std::vector<double> site_sum(tab.nsites, 0.0);
+  const int nlocal = atom->nlocal;
+  for (int t = 0; t < tab.natoms; t++) {
+    const int i = atom->map(tab.tag[t]);
+    if (i < 0 || i >= nlocal) continue;
+    const double q = atom->q[i];
+    if (q == 0.0) continue;
+    site_sum[tab.site[t]] += (tab.qB[t] - tab.qA[t]) * 2.0 * ekspace[i] / q;
+  }
+  require(cph_set_extra_dudl(cph, tab.nsites, site_sum.data()), "cph_set_extra_dudl");
 }
 
 /* ---------------------------------------------------------------------- */

@@ -100,6 +100,7 @@ class FixConstantPH : public Fix {
   // integrate_lambda and modify_water (h:54-58) are kernels of the library (sites.cu)
   void compute_Hs();               // cpp:177-280: host-tallied sources only, the pair part is on the device
   void set_force();                // cpp:149-171
+  void kspace_site_derivative(const double *ekspace);   // cpp:241-244 seen by the charge derivative
 
   void require(int rc, const char *what);
   void run_device_step(bool setup_only);

@@ -10,6 +10,11 @@
 // Harness options (in this order, each optional, before the fix keywords):
 //   nevery N        the fix's nevery argument
 //   bonded SCALE    a synthetic bond style whose per-atom energy is SCALE*(1 + i % 7) (compute_Hs sources, cpp:221-253)
+//   ghosts K        (after `bonded`) every K-th owned atom gets one periodic-image ghost; the bond style tallies a
+//                   quarter of that atom's energy on the ghost (newton_bond on) and the fix must fold it back with
+//                   comm->reverse_comm(this) -> pack/unpack_reverse_comm (cpp:253, 287-308) to get the same HA/HB
+//   kspace SCALE    a synthetic KSpace style: potential phi_i = SCALE*(1 + tag_i % 5) on every atom, per-atom energy
+//                   e_i = q_i phi_i / 2 from the CURRENT atom->q before every force evaluation (cpp:241-244)
 //   runs R          split NSTEPS into R `run` commands: init() + setup() at the start of each, as LAMMPS does
 //   jiggle AMP      atoms move: x_i(t) = x0_i + AMP sin(2 pi t / T_i + phi_i + d) per dimension d, T_i = 60 + i % 80,
 //                   phi_i = 0.37 i (constant_ph_b200.synth.harness_jiggle replays it for the oracle)
@@ -47,7 +52,7 @@ static std::vector<T> pick(const std::vector<T> &v, const std::vector<int> &rows
 }
 
 int main(int argc, char **argv) {
-  if (argc < 3) { fprintf(stderr, "usage: harness BOX.bin NSTEPS [nevery N] [bonded S] [runs R] [jiggle A] [timing] [fix keywords...]\n"); return 1; }
+  if (argc < 3) { fprintf(stderr, "usage: harness BOX.bin NSTEPS [nevery N] [bonded S] [ghosts K] [kspace S] [runs R] [jiggle A] [timing] [fix keywords...]\n"); return 1; }
   FILE *fp = fopen(argv[1], "rb");
   if (!fp) { perror(argv[1]); return 1; }
   const int nsteps = atoi(argv[2]);
@@ -98,6 +103,8 @@ int main(int argc, char **argv) {
   atom->x = xrow.data(); atom->f = frow.data(); atom->q = q.data(); atom->type = type.data();
   atom->tag = tag.data(); atom->mask = mask.data(); atom->molecule = mol.data();
   atom->nspecial = nsrow.data(); atom->special = sprow.data();
+  atom->map_array.assign((size_t)nall + 2, -1);
+  for (int i = 0; i < n; i++) atom->map_array[tag[i]] = i;
   lmp.group->add("Hgrp", hi[6]);
   lmp.group->add("Wgrp", hi[7]);
   lmp.group->count_override = 3;            // group->count is a global (all-rank) count upstream
@@ -136,7 +143,36 @@ int main(int argc, char **argv) {
     bond.eatom = bond_eatom.data();
     lmp.force->bond = &bond;
     kw += 2;
+    if (opt("ghosts")) {
+      const int every = std::max(1, atoi(argv[kw + 1]));
+      for (int i = 0; i < n; i += every) lmp.comm->ghost_owner.push_back(i);
+      const int ng = (int)lmp.comm->ghost_owner.size();
+      lmp.comm->first_ghost = n;
+      atom->nghost = ng;
+      atom->nmax = n + ng;
+      bond_eatom.resize(n + ng);
+      for (int g = 0; g < ng; g++) {
+        const int i = lmp.comm->ghost_owner[g];
+        bond_eatom[n + g] = 0.25 * bond_eatom[i];
+        bond_eatom[i] *= 0.75;
+      }
+      bond.eatom = bond_eatom.data();
+      kw += 2;
+    }
   }
+  KSpace kspace;
+  std::vector<double> kspace_eatom;
+  double kspace_scale = 0.0;
+  if (opt("kspace")) {
+    kspace_scale = atof(argv[kw + 1]);
+    kspace_eatom.assign(n, 0.0);
+    kspace.eatom = kspace_eatom.data();
+    lmp.force->kspace = &kspace;
+    kw += 2;
+  }
+  auto kspace_compute = [&]() {                            // KSpace::compute(eflag_atom) on the current charges
+    for (int i = 0; i < (int)kspace_eatom.size(); i++) kspace_eatom[i] = 0.5 * q[i] * kspace_scale * (1 + tag[i] % 5);
+  };
   int nruns = 1;
   if (opt("runs")) { nruns = std::max(1, atoi(argv[kw + 1])); kw += 2; }
   double jiggle = 0.0;
@@ -177,6 +213,7 @@ int main(int argc, char **argv) {
       lmp.update->ntimestep = step;
       lmp.update->eflag_atom = step;
       std::fill(f.begin(), f.end(), 0.0);
+      kspace_compute();
       fix.setup(0);
       if (run == 0) report(0);
       const long last = (long)nsteps * (run + 1) / nruns;
@@ -193,6 +230,7 @@ int main(int argc, char **argv) {
         const auto t1 = now();
         move_atoms(step);                                   // the host integrator's job
         std::fill(f.begin(), f.end(), 0.0);                 // force_clear(); pair->compute is off
+        kspace_compute();
         const auto t2 = now();
         fix.post_force(0);
         if (mask_bits & FixConst::FINAL_INTEGRATE) fix.final_integrate();

@@ -85,11 +85,27 @@ def oracle_trajectory(box, mode, kw, nsteps, jiggle=0.0):
     vv = kw.get("integrator", capi.INTEGRATE_REFERENCE) == capi.INTEGRATE_VV
 
     def extras(step):
-        if mode != "bonded" or step % nev:
+        if step % nev:
             return
-        e = 0.01 * (1 + np.arange(box.n) % 7)
-        Hm = (box.mask & synth.GROUP_H_BIT) != 0
-        orc.set_extra_partition(float(e.sum()), float(e[~Hm].sum()))
+        if mode in ("bonded", "bonded_ghosts"):
+            e = 0.01 * (1 + np.arange(box.n) % 7)
+            Hm = (box.mask & synth.GROUP_H_BIT) != 0
+            orc.set_extra_partition(float(e.sum()), float(e[~Hm].sum()))
+        if mode == "kspace":
+            # the harness' synthetic KSpace: e_i = q_i phi_i / 2, phi_i = 0.8 (1 + tag_i % 5), from the charges the
+            # host holds when the forces are computed (the data file's at setup, q(lambda) pulled back afterwards)
+            q = box.q if step == 0 else orc.get_q()
+            phi = 0.8 * (1 + box.tag % 5)
+            e = 0.5 * q * phi
+            Hm = (box.mask & synth.GROUP_H_BIT) != 0
+            orc.set_extra_partition(float(e.sum()), float(e[~Hm].sum()))
+            row = {int(t): i for i, t in enumerate(box.tag)}
+            d = np.zeros(box.nsites)
+            for t in range(box.titr_tag.size):
+                i = row[int(box.titr_tag[t])]
+                if q[i] != 0.0:
+                    d[box.titr_site[t]] += (box.qB[t] - box.qA[t]) * 2.0 * e[i] / q[i]
+            orc.set_extra_dudl(d)
 
     def pos(step):
         return box.x if jiggle == 0.0 else synth.harness_jiggle(box.x, jiggle, step * box.dt)
@@ -109,7 +125,7 @@ def oracle_trajectory(box, mode, kw, nsteps, jiggle=0.0):
 
 
 MODES = ["charge", "reference", "vv", "vv_nevery2", "buffer", "theta", "bonded", "thermostat", "biasconst",
-         "two_runs", "moving", "excluded_drop", "ljstates"]
+         "two_runs", "moving", "excluded_drop", "ljstates", "bonded_ghosts", "kspace"]
 
 
 @pytest.mark.gpu
@@ -155,6 +171,18 @@ def test_fix_trajectory_matches_oracle(box_files, mode):
         pre = ["nevery", 2, "bonded", 0.01]
         args = ["mlambda", 2000, "lambda0", 0.5]
         kw = dict(bias=dict(m_lambda=2000.0), dudl=capi.DUDL_REFERENCE, implicit_site=True, nevery=2)
+    elif mode == "bonded_ghosts":
+        # the same source with a quarter of every third atom's energy tallied on a periodic-image ghost: HA/HB only
+        # come out right if compute_Hs folds the ghosts back (comm->reverse_comm -> pack/unpack_reverse_comm, cpp:253)
+        pre = ["nevery", 2, "bonded", 0.01, "ghosts", 3]
+        args = ["mlambda", 2000, "lambda0", 0.5]
+        kw = dict(bias=dict(m_lambda=2000.0), dudl=capi.DUDL_REFERENCE, implicit_site=True, nevery=2)
+    elif mode == "kspace":
+        # a host KSpace style (cpp:241-244): its energy joins HA/HB and, in charge mode, its potential joins
+        # dU/dlambda_s through phi_i = 2 e_i / q_i (cph_set_extra_dudl)
+        pre = ["kspace", 0.8]
+        args = ["sites", s, "mlambda", 2000]
+        kw = dict(bias=dict(m_lambda=2000.0))
     elif mode == "theta":
         args = ["sites", s, "mlambda", 2000, "coordinate", "theta"]
         kw = dict(bias=dict(m_lambda=2000.0), theta=True)

@@ -128,6 +128,36 @@ def test_lambda_trajectory_moving_atoms_with_rebuilds(built):
     close(gpu.get_forces(), orc.get_forces(), rtol=1e-9)
 
 
+def test_host_kspace_site_derivative_feeds_the_lambda_dynamics(built):
+    """cph_set_extra_dudl (cpp:241-244 for north_star's charge derivative): per-site sums handed over by the host
+    enter dU/dlambda_s of the next site reduce only, and the lambda trajectory follows the oracle's."""
+    box = synth.config(2, scale=0.25)
+    gpu, orc = engines(box, bias=HEAVY)
+    f = np.zeros((box.n, 3))
+    rng = np.random.default_rng(11)
+    lg, lo = [], []
+    for step in range(60):
+        extra = rng.normal(0.0, 25.0, box.nsites) if step % 2 == 0 else None
+        for eng, out in ((gpu, lg), (orc, lo)):
+            if extra is not None:
+                eng.set_extra_dudl(extra)
+            eng.post_force(step, box.dt, box.x, f)
+            out.append((eng.get_sites()["lambda"].copy(), eng.get_sites()["dudl"].copy()))
+    for (lam_g, d_g), (lam_o, d_o) in zip(lg, lo):
+        assert np.abs(lam_g - lam_o).max() <= 1e-8
+        close(d_g, d_o)
+    # the extra term is consumed by one reduction: odd steps carry none
+    gpu.pair_pass(1); gpu.site_reduce()
+    plain = gpu.get_sites()["dudl"].copy()
+    gpu.set_extra_dudl(np.full(box.nsites, 7.0))
+    gpu.site_reduce()
+    close(gpu.get_sites()["dudl"], plain + 7.0)
+    gpu.site_reduce()
+    close(gpu.get_sites()["dudl"], plain, rtol=1e-15)
+    with pytest.raises(capi.CphError):
+        gpu.set_extra_dudl(np.zeros(box.nsites + 1))
+
+
 @pytest.mark.parametrize("bias_mode,fscale", [(capi.BIAS_EXACT, capi.FSCALE_ONE_MINUS),
                                               (capi.BIAS_AS_WRITTEN, capi.FSCALE_LAMBDA)])
 def test_reference_mode_single_global_lambda(built, bias_mode, fscale):

@@ -130,6 +130,23 @@ def test_analytic_dudl_equals_perturbed_charge_reevaluation(cfg, scale):
         assert abs(fd - dudl[site]) < 1e-8 * max(1.0, abs(dudl[site]))
 
 
+def test_host_kspace_terms_enter_the_site_sums_once():
+    """cpp:241-244 seen by the charge derivative (cph_set_extra_dudl): a host-tallied dE/dlambda_s is added to the
+    next site reduce and then forgotten; a wrong site count is refused."""
+    box = synth.config(2, scale=0.2)
+    o = capi.configure(capi.Engine("orc"), box)
+    o.pair_pass(1); o.site_reduce()
+    base = o.get_sites()["dudl"].copy()
+    extra = 0.3 * (1 + np.arange(box.nsites))
+    o.set_extra_dudl(extra)
+    o.site_reduce()
+    assert np.allclose(o.get_sites()["dudl"], base + extra, rtol=0, atol=1e-12)
+    o.site_reduce()
+    assert np.array_equal(o.get_sites()["dudl"], base)
+    with pytest.raises(capi.CphError):
+        o.set_extra_dudl(extra[:-1])
+
+
 def test_lj_end_states_limits_and_derivatives():
     """docs/SPEC.md, LJ end states.  lambda = 0: the plain run; lambda = 1: the run with the B types written into
     atom->type; in between: dU/dlambda equals the central difference of the total energy (E is a polynomial of
