@@ -18,7 +18,8 @@ import os
 import numpy as np
 
 HOST, DEVICE = 0, 1
-PAIR_COUL_CUT, PAIR_COUL_DSF = 0, 1
+PAIR_COUL_CUT, PAIR_COUL_DSF, PAIR_COUL_LONG = 0, 1, 2
+KSPACE_NONE, KSPACE_EWALD = 0, 1
 DUDL_REFERENCE, DUDL_CHARGE = 0, 1
 INTEGRATE_REFERENCE, INTEGRATE_VV = 0, 1
 BIAS_EXACT, BIAS_AS_WRITTEN = 0, 1
@@ -172,6 +173,16 @@ class Engine:
     def set_extra_dudl(self, dudl):
         d = _f64(dudl)
         self._call("set_extra_dudl", C.c_int(int(d.size)), _d(d))
+
+    def set_kspace(self, style, g_ewald=0.0, kmax=(0, 0, 0)):
+        """kspace_style ewald on the device (after set_domain); pair style PAIR_COUL_LONG is its real-space part."""
+        self._call("set_kspace", C.c_int(style), C.c_double(g_ewald), C.c_int(int(kmax[0])), C.c_int(int(kmax[1])),
+                   C.c_int(int(kmax[2])))
+
+    def get_kspace_energy(self):
+        e = C.c_double(0.0)
+        self._call("get_kspace_energy", C.byref(e))
+        return float(e.value)
 
     def set_coordinate(self, theta=True):
         self._call("set_coordinate", C.c_int(1 if theta else 0))
@@ -465,7 +476,7 @@ def configure(eng, box, nevery=1, dudl=DUDL_CHARGE, integrator=INTEGRATE_REFEREN
               fscale=FSCALE_LAMBDA, bias_mode=BIAS_EXACT, implicit_site=False, ftm2v=None,
               sublo=None, subhi=None, procgrid=(1, 1, 1), myloc=(0, 0, 0), owned=None, bias=None,
               water_buffer=False, theta=False, cut_lj=None, cut_coul=None, thermostat=0.0,
-              topology=None, velocities=None, drop_excluded=False, lj_typeB=None):
+              topology=None, velocities=None, drop_excluded=False, lj_typeB=None, kspace=None):
     """Push a synth.Box into an engine: the calls FixConstantPH's constructor/init/setup make.
 
     implicit_site=True reproduces the reference's single global lambda over the hydrogen
@@ -473,13 +484,17 @@ def configure(eng, box, nevery=1, dudl=DUDL_CHARGE, integrator=INTEGRATE_REFEREN
     owned: index array of the atoms this rank owns (None = all).
     bias: overrides of the init() constants (fix_constant_pH.cpp:86-96), e.g. m_lambda.
     topology: a synth.Topology -> bonded terms on; velocities: (n,3) -> fix-nve dynamics on.
-    lj_typeB: B-state atom type per titratable atom (LJ end states, docs/SPEC.md), aligned with box.titr_tag."""
+    lj_typeB: B-state atom type per titratable atom (LJ end states, docs/SPEC.md), aligned with box.titr_tag.
+    kspace: dict(g_ewald=..., kmax=(kx, ky, kz)) -> kspace_style ewald on; box.style should be PAIR_COUL_LONG with
+    box.alpha = g_ewald (what pair lj/cut/coul/long's init_style takes from force->kspace)."""
     from . import synth
     eng.set_units(synth.QQRD2E, synth.BOLTZ, synth.FTM2V if ftm2v is None else ftm2v)
     # cut_lj: optional (ntypes+1)^2 table of per-type-pair LJ cutoffs (pair_coeff ... cut_lj); cut_coul: override
     eng.set_pair(box.style, box.ntypes, box.epsilon, box.sigma, cut_lj, box.cut_lj,
                  box.cut_coul if cut_coul is None else cut_coul, box.alpha, box.special_lj, box.special_coul)
     eng.set_domain(box.boxlo, box.boxhi, (1, 1, 1), sublo, subhi, procgrid, myloc, box.skin)
+    if kspace:
+        eng.set_kspace(KSPACE_EWALD, kspace["g_ewald"], kspace["kmax"])
     pK0 = float(box.pK[0]) if box.nsites else 0.0
     eng.set_fix(nevery, synth.GROUP_H_BIT, synth.GROUP_W_BIT, pK0, box.pH, box.T)
     eng.set_bias(bias_mode, **(bias or {}))

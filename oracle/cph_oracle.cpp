@@ -125,6 +125,12 @@ struct Oracle {
   // f2: plain velocity-Verlet of the atoms (fix nve) so that boxes can run real dynamics
   std::vector<double> mass, v;
   bool md = false;
+  // f4: kspace_style ewald (reciprocal part of the Ewald sum; pair style 2 = lj/cut/coul/long is its real-space part)
+  bool kspace = false;
+  double g_ewald = 0;
+  int kmax[3] = {0, 0, 0};
+  std::vector<double> kvec, ug;   // half-space wave vectors (3 per entry) and 4 pi/V exp(-k^2/4g^2)/k^2
+  double e_kspace = 0;
 };
 
 int fail(Oracle *o, int code, const char *msg) {
@@ -197,7 +203,7 @@ void build_list(Oracle *o) {
     sx[k] = (int)std::ceil(rlist / bw[k]);
   }
   // coul/dsf keeps fully excluded pairs for the damped-term correction (Appendix A) unless told to drop them
-  const bool keep_all_special = (o->style == 1) && !o->drop_excluded;
+  const bool keep_all_special = (o->style >= 1) && !o->drop_excluded;
   o->first.assign(n + 1, 0);
   std::vector<int> cnt(n, 0);
   // for each i visit distinct bins within the stencil (periodic wrap may alias bins when nb is small)
@@ -535,6 +541,86 @@ void md_kick(Oracle *o, double dt, bool drift) {
   }
 }
 
+// f4 -- kspace_style ewald [UPSTREAM-LAMMPS ewald.cpp, from memory; standard Ewald summation].  The reference only
+// reads force->kspace->eatom (cpp:241-244); north_star's charge derivative needs the k-space potential as well, so
+// the reciprocal sum joins the path.  With S(k) = sum_j q_j exp(i k.r_j) over the half space of wave vectors
+// k = 2 pi (nx/Lx, ny/Ly, nz/Lz), |n_d| <= kmax_d, k^2 <= gsqmx:
+//   E = qqrd2e [ sum_k ug(k) |S(k)|^2 - g/sqrt(pi) sum q_i^2 - pi (sum q_i)^2 / (2 g^2 V) ],  ug = 4 pi/V exp(-k^2/4g^2)/k^2
+//   phi_i = dE/dq_i = qqrd2e [ sum_k 2 ug (cos(k.r_i) Re S + sin(k.r_i) Im S) - 2 g q_i/sqrt(pi) - pi sum q/(g^2 V) ]
+//   f_i = qqrd2e q_i sum_k 2 ug k (sin(k.r_i) Re S - cos(k.r_i) Im S),   eatom_i = q_i phi_i / 2  (E is a quadratic form)
+// The real-space part erfc(g r)/r is pair style 2 (lj/cut/coul/long).
+void ewald_setup(Oracle *o) {
+  o->kvec.clear(); o->ug.clear();
+  if (!o->kspace) return;
+  double L[3], unitk[3];
+  for (int d = 0; d < 3; d++) { L[d] = o->hi[d] - o->lo[d]; unitk[d] = 2.0 * MY_PI / L[d]; }
+  const double V = L[0] * L[1] * L[2];
+  double gsqmx = 0;
+  for (int d = 0; d < 3; d++) gsqmx = std::max(gsqmx, unitk[d] * unitk[d] * o->kmax[d] * o->kmax[d]);
+  gsqmx *= 1.00001;
+  for (int nx = 0; nx <= o->kmax[0]; nx++)
+    for (int ny = -o->kmax[1]; ny <= o->kmax[1]; ny++)
+      for (int nz = -o->kmax[2]; nz <= o->kmax[2]; nz++) {
+        if (!(nx > 0 || (nx == 0 && ny > 0) || (nx == 0 && ny == 0 && nz > 0))) continue;
+        const double kx = unitk[0] * nx, ky = unitk[1] * ny, kz = unitk[2] * nz;
+        const double sqk = kx * kx + ky * ky + kz * kz;
+        if (sqk > gsqmx) continue;
+        o->kvec.push_back(kx); o->kvec.push_back(ky); o->kvec.push_back(kz);
+        o->ug.push_back(4.0 * MY_PI / V * std::exp(-0.25 * sqk / (o->g_ewald * o->g_ewald)) / sqk);
+      }
+}
+
+void kspace_pass(Oracle *o, int eflag) {
+  if (!o->kspace) return;
+  const int n = o->n;
+  const size_t K = o->ug.size();
+  std::vector<double> Sre(K), Sim(K);
+#pragma omp parallel for schedule(static)
+  for (size_t k = 0; k < K; k++) {
+    long double sr = 0, si = 0;
+    const double kx = o->kvec[3 * k], ky = o->kvec[3 * k + 1], kz = o->kvec[3 * k + 2];
+    for (int j = 0; j < n; j++) {
+      const double a = kx * o->x[3 * j] + ky * o->x[3 * j + 1] + kz * o->x[3 * j + 2];
+      sr += o->q[j] * std::cos(a);
+      si += o->q[j] * std::sin(a);
+    }
+    Sre[k] = (double)sr; Sim[k] = (double)si;
+  }
+  long double qsum = 0;
+  for (int j = 0; j < n; j++) qsum += o->q[j];
+  const double L[3] = {o->hi[0] - o->lo[0], o->hi[1] - o->lo[1], o->hi[2] - o->lo[2]};
+  const double V = L[0] * L[1] * L[2], g = o->g_ewald;
+  std::vector<double> ek(n, 0.0);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; i++) {
+    long double pot = 0, fx = 0, fy = 0, fz = 0;
+    for (size_t k = 0; k < K; k++) {
+      const double kx = o->kvec[3 * k], ky = o->kvec[3 * k + 1], kz = o->kvec[3 * k + 2];
+      const double a = kx * o->x[3 * i] + ky * o->x[3 * i + 1] + kz * o->x[3 * i + 2];
+      const double c = std::cos(a), sn = std::sin(a);
+      pot += 2.0 * o->ug[k] * (c * Sre[k] + sn * Sim[k]);
+      const double w = 2.0 * o->ug[k] * (sn * Sre[k] - c * Sim[k]);
+      fx += w * kx; fy += w * ky; fz += w * kz;
+    }
+    const double qi = o->q[i];
+    const double phi = o->qqrd2e * ((double)pot - 2.0 * g * qi / MY_PIS - MY_PI * (double)qsum / (g * g * V));
+    o->f[3 * i] += o->qqrd2e * qi * (double)fx;
+    o->f[3 * i + 1] += o->qqrd2e * qi * (double)fy;
+    o->f[3 * i + 2] += o->qqrd2e * qi * (double)fz;
+    if (eflag) {
+      o->phi[i] += phi;
+      ek[i] = 0.5 * qi * phi;
+      o->eatom[i] += ek[i];
+    }
+  }
+  if (eflag) {
+    long double e = 0;
+    for (int i = 0; i < n; i++) e += ek[i];
+    o->e_kspace = (double)e;
+    o->ecoul += (double)e;
+  }
+}
+
 // compute_Hs tail (cpp:259-277) plus the per-site sums.
 void site_reduce(Oracle *o) {
   long double HA = 0, HB = 0;
@@ -734,7 +820,8 @@ int orc_set_units(void *h, double qqrd2e, double boltz, double ftm2v) {
 int orc_set_pair(void *h, int style, int ntypes, const double *eps, const double *sig, const double *cut_lj,
                  double cut_lj_global, double cut_coul, double alpha, const double *slj, const double *scoul) {
   Oracle *o = ORC;
-  if (style < 0 || style > 1 || ntypes < 1 || cut_coul <= 0) return fail(o, -1, "bad pair arguments");
+  if (style < 0 || style > 2 || ntypes < 1 || cut_coul <= 0) return fail(o, -1, "bad pair arguments");
+  o->e_shift = o->f_shift = 0.0;   // style 2 (lj/cut/coul/long, alpha = g_ewald): the damped kernel of dsf without its shifts
   o->style = style; o->ntypes = ntypes; o->cut_coul = cut_coul; o->alpha = alpha;
   int m = (ntypes + 1) * (ntypes + 1);
   o->lj1.assign(m, 0); o->lj2.assign(m, 0); o->lj3.assign(m, 0); o->lj4.assign(m, 0); o->cut_ljsq.assign(m, 0);
@@ -766,6 +853,7 @@ int orc_set_domain(void *h, const double *lo, const double *hi, const int *per, 
   Oracle *o = ORC;
   for (int k = 0; k < 3; k++) { o->lo[k] = lo[k]; o->hi[k] = hi[k]; o->periodic[k] = per[k]; }
   o->skin = skin; o->have_domain = true;
+  ewald_setup(o);   // the wave vectors follow the box
   return 0;
 }
 
@@ -895,7 +983,7 @@ int orc_rebuild(void *h) { build_list(ORC); return 0; }
 int orc_forward(void *) { return 0; }
 int orc_pair_pass(void *h, int eflag) {
   if (!ORC->have_atoms) return fail(ORC, -2, "set_atoms first");
-  pair_pass(ORC, eflag); bonded_pass(ORC, eflag); return 0;
+  pair_pass(ORC, eflag); bonded_pass(ORC, eflag); kspace_pass(ORC, eflag); return 0;
 }
 int orc_site_reduce(void *h) {
   if (!ORC->have_pass) return fail(ORC, -2, "pair pass first");
@@ -924,6 +1012,7 @@ static int post_force_impl(Oracle *o, int64_t ntimestep, double dt, const double
   bool active = !advance || (ntimestep % o->nevery) == 0;   // cpp:69
   pair_pass(o, active ? 1 : 0);
   bonded_pass(o, active ? 1 : 0);               // cpp:221-229: bonded eatom joins the partition
+  kspace_pass(o, active ? 1 : 0);               // cpp:241-244: so does the k-space eatom
   if (active) {
     site_reduce(o);                             // cpp:70
     const int phase = (o->integ_mode == 0 && advance) ? 0 : 2;
@@ -943,6 +1032,19 @@ int orc_post_force(void *h, int64_t ntimestep, double dt, int, const double *x, 
 int orc_setup(void *h, int64_t ntimestep, int, const double *x, double *f) {
   return post_force_impl(ORC, ntimestep, 0.0, x, f, false);
 }
+// style 0: none, 1: ewald.  After orc_set_domain (the wave vectors follow the box).
+int orc_set_kspace(void *h, int style, double g_ewald, int kxmax, int kymax, int kzmax) {
+  Oracle *o = ORC;
+  if (style == 0) { o->kspace = false; ewald_setup(o); return 0; }
+  if (style != 1 || g_ewald <= 0 || kxmax < 1 || kymax < 1 || kzmax < 1) return fail(o, -1, "bad kspace arguments");
+  if (!o->have_domain) return fail(o, -2, "set_domain first");
+  if (!(o->periodic[0] && o->periodic[1] && o->periodic[2])) return fail(o, -1, "ewald needs a fully periodic box");
+  o->kspace = true; o->g_ewald = g_ewald;
+  o->kmax[0] = kxmax; o->kmax[1] = kymax; o->kmax[2] = kzmax;
+  ewald_setup(o);
+  return 0;
+}
+int orc_get_kspace_energy(void *h, double *e) { *e = ORC->e_kspace; return 0; }
 int orc_set_excluded_policy(void *h, int drop) { ORC->drop_excluded = drop != 0; return 0; }
 int orc_set_force_mode(void *h, int accumulate) { ORC->force_add = accumulate != 0; return 0; }
 
