@@ -241,6 +241,7 @@ int cph_destroy(cph_handle *h) {
   cph_mail_close(h);
   cph_comm_destroy(h);
   cph_bonded_release(h);
+  cph_kspace_release(h);
   DevBuf<double> *db[] = {&h->d_pK, &h->d_lam, &h->d_vlam, &h->d_alam, &h->d_flam, &h->d_fs, &h->d_dfs, &h->d_Us,
                           &h->d_dUs, &h->d_theta, &h->d_red, &h->d_titr_qA, &h->d_titr_dq, &h->d_scal, &h->d_part, &h->d_xbuild,
                           &h->d_f, &h->d_evdwl, &h->d_phi, &h->d_eatom, &h->d_stage, &h->d_wq, &h->d_dQ};
@@ -285,8 +286,13 @@ int cph_set_units(cph_handle *h, double qqrd2e, double boltz, double ftm2v) {
 int cph_set_pair(cph_handle *h, int style, int ntypes, const double *epsilon, const double *sigma,
                  const double *cut_lj, double cut_lj_global, double cut_coul, double alpha,
                  const double *special_lj, const double *special_coul) {
-  if (style != CPH_PAIR_LJ_CUT_COUL_CUT && style != CPH_PAIR_LJ_CUT_COUL_DSF)
+  if (style != CPH_PAIR_LJ_CUT_COUL_CUT && style != CPH_PAIR_LJ_CUT_COUL_DSF && style != CPH_PAIR_LJ_CUT_COUL_LONG)
     return cph_fail(h, CPH_ERR_ARG, "unknown pair style %d", style);
+  // lj/cut/coul/long (alpha = g_ewald) IS the damped kernel of coul/dsf with both shifts at zero; its self energy
+  // belongs to the k-space part (kspace.cu).  Everything downstream sees the dsf style: same kernels, same list rules
+  // (LAMMPS keeps fully excluded special pairs in the list whenever a KSpace style is defined).
+  h->coul_long = style == CPH_PAIR_LJ_CUT_COUL_LONG;
+  if (h->coul_long) style = CPH_PAIR_LJ_CUT_COUL_DSF;
   if (ntypes < 1 || ntypes + 1 > CPH_MAXNT1) return cph_fail(h, CPH_ERR_ARG, "ntypes %d outside [1,%d]", ntypes, CPH_MAXNT1 - 1);
   if (!epsilon || !sigma || !special_lj || !special_coul) return cph_fail(h, CPH_ERR_ARG, "NULL coefficient table");
   if (!(cut_coul > 0)) return cph_fail(h, CPH_ERR_ARG, "cut_coul must be positive");
@@ -313,7 +319,7 @@ int cph_set_pair(cph_handle *h, int style, int ntypes, const double *epsilon, co
   double cm = std::max(h->cut_lj_max, cut_coul);
   pp.cutsq_max = cm * cm;
   pp.e_shift = pp.f_shift = pp.c_self = 0.0;
-  if (style == CPH_PAIR_LJ_CUT_COUL_DSF) {   // init_style of coul/dsf
+  if (style == CPH_PAIR_LJ_CUT_COUL_DSF && !h->coul_long) {   // init_style of coul/dsf
     const double MY_PIS = 1.77245385090551602729;
     double erfcc = std::erfc(alpha * cut_coul);
     double erfcd = std::exp(-alpha * alpha * cut_coul * cut_coul);
@@ -375,6 +381,7 @@ int cph_set_domain(cph_handle *h, const double *boxlo, const double *boxhi, cons
   }
   h->skin = skin;
   h->have_domain = true;
+  CPH_TRY(cph_kspace_setup(h));   // the wave vectors follow the box
   h->rowcap = 0;
   return CPH_OK;
 }
@@ -410,6 +417,33 @@ int cph_set_extra_partition(cph_handle *h, double dHA, double dHB) {
   h->extra_HA = dHA;
   h->extra_HB = dHB;
   return CPH_OK;
+}
+
+int cph_set_kspace(cph_handle *h, int style, double g_ewald, int kxmax, int kymax, int kzmax) {
+  if (style == CPH_KSPACE_NONE) {
+    h->kspace_style = CPH_KSPACE_NONE;
+    h->nkvec = 0;
+    return CPH_OK;
+  }
+  if (style != CPH_KSPACE_EWALD) return cph_fail(h, CPH_ERR_ARG, "unknown kspace style %d", style);
+  if (!(g_ewald > 0.0) || kxmax < 1 || kymax < 1 || kzmax < 1)
+    return cph_fail(h, CPH_ERR_ARG, "ewald: g_ewald %g, kmax %d %d %d", g_ewald, kxmax, kymax, kzmax);
+  CPH_TRY(need(h, h->have_domain, "cph_set_domain must precede cph_set_kspace"));
+  if (!(h->periodic[0] && h->periodic[1] && h->periodic[2]))
+    return cph_fail(h, CPH_ERR_ARG, "ewald needs a fully periodic box");
+  if ((double)(kxmax + 1) * (2 * kymax + 1) * (2 * kzmax + 1) > 4.0e6)
+    return cph_fail(h, CPH_ERR_ARG, "ewald: %d x %d x %d wave vectors is mesh-solver territory", kxmax, kymax, kzmax);
+  cudaSetDevice(h->device);
+  h->kspace_style = style;
+  h->g_ewald = g_ewald;
+  h->kmax[0] = kxmax; h->kmax[1] = kymax; h->kmax[2] = kzmax;
+  return cph_kspace_setup(h);
+}
+
+int cph_get_kspace_energy(cph_handle *h, double *e) {
+  if (!e) return cph_fail(h, CPH_ERR_ARG, "NULL output");
+  cudaSetDevice(h->device);
+  return cph_kspace_energy(h, e);
 }
 
 int cph_set_extra_dudl(cph_handle *h, int nsites, const double *dudl) {
@@ -642,6 +676,7 @@ int cph_pair_pass(cph_handle *h, int eflag) {
   CPH_TRY(cph_launch_pair(h, eflag ? 1 : 0));
   CPH_TRY(cph_launch_bonded(h, eflag ? 1 : 0));
   CPH_TRY(cph_launch_ljstates(h, eflag ? 1 : 0));
+  CPH_TRY(cph_launch_kspace(h, eflag ? 1 : 0));
   h->have_pass = true;
   return CPH_OK;
 }
@@ -745,6 +780,7 @@ static int post_force_impl(cph_handle *h, int64_t ntimestep, double dt, int wher
   if (!guessed || any || fl[5]) CPH_TRY(cph_launch_pair(h, active ? 1 : 0));
   CPH_TRY(cph_launch_bonded(h, active ? 1 : 0));                        // cpp:221-229: bonded eatom joins the partition
   CPH_TRY(cph_launch_ljstates(h, active ? 1 : 0));                      // LJ end states, when the caller declared any
+  CPH_TRY(cph_launch_kspace(h, active ? 1 : 0));                        // cpp:241-244: the k-space eatom joins the partition
   h->have_pass = true;
   // In charge mode nothing after this point touches the forces, so their way back to the host
   // (gather to caller order + D2H) runs on the side stream under the site reduce / lambda update.
@@ -1081,7 +1117,7 @@ int cph_profile_get(cph_handle *h, int which, double *ms_total, int64_t *launche
     *launches = h->nprunes;
     return CPH_OK;
   }
-  if (which < 0 || which >= 8) return cph_fail(h, CPH_ERR_ARG, "profile slot %d out of range", which);
+  if (which < 0 || which > 10) return cph_fail(h, CPH_ERR_ARG, "profile slot %d out of range", which);
   *ms_total = h->prof[which].ms;
   *launches = h->prof[which].launches;
   return CPH_OK;

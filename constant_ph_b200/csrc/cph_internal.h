@@ -320,13 +320,22 @@ struct cph_handle {
   DevBuf<double> d_bonded_e;         // [2] E_bond, E_angle of the owned shares
   double mass_h[CPH_MAXNT1]{};
   DevBuf<double3> d_v, d_v2;         // internal order velocities (owned atoms)
+  // f4: kspace_style ewald (kspace.cu); pair style CPH_PAIR_LJ_CUT_COUL_LONG is its real-space part
+  int kspace_style = 0;
+  double g_ewald = 0.0, kspace_self2 = 0.0, kspace_bg = 0.0;
+  int kmax[3]{0, 0, 0};
+  int nkvec = 0;                     // half-space wave vectors (the buffer holds one more: the zero vector)
+  bool coul_long = false;            // the damped kernel runs without shifts and without its pair-level self term
+  DevBuf<double4> d_kvec;            // {kx, ky, kz, ug}
+  DevBuf<double2> d_sfac_part, d_sfac;   // structure factors: chunk partials, totals
+  DevBuf<double> d_ekspace;          // [nlocal] per-atom k-space energy, [nlocal] their sum
   // comm
   int nranks = 1, rank = 0;
   void *nccl_comm = nullptr;
   // timing
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool profiling = false;
-  ProfSlot prof[8];
+  ProfSlot prof[11];                 // 0..7 per kernel class, 10 k-space (8 and 9 are counters, see cph_profile_get)
   cudaEvent_t pev0 = nullptr, pev1 = nullptr;
 };
 
@@ -378,6 +387,11 @@ int cph_bonded_set_topology(cph_handle *h, int nlocal, int maxbond, const int *n
 int cph_bonded_energy(cph_handle *h, double *out2);
 int cph_md_set_v(cph_handle *h, int where, const double *v_caller_order);
 int cph_md_kick(cph_handle *h, double dt, int drift);
+// kspace.cu
+int cph_kspace_setup(cph_handle *h);            // wave vectors for the current box
+int cph_launch_kspace(cph_handle *h, int eflag);   // after the pair pass: adds the reciprocal Ewald sum
+int cph_kspace_energy(cph_handle *h, double *out);
+void cph_kspace_release(cph_handle *h);
 // comm.cu
 int cph_comm_allreduce(cph_handle *h, double *buf, int n);            // sum
 int cph_comm_allreduce_max_u32(cph_handle *h, unsigned int *buf, int n);

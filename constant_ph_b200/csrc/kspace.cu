@@ -1,0 +1,210 @@
+// kspace.cu -- SURVEY.md §8 row f4: the k-space source of compute_Hs (fix_constant_pH.cpp:241-244) on the device.
+//
+// The reference adds force->kspace->eatom to its per-atom energy before the HA/HB partition and never looks at the
+// potential; north_star's charge derivative dU/dlambda_s = sum_i dq_i dE/dq_i needs dE_kspace/dq_i as well.  This file
+// is `kspace_style ewald` [upstream LAMMPS ewald.cpp conventions, standard Ewald summation]: the reciprocal sum whose
+// real-space partner erfc(g r)/r is pair style CPH_PAIR_LJ_CUT_COUL_LONG (the damped kernel of pair.cu with its
+// shifts at zero).  With S(k) = sum_j q_j exp(i k.r_j) over the half space of wave vectors k = 2 pi (nx/Lx, ny/Ly,
+// nz/Lz), |n_d| <= kmax_d, k^2 <= gsqmx, and ug(k) = 4 pi/V exp(-k^2/4g^2)/k^2:
+//   E      = qqrd2e [ sum_k ug |S|^2 - g/sqrt(pi) sum q_i^2 - pi (sum q_i)^2 / (2 g^2 V) ]
+//   phi_i  = dE/dq_i = qqrd2e [ sum_k 2 ug (cos(k.r_i) Re S + sin(k.r_i) Im S) - 2 g q_i/sqrt(pi) - pi sum q/(g^2 V) ]
+//   f_i    = qqrd2e q_i sum_k 2 ug k (sin(k.r_i) Re S - cos(k.r_i) Im S)
+//   eatom_i = q_i phi_i / 2   (E is a quadratic form of the charges; what LAMMPS' per-atom tally adds up to)
+// The pass runs right behind the pair pass and ADDS to its forces, phi and per-atom energy (like bonded.cu), so the
+// partition (cpp:264-267) and the per-site sums see the k-space part exactly where cpp:241-244 puts it, and it
+// follows q(lambda) every step.
+//
+// Kernels.  (1) ewald_sfac_kernel: one thread per wave vector, atoms staged through shared memory in tiles, the
+// atom range split into chunks over blockIdx.y so that small boxes still fill the 148 SMs; (2) ewald_sfac_sum_kernel:
+// chunk partials added in a fixed order (bit-reproducible), then -- several ranks -- one all-reduce of the 2(K+1)
+// doubles (a zero wave vector at the end carries sum q); (3) ewald_atom_kernel: one warp per owned atom, lanes stride
+// over the wave vectors (32-byte records, coalesced), shuffle butterfly, lane 0 adds the atom's terms; (4) a
+// one-block fixed-order sum of the per-atom k-space energies for cph_get_kspace_energy.  Both big kernels are bound
+// by the fp64 pipe (one sincos per atom and wave vector, 2 N K in total): this is the O(N K) Ewald sum, meant for the
+// boxes the reference itself targets (configs 1-2); a mesh solver (PPPM) is what 1M atoms would need and is not built.
+#include <cmath>
+
+#include "cph_internal.h"
+
+namespace {
+
+constexpr int KTPB = 128;    // wave vectors per block of the structure-factor kernel
+constexpr int TILE = 256;    // atoms staged per round
+constexpr int ATPB = 256;    // 8 atoms per block in the per-atom kernel
+
+__global__ void __launch_bounds__(KTPB)
+ewald_sfac_kernel(int n, const double4 *__restrict__ xq, int K1, const double4 *__restrict__ kv, int nchunk,
+                  double2 *__restrict__ part) {
+  __shared__ double4 tile[TILE];
+  const int k = blockIdx.x * KTPB + threadIdx.x;
+  const int c = blockIdx.y;
+  const int lo = (int)((long long)n * c / nchunk), hi = (int)((long long)n * (c + 1) / nchunk);
+  const double4 w = k < K1 ? kv[k] : make_double4(0.0, 0.0, 0.0, 0.0);
+  double sr = 0.0, si = 0.0;
+  for (int base = lo; base < hi; base += TILE) {
+    const int m = min(TILE, hi - base);
+    __syncthreads();
+    for (int t = threadIdx.x; t < m; t += KTPB) tile[t] = xq[base + t];
+    __syncthreads();
+    for (int t = 0; t < m; t++) {
+      const double4 p = tile[t];
+      double sn, co;
+      sincos(w.x * p.x + w.y * p.y + w.z * p.z, &sn, &co);
+      sr = fma(p.w, co, sr);
+      si = fma(p.w, sn, si);
+    }
+  }
+  if (k < K1) part[(size_t)c * K1 + k] = make_double2(sr, si);
+}
+
+__global__ void ewald_sfac_sum_kernel(int K1, int nchunk, const double2 *__restrict__ part, double2 *__restrict__ S) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K1) return;
+  double sr = 0.0, si = 0.0;
+  for (int c = 0; c < nchunk; c++) {
+    const double2 v = part[(size_t)c * K1 + k];
+    sr += v.x;
+    si += v.y;
+  }
+  S[k] = make_double2(sr, si);
+}
+
+// self2 = 2 g/sqrt(pi), bg = pi/(g^2 V); S[K].x = sum of all charges (the zero wave vector)
+__global__ void __launch_bounds__(ATPB)
+ewald_atom_kernel(int n, const double4 *__restrict__ xq, int K, const double4 *__restrict__ kv,
+                  const double2 *__restrict__ S, double qqrd2e, double self2, double bg, int eflag, double *f,
+                  double *phi, double *eatom, double *ek) {
+  const int i = (blockIdx.x * ATPB + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const double4 p = xq[i];
+  double pot = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
+  for (int k = lane; k < K; k += 32) {
+    const double4 w = kv[k];
+    const double2 s = S[k];
+    double sn, co;
+    sincos(w.x * p.x + w.y * p.y + w.z * p.z, &sn, &co);
+    const double u2 = 2.0 * w.w;
+    pot = fma(u2, co * s.x + sn * s.y, pot);
+    const double g = u2 * (sn * s.x - co * s.y);
+    fx = fma(g, w.x, fx);
+    fy = fma(g, w.y, fy);
+    fz = fma(g, w.z, fz);
+  }
+  for (int o = 16; o; o >>= 1) {
+    pot += __shfl_xor_sync(0xffffffffu, pot, o);
+    fx += __shfl_xor_sync(0xffffffffu, fx, o);
+    fy += __shfl_xor_sync(0xffffffffu, fy, o);
+    fz += __shfl_xor_sync(0xffffffffu, fz, o);
+  }
+  if (lane == 0) {
+    const double ph = qqrd2e * (pot - self2 * p.w - bg * S[K].x);
+    const double c = qqrd2e * p.w;
+    f[3 * (size_t)i] += c * fx;
+    f[3 * (size_t)i + 1] += c * fy;
+    f[3 * (size_t)i + 2] += c * fz;
+    if (eflag) {
+      const double e = 0.5 * p.w * ph;
+      phi[i] += ph;
+      eatom[i] += e;
+      ek[i] = e;
+    }
+  }
+}
+
+// one block, fixed order: out = sum_i ek[i]
+__global__ void __launch_bounds__(256) ewald_energy_kernel(int n, const double *__restrict__ ek, double *out) {
+  __shared__ double sm[256];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) a += ek[i];
+  sm[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sm[0];
+}
+
+}  // namespace
+
+// wave vectors and their weights for the current box (cph_set_kspace, and again whenever cph_set_domain changes the box)
+int cph_kspace_setup(cph_handle *h) {
+  h->nkvec = 0;
+  if (h->kspace_style != CPH_KSPACE_EWALD) return CPH_OK;
+  cudaSetDevice(h->device);
+  const double PI = 3.14159265358979323846;
+  double L[3], unitk[3];
+  for (int d = 0; d < 3; d++) {
+    L[d] = h->boxhi[d] - h->boxlo[d];
+    unitk[d] = 2.0 * PI / L[d];
+  }
+  const double V = L[0] * L[1] * L[2], g = h->g_ewald;
+  double gsqmx = 0.0;
+  for (int d = 0; d < 3; d++) gsqmx = std::max(gsqmx, unitk[d] * unitk[d] * h->kmax[d] * h->kmax[d]);
+  gsqmx *= 1.00001;
+  std::vector<double4> kv;
+  for (int nx = 0; nx <= h->kmax[0]; nx++)
+    for (int ny = -h->kmax[1]; ny <= h->kmax[1]; ny++)
+      for (int nz = -h->kmax[2]; nz <= h->kmax[2]; nz++) {
+        if (!(nx > 0 || (nx == 0 && ny > 0) || (nx == 0 && ny == 0 && nz > 0))) continue;   // half space
+        const double kx = unitk[0] * nx, ky = unitk[1] * ny, kz = unitk[2] * nz;
+        const double sqk = kx * kx + ky * ky + kz * kz;
+        if (sqk > gsqmx) continue;
+        kv.push_back(make_double4(kx, ky, kz, 4.0 * PI / V * std::exp(-0.25 * sqk / (g * g)) / sqk));
+      }
+  h->nkvec = (int)kv.size();
+  kv.push_back(make_double4(0.0, 0.0, 0.0, 0.0));   // zero wave vector: its "structure factor" is sum q
+  CPH_CUDA(h, h->d_kvec.reserve(kv.size()));
+  CPH_CUDA(h, cudaMemcpyAsync(h->d_kvec.p, kv.data(), kv.size() * sizeof(double4), cudaMemcpyHostToDevice, h->stream));
+  CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->kspace_self2 = 2.0 * g / 1.77245385090551602729;
+  h->kspace_bg = PI / (g * g * V);
+  return CPH_OK;
+}
+
+// after the pair pass (and the other terms that add to it): the reciprocal sum at the current positions and charges
+int cph_launch_kspace(cph_handle *h, int eflag) {
+  if (h->kspace_style != CPH_KSPACE_EWALD) return CPH_OK;
+  ProfScope ps(h, 10);
+  const int n = h->nlocal, K = h->nkvec, K1 = K + 1;
+  cudaStream_t st = h->stream;
+  const int kblocks = (K1 + KTPB - 1) / KTPB;
+  // enough (wave-vector block, atom chunk) pairs for four blocks per SM, chunks of at least one tile
+  const int nchunk = std::max(1, std::min(std::min(64, (n + TILE - 1) / TILE), (4 * h->num_sms + kblocks - 1) / kblocks));
+  CPH_CUDA(h, h->d_sfac_part.reserve((size_t)nchunk * K1));
+  CPH_CUDA(h, h->d_sfac.reserve((size_t)K1));
+  CPH_CUDA(h, h->d_ekspace.reserve((size_t)n + 2));
+  ewald_sfac_kernel<<<dim3(kblocks, nchunk), KTPB, 0, st>>>(n, h->d_xq.p, K1, h->d_kvec.p, nchunk, h->d_sfac_part.p);
+  ewald_sfac_sum_kernel<<<(K1 + 255) / 256, 256, 0, st>>>(K1, nchunk, h->d_sfac_part.p, h->d_sfac.p);
+  h->nlaunch += 2;
+  CPH_CUDA(h, cudaGetLastError());
+  // several ranks: every rank summed over the atoms it owns
+  CPH_TRY(cph_comm_allreduce(h, reinterpret_cast<double *>(h->d_sfac.p), 2 * K1));
+  if (n > 0) {
+    ewald_atom_kernel<<<(n * 32 + ATPB - 1) / ATPB, ATPB, 0, st>>>(n, h->d_xq.p, K, h->d_kvec.p, h->d_sfac.p, h->qqrd2e,
+                                                                  h->kspace_self2, h->kspace_bg, eflag, h->d_f.p,
+                                                                  h->d_phi.p, h->d_eatom.p, h->d_ekspace.p);
+    h->nlaunch++;
+  }
+  if (eflag) {
+    ewald_energy_kernel<<<1, 256, 0, st>>>(n, h->d_ekspace.p, h->d_ekspace.p + n);
+    h->nlaunch++;
+  }
+  CPH_CUDA(h, cudaGetLastError());
+  return CPH_OK;
+}
+
+int cph_kspace_energy(cph_handle *h, double *out) {
+  *out = 0.0;
+  if (h->kspace_style != CPH_KSPACE_EWALD || h->d_ekspace.cap < (size_t)h->nlocal + 1) return CPH_OK;
+  CPH_CUDA(h, cudaMemcpyAsync(out, h->d_ekspace.p + h->nlocal, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CPH_OK;
+}
+
+void cph_kspace_release(cph_handle *h) {
+  h->d_kvec.release();
+  h->d_sfac_part.release();
+  h->d_sfac.release();
+  h->d_ekspace.release();
+}

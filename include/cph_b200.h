@@ -54,6 +54,11 @@ typedef struct cph_handle cph_handle;
 /* pair styles named by BASELINE.json */
 #define CPH_PAIR_LJ_CUT_COUL_CUT 0
 #define CPH_PAIR_LJ_CUT_COUL_DSF 1
+#define CPH_PAIR_LJ_CUT_COUL_LONG 2  /* real-space part of an Ewald sum, alpha = g_ewald */
+
+/* k-space styles (cph_set_kspace) */
+#define CPH_KSPACE_NONE  0
+#define CPH_KSPACE_EWALD 1
 
 /* what drives the lambda force (cph_set_mode) */
 #define CPH_DUDL_REFERENCE 0  /* HB-HA from the per-atom energy partition, cpp:264-267 + cpp:111 */
@@ -181,6 +186,19 @@ int cph_set_extra_partition(cph_handle *h, double dHA, double dHB);
  * all-reduce that replaces cpp:274, at the next site reduce, and are then cleared.  nsites must equal the
  * site count of cph_set_sites. */
 int cph_set_extra_dudl(cph_handle *h, int nsites, const double *dudl);
+/* ... or the k-space source itself on the device: `kspace_style ewald`, the reciprocal part of
+ * the Ewald sum with splitting parameter g_ewald over the wave vectors 2 pi (nx/Lx, ny/Ly, nz/Lz), |n_d| <= k?max,
+ * k^2 <= max_d (2 pi k_d max / L_d)^2 -- what force->kspace holds as g_ewald and kxmax/kymax/kzmax.  The pass runs
+ * behind every pair pass and adds forces, dE/dq_i and the per-atom energy e_i = q_i phi_i / 2 (self and
+ * neutralising-background terms included) to the pair results, so HA/HB (cpp:241-244, 264-267) and every site's
+ * dU/dlambda contain the k-space part and follow q(lambda).  Use it with CPH_PAIR_LJ_CUT_COUL_LONG (alpha =
+ * g_ewald) for the real-space part.  After cph_set_domain (the wave vectors follow the box; a later
+ * cph_set_domain recomputes them); fully periodic boxes only.  The sum is O(atoms x wave vectors): a tool for
+ * boxes up to ~1e5 atoms, not a mesh solver.  style CPH_KSPACE_NONE switches it off. */
+int cph_set_kspace(cph_handle *h, int style, double g_ewald, int kxmax, int kymax, int kzmax);
+/* this rank's share (its owned atoms) of the k-space energy of the last pass with eflag; the sum over ranks is
+ * the E_long LAMMPS prints.  It is part of E_coul in cph_get_scalars. */
+int cph_get_kspace_energy(cph_handle *h, double *e);
 /* calculate_df + calculate_dU + integrate_lambda (cpp:109-145), dt = nevery*update->dt. */
 int cph_integrate_lambda(cph_handle *h, double dt);
 /* north_star hooks absent from the reference. */
@@ -289,8 +307,8 @@ int cph_timer_start(cph_handle *h);
 int cph_timer_stop(cph_handle *h, double *ms);
 /* ... and per kernel class while enabled.  which: 0 pair evaluation, 1 inner-list prune (+ fp32 record
  * refresh), 2 site reduce, 3 lambda integrator, 4 charge / force update, 5 halo + allreduce, 6 list build
- * (all stages), 7 new positions + displacement check.  Always available: 8 -> launches = kernels of this
- * library launched so far, 9 -> launches = inner-list prunes so far. */
+ * (all stages), 7 new positions + displacement check, 10 k-space (structure factors + per-atom sums).  Always
+ * available: 8 -> launches = kernels of this library launched so far, 9 -> launches = inner-list prunes so far. */
 int cph_profile(cph_handle *h, int enable);
 int cph_profile_get(cph_handle *h, int which, double *ms_total, int64_t *launches);
 

@@ -182,6 +182,7 @@ class EnergyStyle {
   double *eatom = nullptr;
   int compute_flag = 1;
   int tip4pflag = 0;
+  double g_ewald = 0.0;            // KSpace only (public upstream): the Ewald splitting parameter
 };
 typedef EnergyStyle Bond;
 typedef EnergyStyle Angle;

@@ -16,6 +16,9 @@
        tlambda TAU           Nose-Hoover thermostat (period TAU) on the site velocities at T; needs integrator vv
        excluded keep|drop    lj/cut/coul/dsf only: keep fully excluded special pairs in the list and subtract their
                              undamped Coulomb term (default), or drop them as plain cut styles do
+       ewald KX KY KZ        run `kspace_style ewald` on the device (reciprocal sum over |n_d| <= K?, g_ewald from
+                             force->kspace); needs pair lj/cut/coul/long and `kspace_modify compute no`.  Without it
+                             a host KSpace style feeds its per-atom energy in as the reference does (cpp:241-244)
        bias_w|bias_s|bias_h|bias_k|bias_a|bias_b|bias_r|bias_m|bias_d VALUE
                              override one constant of the bias potential (init() loads Donnini's table, cpp:86-94)
 
@@ -103,7 +106,7 @@ FixConstantPH::FixConstantPH(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg,
   part[0] = part[1] = 0.0;
   tab = Sites{0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
   opt = Options{CPH_DUDL_REFERENCE, CPH_INTEGRATE_REFERENCE, CPH_FSCALE_LAMBDA, CPH_BIAS_EXACT, 0, CPH_COORD_LAMBDA, 0,
-                0.0, 0.5, nullptr, {}};
+                0.0, 0.5, nullptr, {}, {0, 0, 0}};
   for (double &u : opt.bias_user) u = NAN;
   bias = Bias{0, 0, 0, 0, 0, 0, 0, 0, 0, 20.0};         // mass: cpp:96; the rest is loaded in init()
   lambda_cached = opt.lambda_start;
@@ -153,6 +156,13 @@ FixConstantPH::FixConstantPH(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg,
       opt.thermostat_period = utils::numeric(FLERR, val, false, lmp);
       if (opt.thermostat_period < 0.0)
         error->all(FLERR, "Illegal fix constant_pH tlambda value {}", opt.thermostat_period);
+    } else if (strcmp(key, "ewald") == 0) {
+      if (iarg + 3 >= narg) utils::missing_cmd_args(FLERR, "fix constant_pH", error);
+      for (int d = 0; d < 3; d++) {
+        opt.ewald_kmax[d] = utils::inumeric(FLERR, arg[iarg + 1 + d], false, lmp);
+        if (opt.ewald_kmax[d] < 1) error->all(FLERR, "Illegal fix constant_pH ewald value {}", opt.ewald_kmax[d]);
+      }
+      iarg += 2;      // three values instead of one
     } else if (strcmp(key, "lambda0") == 0) {
       opt.lambda_start = lambda_cached = utils::numeric(FLERR, val, false, lmp);
     } else if (strncmp(key, "bias_", 5) == 0 && key[5] && !key[6] && strchr(kBiasNames, key[5])) {
@@ -283,13 +293,23 @@ void FixConstantPH::init()
   Pair *pair = force->pair_match("lj/cut/coul/dsf", 1);
   if (pair) style = CPH_PAIR_LJ_CUT_COUL_DSF;
   else if ((pair = force->pair_match("lj/cut/coul/cut", 1))) style = CPH_PAIR_LJ_CUT_COUL_CUT;
-  if (style < 0) error->all(FLERR, "fix constant_pH supports pair styles lj/cut/coul/cut and lj/cut/coul/dsf");
+  else if ((pair = force->pair_match("lj/cut/coul/long", 1))) style = CPH_PAIR_LJ_CUT_COUL_LONG;
+  if (style < 0)
+    error->all(FLERR, "fix constant_pH supports pair styles lj/cut/coul/cut, lj/cut/coul/dsf and lj/cut/coul/long");
+  if (style == CPH_PAIR_LJ_CUT_COUL_LONG && !force->kspace)
+    error->all(FLERR, "fix constant_pH: pair style lj/cut/coul/long requires a KSpace style");
+  if (opt.ewald_kmax[0] > 0) {
+    if (style != CPH_PAIR_LJ_CUT_COUL_LONG) error->all(FLERR, "fix constant_pH ewald requires pair style lj/cut/coul/long");
+    if (force->kspace->compute_flag)
+      error->all(FLERR, "fix constant_pH ewald runs the k-space sum itself: use kspace_modify compute no");
+  }
   int dim = 0;
   double **eps = (double **) pair->extract("epsilon", dim);
   double **sig = (double **) pair->extract("sigma", dim);
   const double *cut_coul = (double *) pair->extract("cut_coul", dim);
   const double *cut_lj = (double *) pair->extract("cut_lj", dim);
   const double *alpha = (double *) pair->extract("alpha", dim);
+  if (style == CPH_PAIR_LJ_CUT_COUL_LONG) alpha = &force->kspace->g_ewald;    // what the pair style's init_style takes
   if (!eps || !sig || !cut_coul) error->all(FLERR, "fix constant_pH: pair style does not expose epsilon/sigma/cut_coul");
   if (style == CPH_PAIR_LJ_CUT_COUL_DSF && !alpha) error->all(FLERR, "fix constant_pH: pair style does not expose alpha");
   const int nt1 = atom->ntypes + 1;
@@ -305,6 +325,9 @@ void FixConstantPH::init()
 
   require(cph_set_domain(cph, domain->boxlo, domain->boxhi, domain->periodicity, domain->sublo, domain->subhi,
                          comm->procgrid, comm->myloc, neighbor->skin), "cph_set_domain");
+  if (opt.ewald_kmax[0] > 0)
+    require(cph_set_kspace(cph, CPH_KSPACE_EWALD, force->kspace->g_ewald, opt.ewald_kmax[0], opt.ewald_kmax[1],
+                           opt.ewald_kmax[2]), "cph_set_kspace");
   require(cph_set_fix(cph, nevery, in.hyd_bit, in.wat_bit, in.pK, in.pH, in.temperature), "cph_set_fix");
   require(cph_set_bias(cph, bias.w, bias.s, bias.h, bias.k, bias.a, bias.b, bias.r, bias.m, bias.d, bias.mass,
                        opt.bias_form), "cph_set_bias");

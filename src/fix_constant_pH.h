@@ -70,6 +70,7 @@ class FixConstantPH : public Fix {
     double lambda_start;
     char *site_file;
     double bias_user[9];           // w s h k a b r m d given as keywords (bias_w ... bias_d); NaN = table value
+    int ewald_kmax[3];             // keyword ewald: wave-vector range of the device-side Ewald sum (0 = off)
   } opt;
 
   // per-site table read from the site file (north_star multi-site; none in the reference)

@@ -120,7 +120,7 @@ int main(int argc, char **argv) {
   for (int k = 0; k < 4; k++) { lmp.force->special_lj[k] = hd[10 + k]; lmp.force->special_coul[k] = hd[14 + k]; }
   lmp.update->dt = hd[20];
   Pair pair;
-  pair.style = style == 1 ? "lj/cut/coul/dsf" : "lj/cut/coul/cut";
+  pair.style = style == 2 ? "lj/cut/coul/long" : style == 1 ? "lj/cut/coul/dsf" : "lj/cut/coul/cut";
   pair.compute_flag = 0;   // pair_modify compute no: the fix's GPU pass is the pair computation
   std::vector<double *> erow(ntypes + 1), srow(ntypes + 1);
   for (int i = 0; i <= ntypes; i++) { erow[i] = &eps[(size_t)i * (ntypes + 1)]; srow[i] = &sig[(size_t)i * (ntypes + 1)]; }
@@ -161,6 +161,11 @@ int main(int argc, char **argv) {
     }
   }
   KSpace kspace;
+  if (style == 2) {        // lj/cut/coul/long needs a KSpace style; `kspace_modify compute no`: the fix runs the sum (keyword ewald)
+    kspace.g_ewald = hd[8];
+    kspace.compute_flag = 0;
+    lmp.force->kspace = &kspace;
+  }
   std::vector<double> kspace_eatom;
   double kspace_scale = 0.0;
   if (opt("kspace")) {

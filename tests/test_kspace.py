@@ -191,3 +191,46 @@ def test_ewald_argument_errors_on_the_device(built):
         g.set_kspace(capi.KSPACE_EWALD, -1.0, (5, 5, 5))
     with pytest.raises(capi.CphError):
         g.set_kspace(capi.KSPACE_EWALD, 0.3, (0, 5, 5))
+
+
+# ---- the drop-in fix: keyword `ewald KX KY KZ` -------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ewald_files(built, tmp_path_factory):
+    d = tmp_path_factory.mktemp("harness_ewald")
+    box = ewald_box(1)
+    b, s = str(d / "box.bin"), str(d / "sites.txt")
+    synth.write_harness_input(box, b, s)
+    return box, b, s
+
+
+def test_fix_ewald_keyword_errors(ewald_files):
+    """Constructor-level checks run before any device work (like cpp:36-54)."""
+    from test_fix_dropin import run
+    _, b, s = ewald_files
+    r = run([b, 1, "sites", s, "ewald", 0, 5, 5])
+    assert r.returncode == 2 and "Illegal fix constant_pH ewald value 0" in r.stderr
+    r = run([b, 1, "sites", s, "ewald", 5, 5])
+    assert r.returncode == 2 and "missing argument" in r.stderr
+
+
+@pytest.mark.gpu
+def test_fix_with_device_ewald_matches_oracle(ewald_files):
+    """pair lj/cut/coul/long + `kspace_modify compute no` + fix keyword ewald: the fix takes g_ewald from force->kspace
+    and runs the reciprocal sum in the library; lambda and H_lambda trajectories against the oracle."""
+    from test_fix_dropin import run, parse, oracle_trajectory
+    box, b, s = ewald_files
+    nsteps = 60
+    r = run([b, nsteps, "jiggle", 0.5, "sites", s, "mlambda", 2000, "ewald", 7, 6, 7])
+    assert r.returncode == 0, r.stderr
+    rows, extra = parse(r.stdout)
+    kw = dict(bias=dict(m_lambda=2000.0), kspace=dict(g_ewald=box.alpha, kmax=(7, 6, 7)))
+    lam, H, f = oracle_trajectory(box, "charge", kw, nsteps, jiggle=0.5)
+    assert np.abs(rows[:, 2:] - lam).max() <= 1e-8
+    assert np.abs(rows[:, 1] - H).max() <= 1e-8 * np.abs(H).max()
+    assert abs(extra["FORCES_ABS_SUM"] - np.abs(f).sum()) <= 1e-9 * np.abs(f).sum()
+    # the same input without the keyword is refused only if the host would ALSO compute the sum; with
+    # `kspace_modify compute no` and no keyword nothing computes it -- the pair part alone must differ
+    r0 = run([b, 2, "sites", s, "mlambda", 2000])
+    assert r0.returncode == 0, r0.stderr
+    rows0, _ = parse(r0.stdout)
+    assert abs(rows0[0, 1] - rows[0, 1]) > 1e-6 * abs(rows[0, 1])
