@@ -23,7 +23,11 @@ def main():
     nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 40
     bonded = len(sys.argv) > 3 and sys.argv[3] == "bonded"
     ljstates = len(sys.argv) > 3 and sys.argv[3] == "ljstates"
+    ewald = len(sys.argv) > 3 and sys.argv[3] == "ewald"
     box = synth.config(2, scale=scale, shuffle=True)
+    if ewald:    # lj/cut/coul/long + the reciprocal sum; structure factors all-reduced over the ranks
+        import dataclasses
+        box = dataclasses.replace(box, style=capi.PAIR_COUL_LONG, alpha=0.30)
     # an atom that gains an LJ site must not be driven into its neighbours: gentler motion in that mode
     params = synth.jiggle_params(box, amp=0.35 if len(sys.argv) > 3 and sys.argv[3] == "ljstates" else 0.9,
                                  period_lo=40.0, period_hi=90.0)
@@ -41,6 +45,8 @@ def main():
         kw["topology"] = synth.topology(box)
     if ljstates:  # atoms with LJ end states act on the owned atoms of neighbouring ranks as ghosts
         kw["lj_typeB"] = synth.lj_end_state_types(box)
+    if ewald:
+        kw["kspace"] = dict(g_ewald=box.alpha, kmax=(8, 8, 8))
     capi.configure(eng, box, sublo=sublo, subhi=subhi, procgrid=grid, myloc=loc, owned=owned, **kw)
     ref = capi.configure(capi.Engine("cph", device=lrank), box, **kw) if rank == 0 else None
 

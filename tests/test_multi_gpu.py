@@ -17,12 +17,12 @@ def ngpus():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-@pytest.mark.parametrize("world,mode", [(2, "pair"), (2, "bonded"), (2, "ljstates"), (4, "pair"), (8, "pair")])
+@pytest.mark.parametrize("world,mode", [(2, "pair"), (2, "bonded"), (2, "ljstates"), (2, "ewald"), (4, "pair"), (8, "pair")])
 def test_multi_rank_matches_single_rank(built, world, mode):
     if ngpus() < world:
         pytest.skip("needs %d GPUs" % world)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
-           "--master-addr", "127.0.0.1", "--master-port", str(29600 + world + {"pair": 0, "bonded": 50, "ljstates": 70}[mode]),
+           "--master-addr", "127.0.0.1", "--master-port", str(29600 + world + {"pair": 0, "bonded": 50, "ljstates": 70, "ewald": 90}[mode]),
            os.path.join(ROOT, "tests", "mgpu_worker.py"), "1.0" if world <= 2 else "2.0", "70" if mode == "ljstates" else "40", mode]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     line = [l for l in r.stdout.splitlines() if l.startswith("MGPU_RESULT ")]
