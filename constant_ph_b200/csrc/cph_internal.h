@@ -327,6 +327,10 @@ struct cph_handle {
   int nkvec = 0;                     // half-space wave vectors (the buffer holds one more: the zero vector)
   bool coul_long = false;            // the damped kernel runs without shifts and without its pair-level self term
   DevBuf<double4> d_kvec;            // {kx, ky, kz, ug}
+  DevBuf<int> d_kidx;                // nx | (ny+512)<<10 | (nz+512)<<20 (factorised kernels)
+  double kspace_unitk[3]{0, 0, 0};   // 2 pi / L_d
+  bool kspace_fact = true;           // factorised kernels (CPH_EWALD=direct: one sincos per atom and wave vector)
+  int kspace_tile = 32;              // atoms per shared-memory tile of the factorised structure-factor kernel
   DevBuf<double2> d_sfac_part, d_sfac;   // structure factors: chunk partials, totals
   DevBuf<double> d_ekspace;          // [nlocal] per-atom k-space energy, [nlocal] their sum
   // comm

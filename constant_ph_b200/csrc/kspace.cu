@@ -14,15 +14,24 @@
 // partition (cpp:264-267) and the per-site sums see the k-space part exactly where cpp:241-244 puts it, and it
 // follows q(lambda) every step.
 //
-// Kernels.  (1) ewald_sfac_kernel: one thread per wave vector, atoms staged through shared memory in tiles, the
-// atom range split into chunks over blockIdx.y so that small boxes still fill the 148 SMs; (2) ewald_sfac_sum_kernel:
-// chunk partials added in a fixed order (bit-reproducible), then -- several ranks -- one all-reduce of the 2(K+1)
-// doubles (a zero wave vector at the end carries sum q); (3) ewald_atom_kernel: one warp per owned atom, lanes stride
-// over the wave vectors (32-byte records, coalesced), shuffle butterfly, lane 0 adds the atom's terms; (4) a
-// one-block fixed-order sum of the per-atom k-space energies for cph_get_kspace_energy.  Both big kernels are bound
-// by the fp64 pipe (one sincos per atom and wave vector, 2 N K in total): this is the O(N K) Ewald sum, meant for the
-// boxes the reference itself targets (configs 1-2); a mesh solver (PPPM) is what 1M atoms would need and is not built.
+// Kernels.  (1) structure factors: one thread per wave vector, atoms staged through shared memory in tiles, the atom
+// range split into chunks over blockIdx.y so that small boxes still fill the 148 SMs; (2) ewald_sfac_sum_kernel: chunk
+// partials added in a fixed order (bit-reproducible), then -- several ranks -- one all-reduce of the 2(K+1) doubles (a
+// zero wave vector at the end carries sum q); (3) per-atom sums: one warp per owned atom, lanes stride over the wave
+// vectors (coalesced records), shuffle butterfly, lane 0 adds the atom's terms; (4) a one-block fixed-order sum of
+// the per-atom k-space energies for cph_get_kspace_energy.
+// (1) and (3) exist twice.  The *direct* pair evaluates sincos(k.r) for every atom and wave vector (2 N K calls of
+// ~50 fp64 instructions).  The default *factorised* pair uses exp(i k.r) = exp(i kx x) exp(i ky y) exp(i kz z): per
+// atom only the kxmax+kymax+kzmax+3 phase factors of the three axes are tabulated in shared memory (by the recurrence
+// E[n] = E[n-1] E[1] in the structure-factor kernel, by sincos(n theta) in the per-atom kernel), and a wave vector
+// (nx, ny, nz) costs two complex products of table entries (conjugated for negative indices) -- ~10 fp64 instructions
+// and three LDS.128 instead of a sincos.  CPH_EWALD=direct selects the direct pair (also the fallback when the tables
+// would not fit shared memory).  Either way the pass is bound by the fp64 pipe, not by HBM: this is the O(N K) Ewald
+// sum, meant for the boxes the reference itself targets (configs 1-2); a mesh solver (PPPM) is what 1M atoms would
+// need and is not built.
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 
 #include "cph_internal.h"
 
@@ -111,6 +120,126 @@ ewald_atom_kernel(int n, const double4 *__restrict__ xq, int K, const double4 *_
   }
 }
 
+// ---- factorised variants ------------------------------------------------------------------------------------------
+constexpr int FTPB = 256;    // wave vectors per block
+constexpr int FTA = 32;      // atoms per tile (fewer when the tables are long)
+
+// packed wave-vector indices: nx | (ny + 512) << 10 | (nz + 512) << 20
+__device__ __forceinline__ void unpack_kidx(int w, int nx1, int ny1, int &ix, int &iy, int &iz, double &sy, double &sz) {
+  const int ny = ((w >> 10) & 1023) - 512, nz = ((w >> 20) & 1023) - 512;
+  ix = w & 1023;
+  iy = nx1 + abs(ny);
+  iz = nx1 + ny1 + abs(nz);
+  sy = ny < 0 ? -1.0 : 1.0;      // exp(-i n theta) = conj exp(i n theta)
+  sz = nz < 0 ? -1.0 : 1.0;
+}
+
+// tab[a][0..nx1) = q_a exp(i n ux x_a), [nx1..nx1+ny1) = exp(i n uy y_a), then z: nx1 = kxmax+1, ...
+__global__ void __launch_bounds__(FTPB)
+ewald_sfac_fact_kernel(int n, const double4 *__restrict__ xq, int K1, const int *__restrict__ kidx, int nchunk, int ta,
+                       int nx1, int ny1, int nz1, double ux, double uy, double uz, double2 *__restrict__ part) {
+  extern __shared__ double2 tab[];
+  const int stride = nx1 + ny1 + nz1;
+  const int k = blockIdx.x * FTPB + threadIdx.x;
+  const int c = blockIdx.y;
+  const int lo = (int)((long long)n * c / nchunk), hi = (int)((long long)n * (c + 1) / nchunk);
+  int ix = 0, iy = nx1, iz = nx1 + ny1;
+  double sy = 1.0, sz = 1.0;
+  if (k < K1) unpack_kidx(kidx[k], nx1, ny1, ix, iy, iz, sy, sz);
+  double sr = 0.0, si = 0.0;
+  for (int base = lo; base < hi; base += ta) {
+    const int m = min(ta, hi - base);
+    __syncthreads();
+    if ((int)threadIdx.x < 3 * m) {      // thread (atom a, axis d): E[n] = E[n-1] E[1]
+      const int a = threadIdx.x / 3, d = threadIdx.x - 3 * a;
+      const double4 p = xq[base + a];
+      const double ang = d == 0 ? ux * p.x : d == 1 ? uy * p.y : uz * p.z;
+      const int cnt = d == 0 ? nx1 : d == 1 ? ny1 : nz1;
+      double2 *e = tab + a * stride + (d == 0 ? 0 : d == 1 ? nx1 : nx1 + ny1);
+      double s1, c1;
+      sincos(ang, &s1, &c1);
+      double re = d == 0 ? p.w : 1.0, im = 0.0;      // the charge rides on the x factor
+      e[0] = make_double2(re, im);
+      for (int q = 1; q < cnt; q++) {
+        const double nre = re * c1 - im * s1, nim = re * s1 + im * c1;
+        re = nre;
+        im = nim;
+        e[q] = make_double2(re, im);
+      }
+    }
+    __syncthreads();
+    for (int a = 0; a < m; a++) {
+      const double2 *e = tab + a * stride;
+      const double2 ex = e[ix], ey = e[iy], ez = e[iz];
+      const double eyi = sy * ey.y, ezi = sz * ez.y;
+      const double tr = ex.x * ey.x - ex.y * eyi, ti = ex.x * eyi + ex.y * ey.x;
+      sr += tr * ez.x - ti * ezi;
+      si += tr * ezi + ti * ez.x;
+    }
+  }
+  if (k < K1) part[(size_t)c * K1 + k] = make_double2(sr, si);
+}
+
+__global__ void __launch_bounds__(ATPB)
+ewald_atom_fact_kernel(int n, const double4 *__restrict__ xq, int K, const double4 *__restrict__ kv,
+                       const int *__restrict__ kidx, const double2 *__restrict__ S, int nx1, int ny1, int nz1, double ux,
+                       double uy, double uz, double qqrd2e, double self2, double bg, int eflag, double *f, double *phi,
+                       double *eatom, double *ek) {
+  extern __shared__ double2 tab[];      // one table per warp
+  const int stride = nx1 + ny1 + nz1;
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (ATPB / 32) + wl;
+  if (i >= n) return;                   // whole warps leave; only __syncwarp below
+  double2 *e = tab + wl * stride;
+  const double4 p = xq[i];
+  for (int t = lane; t < stride; t += 32) {
+    const int d = t < nx1 ? 0 : t < nx1 + ny1 ? 1 : 2;
+    const int q = t - (d == 0 ? 0 : d == 1 ? nx1 : nx1 + ny1);
+    const double ang = (d == 0 ? ux * p.x : d == 1 ? uy * p.y : uz * p.z) * q;
+    double sn, co;
+    sincos(ang, &sn, &co);
+    e[t] = make_double2(co, sn);
+  }
+  __syncwarp();
+  double pot = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
+  for (int k = lane; k < K; k += 32) {
+    int ix, iy, iz;
+    double sy, sz;
+    unpack_kidx(kidx[k], nx1, ny1, ix, iy, iz, sy, sz);
+    const double4 w = kv[k];
+    const double2 s = S[k];
+    const double2 ex = e[ix], ey = e[iy], ez = e[iz];
+    const double eyi = sy * ey.y, ezi = sz * ez.y;
+    const double tr = ex.x * ey.x - ex.y * eyi, ti = ex.x * eyi + ex.y * ey.x;
+    const double co = tr * ez.x - ti * ezi, sn = tr * ezi + ti * ez.x;
+    const double u2 = 2.0 * w.w;
+    pot = fma(u2, co * s.x + sn * s.y, pot);
+    const double g = u2 * (sn * s.x - co * s.y);
+    fx = fma(g, w.x, fx);
+    fy = fma(g, w.y, fy);
+    fz = fma(g, w.z, fz);
+  }
+  for (int o = 16; o; o >>= 1) {
+    pot += __shfl_xor_sync(0xffffffffu, pot, o);
+    fx += __shfl_xor_sync(0xffffffffu, fx, o);
+    fy += __shfl_xor_sync(0xffffffffu, fy, o);
+    fz += __shfl_xor_sync(0xffffffffu, fz, o);
+  }
+  if (lane == 0) {
+    const double ph = qqrd2e * (pot - self2 * p.w - bg * S[K].x);
+    const double c = qqrd2e * p.w;
+    f[3 * (size_t)i] += c * fx;
+    f[3 * (size_t)i + 1] += c * fy;
+    f[3 * (size_t)i + 2] += c * fz;
+    if (eflag) {
+      const double en = 0.5 * p.w * ph;
+      phi[i] += ph;
+      eatom[i] += en;
+      ek[i] = en;
+    }
+  }
+}
+
 // one block, fixed order: out = sum_i ek[i]
 __global__ void __launch_bounds__(256) ewald_energy_kernel(int n, const double *__restrict__ ek, double *out) {
   __shared__ double sm[256];
@@ -143,6 +272,7 @@ int cph_kspace_setup(cph_handle *h) {
   for (int d = 0; d < 3; d++) gsqmx = std::max(gsqmx, unitk[d] * unitk[d] * h->kmax[d] * h->kmax[d]);
   gsqmx *= 1.00001;
   std::vector<double4> kv;
+  std::vector<int> kidx;
   for (int nx = 0; nx <= h->kmax[0]; nx++)
     for (int ny = -h->kmax[1]; ny <= h->kmax[1]; ny++)
       for (int nz = -h->kmax[2]; nz <= h->kmax[2]; nz++) {
@@ -151,12 +281,24 @@ int cph_kspace_setup(cph_handle *h) {
         const double sqk = kx * kx + ky * ky + kz * kz;
         if (sqk > gsqmx) continue;
         kv.push_back(make_double4(kx, ky, kz, 4.0 * PI / V * std::exp(-0.25 * sqk / (g * g)) / sqk));
+        kidx.push_back((nx & 1023) | (((ny + 512) & 1023) << 10) | (((nz + 512) & 1023) << 20));
       }
   h->nkvec = (int)kv.size();
   kv.push_back(make_double4(0.0, 0.0, 0.0, 0.0));   // zero wave vector: its "structure factor" is sum q
+  kidx.push_back(0 | (512 << 10) | (512 << 20));
   CPH_CUDA(h, h->d_kvec.reserve(kv.size()));
+  CPH_CUDA(h, h->d_kidx.reserve(kidx.size()));
   CPH_CUDA(h, cudaMemcpyAsync(h->d_kvec.p, kv.data(), kv.size() * sizeof(double4), cudaMemcpyHostToDevice, h->stream));
+  CPH_CUDA(h, cudaMemcpyAsync(h->d_kidx.p, kidx.data(), kidx.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int d = 0; d < 3; d++) h->kspace_unitk[d] = unitk[d];
+  // factorised kernels: phase tables of kxmax+kymax+kzmax+3 entries per atom in shared memory (48 KB without opt-in)
+  const int stride = h->kmax[0] + h->kmax[1] + h->kmax[2] + 3;
+  const char *mode = getenv("CPH_EWALD");
+  h->kspace_tile = std::min(FTA, (int)(48 * 1024 / ((size_t)stride * sizeof(double2))));
+  h->kspace_fact = !(mode && !strcmp(mode, "direct")) && h->kspace_tile >= 4 &&
+                   (size_t)(ATPB / 32) * stride * sizeof(double2) <= 48 * 1024 &&
+                   h->kmax[0] <= 511 && h->kmax[1] <= 511 && h->kmax[2] <= 511;
   h->kspace_self2 = 2.0 * g / 1.77245385090551602729;
   h->kspace_bg = PI / (g * g * V);
   return CPH_OK;
@@ -168,22 +310,36 @@ int cph_launch_kspace(cph_handle *h, int eflag) {
   ProfScope ps(h, 10);
   const int n = h->nlocal, K = h->nkvec, K1 = K + 1;
   cudaStream_t st = h->stream;
-  const int kblocks = (K1 + KTPB - 1) / KTPB;
+  const bool fact = h->kspace_fact;
+  const int ktpb = fact ? FTPB : KTPB, tile = fact ? h->kspace_tile : TILE;
+  const int kblocks = (K1 + ktpb - 1) / ktpb;
   // enough (wave-vector block, atom chunk) pairs for four blocks per SM, chunks of at least one tile
-  const int nchunk = std::max(1, std::min(std::min(64, (n + TILE - 1) / TILE), (4 * h->num_sms + kblocks - 1) / kblocks));
+  const int nchunk = std::max(1, std::min(std::min(64, (n + tile - 1) / tile), (4 * h->num_sms + kblocks - 1) / kblocks));
+  const int nx1 = h->kmax[0] + 1, ny1 = h->kmax[1] + 1, nz1 = h->kmax[2] + 1;
+  const size_t stride_bytes = (size_t)(nx1 + ny1 + nz1) * sizeof(double2);
+  const double *u = h->kspace_unitk;
   CPH_CUDA(h, h->d_sfac_part.reserve((size_t)nchunk * K1));
   CPH_CUDA(h, h->d_sfac.reserve((size_t)K1));
   CPH_CUDA(h, h->d_ekspace.reserve((size_t)n + 2));
-  ewald_sfac_kernel<<<dim3(kblocks, nchunk), KTPB, 0, st>>>(n, h->d_xq.p, K1, h->d_kvec.p, nchunk, h->d_sfac_part.p);
+  if (fact)
+    ewald_sfac_fact_kernel<<<dim3(kblocks, nchunk), FTPB, tile * stride_bytes, st>>>(
+        n, h->d_xq.p, K1, h->d_kidx.p, nchunk, tile, nx1, ny1, nz1, u[0], u[1], u[2], h->d_sfac_part.p);
+  else
+    ewald_sfac_kernel<<<dim3(kblocks, nchunk), KTPB, 0, st>>>(n, h->d_xq.p, K1, h->d_kvec.p, nchunk, h->d_sfac_part.p);
   ewald_sfac_sum_kernel<<<(K1 + 255) / 256, 256, 0, st>>>(K1, nchunk, h->d_sfac_part.p, h->d_sfac.p);
   h->nlaunch += 2;
   CPH_CUDA(h, cudaGetLastError());
   // several ranks: every rank summed over the atoms it owns
   CPH_TRY(cph_comm_allreduce(h, reinterpret_cast<double *>(h->d_sfac.p), 2 * K1));
   if (n > 0) {
-    ewald_atom_kernel<<<(n * 32 + ATPB - 1) / ATPB, ATPB, 0, st>>>(n, h->d_xq.p, K, h->d_kvec.p, h->d_sfac.p, h->qqrd2e,
-                                                                  h->kspace_self2, h->kspace_bg, eflag, h->d_f.p,
-                                                                  h->d_phi.p, h->d_eatom.p, h->d_ekspace.p);
+    const int ablocks = (n + ATPB / 32 - 1) / (ATPB / 32);
+    if (fact)
+      ewald_atom_fact_kernel<<<ablocks, ATPB, (ATPB / 32) * stride_bytes, st>>>(
+          n, h->d_xq.p, K, h->d_kvec.p, h->d_kidx.p, h->d_sfac.p, nx1, ny1, nz1, u[0], u[1], u[2], h->qqrd2e,
+          h->kspace_self2, h->kspace_bg, eflag, h->d_f.p, h->d_phi.p, h->d_eatom.p, h->d_ekspace.p);
+    else
+      ewald_atom_kernel<<<ablocks, ATPB, 0, st>>>(n, h->d_xq.p, K, h->d_kvec.p, h->d_sfac.p, h->qqrd2e, h->kspace_self2,
+                                                 h->kspace_bg, eflag, h->d_f.p, h->d_phi.p, h->d_eatom.p, h->d_ekspace.p);
     h->nlaunch++;
   }
   if (eflag) {
@@ -204,6 +360,7 @@ int cph_kspace_energy(cph_handle *h, double *out) {
 
 void cph_kspace_release(cph_handle *h) {
   h->d_kvec.release();
+  h->d_kidx.release();
   h->d_sfac_part.release();
   h->d_sfac.release();
   h->d_ekspace.release();

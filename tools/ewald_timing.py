@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Time the device Ewald pass (cph_profile slot 10: structure factors + per-atom sums) on BASELINE configs 1 and 2 under
+lj/cut/coul/long, for the factorised kernels (default) and the direct ones (CPH_EWALD=direct), and cross-check the two
+against each other.  Prints one JSON line.  Needs a B200:  python tools/ewald_timing.py > profiles/<name>.json"""
+import dataclasses
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from constant_ph_b200 import capi, synth  # noqa: E402
+
+
+def run(box, kmax, mode, passes=10):
+    if mode == "direct":
+        os.environ["CPH_EWALD"] = "direct"
+    else:
+        os.environ.pop("CPH_EWALD", None)
+    eng = capi.configure(capi.Engine("cph", device=0), box, kspace=dict(g_ewald=box.alpha, kmax=kmax))
+    for _ in range(3):
+        eng.pair_pass(1)
+    eng.sync()
+    eng.profile(True)
+    for _ in range(passes):
+        eng.pair_pass(1)
+    eng.sync()
+    ms_k, n_k = eng.profile_get(10)
+    ms_p, n_p = eng.profile_get(0)
+    eng.profile(False)
+    eng.site_reduce()
+    out = dict(f=eng.get_forces().copy(), phi=eng.get_phi().copy(), ek=eng.get_kspace_energy(),
+               kspace_ms=ms_k / max(n_k, 1), pair_ms=ms_p / max(n_p, 1))
+    eng.close()
+    return out
+
+
+def main():
+    res = {}
+    peak_warp_dfma, _ = capi.bench_fp64_peak(0)
+    for name, cfg, kmax in (("config1_3k_atoms", 1, (7, 7, 7)), ("config2_32k_atoms", 2, (22, 22, 22))):
+        box = synth.config(cfg)
+        box = dataclasses.replace(box, style=capi.PAIR_COUL_LONG, alpha=0.30)
+        a = run(box, kmax, "factorised")
+        b = run(box, kmax, "direct")
+        L = box.boxhi - box.boxlo
+        unitk = 2 * np.pi / L
+        gsq = max((unitk * np.array(kmax)) ** 2) * 1.00001
+        g = np.stack(np.meshgrid(np.arange(0, kmax[0] + 1), np.arange(-kmax[1], kmax[1] + 1),
+                                 np.arange(-kmax[2], kmax[2] + 1), indexing="ij"), -1).reshape(-1, 3)
+        half = (g[:, 0] > 0) | ((g[:, 0] == 0) & (g[:, 1] > 0)) | ((g[:, 0] == 0) & (g[:, 1] == 0) & (g[:, 2] > 0))
+        K = int((half & (((g * unitk) ** 2).sum(1) <= gsq)).sum())
+        pairs = 2.0 * box.n * K             # (atom, wave vector) evaluations of both kernels of a pass
+        res[name] = dict(
+            atoms=box.n, kmax=list(kmax), wave_vectors=K,
+            factorised_ms_per_pass=a["kspace_ms"], direct_ms_per_pass=b["kspace_ms"], pair_pass_ms=a["pair_ms"],
+            speedup=b["kspace_ms"] / a["kspace_ms"],
+            atom_wavevector_evaluations_per_s=pairs / (a["kspace_ms"] * 1e-3),
+            # ~14 fp64 instructions per evaluation in the factorised loops (two complex products + accumulation)
+            fp64_frac_of_measured_peak=14.0 * pairs / 32.0 / (a["kspace_ms"] * 1e-3) / peak_warp_dfma,
+            force_rel_diff_between_variants=float(np.abs(a["f"] - b["f"]).max() / np.abs(b["f"]).max()),
+            phi_rel_diff_between_variants=float(np.abs(a["phi"] - b["phi"]).max() / np.abs(b["phi"]).max()),
+            e_kspace=a["ek"], e_kspace_rel_diff=abs(a["ek"] - b["ek"]) / abs(b["ek"]))
+    res["fp64_peak_warp_dfma_per_s"] = peak_warp_dfma
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
