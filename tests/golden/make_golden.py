@@ -101,8 +101,43 @@ def make_bench_golden(path, config, nranks):
     print("wrote", path, box.n, box.nsites)
 
 
+# lj/cut/coul/long + kspace_style ewald on configs 1 and 2 (oracle output after 3 steps of lambda
+# dynamics with frozen atoms), so the oracle's k-space part cannot drift either.  tests/test_kspace.py reads it.
+EWALD_CASES = [
+    dict(name="cfg1_ewald", config=1, scale=1.0, steps=3, g_ewald=0.30, kmax=[7, 7, 7]),
+    dict(name="cfg2_ewald", config=2, scale=0.25, steps=3, g_ewald=0.30, kmax=[9, 8, 10]),
+]
+
+
+def ewald_case_engine(case, prefix="orc", **engine_kw):
+    import dataclasses
+    box = synth.config(case["config"], scale=case["scale"])
+    box = dataclasses.replace(box, style=capi.PAIR_COUL_LONG, alpha=case["g_ewald"])
+    eng = capi.configure(capi.Engine(prefix, **engine_kw), box, bias=dict(m_lambda=2000.0),
+                         kspace=dict(g_ewald=case["g_ewald"], kmax=case["kmax"]))
+    for step in range(case["steps"]):
+        eng.post_force(step, box.dt, box.x, None)
+    return box, eng
+
+
+def make_ewald_golden(path):
+    out = {"generated_by": "tests/golden/make_golden.py --ewald (oracle output; the reference holds no vectors)", "cases": []}
+    for case in EWALD_CASES:
+        box, o = ewald_case_engine(case)
+        rec = dict(case)
+        rec.update(snapshot(o))
+        rec["e_kspace"] = o.get_kspace_energy()
+        out["cases"].append(rec)
+    with open(path, "w") as fh:
+        json.dump(out, fh, indent=1)
+    print("wrote", path)
+
+
 def main():
     here = os.path.dirname(os.path.abspath(__file__))
+    if "--ewald" in sys.argv:
+        make_ewald_golden(os.path.join(here, "ewald_golden.json"))
+        return
     if "--bench" in sys.argv:
         k = sys.argv.index("--bench")
         config, nranks = int(sys.argv[k + 1]), int(sys.argv[k + 2])

@@ -234,3 +234,44 @@ def test_fix_with_device_ewald_matches_oracle(ewald_files):
     assert r0.returncode == 0, r0.stderr
     rows0, _ = parse(r0.stdout)
     assert abs(rows0[0, 1] - rows[0, 1]) > 1e-6 * abs(rows[0, 1])
+
+
+# ---- frozen oracle outputs (tests/golden/ewald_golden.json, written by tests/golden/make_golden.py --ewald) -------
+def _golden_cases():
+    import json
+    import os
+    import sys
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, here)
+    import make_golden
+    return json.load(open(os.path.join(here, "ewald_golden.json")))["cases"], make_golden.ewald_case_engine
+
+
+def _check_against_golden(eng, case, rtol):
+    s, t, c = eng.get_scalars(), eng.get_sites(), eng.get_counts()
+    # E_coul is the small difference of large parts (pair + reciprocal + self): the k-space energy sets the scale
+    slack = 1e-2 * rtol * abs(case["e_kspace"])
+    for k, v in case["scalars"].items():
+        assert abs(s[k] - v) <= rtol * abs(v) + slack, (case["name"], k, s[k], v)
+    assert abs(eng.get_kspace_energy() - case["e_kspace"]) <= rtol * abs(case["e_kspace"])
+    assert np.abs(t["lambda"] - np.array(case["lambda"])).max() <= 1e-10
+    assert np.allclose(t["dudl"], case["dudl"], rtol=rtol, atol=slack)
+    f = eng.get_forces()
+    assert abs(np.abs(f).sum() - case["f_abs_sum"]) <= rtol * case["f_abs_sum"]
+    assert c["neighbors"] == case["neighbors"] and c["special_pairs"] == case["special_pairs"]
+
+
+def test_oracle_ewald_matches_golden_fixture(built):
+    cases, make = _golden_cases()
+    for case in cases:
+        _, o = make(case)
+        _check_against_golden(o, case, 1e-11)
+
+
+@pytest.mark.gpu
+def test_cuda_ewald_matches_golden_fixture(built):
+    """The CUDA path alone against the committed values: no oracle in the loop."""
+    cases, make = _golden_cases()
+    for case in cases:
+        _, g = make(case, prefix="cph", device=0)
+        _check_against_golden(g, case, 1e-10)
