@@ -331,6 +331,10 @@ struct cph_handle {
   double kspace_unitk[3]{0, 0, 0};   // 2 pi / L_d
   bool kspace_fact = true;           // factorised kernels (CPH_EWALD=direct: one sincos per atom and wave vector)
   int kspace_tile = 32;              // atoms per shared-memory tile of the factorised structure-factor kernel
+  bool kspace_rows = true;           // per-atom sums by the row-walking kernel (CPH_EWALD=tables: the table kernel)
+  int kspace_nrows = 0;
+  DevBuf<int4> d_krows;              // (nx, ny) rows of the wave-vector list
+  DevBuf<double4> d_kpart;           // [slice][atom] partial {pot, fx, fy, fz} of the row-walking kernel
   DevBuf<double2> d_sfac_part, d_sfac;   // structure factors: chunk partials, totals
   DevBuf<double> d_ekspace;          // [nlocal] per-atom k-space energy, [nlocal] their sum
   // comm

@@ -240,6 +240,89 @@ ewald_atom_fact_kernel(int n, const double4 *__restrict__ xq, int K, const doubl
   }
 }
 
+// ---- per-atom sums, row-walking variant ------------------------------------------------------------------------------
+// The wave-vector list is ordered (nx, ny) row by row with nz ascending inside a row, so a row is a contiguous run
+// [zlo, zhi] of nz (row descriptor: nx | (ny+512)<<10, zlo, zhi, index of its first entry).  One THREAD per atom walks
+// the rows of its slice: exp(i nx thetax) and exp(i ny thetay) by sincos once per row, exp(i nz thetaz) by the recurrence
+// E <- E * exp(i thetaz) along the row, everything in registers.  The per-wave-vector data (S, ug) are the same for all
+// lanes of a warp: one broadcast load instead of 32.  No tables, no shuffles; rows are split into slices over
+// blockIdx.y so that small boxes fill the machine, and a second kernel adds the slices in a fixed order.
+constexpr int RTPB = 128;
+
+__global__ void __launch_bounds__(RTPB)
+ewald_atom_rows_kernel(int n, const double4 *__restrict__ xq, int nrows, const int4 *__restrict__ rows,
+                       const double4 *__restrict__ kv, const double2 *__restrict__ S, double ux, double uy, double uz,
+                       int nslice, double4 *__restrict__ part) {
+  const int i = blockIdx.x * RTPB + threadIdx.x;
+  const int sl = blockIdx.y;
+  const int r0 = (int)((long long)nrows * sl / nslice), r1 = (int)((long long)nrows * (sl + 1) / nslice);
+  const double4 p = xq[min(i, n - 1)];
+  const double tx = ux * p.x, ty = uy * p.y, tz = uz * p.z;
+  double s1, c1;
+  sincos(tz, &s1, &c1);
+  double pot = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
+  int cur_nx = -1;
+  double exr = 1.0, exi = 0.0;
+  for (int r = r0; r < r1; r++) {
+    const int4 row = rows[r];
+    const int nx = row.x & 1023, ny = ((row.x >> 10) & 1023) - 512;
+    if (nx != cur_nx) {        // warp-uniform
+      sincos(tx * nx, &exi, &exr);
+      cur_nx = nx;
+    }
+    double eyr, eyi, ezr, ezi;
+    sincos(ty * ny, &eyi, &eyr);
+    sincos(tz * row.y, &ezi, &ezr);
+    const double er = exr * eyr - exi * eyi, ei = exr * eyi + exi * eyr;     // exp(i (nx thetax + ny thetay))
+    double grow = 0.0, gz = 0.0, dnz = (double)row.y;
+    const double4 *kvr = kv + row.w;
+    const double2 *Sr = S + row.w;
+    const int len = row.z - row.y + 1;
+    for (int m = 0; m < len; m++) {
+      const double2 s = Sr[m];
+      const double u2 = 2.0 * kvr[m].w;
+      const double co = er * ezr - ei * ezi, sn = er * ezi + ei * ezr;
+      pot = fma(u2, co * s.x + sn * s.y, pot);
+      const double g = u2 * (sn * s.x - co * s.y);
+      grow += g;
+      gz = fma(g, dnz, gz);
+      dnz += 1.0;
+      const double nr = ezr * c1 - ezi * s1, ni = ezr * s1 + ezi * c1;
+      ezr = nr;
+      ezi = ni;
+    }
+    fx = fma(ux * nx, grow, fx);
+    fy = fma(uy * ny, grow, fy);
+    fz = fma(uz, gz, fz);
+  }
+  if (i < n) part[(size_t)sl * n + i] = make_double4(pot, fx, fy, fz);
+}
+
+__global__ void ewald_atom_combine_kernel(int n, const double4 *__restrict__ xq, int nslice,
+                                          const double4 *__restrict__ part, const double2 *__restrict__ S, int K,
+                                          double qqrd2e, double self2, double bg, int eflag, double *f, double *phi,
+                                          double *eatom, double *ek) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double pot = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
+  for (int sl = 0; sl < nslice; sl++) {
+    const double4 v = part[(size_t)sl * n + i];
+    pot += v.x; fx += v.y; fy += v.z; fz += v.w;
+  }
+  const double q = xq[i].w;
+  const double ph = qqrd2e * (pot - self2 * q - bg * S[K].x);
+  const double c = qqrd2e * q;
+  f[3 * (size_t)i] += c * fx;
+  f[3 * (size_t)i + 1] += c * fy;
+  f[3 * (size_t)i + 2] += c * fz;
+  if (eflag) {
+    const double en = 0.5 * q * ph;
+    phi[i] += ph;
+    eatom[i] += en;
+    ek[i] = en;
+  }
+}
+
 // one block, fixed order: out = sum_i ek[i]
 __global__ void __launch_bounds__(256) ewald_energy_kernel(int n, const double *__restrict__ ek, double *out) {
   __shared__ double sm[256];
@@ -273,8 +356,11 @@ int cph_kspace_setup(cph_handle *h) {
   gsqmx *= 1.00001;
   std::vector<double4> kv;
   std::vector<int> kidx;
+  std::vector<int4> rows;      // (nx, ny) rows of the list: nx | (ny+512)<<10, first nz, last nz, index of the first entry
   for (int nx = 0; nx <= h->kmax[0]; nx++)
-    for (int ny = -h->kmax[1]; ny <= h->kmax[1]; ny++)
+    for (int ny = -h->kmax[1]; ny <= h->kmax[1]; ny++) {
+      const size_t row_first = kv.size();
+      int zlo = 0, zhi = -1;
       for (int nz = -h->kmax[2]; nz <= h->kmax[2]; nz++) {
         if (!(nx > 0 || (nx == 0 && ny > 0) || (nx == 0 && ny == 0 && nz > 0))) continue;   // half space
         const double kx = unitk[0] * nx, ky = unitk[1] * ny, kz = unitk[2] * nz;
@@ -282,7 +368,16 @@ int cph_kspace_setup(cph_handle *h) {
         if (sqk > gsqmx) continue;
         kv.push_back(make_double4(kx, ky, kz, 4.0 * PI / V * std::exp(-0.25 * sqk / (g * g)) / sqk));
         kidx.push_back((nx & 1023) | (((ny + 512) & 1023) << 10) | (((nz + 512) & 1023) << 20));
+        if (zhi < zlo) zlo = nz;
+        zhi = nz;
       }
+      // the sphere and the half space both cut a row down to ONE run of consecutive nz (checked: the run is as long
+      // as the number of entries the row added)
+      if (zhi >= zlo) {
+        if ((size_t)(zhi - zlo + 1) != kv.size() - row_first) return cph_fail(h, CPH_ERR_STATE, "ewald: broken row of wave vectors");
+        rows.push_back(make_int4((nx & 1023) | (((ny + 512) & 1023) << 10), zlo, zhi, (int)row_first));
+      }
+    }
   h->nkvec = (int)kv.size();
   kv.push_back(make_double4(0.0, 0.0, 0.0, 0.0));   // zero wave vector: its "structure factor" is sum q
   kidx.push_back(0 | (512 << 10) | (512 << 20));
@@ -290,6 +385,9 @@ int cph_kspace_setup(cph_handle *h) {
   CPH_CUDA(h, h->d_kidx.reserve(kidx.size()));
   CPH_CUDA(h, cudaMemcpyAsync(h->d_kvec.p, kv.data(), kv.size() * sizeof(double4), cudaMemcpyHostToDevice, h->stream));
   CPH_CUDA(h, cudaMemcpyAsync(h->d_kidx.p, kidx.data(), kidx.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  h->kspace_nrows = (int)rows.size();
+  CPH_CUDA(h, h->d_krows.reserve(rows.size() + 1));
+  CPH_CUDA(h, cudaMemcpyAsync(h->d_krows.p, rows.data(), rows.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
   CPH_CUDA(h, cudaStreamSynchronize(h->stream));
   for (int d = 0; d < 3; d++) h->kspace_unitk[d] = unitk[d];
   // factorised kernels: phase tables of kxmax+kymax+kzmax+3 entries per atom in shared memory (48 KB without opt-in)
@@ -299,6 +397,8 @@ int cph_kspace_setup(cph_handle *h) {
   h->kspace_fact = !(mode && !strcmp(mode, "direct")) && h->kspace_tile >= 4 &&
                    (size_t)(ATPB / 32) * stride * sizeof(double2) <= 48 * 1024 &&
                    h->kmax[0] <= 511 && h->kmax[1] <= 511 && h->kmax[2] <= 511;
+  // per-atom sums: row-walking kernel (default) or the table kernel (CPH_EWALD=tables)
+  h->kspace_rows = h->kspace_fact && !(mode && !strcmp(mode, "tables"));
   h->kspace_self2 = 2.0 * g / 1.77245385090551602729;
   h->kspace_bg = PI / (g * g * V);
   return CPH_OK;
@@ -333,7 +433,18 @@ int cph_launch_kspace(cph_handle *h, int eflag) {
   CPH_TRY(cph_comm_allreduce(h, reinterpret_cast<double *>(h->d_sfac.p), 2 * K1));
   if (n > 0) {
     const int ablocks = (n + ATPB / 32 - 1) / (ATPB / 32);
-    if (fact)
+    if (h->kspace_rows) {
+      const int rblocks = (n + RTPB - 1) / RTPB;
+      const int nslice = std::max(1, std::min(std::min(64, h->kspace_nrows), (4 * h->num_sms + rblocks - 1) / rblocks));
+      CPH_CUDA(h, h->d_kpart.reserve((size_t)nslice * n));
+      ewald_atom_rows_kernel<<<dim3(rblocks, nslice), RTPB, 0, st>>>(n, h->d_xq.p, h->kspace_nrows, h->d_krows.p,
+                                                                    h->d_kvec.p, h->d_sfac.p, u[0], u[1], u[2], nslice,
+                                                                    h->d_kpart.p);
+      ewald_atom_combine_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, h->d_xq.p, nslice, h->d_kpart.p, h->d_sfac.p, K,
+                                                                h->qqrd2e, h->kspace_self2, h->kspace_bg, eflag, h->d_f.p,
+                                                                h->d_phi.p, h->d_eatom.p, h->d_ekspace.p);
+      h->nlaunch++;
+    } else if (fact)
       ewald_atom_fact_kernel<<<ablocks, ATPB, (ATPB / 32) * stride_bytes, st>>>(
           n, h->d_xq.p, K, h->d_kvec.p, h->d_kidx.p, h->d_sfac.p, nx1, ny1, nz1, u[0], u[1], u[2], h->qqrd2e,
           h->kspace_self2, h->kspace_bg, eflag, h->d_f.p, h->d_phi.p, h->d_eatom.p, h->d_ekspace.p);
@@ -361,6 +472,8 @@ int cph_kspace_energy(cph_handle *h, double *out) {
 void cph_kspace_release(cph_handle *h) {
   h->d_kvec.release();
   h->d_kidx.release();
+  h->d_krows.release();
+  h->d_kpart.release();
   h->d_sfac_part.release();
   h->d_sfac.release();
   h->d_ekspace.release();
