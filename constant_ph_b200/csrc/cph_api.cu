@@ -1117,7 +1117,7 @@ int cph_profile_get(cph_handle *h, int which, double *ms_total, int64_t *launche
     *launches = h->nprunes;
     return CPH_OK;
   }
-  if (which < 0 || which > 10) return cph_fail(h, CPH_ERR_ARG, "profile slot %d out of range", which);
+  if (which < 0 || which > 11) return cph_fail(h, CPH_ERR_ARG, "profile slot %d out of range", which);
   *ms_total = h->prof[which].ms;
   *launches = h->prof[which].launches;
   return CPH_OK;

@@ -331,6 +331,7 @@ struct cph_handle {
   double kspace_unitk[3]{0, 0, 0};   // 2 pi / L_d
   bool kspace_fact = true;           // factorised kernels (CPH_EWALD=direct: one sincos per atom and wave vector)
   int kspace_tile = 32;              // atoms per shared-memory tile of the factorised structure-factor kernel
+  int kspace_tune[5]{256, 6, 256, 32, 6};   // launch shapes of the k-space kernels (kspace.cu, CPH_EWALD_TUNE)
   bool kspace_rows = true;           // per-atom sums by the row-walking kernel (CPH_EWALD=tables: the table kernel)
   int kspace_nrows = 0;
   DevBuf<int4> d_krows;              // (nx, ny) rows of the wave-vector list
@@ -343,7 +344,7 @@ struct cph_handle {
   // timing
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool profiling = false;
-  ProfSlot prof[11];                 // 0..7 per kernel class, 10 k-space (8 and 9 are counters, see cph_profile_get)
+  ProfSlot prof[12];                 // 0..7 per kernel class, 10 / 11 k-space (8 and 9 are counters, see cph_profile_get)
   cudaEvent_t pev0 = nullptr, pev1 = nullptr;
 };
 

@@ -140,7 +140,7 @@ ewald_sfac_fact_kernel(int n, const double4 *__restrict__ xq, int K1, const int 
                        int nx1, int ny1, int nz1, double ux, double uy, double uz, double2 *__restrict__ part) {
   extern __shared__ double2 tab[];
   const int stride = nx1 + ny1 + nz1;
-  const int k = blockIdx.x * FTPB + threadIdx.x;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int c = blockIdx.y;
   const int lo = (int)((long long)n * c / nchunk), hi = (int)((long long)n * (c + 1) / nchunk);
   int ix = 0, iy = nx1, iz = nx1 + ny1;
@@ -247,13 +247,13 @@ ewald_atom_fact_kernel(int n, const double4 *__restrict__ xq, int K, const doubl
 // E <- E * exp(i thetaz) along the row, everything in registers.  The per-wave-vector data (S, ug) are the same for all
 // lanes of a warp: one broadcast load instead of 32.  No tables, no shuffles; rows are split into slices over
 // blockIdx.y so that small boxes fill the machine, and a second kernel adds the slices in a fixed order.
-constexpr int RTPB = 128;
+constexpr int RTPB = 256;      // default block; the launch may use 64..256 (CPH_EWALD_TUNE)
 
-__global__ void __launch_bounds__(RTPB)
+__global__ void __launch_bounds__(256)
 ewald_atom_rows_kernel(int n, const double4 *__restrict__ xq, int nrows, const int4 *__restrict__ rows,
                        const double4 *__restrict__ kv, const double2 *__restrict__ S, double ux, double uy, double uz,
                        int nslice, double4 *__restrict__ part) {
-  const int i = blockIdx.x * RTPB + threadIdx.x;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int sl = blockIdx.y;
   const int r0 = (int)((long long)nrows * sl / nslice), r1 = (int)((long long)nrows * (sl + 1) / nslice);
   const double4 p = xq[min(i, n - 1)];
@@ -399,6 +399,16 @@ int cph_kspace_setup(cph_handle *h) {
                    h->kmax[0] <= 511 && h->kmax[1] <= 511 && h->kmax[2] <= 511;
   // per-atom sums: row-walking kernel (default) or the table kernel (CPH_EWALD=tables)
   h->kspace_rows = h->kspace_fact && !(mode && !strcmp(mode, "tables"));
+  // launch shapes (CPH_EWALD_TUNE="rows_block,rows_blocks_per_sm,sfac_block,sfac_tile,sfac_blocks_per_sm" overrides)
+  // defaults from the sweep on config 2 (profiles/r2z6_ewald_tune.json): rows 256 threads x 6 blocks per SM (1.12 ms
+  // against 1.44 at 128 x 4), structure factors 256 threads, 32-atom tiles, 6 blocks per SM (0.98 against 1.11 ms)
+  int tune[5] = {RTPB, 6, FTPB, FTA, 6};
+  if (const char *t = getenv("CPH_EWALD_TUNE")) sscanf(t, "%d,%d,%d,%d,%d", &tune[0], &tune[1], &tune[2], &tune[3], &tune[4]);
+  h->kspace_tune[0] = std::max(32, std::min(256, tune[0] & ~31));
+  h->kspace_tune[1] = std::max(1, std::min(16, tune[1]));
+  h->kspace_tune[2] = std::max(96, std::min(256, tune[2] & ~31));
+  h->kspace_tune[3] = std::max(4, std::min(h->kspace_tile, std::min(tune[3], h->kspace_tune[2] / 3)));
+  h->kspace_tune[4] = std::max(1, std::min(16, tune[4]));
   h->kspace_self2 = 2.0 * g / 1.77245385090551602729;
   h->kspace_bg = PI / (g * g * V);
   return CPH_OK;
@@ -407,37 +417,44 @@ int cph_kspace_setup(cph_handle *h) {
 // after the pair pass (and the other terms that add to it): the reciprocal sum at the current positions and charges
 int cph_launch_kspace(cph_handle *h, int eflag) {
   if (h->kspace_style != CPH_KSPACE_EWALD) return CPH_OK;
-  ProfScope ps(h, 10);
   const int n = h->nlocal, K = h->nkvec, K1 = K + 1;
   cudaStream_t st = h->stream;
   const bool fact = h->kspace_fact;
-  const int ktpb = fact ? FTPB : KTPB, tile = fact ? h->kspace_tile : TILE;
+  const int ktpb = fact ? h->kspace_tune[2] : KTPB, tile = fact ? h->kspace_tune[3] : TILE;
   const int kblocks = (K1 + ktpb - 1) / ktpb;
-  // enough (wave-vector block, atom chunk) pairs for four blocks per SM, chunks of at least one tile
-  const int nchunk = std::max(1, std::min(std::min(64, (n + tile - 1) / tile), (4 * h->num_sms + kblocks - 1) / kblocks));
+  // enough (wave-vector block, atom chunk) pairs for a few blocks per SM, chunks of at least one tile
+  const int bps = fact ? h->kspace_tune[4] : 4;
+  const int nchunk = std::max(1, std::min(std::min(64, (n + tile - 1) / tile), (bps * h->num_sms + kblocks - 1) / kblocks));
   const int nx1 = h->kmax[0] + 1, ny1 = h->kmax[1] + 1, nz1 = h->kmax[2] + 1;
   const size_t stride_bytes = (size_t)(nx1 + ny1 + nz1) * sizeof(double2);
   const double *u = h->kspace_unitk;
+  {
+  ProfScope ps(h, 10);      // structure factors
   CPH_CUDA(h, h->d_sfac_part.reserve((size_t)nchunk * K1));
   CPH_CUDA(h, h->d_sfac.reserve((size_t)K1));
   CPH_CUDA(h, h->d_ekspace.reserve((size_t)n + 2));
   if (fact)
-    ewald_sfac_fact_kernel<<<dim3(kblocks, nchunk), FTPB, tile * stride_bytes, st>>>(
+    ewald_sfac_fact_kernel<<<dim3(kblocks, nchunk), ktpb, tile * stride_bytes, st>>>(
         n, h->d_xq.p, K1, h->d_kidx.p, nchunk, tile, nx1, ny1, nz1, u[0], u[1], u[2], h->d_sfac_part.p);
   else
     ewald_sfac_kernel<<<dim3(kblocks, nchunk), KTPB, 0, st>>>(n, h->d_xq.p, K1, h->d_kvec.p, nchunk, h->d_sfac_part.p);
   ewald_sfac_sum_kernel<<<(K1 + 255) / 256, 256, 0, st>>>(K1, nchunk, h->d_sfac_part.p, h->d_sfac.p);
   h->nlaunch += 2;
   CPH_CUDA(h, cudaGetLastError());
+  }
   // several ranks: every rank summed over the atoms it owns
   CPH_TRY(cph_comm_allreduce(h, reinterpret_cast<double *>(h->d_sfac.p), 2 * K1));
+  ProfScope ps(h, 11);      // per-atom sums
   if (n > 0) {
     const int ablocks = (n + ATPB / 32 - 1) / (ATPB / 32);
-    if (h->kspace_rows) {
-      const int rblocks = (n + RTPB - 1) / RTPB;
-      const int nslice = std::max(1, std::min(std::min(64, h->kspace_nrows), (4 * h->num_sms + rblocks - 1) / rblocks));
+    // small boxes: the warp-per-atom table kernel has more parallelism (0.025 against 0.042 ms at 3k atoms)
+    if (h->kspace_rows && n >= 4096) {
+      const int rtpb = h->kspace_tune[0];
+      const int rblocks = (n + rtpb - 1) / rtpb;
+      const int nslice = std::max(1, std::min(std::min(64, h->kspace_nrows),
+                                              (h->kspace_tune[1] * h->num_sms + rblocks - 1) / rblocks));
       CPH_CUDA(h, h->d_kpart.reserve((size_t)nslice * n));
-      ewald_atom_rows_kernel<<<dim3(rblocks, nslice), RTPB, 0, st>>>(n, h->d_xq.p, h->kspace_nrows, h->d_krows.p,
+      ewald_atom_rows_kernel<<<dim3(rblocks, nslice), rtpb, 0, st>>>(n, h->d_xq.p, h->kspace_nrows, h->d_krows.p,
                                                                     h->d_kvec.p, h->d_sfac.p, u[0], u[1], u[2], nslice,
                                                                     h->d_kpart.p);
       ewald_atom_combine_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, h->d_xq.p, nslice, h->d_kpart.p, h->d_sfac.p, K,

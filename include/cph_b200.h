@@ -307,7 +307,7 @@ int cph_timer_start(cph_handle *h);
 int cph_timer_stop(cph_handle *h, double *ms);
 /* ... and per kernel class while enabled.  which: 0 pair evaluation, 1 inner-list prune (+ fp32 record
  * refresh), 2 site reduce, 3 lambda integrator, 4 charge / force update, 5 halo + allreduce, 6 list build
- * (all stages), 7 new positions + displacement check, 10 k-space (structure factors + per-atom sums).  Always
+ * (all stages), 7 new positions + displacement check, 10 k-space structure factors, 11 k-space per-atom sums.  Always
  * available: 8 -> launches = kernels of this library launched so far, 9 -> launches = inner-list prunes so far. */
 int cph_profile(cph_handle *h, int enable);
 int cph_profile_get(cph_handle *h, int which, double *ms_total, int64_t *launches);

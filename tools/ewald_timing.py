@@ -27,12 +27,15 @@ def run(box, kmax, mode, passes=10):
     for _ in range(passes):
         eng.pair_pass(1)
     eng.sync()
-    ms_k, n_k = eng.profile_get(10)
+    ms_s, n_k = eng.profile_get(10)      # structure factors
+    ms_a, _ = eng.profile_get(11)        # per-atom sums
+    ms_k = ms_s + ms_a
     ms_p, n_p = eng.profile_get(0)
     eng.profile(False)
     eng.site_reduce()
     out = dict(f=eng.get_forces().copy(), phi=eng.get_phi().copy(), ek=eng.get_kspace_energy(),
-               kspace_ms=ms_k / max(n_k, 1), pair_ms=ms_p / max(n_p, 1))
+               kspace_ms=ms_k / max(n_k, 1), sfac_ms=ms_s / max(n_k, 1), atom_ms=ms_a / max(n_k, 1),
+               pair_ms=ms_p / max(n_p, 1))
     eng.close()
     return out
 
@@ -42,6 +45,21 @@ def main():
         box = dataclasses.replace(synth.config(2), style=capi.PAIR_COUL_LONG, alpha=0.30)
         r = run(box, (22, 22, 22), "rows", passes=3)
         print(json.dumps(dict(kspace_ms=r["kspace_ms"])))
+        return
+    if "--tune" in sys.argv:            # launch-shape sweep (CPH_EWALD_TUNE) on config 2
+        box = dataclasses.replace(synth.config(2), style=capi.PAIR_COUL_LONG, alpha=0.30)
+        out = {"rows": {}, "sfac": {}}
+        for blk in (64, 128, 256):
+            for bps in (4, 6, 8, 12):
+                os.environ["CPH_EWALD_TUNE"] = "%d,%d,256,32,4" % (blk, bps)
+                out["rows"]["%d,%d" % (blk, bps)] = round(run(box, (22, 22, 22), "rows", passes=4)["atom_ms"], 4)
+        for blk in (128, 256):
+            for tile in (16, 32):
+                for bps in (4, 6, 8):
+                    os.environ["CPH_EWALD_TUNE"] = "128,4,%d,%d,%d" % (blk, tile, bps)
+                    out["sfac"]["%d,%d,%d" % (blk, tile, bps)] = round(run(box, (22, 22, 22), "rows", passes=4)["sfac_ms"], 4)
+        os.environ.pop("CPH_EWALD_TUNE", None)
+        print(json.dumps(out))
         return
     res = {}
     peak_warp_dfma, _ = capi.bench_fp64_peak(0)
@@ -61,7 +79,7 @@ def main():
         pairs = 2.0 * box.n * K             # (atom, wave vector) evaluations of both kernels of a pass
         res[name] = dict(
             atoms=box.n, kmax=list(kmax), wave_vectors=K,
-            default_ms_per_pass=a["kspace_ms"], tables_ms_per_pass=t["kspace_ms"], direct_ms_per_pass=b["kspace_ms"],
+            default_ms_per_pass=a["kspace_ms"], default_structure_factors_ms=a["sfac_ms"], default_atom_sums_ms=a["atom_ms"], tables_ms_per_pass=t["kspace_ms"], direct_ms_per_pass=b["kspace_ms"],
             pair_pass_ms=a["pair_ms"], speedup_over_direct=b["kspace_ms"] / a["kspace_ms"],
             tables_force_rel_diff=float(np.abs(t["f"] - b["f"]).max() / np.abs(b["f"]).max()),
             atom_wavevector_evaluations_per_s=pairs / (a["kspace_ms"] * 1e-3),
