@@ -50,6 +50,25 @@ def test_constructor_argument_errors(box_files):
     assert r.returncode == 2 and "Cannot open" in r.stderr
 
 
+def test_every_keyword_rejects_a_bad_value(box_files):
+    """The keyword loop the reference leaves empty (cpp:51-54): every two-word keyword refuses a third word, numeric
+    keywords refuse text and out-of-range values -- all before any device work."""
+    _, b, s = box_files
+    for key in ("dudl", "integrator", "fscale", "bias", "buffer", "coordinate", "excluded"):
+        r = run([b, 1, key, "bogus"])
+        assert r.returncode == 2 and "Illegal fix constant_pH %s value bogus" % key in r.stderr, (key, r.stderr)
+    for key, val, msg in (("mlambda", "-1", "Illegal fix constant_pH mlambda value"),
+                          ("tlambda", "-5", "Illegal fix constant_pH tlambda value"),
+                          ("mlambda", "heavy", "Expected floating point parameter"),
+                          ("bias_w", "wide", "Expected floating point parameter"),
+                          ("bias_q", "1.0", "Unknown fix constant_pH keyword")):
+        r = run([b, 1, key, val])
+        assert r.returncode == 2 and msg in r.stderr, (key, val, r.stderr)
+    # positional arguments (cpp:36-49): too few, unknown groups
+    r = subprocess.run([HARNESS, b], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1                                   # the harness' own usage line
+
+
 def test_no_gpu_is_a_loud_error(box_files):
     import torch
     if torch.cuda.is_available():
