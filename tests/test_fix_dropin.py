@@ -286,19 +286,14 @@ def test_fix_two_ranks_matches_one_rank(dsf_box_files, nranks):
     assert one.returncode == 0, one.stderr
     rows1, extra1 = parse(one.stdout)
     import tempfile
-    # The library binds NCCL with dlopen("libnccl.so.2") -- inside LAMMPS that is the system's.  Here the search path
-    # leads to the copy PyTorch ships: the same library the torchrun tests use, and already paged in on a fresh box
-    # (the system's 400 MB libnccl took 200 s to fault in from the image on first use).
-    import torch
-    nccl_dir = os.path.join(os.path.dirname(os.path.dirname(torch.__file__)), "nvidia", "nccl", "lib")
-    ld = os.environ.get("LD_LIBRARY_PATH", "")
-    if os.path.isdir(nccl_dir):
-        ld = nccl_dir + (":" + ld if ld else "")
+    # The library binds NCCL with dlopen("libnccl.so.2"): in these harness processes (no PyTorch) that is the system's
+    # 400 MB library, which a fresh GPU box faults in from the image on first use -- this test took 212 s there, almost
+    # all of it in that first load (profiles/r2z_summary.md).  Inside LAMMPS the library is resident long before.
     with tempfile.TemporaryDirectory(dir=d) as scratch:
         procs = []
         for rank in range(nranks):
             env = dict(os.environ, CPH_SHIM_RANK=str(rank), CPH_SHIM_NRANKS=str(nranks), CPH_SHIM_DIR=scratch,
-                       LOCAL_RANK=str(rank), LD_LIBRARY_PATH=ld)
+                       LOCAL_RANK=str(rank))
             procs.append(subprocess.Popen([HARNESS] + [str(a) for a in args], stdout=subprocess.PIPE,
                                           stderr=subprocess.PIPE, text=True, env=env))
         outs = [p.communicate(timeout=600) for p in procs]
