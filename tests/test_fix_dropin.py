@@ -287,8 +287,9 @@ def test_fix_two_ranks_matches_one_rank(dsf_box_files, nranks):
     rows1, extra1 = parse(one.stdout)
     import tempfile
     # The library binds NCCL with dlopen("libnccl.so.2"): in these harness processes (no PyTorch) that is the system's
-    # 400 MB library, which a fresh GPU box faults in from the image on first use -- this test took 212 s there, almost
-    # all of it in that first load (profiles/r2z_summary.md).  Inside LAMMPS the library is resident long before.
+    # 400 MB library, which a fresh GPU box faults in from the image on first use.  This test took 212 s on such a box
+    # (profiles/r2z_summary.md) against 10-20 s for the torchrun-based 2-rank tests that use PyTorch's resident copy;
+    # that first load is the likely cause, it was not timed separately.
     with tempfile.TemporaryDirectory(dir=d) as scratch:
         procs = []
         for rank in range(nranks):
