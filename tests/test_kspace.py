@@ -105,6 +105,33 @@ def test_oracle_ewald_forces_are_the_energy_gradient_and_dudl_the_lambda_derivat
     assert abs(e0) > 0
 
 
+def test_oracle_ewald_is_invariant_under_translation_and_atom_order(built):
+    """Moving every atom by the same vector (periodic box) or handing the atoms over in another order must not change
+    the energy, and forces must follow their atoms -- for the pair part and the reciprocal sum together."""
+    box = ewald_box(1)
+    kw = dict(kspace=dict(g_ewald=box.alpha, kmax=(6, 6, 6)))
+    o = capi.configure(capi.Engine("orc"), box, **kw)
+    e0 = total_energy(o)
+    f0 = o.get_forces().copy()
+    d0 = o.get_sites()["dudl"].copy()
+    # rigid shift, atoms wrapped back into the box
+    L = box.boxhi - box.boxlo
+    shifted = dataclasses.replace(box, x=box.boxlo + np.mod(box.x + np.array([3.7, -11.2, 0.9]) - box.boxlo, L))
+    o1 = capi.configure(capi.Engine("orc"), shifted, **kw)
+    assert abs(total_energy(o1) - e0) <= 1e-9 * max(1.0, abs(e0))
+    assert np.abs(o1.get_forces() - f0).max() <= 1e-9 * np.abs(f0).max()
+    assert np.allclose(o1.get_sites()["dudl"], d0, rtol=1e-9, atol=1e-9)
+    # another atom order (tags travel with the atoms, so sites and special lists still resolve)
+    perm = np.random.default_rng(5).permutation(box.n)
+    mixed = dataclasses.replace(box, x=box.x[perm], q=box.q[perm], type=box.type[perm], tag=box.tag[perm],
+                                mask=box.mask[perm], molecule=box.molecule[perm], nspecial=box.nspecial[perm],
+                                special=box.special[perm])
+    o2 = capi.configure(capi.Engine("orc"), mixed, **kw)
+    assert abs(total_energy(o2) - e0) <= 1e-10 * max(1.0, abs(e0))
+    assert np.abs(o2.get_forces() - f0[perm]).max() <= 1e-10 * np.abs(f0).max()
+    assert np.allclose(o2.get_sites()["dudl"], d0, rtol=1e-10, atol=1e-10)
+
+
 def test_kspace_argument_errors(built):
     box = ewald_box(1)
     o = capi.Engine("orc")
